@@ -1,0 +1,149 @@
+// Register/shared-memory FFT building blocks.
+//
+// A length-M complex transform (M = nperseg/2: the real segment is packed as M complex numbers) is
+// done by a group of G = M/R0 threads as a Stockham autosort FFT: every pass each thread holds R0
+// complex values in registers, performs R0/R radix-R butterflies on them, and exchanges through a
+// padded shared-memory line.  Radices per size (first pass = R0):
+//   M:   4    8    16    32     64    128     256      512      1024      2048       4096
+//        4    8    16   8,4    8,8   16,8   16,16    8,8,8    16,8,8   16,16,8   16,16,16
+#pragma once
+#include "common.cuh"
+
+namespace specgpu {
+
+__host__ __device__ constexpr int fft_radix_at(int log2m, int idx) {
+  constexpr int T[13][3] = {{1, 1, 1},  {1, 1, 1},   {4, 1, 1},   {8, 1, 1},   {16, 1, 1},
+                            {8, 4, 1},  {8, 8, 1},   {16, 8, 1},  {16, 16, 1}, {8, 8, 8},
+                            {16, 8, 8}, {16, 16, 8}, {16, 16, 16}};
+  return T[log2m][idx];
+}
+__host__ __device__ constexpr int fft_num_passes(int log2m) {
+  return (fft_radix_at(log2m, 1) == 1) ? 1 : ((fft_radix_at(log2m, 2) == 1) ? 2 : 3);
+}
+
+// Padded index into a shared-memory FFT line: one float2 of padding per 16 keeps the strided
+// first-pass stores and last-pass loads off a single bank.
+__host__ __device__ __forceinline__ constexpr int fft_pad(int i) { return i + (i >> 4); }
+
+// cos/sin(2*pi*k/16), k = 0..7 -- every twiddle of an in-register radix <= 16 butterfly.
+__device__ __forceinline__ float2 w16(int k) {
+  constexpr float C[8] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                          0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+  constexpr float S[8] = {0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
+                          1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+  return make_float2(C[k], -S[k]);  // exp(-2*pi*i*k/16)
+}
+
+// Forward DFT of R values held in registers (natural order in, natural order out).
+template <int R>
+__device__ __forceinline__ void dft_reg(float2 (&v)[R]) {
+  if constexpr (R == 2) {
+    float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  } else if constexpr (R == 4) {
+    float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    float2 t2 = cadd(v[1], v[3]), t3 = csub(v[1], v[3]);
+    v[0] = cadd(t0, t2);
+    v[2] = csub(t0, t2);
+    v[1] = make_float2(t1.x + t3.y, t1.y - t3.x);  // t1 - i*t3
+    v[3] = make_float2(t1.x - t3.y, t1.y + t3.x);  // t1 + i*t3
+  } else if constexpr (R > 4) {
+    float2 e[R / 2], o[R / 2];
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      e[k] = v[2 * k];
+      o[k] = v[2 * k + 1];
+    }
+    dft_reg<R / 2>(e);
+    dft_reg<R / 2>(o);
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      float2 t;
+      if (k == 0) {
+        t = o[k];
+      } else if (4 * k == R) {
+        t = make_float2(o[k].y, -o[k].x);  // -i * o
+      } else {
+        t = cmul(w16(k * (16 / R)), o[k]);
+      }
+      v[k] = cadd(e[k], t);
+      v[k + R / 2] = csub(e[k], t);
+    }
+  }
+}
+
+// One Stockham pass (radix R, p = product of the radices of earlier passes) on the R0 register values of
+// thread `tg` of a G-thread group.  Registers v[q*R + r] hold element r of butterfly i_q = tg + q*G.
+//   load : v <- line[i_q + r*M/R] * W_M^(k*r*M/(p*R)),  k = i_q mod p
+//   store: line[(i_q-k)*R + k + r*p] <- DFT_R(v)
+template <int M, int R0, int R, int P>
+struct FftPass {
+  static constexpr int G = M / R0;
+  static constexpr int NB = R0 / R;
+  static __device__ __forceinline__ void load(float2 (&v)[R0], const float2* line, const float2* twM, int tg) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int i = tg + q * G;
+      const int k = i & (P - 1);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float2 a = line[fft_pad(i + r * (M / R))];
+        if (r > 0 && P > 1) a = cmul(a, twM[k * r * (M / (P * R))]);
+        v[q * R + r] = a;
+      }
+    }
+  }
+  static __device__ __forceinline__ void butterflies(float2 (&v)[R0]) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      float2 u[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) u[r] = v[q * R + r];
+      dft_reg<R>(u);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[q * R + r] = u[r];
+    }
+  }
+  static __device__ __forceinline__ void store(const float2 (&v)[R0], float2* line, int tg) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int i = tg + q * G;
+      const int k = i & (P - 1);
+      const int j = (i - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) line[fft_pad(j + r * P)] = v[q * R + r];
+    }
+  }
+};
+
+// Full transform.  On entry v holds the first-pass inputs of thread tg (element r = z[tg + r*G]);
+// on exit line[fft_pad(k)] = Z[k], k < M, and every thread of the CTA has passed a barrier.
+// All threads of the CTA must call this together (it uses __syncthreads()).
+template <int LOG2M>
+__device__ __forceinline__ void fft_group(float2 (&v)[fft_radix_at(LOG2M, 0)], float2* line, const float2* twM, int tg) {
+  constexpr int M = 1 << LOG2M;
+  constexpr int R0 = fft_radix_at(LOG2M, 0);
+  constexpr int R1 = fft_radix_at(LOG2M, 1);
+  constexpr int R2 = fft_radix_at(LOG2M, 2);
+  // pass 0: a single radix-R0 butterfly straight from registers
+  FftPass<M, R0, R0, 1>::butterflies(v);
+  FftPass<M, R0, R0, 1>::store(v, line, tg);
+  __syncthreads();
+  if constexpr (R1 > 1) {
+    FftPass<M, R0, R1, R0>::load(v, line, twM, tg);
+    FftPass<M, R0, R1, R0>::butterflies(v);
+    __syncthreads();
+    FftPass<M, R0, R1, R0>::store(v, line, tg);
+    __syncthreads();
+  }
+  if constexpr (R2 > 1) {
+    FftPass<M, R0, R2, R0 * R1>::load(v, line, twM, tg);
+    FftPass<M, R0, R2, R0 * R1>::butterflies(v);
+    __syncthreads();
+    FftPass<M, R0, R2, R0 * R1>::store(v, line, tg);
+    __syncthreads();
+  }
+}
+
+}  // namespace specgpu

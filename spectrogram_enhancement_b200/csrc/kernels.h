@@ -1,0 +1,69 @@
+// Internal launcher interface between the C ABI (specgpu.cu) and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace specgpu {
+
+enum { STFT_MODE_PSD = 0, STFT_MODE_LOGPSD = 1, STFT_MODE_COMPLEX = 2, STFT_MODE_SPECTRA = 3 };
+
+struct StftArgs {
+  const float* x;        // [B][ldx]
+  int64_t n;             // valid samples per signal
+  int64_t ldx;
+  int64_t first_start;   // sample index of segment 0 (negative with boundary='zeros')
+  int64_t nseg;
+  int hop;
+  int detrend;
+  int vec_ok;            // float2 loads are aligned
+  float scale;           // psd scale (sqrt(scale) for STFT_MODE_COMPLEX)
+  float eps;
+  const float* window;   // [nperseg]
+  const float2* twM;     // exp(-2 pi i j / M), j < M
+  const float2* twN;     // exp(-2 pi i k / N), k <= M/2
+  void* out;
+  int64_t ld_out;
+  unsigned* minmax;      // [B][2] ordered-uint min / max (STFT_MODE_LOGPSD)
+};
+
+// stft.cu
+int launch_stft(int log2n, int mode, const StftArgs& a, int64_t B, cudaStream_t stream);
+int launch_minmax_init(unsigned* mm, int64_t B, cudaStream_t stream);
+int launch_lognorm(float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* mm, float* mm_out,
+                   cudaStream_t stream);
+
+// elementwise.cu
+int launch_rescale(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst, unsigned* mm_ws,
+                   cudaStream_t stream);
+int launch_norm(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst, double* sums_ws,
+                cudaStream_t stream);
+int launch_patch(const float* src, int64_t n, int64_t rows, int64_t ld, int tile_w, int ntiles, void* out, int out_f64,
+                 cudaStream_t stream);
+int launch_unpatch(const void* tiles, int in_f64, int64_t n, int64_t rows, int tile_w, int ntiles, void* dst,
+                   int out_f64, int64_t ld, cudaStream_t stream);
+
+// quantile.cu
+int launch_quantfilt(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, int lo, float g, float* dst,
+                     float* thr_out, uint8_t* mask, cudaStream_t stream);
+
+// svd.cu
+struct SvdWorkspace {
+  float* G;        // [B][n][n] Gram matrices (overwritten by the eigen-solver)
+  float* U;        // [B][n][n] eigenvectors, column k = k-th largest (row-major, U[i*n+k])
+  float* lam;      // [B][n] eigenvalues, descending
+  int32_t* plan;   // [B][4] {a, b, num_sing, status}
+};
+size_t svd_workspace_bytes(int64_t B, int64_t n);
+int launch_gram(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* G, cudaStream_t stream);
+int launch_eig_power(const float* G, int64_t B, int n, float* U, float* lam, int32_t* plan, cudaStream_t stream);
+int launch_eig_jacobi(float* G, int64_t B, int n, float* U, float* lam, int32_t* plan, cudaStream_t stream);
+int launch_svd_plan(const float* lam, int64_t B, int n, int64_t cols, int start, int stop, int mode, int32_t* plan,
+                    float* s_out, cudaStream_t stream);
+int launch_svd_reconstruct(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U,
+                           const int32_t* plan, int clip, void* out, int out_f64, int64_t ldo, cudaStream_t stream);
+
+// csd.cu
+int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t ldf, int nfreq, int64_t i0, int64_t ni,
+                     float scale, float* partial_ws, float* P, cudaStream_t stream);
+size_t csd_pairs_workspace_bytes(int64_t C, int64_t ni, int nfreq, int64_t nseg);
+
+}  // namespace specgpu

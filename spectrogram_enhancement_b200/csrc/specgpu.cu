@@ -1,0 +1,333 @@
+// libspecgpu C ABI: context / plan plumbing and the entry points declared in include/specgpu.h.
+#include <cmath>
+#include <cstdarg>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace specgpu;
+
+struct specgpu_ctx {
+  int device = 0;
+  std::string err;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  int64_t launches = 0;
+  int num_sms = 148;
+};
+
+struct specgpu_plan {
+  specgpu_ctx* ctx = nullptr;
+  specgpu_stft_params p{};
+  int log2n = 0;
+  int hop = 0;
+  double scale = 0.0;  // psd scale in double: 1/(fs*sum w^2) or 1/(sum w)^2
+  float* d_window = nullptr;
+  float2* d_twM = nullptr;
+  float2* d_twN = nullptr;
+};
+
+namespace {
+
+int fail(specgpu_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    ctx->err = buf;
+  }
+  return code;
+}
+
+int cuda_fail(specgpu_ctx* ctx, int e, const char* what) {
+  return fail(ctx, SPECGPU_ERR_CUDA, "%s: CUDA error %d (%s)", what, e, cudaGetErrorString((cudaError_t)e));
+}
+
+#define CHECK_LAUNCH(ctx, expr, what, nlaunch)         \
+  do {                                                 \
+    int e__ = (expr);                                  \
+    if (e__ != 0) return cuda_fail(ctx, e__, what);    \
+    (ctx)->launches += (nlaunch);                      \
+  } while (0)
+
+// Grow-on-demand device workspace.  Growing synchronises the device (cudaFree), so production callers
+// reserve once with specgpu_workspace_reserve().
+int ensure_ws(specgpu_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return SPECGPU_OK;
+  if (ctx->ws) {
+    cudaDeviceSynchronize();
+    cudaFree(ctx->ws);
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+  }
+  size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) return fail(ctx, SPECGPU_ERR_WORKSPACE, "workspace of %zu bytes: %s", want, cudaGetErrorString(e));
+  ctx->ws = p;
+  ctx->ws_bytes = want;
+  return SPECGPU_OK;
+}
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+};
+inline size_t carve_size(std::initializer_list<size_t> parts) {
+  size_t off = 0;
+  for (size_t b : parts) off = ((off + 255) & ~(size_t)255) + b;
+  return off + 256;
+}
+
+int64_t num_segments(int64_t n, int nperseg, int noverlap) {
+  if (n < nperseg) return 0;
+  return (n - noverlap) / (nperseg - noverlap);
+}
+
+StftArgs make_args(const specgpu_plan* plan, const float* x, int64_t n, int64_t ldx, int64_t first_start, int64_t nseg,
+                   float scale, void* out, int64_t ld_out, unsigned* mm) {
+  StftArgs a{};
+  a.x = x;
+  a.n = n;
+  a.ldx = ldx;
+  a.first_start = first_start;
+  a.nseg = nseg;
+  a.hop = plan->hop;
+  a.detrend = plan->p.detrend;
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(x) & 7) == 0) && (ldx % 2 == 0) && (plan->hop % 2 == 0) &&
+             (first_start % 2 == 0);
+  a.scale = scale;
+  a.eps = (float)plan->p.eps;
+  a.window = plan->d_window;
+  a.twM = plan->d_twM;
+  a.twN = plan->d_twN;
+  a.out = out;
+  a.ld_out = ld_out;
+  a.minmax = mm;
+  return a;
+}
+
+int check_signal_args(specgpu_ctx* ctx, const specgpu_plan* plan, const void* x, int64_t B, int64_t n, int64_t ldx) {
+  if (!ctx || !plan) return SPECGPU_ERR_INVALID_ARG;
+  if (B < 0 || n < 0 || ldx < n) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad signal shape B=%lld n=%lld ldx=%lld", (long long)B, (long long)n, (long long)ldx);
+  if (B > 65535) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "batch %lld exceeds 65535 per call", (long long)B);
+  if (B > 0 && n > 0 && x == nullptr) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null signal pointer");
+  return SPECGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int specgpu_version(void) { return SPECGPU_VERSION_MAJOR * 1000 + SPECGPU_VERSION_MINOR; }
+
+int specgpu_init(int device, specgpu_ctx** out) {
+  if (!out) return SPECGPU_ERR_INVALID_ARG;
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return SPECGPU_ERR_CUDA;
+  specgpu_ctx* ctx = new (std::nothrow) specgpu_ctx();
+  if (!ctx) return SPECGPU_ERR_WORKSPACE;
+  ctx->device = device;
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->num_sms = v;
+#ifndef SPECGPU_EMULATE
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (major != 10) {
+    delete ctx;
+    return SPECGPU_ERR_CUDA;  // sm_100a cubin only: no other architecture, no fallback
+  }
+#endif
+  *out = ctx;
+  return SPECGPU_OK;
+}
+
+int specgpu_destroy(specgpu_ctx* ctx) {
+  if (!ctx) return SPECGPU_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->ws) cudaFree(ctx->ws);
+  delete ctx;
+  return SPECGPU_OK;
+}
+
+const char* specgpu_last_error(const specgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int specgpu_workspace_reserve(specgpu_ctx* ctx, int64_t bytes) {
+  if (!ctx || bytes < 0) return SPECGPU_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  return ensure_ws(ctx, (size_t)bytes);
+}
+
+int64_t specgpu_launch_count(const specgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int specgpu_plan_create(specgpu_ctx* ctx, const specgpu_stft_params* p, const double* window_host, specgpu_plan** out) {
+  if (!ctx || !p || !out) return SPECGPU_ERR_INVALID_ARG;
+  *out = nullptr;
+  const int N = p->nperseg;
+  int log2n = 0;
+  while ((1 << log2n) < N) ++log2n;
+  if (N < 8 || N > 8192 || (1 << log2n) != N)
+    return fail(ctx, SPECGPU_ERR_UNSUPPORTED_NPERSEG, "nperseg=%d: must be a power of two in [8, 8192]", N);
+  if (p->noverlap < 0 || p->noverlap >= N) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "noverlap must be less than nperseg.");
+  if (p->detrend < 0 || p->detrend > 2) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "unknown detrend %d", p->detrend);
+  if (p->scaling != SPECGPU_SCALING_DENSITY && p->scaling != SPECGPU_SCALING_SPECTRUM)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "Unknown scaling: %d", p->scaling);
+  if (p->window == SPECGPU_WINDOW_CUSTOM && !window_host) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "custom window needs window_host");
+  if (p->window < 0 || p->window > 3) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "unknown window %d", p->window);
+  if (!(p->fs > 0.0)) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "fs must be positive");
+
+  std::vector<double> w(N);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int i = 0; i < N; ++i) {
+    switch (p->window) {
+      case SPECGPU_WINDOW_CUSTOM: w[i] = window_host[i]; break;
+      case SPECGPU_WINDOW_HANN: w[i] = 0.5 - 0.5 * std::cos(two_pi * i / N); break;      // periodic (fftbins=True)
+      case SPECGPU_WINDOW_HAMMING: w[i] = 0.54 - 0.46 * std::cos(two_pi * i / N); break;
+      default: w[i] = 1.0;
+    }
+  }
+  double sw = 0.0, sw2 = 0.0;
+  for (double v : w) {
+    sw += v;
+    sw2 += v * v;
+  }
+  specgpu_plan* plan = new (std::nothrow) specgpu_plan();
+  if (!plan) return SPECGPU_ERR_WORKSPACE;
+  plan->ctx = ctx;
+  plan->p = *p;
+  plan->log2n = log2n;
+  plan->hop = N - p->noverlap;
+  plan->scale = (p->scaling == SPECGPU_SCALING_DENSITY) ? 1.0 / (p->fs * sw2) : 1.0 / (sw * sw);
+
+  const int M = N / 2;
+  std::vector<float> wf(N);
+  for (int i = 0; i < N; ++i) wf[i] = (float)w[i];
+  std::vector<float2> twM(M), twN(M / 2 + 1);
+  for (int j = 0; j < M; ++j) {
+    twM[j].x = (float)std::cos(two_pi * j / M);
+    twM[j].y = (float)(-std::sin(two_pi * j / M));
+  }
+  for (int k = 0; k <= M / 2; ++k) {
+    twN[k].x = (float)std::cos(two_pi * k / N);
+    twN[k].y = (float)(-std::sin(two_pi * k / N));
+  }
+  cudaSetDevice(ctx->device);
+  cudaError_t e;
+  if ((e = cudaMalloc(&plan->d_window, N * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&plan->d_twM, M * sizeof(float2))) != cudaSuccess ||
+      (e = cudaMalloc(&plan->d_twN, (M / 2 + 1) * sizeof(float2))) != cudaSuccess) {
+    specgpu_plan_destroy(plan);
+    return cuda_fail(ctx, (int)e, "plan tables");
+  }
+  cudaMemcpy(plan->d_window, wf.data(), N * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(plan->d_twM, twM.data(), M * sizeof(float2), cudaMemcpyHostToDevice);
+  cudaMemcpy(plan->d_twN, twN.data(), (M / 2 + 1) * sizeof(float2), cudaMemcpyHostToDevice);
+  *out = plan;
+  return SPECGPU_OK;
+}
+
+int specgpu_plan_destroy(specgpu_plan* plan) {
+  if (!plan) return SPECGPU_OK;
+  if (plan->ctx) cudaSetDevice(plan->ctx->device);
+  if (plan->d_window) cudaFree(plan->d_window);
+  if (plan->d_twM) cudaFree(plan->d_twM);
+  if (plan->d_twN) cudaFree(plan->d_twN);
+  delete plan;
+  return SPECGPU_OK;
+}
+
+int64_t specgpu_plan_num_segments(const specgpu_plan* plan, int64_t n) {
+  if (!plan) return 0;
+  return num_segments(n, plan->p.nperseg, plan->p.noverlap);
+}
+
+int32_t specgpu_plan_num_freqs(const specgpu_plan* plan) { return plan ? plan->p.nperseg / 2 + 1 : 0; }
+
+int specgpu_plan_axes(const specgpu_plan* plan, int64_t n, double* f_host, double* t_host) {
+  if (!plan) return SPECGPU_ERR_INVALID_ARG;
+  const int N = plan->p.nperseg;
+  // np.fft.rfftfreq(N, 1/fs): arange(N/2+1) / (N * (1/fs)) ; segment centres (j*hop + N/2) / fs
+  if (f_host) {
+    const double val = 1.0 / (N * (1.0 / plan->p.fs));
+    for (int k = 0; k <= N / 2; ++k) f_host[k] = k * val;
+  }
+  if (t_host) {
+    const int64_t nseg = num_segments(n, N, plan->p.noverlap);
+    for (int64_t j = 0; j < nseg; ++j) t_host[j] = (double)(j * plan->hop + N / 2) / plan->p.fs;
+  }
+  return SPECGPU_OK;
+}
+
+int specgpu_spectrogram(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t B, int64_t n, int64_t ldx,
+                        float* Sxx, int64_t ldt, void* stream) {
+  int rc = check_signal_args(ctx, plan, x, B, n, ldx);
+  if (rc) return rc;
+  const int64_t nseg = num_segments(n, plan->p.nperseg, plan->p.noverlap);
+  if (nseg == 0 || B == 0) return SPECGPU_OK;
+  if (!Sxx || ldt < nseg) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output (ldt=%lld < nseg=%lld)", (long long)ldt, (long long)nseg);
+  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, (float)plan->scale, Sxx, ldt, nullptr);
+  CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_PSD, a, B, (cudaStream_t)stream), "stft_kernel", 1);
+  return SPECGPU_OK;
+}
+
+int specgpu_specgr(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t B, int64_t n, int64_t ldx,
+                   float* S, int64_t ldt, float* minmax, void* stream) {
+  int rc = check_signal_args(ctx, plan, x, B, n, ldx);
+  if (rc) return rc;
+  const int64_t nseg = num_segments(n, plan->p.nperseg, plan->p.noverlap);
+  if (nseg == 0 || B == 0) return SPECGPU_OK;
+  if (!S || ldt < nseg) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output (ldt=%lld < nseg=%lld)", (long long)ldt, (long long)nseg);
+  cudaSetDevice(ctx->device);
+  if ((rc = ensure_ws(ctx, carve_size({(size_t)B * 2 * sizeof(unsigned)})))) return rc;
+  Carver cv(ctx->ws);
+  unsigned* mm = cv.take<unsigned>(B * 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  CHECK_LAUNCH(ctx, launch_minmax_init(mm, B, st), "minmax_init", 1);
+  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, (float)plan->scale, S, ldt, mm);
+  CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, B, st), "stft_kernel", 1);
+  CHECK_LAUNCH(ctx, launch_lognorm(S, B, plan->p.nperseg / 2, nseg, ldt, mm, minmax, st), "lognorm", 1);
+  return SPECGPU_OK;
+}
+
+int64_t specgpu_stft_num_segments(const specgpu_plan* plan, int64_t n, int boundary_zeros, int padded) {
+  if (!plan) return 0;
+  const int N = plan->p.nperseg;
+  const int hop = plan->hop;
+  int64_t len = n + (boundary_zeros ? 2 * (int64_t)(N / 2) : 0);
+  if (padded) {
+    // scipy: nadd = (-(len - nperseg) % nstep) % nperseg
+    int64_t r = (len - N) % hop;
+    if (r < 0) r += hop;
+    int64_t nadd = ((hop - r) % hop) % N;
+    len += nadd;
+  }
+  return num_segments(len, N, plan->p.noverlap);
+}
+
+int specgpu_stft(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t B, int64_t n, int64_t ldx,
+                 int boundary_zeros, int padded, float* Z, int64_t ldt, void* stream) {
+  int rc = check_signal_args(ctx, plan, x, B, n, ldx);
+  if (rc) return rc;
+  const int64_t nseg = specgpu_stft_num_segments(plan, n, boundary_zeros, padded);
+  if (nseg == 0 || B == 0) return SPECGPU_OK;
+  if (!Z || ldt < nseg) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output (ldt=%lld < nseg=%lld)", (long long)ldt, (long long)nseg);
+  const int64_t first = boundary_zeros ? -(int64_t)(plan->p.nperseg / 2) : 0;
+  StftArgs a = make_args(plan, x, n, ldx, first, nseg, (float)std::sqrt(plan->scale), Z, ldt, nullptr);
+  CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_COMPLEX, a, B, (cudaStream_t)stream), "stft_kernel", 1);
+  return SPECGPU_OK;
+}
+
+}  // extern "C"
