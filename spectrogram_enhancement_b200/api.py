@@ -1,0 +1,600 @@
+"""Host-side mirror of the reference's Python functions on top of libspecgpu (ctypes, C ABI).
+
+Every function keeps the name, argument meaning and error behaviour of the reference function it
+replaces (file:line into PlasmaControl/spectrogram-enhancement):
+
+    specgr / norm / rescale / quantfilt     spec_denoising/pipeline_data.py:28-49
+    omega / computeSignal / denoiseSignal   spec_denoising/denoising_by_svd.ipynb:155-229, clip :280-281
+    patch / unpatch / reshape               VAE/manual_scan.py:28-54
+    ae_co2                                  interferometer/crosspowerspec.py:39 (body absent upstream)
+    spectrogram / stft / csd                scipy.signal call sites of the above (pipeline_data.py:32)
+
+plus the batched array-level entry points the reference's `for shot: for channel:` loops collapse
+into (`spectrogram_batch`, `csd_allpairs`, `pipeline`).
+
+Buffers: numpy arrays are staged to the device and results come back as numpy; torch CUDA tensors
+are used in place (zero copy) and results come back as torch tensors on the same device.  All
+arithmetic runs in float32 on the GPU (the reference's own dtype for float32 ECE data).  There is
+no CPU implementation behind these functions: without libspecgpu.so and a B200 they raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pickle
+import threading
+
+import numpy as np
+import torch
+
+from . import _ffi
+
+__all__ = [
+    "Runtime", "default_runtime", "DEFAULT_SPEC_PARAMS", "spectrogram", "stft", "csd", "csd_allpairs",
+    "spectrogram_batch", "specgr_array", "specgr", "norm", "rescale", "quantfilt", "quantfilt_mask", "omega",
+    "computeSignal", "denoiseSignal", "clip", "patch", "unpatch", "reshape", "pipeline", "ae_co2",
+]
+
+# spec_denoising/pipeline_data.py:77-84
+DEFAULT_SPEC_PARAMS = {"nperseg": 512, "noverlap": 256, "fs": 500000, "window": "hamm", "scaling": "density",
+                       "detrend": "linear", "eps": 1e-11}
+
+
+def _is_torch(x):
+    return isinstance(x, torch.Tensor)
+
+
+class Runtime:
+    """One libspecgpu context on one device, with a plan cache.
+
+    `lib`/`device` exist so the CPU test-suite can drive the same host logic against the emulation
+    build of the kernels (tests/emu); the package itself only ever creates the CUDA runtime."""
+
+    def __init__(self, lib: _ffi.Library | None = None, device=None):
+        self.lib = lib if lib is not None else _ffi.load()
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("libspecgpu needs a CUDA device (sm_100a); there is no CPU fallback")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self._ctx = C.c_void_p()
+        index = self.device.index if self.device.type == "cuda" and self.device.index is not None else 0
+        rc = self.lib.init(index, C.byref(self._ctx))
+        if rc != 0:
+            raise _ffi.SpecGpuError(rc, "specgpu_init failed (is this an sm_100 device?)")
+        self._plans = {}
+        self._lock = threading.Lock()
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def close(self):
+        if self._ctx:
+            for h in self._plans.values():
+                self.lib.plan_destroy(h)
+            self._plans.clear()
+            self.lib.destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.lib.last_error(self._ctx)
+            msg = msg.decode() if msg else ""
+            if rc in (_ffi.ERR_INVALID_ARG, _ffi.ERR_UNSUPPORTED_NPERSEG, _ffi.ERR_UNSUPPORTED_SHAPE):
+                raise ValueError(msg)
+            raise _ffi.SpecGpuError(rc, msg)
+
+    def stream(self):
+        if self.device.type == "cuda":
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return None
+
+    def launch_count(self) -> int:
+        return int(self.lib.launch_count(self._ctx))
+
+    def reserve(self, nbytes: int):
+        self.check(self.lib.workspace_reserve(self._ctx, int(nbytes)))
+
+    def empty(self, shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def to_device(self, x, dtype=torch.float32):
+        """-> (contiguous device tensor, came_from_torch)."""
+        if _is_torch(x):
+            return x.to(device=self.device, dtype=dtype).contiguous(), True
+        a = np.ascontiguousarray(np.asarray(x))
+        if a.dtype == object:
+            raise TypeError("object arrays are not supported")
+        t = torch.from_numpy(a)
+        return t.to(device=self.device, dtype=dtype).contiguous(), False
+
+    @staticmethod
+    def ret(t, as_torch):
+        return t if as_torch else t.cpu().numpy()
+
+    def plan(self, nperseg, noverlap, fs, window, scaling, detrend, eps=0.0):
+        nperseg = int(nperseg)
+        noverlap = int(noverlap)
+        if nperseg < 1:
+            raise ValueError("nperseg must be a positive integer")
+        if noverlap >= nperseg:
+            raise ValueError("noverlap must be less than nperseg.")      # scipy's message
+        if isinstance(window, str):
+            if window.lower() not in _ffi.WINDOW:
+                raise ValueError(f"Unknown window type: {window!r}")
+            wcode, warr, wkey = _ffi.WINDOW[window.lower()], None, window.lower()
+        else:
+            w = np.ascontiguousarray(np.asarray(window, dtype=np.float64))
+            if w.ndim != 1:
+                raise ValueError("window must be 1-D")
+            if w.shape[0] != nperseg:
+                raise ValueError("window must have length of nperseg")
+            wcode, warr, wkey = 0, w, ("array", w.tobytes())
+        if scaling not in _ffi.SCALING:
+            raise ValueError(f"Unknown scaling: {scaling!r}")
+        if isinstance(detrend, str) and detrend not in ("constant", "linear"):
+            raise ValueError("Trend type must be 'linear' or 'constant'.")
+        if callable(detrend):
+            raise ValueError("callable detrend is not supported by libspecgpu")
+        dcode = _ffi.DETREND[detrend if detrend else False]
+        key = (nperseg, noverlap, float(fs), wkey, scaling, dcode, float(eps))
+        with self._lock:
+            h = self._plans.get(key)
+            if h is None:
+                p = _ffi.StftParams(nperseg, noverlap, dcode, _ffi.SCALING[scaling], wcode, 0, float(fs), float(eps))
+                h = C.c_void_p()
+                wp = warr.ctypes.data_as(C.POINTER(C.c_double)) if warr is not None else None
+                self.check(self.lib.plan_create(self._ctx, C.byref(p), wp, C.byref(h)))
+                self._plans[key] = h
+        return h
+
+    def plan_from_params(self, sp):
+        return self.plan(sp["nperseg"], sp["noverlap"], sp["fs"], sp["window"], sp["scaling"], sp["detrend"],
+                         sp.get("eps", 0.0))
+
+    def axes(self, plan, n):
+        F = self.lib.plan_num_freqs(plan)
+        T = self.lib.plan_num_segments(plan, n)
+        f = np.empty(F, np.float64)
+        t = np.empty(max(T, 0), np.float64)
+        self.check(self.lib.plan_axes(plan, n, f.ctypes.data_as(C.POINTER(C.c_double)),
+                                      t.ctypes.data_as(C.POINTER(C.c_double))))
+        return f, t
+
+    # ---- raw entry points on device tensors (used by bench.py and the wrappers below) -------------
+    def specgr_dev(self, plan, x2d, S=None, minmax=None):
+        B, n = x2d.shape
+        T = self.lib.plan_num_segments(plan, n)
+        F = self.lib.plan_num_freqs(plan)
+        if S is None:
+            S = self.empty((B, F - 1, T))
+        mmp = minmax.data_ptr() if minmax is not None else None
+        self.check(self.lib.specgr(self._ctx, plan, x2d.data_ptr(), B, n, x2d.stride(0), S.data_ptr(), S.stride(1), mmp,
+                                   self.stream()))
+        return S
+
+    def spectrogram_dev(self, plan, x2d, Sxx=None):
+        B, n = x2d.shape
+        T = self.lib.plan_num_segments(plan, n)
+        F = self.lib.plan_num_freqs(plan)
+        if Sxx is None:
+            Sxx = self.empty((B, F, T))
+        self.check(self.lib.spectrogram(self._ctx, plan, x2d.data_ptr(), B, n, x2d.stride(0), Sxx.data_ptr(),
+                                        Sxx.stride(1) if T else 1, self.stream()))
+        return Sxx
+
+    def pipeline_dev(self, plan, x2d, S=None, D=None, clip=True, tiles=None, tile_w=128, ntiles=0, info=None):
+        B, n = x2d.shape
+        T = self.lib.plan_num_segments(plan, n)
+        F = self.lib.plan_num_freqs(plan)
+        if S is None:
+            S = self.empty((B, F - 1, T))
+        if D is None:
+            D = self.empty((B, F - 1, T))
+        self.check(self.lib.pipeline(self._ctx, plan, x2d.data_ptr(), B, n, x2d.stride(0), S.data_ptr(), D.data_ptr(),
+                                     S.stride(1), 1 if clip else 0, tiles.data_ptr() if tiles is not None else None,
+                                     tile_w, ntiles, info.data_ptr() if info is not None else None, self.stream()))
+        return S, D
+
+
+_default = None
+_default_lock = threading.Lock()
+
+
+def default_runtime() -> Runtime:
+    global _default
+    with _default_lock:
+        if _default is None:
+            _default = Runtime()
+        return _default
+
+
+def _rt(rt):
+    return rt if rt is not None else default_runtime()
+
+
+def _as_2d(t):
+    """[..., N] -> ([B, N], leading shape)."""
+    lead = tuple(t.shape[:-1])
+    return t.reshape(-1, t.shape[-1]) if t.dim() != 2 else t, lead
+
+
+# ================================================================================================
+# scipy.signal call sites
+# ================================================================================================
+def spectrogram(x, fs=1.0, window="hann", nperseg=256, noverlap=None, detrend="constant", scaling="density",
+                runtime=None):
+    """scipy.signal.spectrogram(x, fs, window, nperseg, noverlap, detrend=, scaling=, mode='psd'),
+    real input, one-sided, over the last axis.  Returns (f, t, Sxx[..., F, T]).
+    (scipy's own defaults differ in two places: window=('tukey', .25) and nperseg=None.)"""
+    rt = _rt(runtime)
+    if noverlap is None:
+        noverlap = int(nperseg) // 8
+    plan = rt.plan(nperseg, noverlap, fs, window, scaling, detrend)
+    xd, as_torch = rt.to_device(x)
+    x2, lead = _as_2d(xd)
+    f, t = rt.axes(plan, x2.shape[-1])
+    Sxx = rt.spectrogram_dev(plan, x2)
+    Sxx = Sxx.reshape(lead + tuple(Sxx.shape[1:]))
+    return f, t, rt.ret(Sxx, as_torch)
+
+
+def stft(x, fs=1.0, window="hann", nperseg=256, noverlap=None, detrend=False, boundary="zeros", padded=True,
+         scaling="spectrum", runtime=None):
+    """scipy.signal.stft (real input, one-sided).  Returns (f, t, Zxx[..., F, T]) complex64."""
+    rt = _rt(runtime)
+    if noverlap is None:
+        noverlap = int(nperseg) // 2
+    if boundary not in (None, "zeros"):
+        raise ValueError(f"Unknown boundary option '{boundary}', must be one of: ['zeros', None]")
+    if scaling == "psd":
+        scaling = "density"
+    plan = rt.plan(nperseg, noverlap, fs, window, scaling, detrend)
+    xd, as_torch = rt.to_device(x)
+    x2, lead = _as_2d(xd)
+    B, n = x2.shape
+    bz, pd = (1 if boundary == "zeros" else 0), (1 if padded else 0)
+    T = rt.lib.stft_num_segments(plan, n, bz, pd)
+    F = rt.lib.plan_num_freqs(plan)
+    Z = rt.empty((B, F, T, 2))
+    rt.check(rt.lib.stft(rt._ctx, plan, x2.data_ptr(), B, n, x2.stride(0), bz, pd, Z.data_ptr(), T if T else 1, rt.stream()))
+    Zc = torch.view_as_complex(Z).reshape(lead + (F, T))
+    hop = int(nperseg) - int(noverlap)
+    f = np.fft.rfftfreq(int(nperseg), 1.0 / fs)
+    # scipy: time = arange(nperseg/2, padded_len - nperseg/2 + 1, hop)/fs, shifted by -nperseg/2/fs with a boundary
+    t = (np.arange(T) * hop + int(nperseg) / 2) / float(fs)
+    if boundary is not None:
+        t = t - (int(nperseg) / 2) / float(fs)
+    return f, t, rt.ret(Zc, as_torch)
+
+
+def csd_allpairs(x, fs=1.0, window="hann", nperseg=256, noverlap=None, detrend="constant", scaling="density",
+                 runtime=None):
+    """All-pairs Welch cross-power spectrum of x[C, N]:
+    P[i, j] = scipy.signal.csd(x[i], x[j], fs, window, nperseg, noverlap, detrend=, scaling=, average='mean').
+    Returns (f, P[C, C, F]) complex64."""
+    rt = _rt(runtime)
+    if noverlap is None:
+        noverlap = int(nperseg) // 2
+    plan = rt.plan(nperseg, noverlap, fs, window, scaling, detrend)
+    xd, as_torch = rt.to_device(x)
+    if xd.dim() != 2:
+        raise ValueError("csd_allpairs expects x[C, N]")
+    Cn, n = xd.shape
+    F = rt.lib.plan_num_freqs(plan)
+    P = rt.empty((Cn, Cn, F, 2))
+    rt.check(rt.lib.csd_allpairs(rt._ctx, plan, xd.data_ptr(), Cn, n, xd.stride(0), P.data_ptr(), rt.stream()))
+    f = np.fft.rfftfreq(int(nperseg), 1.0 / fs)
+    return f, rt.ret(torch.view_as_complex(P), as_torch)
+
+
+def csd(x, y, fs=1.0, window="hann", nperseg=256, noverlap=None, detrend="constant", scaling="density", runtime=None):
+    """scipy.signal.csd(x, y, ...) for two real 1-D records (average='mean', one-sided):
+    Pxy = mean over segments of conj(X) Y.  Returns (f, Pxy[F]) complex64."""
+    rt = _rt(runtime)
+    xd, as_torch = rt.to_device(x)
+    yd, _ = rt.to_device(y)
+    if xd.dim() != 1 or yd.dim() != 1:
+        raise ValueError("csd expects 1-D x and y (use csd_allpairs for channel stacks)")
+    if xd.shape != yd.shape:
+        raise ValueError("x and y must have the same length")   # scipy zero-pads the shorter; not supported
+    f, P = csd_allpairs(torch.stack([xd, yd]), fs, window, nperseg, noverlap, detrend, scaling, runtime=rt)
+    return f, rt.ret(P[0, 1], as_torch)
+
+
+# ================================================================================================
+# spec_denoising/pipeline_data.py
+# ================================================================================================
+def spectrogram_batch(x, spec_params=DEFAULT_SPEC_PARAMS, runtime=None):
+    """Body of `specgr` after the pickle slice (pipeline_data.py:32-35) for a stack of signals
+    x[..., N]: spectrogram -> log(Sxx+eps) -> global min-max over all nperseg/2+1 rows (per signal)
+    -> Nyquist row dropped.  Returns (Sxx[..., nperseg/2, T], f, t) in the reference's order."""
+    rt = _rt(runtime)
+    plan = rt.plan_from_params(spec_params)
+    xd, as_torch = rt.to_device(x)
+    x2, lead = _as_2d(xd)
+    f, t = rt.axes(plan, x2.shape[-1])
+    S = rt.specgr_dev(plan, x2)
+    S = S.reshape(lead + tuple(S.shape[1:]))
+    return rt.ret(S, as_torch), f[:-1], t
+
+
+def specgr_array(sig_in, spec_params=DEFAULT_SPEC_PARAMS, runtime=None):
+    return spectrogram_batch(sig_in, spec_params, runtime)
+
+
+def specgr(fname, ecen, spec_params, cut_shot=2, runtime=None):
+    """pipeline_data.py:28-36, same signature: load the shot pickle, take channel `ecen`, the first
+    cut_shot*fs samples, and return (Sxx[nperseg/2, T], f, t)."""
+    ece_data = pickle.load(open(fname, "rb"))
+    ece_num = "\\tecef%.2i" % (ecen)
+    sig_in = ece_data[ece_num][:np.int_(cut_shot * spec_params["fs"])]
+    return spectrogram_batch(np.asarray(sig_in), spec_params, runtime)
+
+
+def _matrix_batch(rt, data):
+    """[rows, cols] or [B, rows, cols] -> (device [B, rows, cols], as_torch, squeeze)."""
+    d, as_torch = rt.to_device(data)
+    if d.dim() == 2:
+        return d.unsqueeze(0), as_torch, True
+    if d.dim() == 3:
+        return d, as_torch, False
+    raise ValueError("expected a 2-D matrix or a [B, rows, cols] stack")
+
+
+def rescale(data, runtime=None):
+    """pipeline_data.py:43-44: (data-min)/(max-min) over the whole array."""
+    rt = _rt(runtime)
+    d, as_torch = rt.to_device(data)
+    flat = d.reshape(1, 1, -1)
+    out = torch.empty_like(flat)
+    rt.check(rt.lib.rescale(rt._ctx, flat.data_ptr(), 1, 1, flat.shape[-1], flat.shape[-1], out.data_ptr(), rt.stream()))
+    return rt.ret(out.reshape(d.shape), as_torch)
+
+
+def norm(data, runtime=None):
+    """pipeline_data.py:38-41: (data-mean)/std (population std) over the whole array."""
+    rt = _rt(runtime)
+    d, as_torch = rt.to_device(data)
+    flat = d.reshape(1, 1, -1)
+    out = torch.empty_like(flat)
+    rt.check(rt.lib.norm(rt._ctx, flat.data_ptr(), 1, 1, flat.shape[-1], flat.shape[-1], out.data_ptr(), rt.stream()))
+    return rt.ret(out.reshape(d.shape), as_torch)
+
+
+def _quantfilt_impl(rt, src, thr, want_mask):
+    d, as_torch = rt.to_device(src)
+    if d.dim() == 2:
+        batch = d.unsqueeze(0)
+    elif d.dim() == 3:
+        # denoising_spectrogram.ipynb:115 passes [F, T, C]; np.quantile(axis=0) is per (t, c) column
+        batch = d.permute(2, 0, 1).contiguous()
+    else:
+        raise ValueError("quantfilt expects [F, T] or [F, T, C]")
+    B, rows, cols = batch.shape
+    out = torch.empty_like(batch)
+    mask = torch.empty(batch.shape, dtype=torch.uint8, device=rt.device) if want_mask else None
+    thr_out = rt.empty((B, cols))
+    rt.check(rt.lib.quantfilt(rt._ctx, batch.data_ptr(), B, rows, cols, cols, float(thr), out.data_ptr(),
+                              thr_out.data_ptr(), mask.data_ptr() if want_mask else None, rt.stream()))
+    if d.dim() == 2:
+        out, thr_out = out[0], thr_out[0]
+        mask = mask[0] if want_mask else None
+    else:
+        out, thr_out = out.permute(1, 2, 0), thr_out.permute(1, 0)
+        mask = mask.permute(1, 2, 0) if want_mask else None
+    return out, thr_out, mask, as_torch
+
+
+def quantfilt(src, thr=0.9, runtime=None):
+    """pipeline_data.py:46-49: zero everything strictly below the per-column `thr` quantile taken
+    over axis 0 (np.quantile, linear interpolation; bit-exact for float32 input)."""
+    rt = _rt(runtime)
+    if not (0.0 <= float(thr) <= 1.0):
+        raise ValueError("Quantiles must be in the range [0, 1]")      # numpy's message
+    out, _, _, as_torch = _quantfilt_impl(rt, src, thr, False)
+    return rt.ret(out, as_torch)
+
+
+def quantfilt_mask(src, thr=0.9, runtime=None):
+    """quantfilt plus its integer outputs: (out, threshold[T], mask uint8 (1 = kept))."""
+    rt = _rt(runtime)
+    if not (0.0 <= float(thr) <= 1.0):
+        raise ValueError("Quantiles must be in the range [0, 1]")
+    out, thr_out, mask, as_torch = _quantfilt_impl(rt, src, thr, True)
+    return rt.ret(out, as_torch), rt.ret(thr_out, as_torch), rt.ret(mask, as_torch)
+
+
+# ================================================================================================
+# spec_denoising/denoising_by_svd.ipynb
+# ================================================================================================
+def omega(beta):
+    """denoising_by_svd.ipynb:155-159 (host scalar)."""
+    return 0.56 * beta ** 3 - 0.95 * beta ** 2 + 1.82 * beta + 1.43
+
+
+def _svd_call(rt, matrix, kind, start, stop, use_optimal, clip_neg, method, want_s):
+    m, as_torch, squeeze = _matrix_batch(rt, matrix)
+    transposed = m.shape[1] > m.shape[2]
+    if transposed:                       # A^T = V S U^T: the same singular-index range, transposed back below
+        m = m.transpose(1, 2).contiguous()
+    B, rows, cols = m.shape
+    info = torch.empty((B, 4), dtype=torch.int32, device=rt.device)
+    s_out = rt.empty((B, rows)) if want_s else None
+    sp = s_out.data_ptr() if want_s else None
+    if kind == 2:
+        out = torch.empty((B, rows, cols), dtype=torch.float64, device=rt.device)
+        rt.check(rt.lib.compute_signal(rt._ctx, m.data_ptr(), B, rows, cols, cols, out.data_ptr(), cols, sp,
+                                       info.data_ptr(), rt.stream()))
+    else:
+        out = rt.empty((B, rows, cols))
+        rt.check(rt.lib.svd_denoise(rt._ctx, m.data_ptr(), B, rows, cols, cols, int(start), int(stop),
+                                    1 if use_optimal else 0, 1 if clip_neg else 0, 1 if method == "jacobi" else 0,
+                                    out.data_ptr(), cols, sp, info.data_ptr(), rt.stream()))
+    if transposed:
+        out = out.transpose(1, 2).contiguous()
+    if squeeze:
+        out = out[0]
+        info = info[0]
+        s_out = s_out[0] if want_s else None
+    return out, s_out, info, as_torch
+
+
+def denoiseSignal(matrix, start=None, stop=None, use_optimal=False, clip=False, method="auto", return_info=False,
+                  runtime=None):
+    """denoising_by_svd.ipynb:188-229: U[:, start:stop] diag(s[start:stop]) Vh[start:stop, :] of the thin
+    SVD (defaults start=1, stop=len(s): drop the leading component); `use_optimal` keeps
+    start=0, stop=num_sing-1 with num_sing = #(s > omega(beta)*median(s)).
+    Extras (keyword-only in spirit): clip=True fuses the notebook's `hacked[hacked<0]=0` (:280-281);
+    method='jacobi' forces the full eigen-decomposition; return_info=True also returns
+    (s[len], (start, stop, num_sing)) with the reference's integer bookkeeping."""
+    rt = _rt(runtime)
+    shape = tuple(matrix.shape)
+    k = min(shape[-2], shape[-1])
+    a = 1 if start is None else int(start)
+    b = k if stop is None else int(stop)
+    out, s_out, info, as_torch = _svd_call(rt, matrix, 1 if use_optimal else 0, a, b, use_optimal, clip, method,
+                                           return_info)
+    if not return_info:
+        return rt.ret(out, as_torch)
+    return rt.ret(out, as_torch), rt.ret(s_out, as_torch), info.cpu().numpy()
+
+
+def computeSignal(matrix, return_info=False, runtime=None):
+    """denoising_by_svd.ipynb:161-186: sum over idx in range(1, 2*num_sing) of s[idx] u_idx v_idx^T,
+    float64 output.  Like the reference it raises IndexError when 2*num_sing-1 >= len(s)."""
+    rt = _rt(runtime)
+    out, s_out, info, as_torch = _svd_call(rt, matrix, 2, 0, 0, False, False, "jacobi", True)
+    inf = info.cpu().numpy().reshape(-1, 4)
+    k = min(matrix.shape[-2], matrix.shape[-1])
+    for row in inf:
+        if 2 * int(row[2]) - 1 >= k and int(row[2]) > 0:
+            raise IndexError(f"index {k} is out of bounds for axis 0 with size {k}")
+    if not return_info:
+        return rt.ret(out, as_torch)
+    return rt.ret(out, as_torch), rt.ret(s_out, as_torch), info.cpu().numpy()
+
+
+def clip(x, runtime=None):
+    """denoising_by_svd.ipynb:280-281: copy with negatives set to 0 (fused into denoiseSignal(clip=True)
+    and `pipeline` on the hot path; this standalone form is a device elementwise op)."""
+    rt = _rt(runtime)
+    d, as_torch = rt.to_device(x)
+    return rt.ret(torch.where(d < 0, torch.zeros_like(d), d), as_torch)
+
+
+# ================================================================================================
+# VAE/manual_scan.py tile cut
+# ================================================================================================
+def patch(arr, tile=128, ntiles=30, dtype=np.float64, runtime=None):
+    """VAE/manual_scan.py:28-36: list (or stack) of [rows, >= tile*ntiles] spectrograms ->
+    [len(arr)*ntiles, rows, tile]; float64 like the reference's np.empty (dtype=np.float32 halves the
+    bytes for the VAE input)."""
+    rt = _rt(runtime)
+    as_torch = _is_torch(arr) or (len(arr) > 0 and _is_torch(arr[0]))
+    if isinstance(arr, (list, tuple)):
+        if len(arr) == 0:
+            out = torch.empty((0, 0, tile), dtype=torch.float64)
+            return out if as_torch else out.numpy()
+        width = tile * ntiles
+        parts = [rt.to_device(a)[0][:, :width] for a in arr]
+        d = torch.stack(parts)
+    else:
+        d, _ = rt.to_device(arr)
+    n, rows, ld = d.shape
+    if ld < tile * ntiles:
+        raise ValueError(f"could not broadcast input array: need at least {tile * ntiles} columns, got {ld}")
+    f64 = np.dtype(dtype) == np.float64
+    out = torch.empty((n * ntiles, rows, tile), dtype=torch.float64 if f64 else torch.float32, device=rt.device)
+    rt.check(rt.lib.patch(rt._ctx, d.data_ptr(), n, rows, d.stride(1), tile, ntiles, out.data_ptr(), 1 if f64 else 0,
+                          rt.stream()))
+    return rt.ret(out, as_torch)
+
+
+def unpatch(arr, ntiles=30, runtime=None):
+    """VAE/manual_scan.py:39-49: [n*ntiles, rows, tile] -> [n, rows, tile*ntiles] (dtype kept)."""
+    rt = _rt(runtime)
+    as_torch = _is_torch(arr)
+    a = arr if as_torch else np.asarray(arr)
+    f64 = (a.dtype == torch.float64) if as_torch else (a.dtype == np.float64)
+    d, _ = rt.to_device(a, torch.float64 if f64 else torch.float32)
+    total, rows, tile = d.shape
+    n = int(total / ntiles)
+    out = torch.empty((n, rows, tile * ntiles), dtype=d.dtype, device=rt.device)
+    rt.check(rt.lib.unpatch(rt._ctx, d.data_ptr(), 1 if f64 else 0, n, rows, tile, ntiles, out.data_ptr(), 1 if f64 else 0,
+                            tile * ntiles, rt.stream()))
+    return rt.ret(out, as_torch)
+
+
+def reshape(arr):
+    """VAE/manual_scan.py:52-54."""
+    if _is_torch(arr):
+        return arr.reshape(len(arr), 256, 128, 1)
+    return np.reshape(arr, (len(arr), 256, 128, 1))
+
+
+# ================================================================================================
+# the whole path, batched
+# ================================================================================================
+def pipeline(x, spec_params=DEFAULT_SPEC_PARAMS, clip=True, tiles=False, tile=128, return_info=False, runtime=None):
+    """x[B, N] -> (S, D[, tiles]): S = specgr body, D = denoiseSignal(S) (default range: leading
+    component removed) with the clip fused, tiles = patch(D) as float32 [B*(T//tile), rows, tile]."""
+    rt = _rt(runtime)
+    plan = rt.plan_from_params(spec_params)
+    xd, as_torch = rt.to_device(x)
+    x2, lead = _as_2d(xd)
+    B, n = x2.shape
+    T = rt.lib.plan_num_segments(plan, n)
+    rows = rt.lib.plan_num_freqs(plan) - 1
+    ntiles = T // tile if tiles else 0
+    tl = rt.empty((B * ntiles, rows, tile)) if tiles else None
+    info = torch.empty((B, 4), dtype=torch.int32, device=rt.device)
+    S, D = rt.pipeline_dev(plan, x2, clip=clip, tiles=tl, tile_w=tile, ntiles=ntiles, info=info)
+    S = S.reshape(lead + tuple(S.shape[1:]))
+    D = D.reshape(lead + tuple(D.shape[1:]))
+    res = [rt.ret(S, as_torch), rt.ret(D, as_torch)]
+    if tiles:
+        res.append(rt.ret(tl, as_torch))
+    if return_info:
+        res.append(info.cpu().numpy())
+    return tuple(res)
+
+
+# ================================================================================================
+# interferometer/crosspowerspec.py
+# ================================================================================================
+def ae_co2(signal1, signal2, t, nperseg=1024, noverlap=None, navg=8, window="hann", detrend="constant", runtime=None):
+    """interferometer/crosspowerspec.py:39 call signature: (signal1, signal2, t[ms]) ->
+    (ampsp[n_time, n_freq], freq[kHz], time[ms]).
+
+    The body (`co2_deps.ae_co2`) is not in the reference tree; per the project brief its arithmetic is
+    the segment-averaged cross-power spectrum conj(X1) X2 (scipy.signal.csd, mean).  Here the record is
+    cut into consecutive frames of `navg` half-overlapped segments and ampsp[k] = |csd(frame k)|, so
+    that ampsp is the time-resolved cross-power amplitude the script plots (PARITY-UNPINNED: frame
+    length and overlap are this library's choice)."""
+    rt = _rt(runtime)
+    if noverlap is None:
+        noverlap = nperseg // 2
+    hop = nperseg - noverlap
+    s1, as_torch = rt.to_device(signal1)
+    s2, _ = rt.to_device(signal2)
+    tt = np.asarray(t.cpu() if _is_torch(t) else t, dtype=np.float64)
+    fs = 1000.0 / float(np.mean(np.diff(tt)))        # t in ms -> Hz
+    frame = nperseg + (navg - 1) * hop
+    nframes = s1.shape[-1] // frame
+    if nframes == 0:
+        raise ValueError("record shorter than one averaging frame")
+    F = nperseg // 2 + 1
+    amps = rt.empty((nframes, F))
+    plan = rt.plan(nperseg, noverlap, fs, window, "density", detrend)
+    P = rt.empty((2, 2, F, 2))
+    for k in range(nframes):            # frames are independent all-pairs problems of C = 2
+        xk = torch.stack([s1[k * frame:(k + 1) * frame], s2[k * frame:(k + 1) * frame]])
+        rt.check(rt.lib.csd_allpairs(rt._ctx, plan, xk.data_ptr(), 2, frame, xk.stride(0), P.data_ptr(), rt.stream()))
+        amps[k] = torch.view_as_complex(P)[0, 1].abs()
+    freq = np.fft.rfftfreq(nperseg, 1.0 / fs) / 1e3
+    time = tt[0] + (np.arange(nframes) * frame + frame / 2.0) / fs * 1e3
+    return rt.ret(amps, as_torch), freq, time

@@ -34,6 +34,7 @@ int launch_lognorm(float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, 
 // elementwise.cu
 int launch_rescale(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst, unsigned* mm_ws,
                    cudaStream_t stream);
+int norm_num_parts(int64_t rows, int64_t cols);
 int launch_norm(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst, double* sums_ws,
                 cudaStream_t stream);
 int launch_patch(const float* src, int64_t n, int64_t rows, int64_t ld, int tile_w, int ntiles, void* out, int out_f64,
@@ -46,20 +47,22 @@ int launch_quantfilt(const float* src, int64_t B, int64_t rows, int64_t cols, in
                      float* thr_out, uint8_t* mask, cudaStream_t stream);
 
 // svd.cu
-struct SvdWorkspace {
-  float* G;        // [B][n][n] Gram matrices (overwritten by the eigen-solver)
-  float* U;        // [B][n][n] eigenvectors, column k = k-th largest (row-major, U[i*n+k])
-  float* lam;      // [B][n] eigenvalues, descending
-  int32_t* plan;   // [B][4] {a, b, num_sing, status}
-};
-size_t svd_workspace_bytes(int64_t B, int64_t n);
-int launch_gram(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* G, cudaStream_t stream);
+int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* G, cudaStream_t stream);
 int launch_eig_power(const float* G, int64_t B, int n, float* U, float* lam, int32_t* plan, cudaStream_t stream);
-int launch_eig_jacobi(float* G, int64_t B, int n, float* U, float* lam, int32_t* plan, cudaStream_t stream);
-int launch_svd_plan(const float* lam, int64_t B, int n, int64_t cols, int start, int stop, int mode, int32_t* plan,
+size_t jacobi_workspace_bytes(int64_t B, int n);
+int launch_eig_jacobi(const float* G, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan, void* ws,
+                      cudaStream_t stream);
+// kind 0: explicit (start, stop); 1: use_optimal; 2: computeSignal.  plan[b] = {a, e, num_sing, status}
+int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int stop, float omega_f, int32_t* plan,
                     float* s_out, cudaStream_t stream);
-int launch_svd_reconstruct(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U,
-                           const int32_t* plan, int clip, void* out, int out_f64, int64_t ldo, cudaStream_t stream);
+int launch_svd_project(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U, const int32_t* plan,
+                       int clip, void* out, int out_f64, int64_t ldo, cudaStream_t stream);
+
+// gram_tc.cu
+bool gram_tc_supported(int64_t rows);
+size_t gram_tc_workspace_bytes(int64_t B, int64_t rows);
+int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* partial_ws, float* G,
+                   int num_sms, cudaStream_t stream);
 
 // csd.cu
 int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t ldf, int nfreq, int64_t i0, int64_t ni,

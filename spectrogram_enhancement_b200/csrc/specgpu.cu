@@ -16,6 +16,7 @@ struct specgpu_ctx {
   size_t ws_bytes = 0;
   int64_t launches = 0;
   int num_sms = 148;
+  size_t ws_csd_off = 0;   // offset of the pair partials inside ws (set by specgpu_csd_allpairs)
 };
 
 struct specgpu_plan {
@@ -327,6 +328,279 @@ int specgpu_stft(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int
   const int64_t first = boundary_zeros ? -(int64_t)(plan->p.nperseg / 2) : 0;
   StftArgs a = make_args(plan, x, n, ldx, first, nseg, (float)std::sqrt(plan->scale), Z, ldt, nullptr);
   CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_COMPLEX, a, B, (cudaStream_t)stream), "stft_kernel", 1);
+  return SPECGPU_OK;
+}
+
+
+// ---- array helpers -------------------------------------------------------------------------------
+static int check_matrix_args(specgpu_ctx* ctx, const void* src, int64_t B, int64_t rows, int64_t cols, int64_t ld) {
+  if (!ctx) return SPECGPU_ERR_INVALID_ARG;
+  if (B < 0 || rows < 0 || cols < 0 || ld < cols)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad matrix shape B=%lld rows=%lld cols=%lld ld=%lld", (long long)B,
+                (long long)rows, (long long)cols, (long long)ld);
+  if (B > 65535) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "batch %lld exceeds 65535 per call", (long long)B);
+  if (B * rows * cols > 0 && src == nullptr) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null matrix pointer");
+  return SPECGPU_OK;
+}
+
+int specgpu_rescale(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst,
+                    void* stream) {
+  int rc = check_matrix_args(ctx, src, B, rows, cols, ld);
+  if (rc) return rc;
+  if (B * rows * cols == 0) return SPECGPU_OK;
+  if (!dst) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null output pointer");
+  cudaSetDevice(ctx->device);
+  if ((rc = ensure_ws(ctx, carve_size({(size_t)B * 2 * sizeof(unsigned)})))) return rc;
+  Carver cv(ctx->ws);
+  unsigned* mm = cv.take<unsigned>(B * 2);
+  CHECK_LAUNCH(ctx, launch_rescale(src, B, rows, cols, ld, dst, mm, (cudaStream_t)stream), "rescale", 3);
+  return SPECGPU_OK;
+}
+
+int specgpu_norm(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst,
+                 void* stream) {
+  int rc = check_matrix_args(ctx, src, B, rows, cols, ld);
+  if (rc) return rc;
+  if (B * rows * cols == 0) return SPECGPU_OK;
+  if (!dst) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null output pointer");
+  cudaSetDevice(ctx->device);
+  const int parts = norm_num_parts(rows, cols);
+  if ((rc = ensure_ws(ctx, carve_size({(size_t)B * parts * 2 * sizeof(double)})))) return rc;
+  Carver cv(ctx->ws);
+  double* sums = cv.take<double>(B * parts * 2);
+  CHECK_LAUNCH(ctx, launch_norm(src, B, rows, cols, ld, dst, sums, (cudaStream_t)stream), "norm", 2);
+  return SPECGPU_OK;
+}
+
+int specgpu_quantfilt(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float thr,
+                      float* dst, float* thr_out, uint8_t* mask, void* stream) {
+  int rc = check_matrix_args(ctx, src, B, rows, cols, ld);
+  if (rc) return rc;
+  if (!(thr >= 0.0f && thr <= 1.0f)) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "Quantiles must be in the range [0, 1]");
+  if (rows > 1024) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "quantfilt: rows=%lld > 1024", (long long)rows);
+  if (B * rows * cols == 0) return SPECGPU_OK;
+  // numpy (float32 array): pos = float32(rows-1) * float32(thr); lo = floor(pos); g = pos - lo
+  volatile float pos = (float)(rows - 1) * thr;
+  int lo = (int)std::floor((float)pos);
+  float g = (float)pos - (float)lo;
+  if (lo >= rows - 1) {
+    lo = (int)rows - 1;
+    g = 0.f;
+  }
+  CHECK_LAUNCH(ctx, launch_quantfilt(src, B, rows, cols, ld, lo, g, dst, thr_out, mask, (cudaStream_t)stream), "quantfilt", 1);
+  return SPECGPU_OK;
+}
+
+// ---- SVD denoise ---------------------------------------------------------------------------------
+namespace {
+
+// omega(beta) of the notebook (denoising_by_svd.ipynb:155-159), evaluated in double as Python does.  With a
+// float32 matrix np.median(s) is a float32 scalar and NumPy >= 2 keeps `omega * median` in float32 (the
+// Python float is a weak scalar), so the device multiplies float32(omega) by the float32 median.
+double omega_of(double beta) { return 0.56 * beta * beta * beta - 0.95 * beta * beta + 1.82 * beta + 1.43; }
+
+struct SvdWs {
+  float* G;
+  float* U;
+  float* lam;
+  int32_t* plan;
+  float* gram_partial;
+  void* jacobi;
+};
+
+size_t svd_ws_bytes(int64_t B, int64_t rows, bool tc, bool full) {
+  return carve_size({(size_t)B * rows * rows * 4, (size_t)B * rows * rows * 4, (size_t)B * rows * 4, (size_t)B * 16,
+                     tc ? gram_tc_workspace_bytes(B, rows) : 0, full ? jacobi_workspace_bytes(B, (int)rows) : 0});
+}
+
+SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
+  Carver cv(ws);
+  SvdWs w{};
+  w.G = cv.take<float>(B * rows * rows);
+  w.U = cv.take<float>(B * rows * rows);
+  w.lam = cv.take<float>(B * rows);
+  w.plan = cv.take<int32_t>(B * 4);
+  w.gram_partial = tc ? cv.take<float>(gram_tc_workspace_bytes(B, rows) / 4) : nullptr;
+  w.jacobi = full ? (void*)cv.take<char>(jacobi_workspace_bytes(B, (int)rows)) : nullptr;
+  return w;
+}
+
+// Shared body of svd_denoise / compute_signal / pipeline.  kind: 0 explicit range, 1 use_optimal,
+// 2 computeSignal.  `ws_base` lets the pipeline place the SVD scratch behind its own.
+int svd_run(specgpu_ctx* ctx, void* ws_base, const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, int kind,
+            int start, int stop, int clip, bool power_ok, void* out, int out_f64, int64_t ldo, float* s_out,
+            int32_t* info, cudaStream_t st) {
+  const bool tc = power_ok && gram_tc_supported(rows);   // TF32 Gram only feeds the leading-pair route
+  const bool full = true;                                // Jacobi scratch is always carved (fallback for power)
+  SvdWs w = svd_carve(ws_base, B, rows, tc, full);
+  if (tc) {
+    CHECK_LAUNCH(ctx, launch_gram_tc(S, B, rows, cols, ld, w.gram_partial, w.G, ctx->num_sms, st), "gram_tc", 2);
+  } else {
+    CHECK_LAUNCH(ctx, launch_gram_simt(S, B, rows, cols, ld, w.G, st), "gram_simt", 1);
+  }
+  if (power_ok) {
+    CHECK_LAUNCH(ctx, launch_eig_power(w.G, B, (int)rows, w.U, w.lam, w.plan, st), "eig_power", 1);
+    // matrices whose iteration hit its cap are redone by the full solver (it skips the others)
+    CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+  } else {
+    CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, B, (int)rows, 0, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+  }
+  const double beta = (double)std::min(rows, cols) / (double)std::max(rows, cols);
+  CHECK_LAUNCH(ctx, launch_svd_plan(w.lam, B, (int)rows, kind, start, stop, (float)omega_of(beta), w.plan, s_out, st),
+               "svd_plan", 1);
+  CHECK_LAUNCH(ctx, launch_svd_project(S, B, (int)rows, cols, ld, w.U, w.plan, clip, out, out_f64, ldo, st), "svd_project", 1);
+  if (info) {
+    cudaError_t e = cudaMemcpyAsync(info, w.plan, (size_t)B * 16, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(ctx, (int)e, "info copy");
+  }
+  return SPECGPU_OK;
+}
+
+int check_svd_args(specgpu_ctx* ctx, const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const void* out,
+                   int64_t ldo) {
+  int rc = check_matrix_args(ctx, S, B, rows, cols, ld);
+  if (rc) return rc;
+  if (rows > cols) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "svd: rows=%lld > cols=%lld (pass the transpose)", (long long)rows, (long long)cols);
+  if (rows > 512) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "svd: rows=%lld > 512", (long long)rows);
+  if (B * rows * cols > 0 && (!out || ldo < cols)) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output (ldo=%lld)", (long long)ldo);
+  return SPECGPU_OK;
+}
+
+}  // namespace
+
+int specgpu_svd_denoise(specgpu_ctx* ctx, const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld,
+                        int32_t start, int32_t stop, int32_t use_optimal, int32_t clip, int32_t mode, float* out,
+                        int64_t ldo, float* s_out, int32_t* info, void* stream) {
+  int rc = check_svd_args(ctx, S, B, rows, cols, ld, out, ldo);
+  if (rc) return rc;
+  if (B * rows * cols == 0) return SPECGPU_OK;
+  cudaSetDevice(ctx->device);
+  const bool power_ok = (mode == 0) && !use_optimal && start == 1 && stop >= rows && s_out == nullptr && rows <= 256;
+  if ((rc = ensure_ws(ctx, svd_ws_bytes(B, rows, power_ok && gram_tc_supported(rows), true)))) return rc;
+  return svd_run(ctx, ctx->ws, S, B, rows, cols, ld, use_optimal ? 1 : 0, start, stop, clip, power_ok, out, 0, ldo, s_out,
+                 info, (cudaStream_t)stream);
+}
+
+int specgpu_compute_signal(specgpu_ctx* ctx, const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, double* out,
+                           int64_t ldo, float* s_out, int32_t* info, void* stream) {
+  int rc = check_svd_args(ctx, S, B, rows, cols, ld, out, ldo);
+  if (rc) return rc;
+  if (B * rows * cols == 0) return SPECGPU_OK;
+  cudaSetDevice(ctx->device);
+  if ((rc = ensure_ws(ctx, svd_ws_bytes(B, rows, false, true)))) return rc;
+  return svd_run(ctx, ctx->ws, S, B, rows, cols, ld, 2, 0, 0, 0, false, out, 1, ldo, s_out, info, (cudaStream_t)stream);
+}
+
+// ---- tiles -----------------------------------------------------------------------------------------
+int specgpu_patch(specgpu_ctx* ctx, const float* src, int64_t n, int64_t rows, int64_t ld, int32_t tile_w, int32_t ntiles,
+                  void* out, int32_t out_f64, void* stream) {
+  if (!ctx) return SPECGPU_ERR_INVALID_ARG;
+  if (n < 0 || rows < 0 || tile_w <= 0 || ntiles < 0 || ld < (int64_t)tile_w * ntiles)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "patch: need ld >= tile_w*ntiles (ld=%lld, %d x %d)", (long long)ld, tile_w, ntiles);
+  if (n > 65535 || rows > 65535) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "patch: n and rows must be <= 65535");
+  if (n * rows * ntiles == 0) return SPECGPU_OK;
+  if (!src || !out) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null pointer");
+  CHECK_LAUNCH(ctx, launch_patch(src, n, rows, ld, tile_w, ntiles, out, out_f64, (cudaStream_t)stream), "patch", 1);
+  return SPECGPU_OK;
+}
+
+int specgpu_unpatch(specgpu_ctx* ctx, const void* tiles, int32_t in_f64, int64_t n, int64_t rows, int32_t tile_w,
+                    int32_t ntiles, void* dst, int32_t out_f64, int64_t ld, void* stream) {
+  if (!ctx) return SPECGPU_ERR_INVALID_ARG;
+  if (n < 0 || rows < 0 || tile_w <= 0 || ntiles < 0 || ld < (int64_t)tile_w * ntiles)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "unpatch: need ld >= tile_w*ntiles (ld=%lld, %d x %d)", (long long)ld, tile_w, ntiles);
+  if (n > 65535 || rows > 65535) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "unpatch: n and rows must be <= 65535");
+  if (n * rows * ntiles == 0) return SPECGPU_OK;
+  if (!tiles || !dst) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null pointer");
+  CHECK_LAUNCH(ctx, launch_unpatch(tiles, in_f64, n, rows, tile_w, ntiles, dst, out_f64, ld, (cudaStream_t)stream), "unpatch", 1);
+  return SPECGPU_OK;
+}
+
+// ---- cross-power spectrum ----------------------------------------------------------------------------
+int specgpu_csd_spectra(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n, int64_t ldx,
+                        float* X, int64_t ldf, void* stream) {
+  int rc = check_signal_args(ctx, plan, x, C, n, ldx);
+  if (rc) return rc;
+  const int64_t nseg = num_segments(n, plan->p.nperseg, plan->p.noverlap);
+  if (nseg == 0 || C == 0) return SPECGPU_OK;
+  const int nfreq = plan->p.nperseg / 2 + 1;
+  if (!X || ldf < nfreq) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad spectra buffer (ldf=%lld < nfreq=%d)", (long long)ldf, nfreq);
+  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, 1.0f, X, ldf, nullptr);
+  CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_SPECTRA, a, C, (cudaStream_t)stream), "stft_kernel", 1);
+  return SPECGPU_OK;
+}
+
+int specgpu_csd_pairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg, int64_t ldf,
+                      int64_t i0, int64_t ni, float* P, void* stream) {
+  if (!ctx || !plan) return SPECGPU_ERR_INVALID_ARG;
+  const int nfreq = plan->p.nperseg / 2 + 1;
+  if (C < 0 || nseg < 0 || ldf < nfreq || i0 < 0 || ni < 0 || i0 + ni > C)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_pairs: bad shape C=%lld nseg=%lld ldf=%lld i0=%lld ni=%lld", (long long)C,
+                (long long)nseg, (long long)ldf, (long long)i0, (long long)ni);
+  if (C > 64) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "csd_pairs: C=%lld > 64 channels", (long long)C);
+  if (C == 0 || ni == 0) return SPECGPU_OK;
+  if (nseg == 0) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_pairs: no segments to average");
+  if (!X || !P) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null pointer");
+  cudaSetDevice(ctx->device);
+  // the pair partials live behind whatever specgpu_csd_allpairs put in front (its spectra)
+  const size_t need = ctx->ws_csd_off + csd_pairs_workspace_bytes(C, ni, nfreq, nseg) + 256;
+  int rc = ensure_ws(ctx, need);
+  if (rc) return rc;
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(ctx->ws) + ctx->ws_csd_off);
+  CHECK_LAUNCH(ctx, launch_csd_pairs(X, C, nseg, ldf, nfreq, i0, ni, (float)plan->scale, partial, P, (cudaStream_t)stream),
+               "csd_pairs", 2);
+  return SPECGPU_OK;
+}
+
+int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n, int64_t ldx,
+                         float* P, void* stream) {
+  int rc = check_signal_args(ctx, plan, x, C, n, ldx);
+  if (rc) return rc;
+  if (C > 64) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "csd_allpairs: C=%lld > 64 channels", (long long)C);
+  const int64_t nseg = num_segments(n, plan->p.nperseg, plan->p.noverlap);
+  if (C == 0) return SPECGPU_OK;
+  if (nseg == 0) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_allpairs: record shorter than nperseg");
+  if (!P) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null output pointer");
+  const int nfreq = plan->p.nperseg / 2 + 1;
+  const int64_t ldf = (nfreq + 1) & ~(int64_t)1;  // 16-byte aligned rows of float2
+  cudaSetDevice(ctx->device);
+  const size_t xbytes = (((size_t)C * nseg * ldf * 8) + 255) & ~(size_t)255;
+  if ((rc = ensure_ws(ctx, xbytes + csd_pairs_workspace_bytes(C, C, nfreq, nseg) + 512))) return rc;
+  float* X = static_cast<float*>(ctx->ws);
+  if ((rc = specgpu_csd_spectra(ctx, plan, x, C, n, ldx, X, ldf, stream))) return rc;
+  ctx->ws_csd_off = xbytes;
+  rc = specgpu_csd_pairs(ctx, plan, X, C, nseg, ldf, 0, C, P, stream);
+  ctx->ws_csd_off = 0;
+  return rc;
+}
+
+// ---- whole path --------------------------------------------------------------------------------------
+int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t B, int64_t n, int64_t ldx, float* S,
+                     float* D, int64_t ldt, int32_t clip, float* tiles, int32_t tile_w, int32_t ntiles, int32_t* info,
+                     void* stream) {
+  int rc = check_signal_args(ctx, plan, x, B, n, ldx);
+  if (rc) return rc;
+  const int64_t nseg = num_segments(n, plan->p.nperseg, plan->p.noverlap);
+  if (nseg == 0 || B == 0) return SPECGPU_OK;
+  const int64_t rows = plan->p.nperseg / 2;
+  if (!S || !D || ldt < nseg) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output (ldt=%lld < nseg=%lld)", (long long)ldt, (long long)nseg);
+  if (rows > nseg) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "pipeline: %lld frequency rows > %lld segments", (long long)rows, (long long)nseg);
+  if (rows > 512) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "pipeline: nperseg/2=%lld > 512 rows for the SVD stage", (long long)rows);
+  if (tiles && (tile_w <= 0 || ntiles < 0 || (int64_t)tile_w * ntiles > nseg))
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "pipeline: tile_w*ntiles exceeds the %lld columns", (long long)nseg);
+  cudaSetDevice(ctx->device);
+  const bool power_ok = rows <= 256;
+  const size_t mm_bytes = carve_size({(size_t)B * 2 * sizeof(unsigned)});
+  if ((rc = ensure_ws(ctx, mm_bytes + svd_ws_bytes(B, rows, power_ok && gram_tc_supported(rows), true)))) return rc;
+  unsigned* mm = static_cast<unsigned*>(ctx->ws);
+  void* svd_ws = static_cast<char*>(ctx->ws) + mm_bytes;
+  cudaStream_t st = (cudaStream_t)stream;
+  CHECK_LAUNCH(ctx, launch_minmax_init(mm, B, st), "minmax_init", 1);
+  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, (float)plan->scale, S, ldt, mm);
+  CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, B, st), "stft_kernel", 1);
+  CHECK_LAUNCH(ctx, launch_lognorm(S, B, rows, nseg, ldt, mm, nullptr, st), "lognorm", 1);
+  if ((rc = svd_run(ctx, svd_ws, S, B, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, D, 0, ldt, nullptr, info, st))) return rc;
+  if (tiles && ntiles > 0) CHECK_LAUNCH(ctx, launch_patch(D, B, rows, ldt, tile_w, ntiles, tiles, 0, st), "patch", 1);
   return SPECGPU_OK;
 }
 

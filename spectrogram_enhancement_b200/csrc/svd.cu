@@ -1,0 +1,620 @@
+// K3: SVD range-truncation denoise (spec_denoising/denoising_by_svd.ipynb:155-229, 280-281).
+//
+// For a rows x cols matrix S (rows <= cols) the left singular vectors are the eigenvectors of the
+// rows x rows Gram matrix G = S S^T and s_k = sqrt(lambda_k);   U[:,a:b] diag(s[a:b]) Vh[a:b,:] equals
+// U_r U_r^T S, so V is never formed.  Stages:
+//   gram      G = S S^T                      (gram_tc.cu: tcgen05 TF32 for rows in {128,256}; here: SIMT fp32)
+//   eig       power iteration (leading pair only)  or  cluster-resident one-sided Jacobi (all pairs)
+//   plan      singular values, median, Gavish-Donoho count, the reference's start/stop bookkeeping
+//   project   out = U_r U_r^T S  (or S - U_c U_c^T S when the complement is smaller), optional clip
+#include "kernels.h"
+
+#ifndef SPECGPU_EMULATE
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#define SPECGPU_CLUSTER_SYNC() cg::this_cluster().sync()
+#define SPECGPU_CLUSTER_RANK() ((int)cg::this_cluster().block_rank())
+#define SPECGPU_MAP_SHARED(p, r) cg::this_cluster().map_shared_rank((p), (r))
+#else
+#define SPECGPU_CLUSTER_SYNC() emu::cluster_sync()
+#define SPECGPU_CLUSTER_RANK() ((int)emu::cluster_ctarank())
+#define SPECGPU_MAP_SHARED(p, r) emu::map_shared_rank((p), (r))
+#endif
+
+namespace specgpu {
+
+// ======================================================================================================
+// Gram matrix, SIMT fp32 (any shape).  64x64 output tile per CTA, split along K; partial sums are
+// accumulated with float atomics into a zeroed G, lower triangle mirrored from the upper.
+// ======================================================================================================
+constexpr int kGramTile = 64, kGramKB = 32, kGramThreads = 256;
+
+__global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S, int rows, int64_t cols, int64_t ld,
+                                                                 int ksplit, float* G) {
+  __shared__ float sa[kGramTile][kGramKB + 1];
+  __shared__ float sb[kGramTile][kGramKB + 1];
+  const int64_t b = blockIdx.z;
+  const int nt = (rows + kGramTile - 1) / kGramTile;
+  // blockIdx.x enumerates tile pairs (ti <= tj)
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= nt - ti) {
+    rem -= nt - ti;
+    ++ti;
+  }
+  const int tj = ti + rem;
+  const int64_t kchunk = ((cols + ksplit - 1) / ksplit + kGramKB - 1) / kGramKB * kGramKB;
+  const int64_t k0 = (int64_t)blockIdx.y * kchunk;
+  const int64_t k1 = (k0 + kchunk < cols) ? k0 + kchunk : cols;
+  const float* Sb = S + b * rows * ld;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4] = {};
+  for (int64_t k = k0; k < k1; k += kGramKB) {
+    for (int i = tid; i < kGramTile * kGramKB; i += kGramThreads) {
+      const int r = i / kGramKB, c = i % kGramKB;
+      const int ra = ti * kGramTile + r, rb = tj * kGramTile + r;
+      sa[r][c] = (ra < rows && k + c < k1) ? Sb[(int64_t)ra * ld + k + c] : 0.f;
+      sb[r][c] = (rb < rows && k + c < k1) ? Sb[(int64_t)rb * ld + k + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < kGramKB; ++c) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = sa[ty + 16 * i][c];
+        bv[i] = sb[tx + 16 * i][c];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+    }
+    __syncthreads();
+  }
+  float* Gb = G + b * (int64_t)rows * rows;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = ti * kGramTile + ty + 16 * i, c = tj * kGramTile + tx + 16 * j;
+      if (r < rows && c < rows) {
+        if (ti != tj || c >= r) {
+          atomicAdd(Gb + (int64_t)r * rows + c, acc[i][j]);
+          if (r != c) atomicAdd(Gb + (int64_t)c * rows + r, acc[i][j]);
+        }
+      }
+    }
+}
+
+int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* G, cudaStream_t stream) {
+  if (B == 0 || rows == 0) return 0;
+  cudaError_t e = cudaMemsetAsync(G, 0, (size_t)B * rows * rows * sizeof(float), stream);
+  if (e != cudaSuccess) return (int)e;
+  const int nt = (int)ceil_div(rows, kGramTile);
+  const int npairs = nt * (nt + 1) / 2;
+  int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(cols, 512), 16));
+  SPECGPU_LAUNCH(gram_simt_kernel, dim3((unsigned)npairs, (unsigned)ksplit, (unsigned)B), kGramThreads, 0, stream, S,
+                 (int)rows, cols, ld, ksplit, G);
+  return (int)cudaGetLastError();
+}
+
+// ======================================================================================================
+// Leading eigenpair by power iteration: one CTA per matrix, G held in registers (n <= 256) so that an
+// iteration costs one pass over shared memory only.  Writes U[:,0], lam[0] and status (plan[3]).
+// ======================================================================================================
+constexpr int kPowThreads = 1024;
+constexpr int kPowMaxIter = 200;
+
+__global__ void __launch_bounds__(kPowThreads) eig_power_kernel(const float* G, int n, float* U, float* lam, int32_t* plan) {
+  __shared__ __align__(16) float sx[256];
+  __shared__ __align__(16) float sy[256];
+  const int64_t b = blockIdx.x;
+  const float* Gb = G + b * (int64_t)n * n;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int row = tid >> 2, q = tid & 3;  // 4 threads per row; thread q holds columns q*4 + 16*i + {0..3}
+  float4 g[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = q * 4 + 16 * i;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) {
+      const float* p = Gb + (int64_t)row * n + c;
+      if (c + 0 < n) v.x = p[0];
+      if (c + 1 < n) v.y = p[1];
+      if (c + 2 < n) v.z = p[2];
+      if (c + 3 < n) v.w = p[3];
+    }
+    g[i] = v;
+  }
+  if (tid < 256) sx[tid] = (tid < n) ? rsqrtf((float)n) : 0.f;
+  __syncthreads();
+  float lambda = 0.f, prev_delta = INFINITY;
+  int status = 1;
+  for (int it = 0; it < kPowMaxIter; ++it) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 xv = *reinterpret_cast<const float4*>(sx + q * 4 + 16 * i);
+      acc += g[i].x * xv.x + g[i].y * xv.y + g[i].z * xv.z + g[i].w * xv.w;
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0) sy[row] = acc;
+    __syncthreads();
+    // every warp redundantly reduces |y|^2, x.y and |y/|y| - x|^2 (uniform control flow, no extra barriers)
+    float yy = 0.f, xy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = sy[lane + 32 * i], x = sx[lane + 32 * i];
+      yy += y * y;
+      xy += x * y;
+    }
+    yy = warp_sum(yy);
+    xy = warp_sum(xy);
+    const float inv = (yy > 0.f) ? rsqrtf(yy) : 0.f;
+    float dd = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = sy[lane + 32 * i] * inv - sx[lane + 32 * i];
+      dd += d * d;
+    }
+    dd = warp_sum(dd);
+    lambda = xy;  // Rayleigh quotient x^T G x with |x| = 1
+    __syncthreads();
+    if (tid < 256) sx[tid] = sy[tid] * inv;
+    __syncthreads();
+    if (dd < 1e-13f || (dd < 1e-10f && dd >= prev_delta)) {
+      status = 0;
+      break;
+    }
+    prev_delta = dd;
+  }
+  if (tid < n) U[b * (int64_t)n * n + (int64_t)tid * n] = sx[tid];
+  if (tid == 0) {
+    lam[b * n] = lambda;
+    plan[b * 4 + 3] = status;
+  }
+}
+
+int launch_eig_power(const float* G, int64_t B, int n, float* U, float* lam, int32_t* plan, cudaStream_t stream) {
+  if (B == 0) return 0;
+  if (n > 256) return -1;
+  SPECGPU_LAUNCH(eig_power_kernel, (unsigned)B, kPowThreads, 0, stream, G, n, U, lam, plan);
+  return (int)cudaGetLastError();
+}
+
+// ======================================================================================================
+// Full symmetric eigen-decomposition: one-sided (Hestenes) Jacobi on the columns of G, resident in the
+// shared memory of a thread-block cluster.  The n_pad columns are cut into 2*CL blocks of cb columns;
+// CTA r of the cluster holds two blocks ("top", "bot") plus one spare slot.  A sweep is 2*CL-1
+// block-rounds of the round-robin tournament; between block-rounds the blocks move one position round
+// the ring through distributed shared memory (two cluster barriers).  Within a block-round every CTA
+// orthogonalises its 2*cb columns pairwise (one warp per pair): the full local tournament in the first
+// block-round of a sweep, only the cross pairs (top_i, bot_j) afterwards.  At convergence column k is
+// lambda_k * u_k; eig_sort_kernel orders the pairs by descending lambda.
+// ======================================================================================================
+constexpr int kJacThreads = 1024;
+constexpr int kJacMaxSweeps = 40;
+constexpr float kJacTol = 1e-6f;
+
+struct JacobiArgs {
+  const float* G;     // [B][n][n]
+  int n, n_pad, cb, cl;
+  const int32_t* plan;  // skip matrices whose plan[b][3] == 0 when skip_converged
+  int skip_converged;
+  float* Ucols;       // [B][n_pad][n_pad] : row k = (unsorted) eigenvector k (contiguous)
+  float* lam_raw;     // [B][n_pad]
+  int32_t* status;    // [B] sweeps used (negative: hit the cap)
+};
+
+// Orthogonalise columns x, y (length n, one warp).  Returns true if a rotation was applied.
+__device__ __forceinline__ bool jacobi_pair(float* x, float* y, int n, int lane) {
+  float a = 0.f, bq = 0.f, g = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const float xv = x[i], yv = y[i];
+    a += xv * xv;
+    bq += yv * yv;
+    g += xv * yv;
+  }
+  a = warp_sum(a);
+  bq = warp_sum(bq);
+  g = warp_sum(g);
+  if (!(fabsf(g) > kJacTol * sqrtf(a * bq))) return false;
+  const float zeta = (bq - a) / (2.0f * g);
+  const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+  const float c = rsqrtf(1.0f + t * t), s = c * t;
+  for (int i = lane; i < n; i += 32) {
+    const float xv = x[i], yv = y[i];
+    x[i] = c * xv - s * yv;
+    y[i] = s * xv + c * yv;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
+  SPECGPU_DYN_SMEM(smem);
+  const int n = a.n, np = a.n_pad, cb = a.cb, CL = a.cl;
+  const int rank = SPECGPU_CLUSTER_RANK();
+  const int64_t b = blockIdx.x / CL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kJacThreads / 32;
+  const size_t slot_floats = (size_t)cb * np;
+  float* slots = reinterpret_cast<float*>(smem);
+  int* s_flag = reinterpret_cast<int*>(slots + 3 * slot_floats);  // [CL] per-rank "rotated" flags + [1] local
+  // Slot roles.  Rank 0 never re-labels (top 0, bot 1, spare 2); every rank >= 1 applies the same
+  // permutation after each ring step, so all of them share (p_top, p_bot, p_spare), which every rank
+  // (rank 0 included) tracks in order to address its neighbours' slots.
+  int p_top = 0, p_bot = 1, p_spare = 2;
+  const bool skip = a.skip_converged && a.plan[b * 4 + 3] == 0;   // uniform over the whole cluster
+
+  if (!skip) {
+    // block ids: rank r starts with blocks 2r (top) and 2r+1 (bot); column j of G == row j (symmetric)
+    const float* Gb = a.G + b * (int64_t)n * n;
+    for (int s = 0; s < 2; ++s) {
+      float* dst = slots + (size_t)s * slot_floats;   // initially top = slot 0, bot = slot 1 everywhere
+      const int col0 = (2 * rank + s) * cb;
+      for (int i = tid; i < cb * np; i += kJacThreads) {
+        const int c = col0 + i / np, r = i % np;
+        dst[i] = (c < n && r < n) ? Gb[(int64_t)c * n + r] : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  int sweeps_used = 0;
+  bool converged = skip;
+  if (!skip) {
+    for (int sweep = 0; sweep < kJacMaxSweeps && !converged; ++sweep) {
+      if (tid == 0) s_flag[CL] = 0;
+      __syncthreads();
+      bool rotated = false;
+      for (int br = 0; br < 2 * CL - 1; ++br) {
+        const int top = (rank == 0) ? 0 : p_top, bot = (rank == 0) ? 1 : p_bot;
+        float* T = slots + top * slot_floats;
+        float* Bt = slots + bot * slot_floats;
+        if (br == 0) {
+          // full tournament over the m = 2*cb local columns (player m-1 fixed)
+          const int m = 2 * cb;
+          for (int r = 0; r < m - 1; ++r) {
+            for (int i = warp; i < cb; i += NW) {
+              int p, q;
+              if (i == 0) {
+                p = m - 1;
+                q = r;
+              } else {
+                p = (r + i) % (m - 1);
+                q = (r - i + (m - 1)) % (m - 1);
+              }
+              float* x = (p < cb) ? T + (size_t)p * np : Bt + (size_t)(p - cb) * np;
+              float* y = (q < cb) ? T + (size_t)q * np : Bt + (size_t)(q - cb) * np;
+              rotated |= jacobi_pair(x, y, np, lane);
+            }
+            __syncthreads();
+          }
+        } else {
+          for (int r = 0; r < cb; ++r) {
+            for (int i = warp; i < cb; i += NW) {
+              float* x = T + (size_t)i * np;
+              float* y = Bt + (size_t)((i + r) % cb) * np;
+              rotated |= jacobi_pair(x, y, np, lane);
+            }
+            __syncthreads();
+          }
+        }
+        if (CL > 1) {
+          // ---- move the blocks one step round the ring (see header comment) ----
+          // phase 1: rank 0 sends bot, ranks 1..CL-2 send top, to the right neighbour's spare slot
+          if (rank < CL - 1) {
+            const float* srcp = slots + (rank == 0 ? bot : top) * slot_floats;
+            float* dstp = SPECGPU_MAP_SHARED(slots + p_spare * slot_floats, rank + 1);
+            for (size_t i = tid; i < slot_floats; i += kJacThreads) dstp[i] = srcp[i];
+          }
+          SPECGPU_CLUSTER_SYNC();
+          // phase 2: ranks 1..CL-1 send their old bot to the left neighbour's freed slot
+          //          (rank 0: its old bot slot; rank i-1 >= 1: its old top slot)
+          if (rank >= 1) {
+            const float* srcp = slots + bot * slot_floats;
+            const int left_free = (rank - 1 == 0) ? 1 : p_top;
+            float* dstp = SPECGPU_MAP_SHARED(slots + left_free * slot_floats, rank - 1);
+            for (size_t i = tid; i < slot_floats; i += kJacThreads) dstp[i] = srcp[i];
+          }
+          SPECGPU_CLUSTER_SYNC();
+          {
+            const int old_top = p_top, old_bot = p_bot;
+            p_top = p_spare;     // received in phase 1
+            p_bot = old_top;     // rank CL-1: its own old top; others: received in phase 2 into the old top slot
+            p_spare = old_bot;   // sent away in phase 2
+          }
+          // rank 0: top fixed, bot slot refilled in phase 2, spare untouched
+        }
+      }
+      // ---- did anybody rotate during this sweep? ----
+      if (rotated && lane == 0) s_flag[CL] = 1;
+      __syncthreads();
+      int any = s_flag[CL];
+      if (CL > 1) {
+        if (tid < CL) {
+          int* remote = SPECGPU_MAP_SHARED(s_flag, tid);
+          remote[rank] = any;
+        }
+        SPECGPU_CLUSTER_SYNC();
+        any = 0;
+        for (int r = 0; r < CL; ++r) any |= s_flag[r];
+        SPECGPU_CLUSTER_SYNC();
+      }
+      __syncthreads();   // everybody has read the flag before thread 0 clears it for the next sweep
+      sweeps_used = sweep + 1;
+      converged = (any == 0);
+    }
+    // ---- write lambda_k = |a_k|, u_k = a_k / |a_k| for the 2*cb local columns ----
+    for (int s = 0; s < 2; ++s) {
+      const int slot = (rank == 0) ? s : (s == 0 ? p_top : p_bot);
+      const float* src = slots + slot * slot_floats;
+      for (int i = warp; i < cb; i += NW) {
+        const float* x = src + (size_t)i * np;
+        float nn = 0.f;
+        for (int r = lane; r < np; r += 32) nn += x[r] * x[r];
+        nn = warp_sum(nn);
+        const float nrm = sqrtf(nn);
+        const float inv = nrm > 0.f ? 1.0f / nrm : 0.f;
+        // any slot order is fine: eig_sort_kernel orders by lambda
+        const int64_t k = (int64_t)(2 * rank + s) * cb + i;
+        float* u = a.Ucols + (b * np + k) * np;
+        for (int r = lane; r < np; r += 32) u[r] = x[r] * inv;
+        if (lane == 0) a.lam_raw[b * np + k] = nrm;
+      }
+    }
+    if (rank == 0 && tid == 0) a.status[b] = converged ? sweeps_used : -sweeps_used;
+  }
+}
+
+// Order eigenpairs by descending lambda (rank by counting; ties by index) and lay U out as
+// U[b][i][k] (row-major n x n, column k = k-th largest).  One CTA per matrix.
+__global__ void eig_sort_kernel(const float* Ucols, const float* lam_raw, const int32_t* jstatus, int n, int n_pad,
+                                int skip_converged, float* U, float* lam, int32_t* plan) {
+  const int64_t b = blockIdx.x;
+  if (skip_converged && plan[b * 4 + 3] == 0) return;
+  __shared__ int s_rank[512];
+  const float* lr = lam_raw + b * n_pad;
+  for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
+    const float v = lr[k];
+    int rk = 0;
+    for (int j = 0; j < n_pad; ++j) {
+      const float w = lr[j];
+      rk += (w > v || (w == v && j < k)) ? 1 : 0;
+    }
+    s_rank[k] = rk;
+    if (rk < n) lam[b * n + rk] = v;
+  }
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < (int64_t)n_pad * n; i += blockDim.x) {
+    const int k = (int)(i / n), r = (int)(i % n);
+    const int rk = s_rank[k];
+    if (rk < n) U[b * (int64_t)n * n + (int64_t)r * n + rk] = Ucols[(b * n_pad + k) * n_pad + r];
+  }
+  if (threadIdx.x == 0) plan[b * 4 + 3] = (jstatus[b] > 0) ? 0 : 1;
+}
+
+struct JacobiGeom {
+  int n_pad, cb, cl;
+  size_t smem;
+};
+
+static JacobiGeom jacobi_geom(int n) {
+  JacobiGeom g;
+  g.cl = (n <= 128) ? 1 : (n <= 256 ? 2 : 8);
+  const int nb = 2 * g.cl;
+  g.cb = (n + nb - 1) / nb;
+  g.n_pad = g.cb * nb;
+  g.smem = 3 * (size_t)g.cb * g.n_pad * sizeof(float) + (g.cl + 2) * sizeof(int) + 16;
+  return g;
+}
+
+size_t jacobi_workspace_bytes(int64_t B, int n) {
+  const JacobiGeom g = jacobi_geom(n);
+  return (size_t)B * g.n_pad * g.n_pad * sizeof(float) + (size_t)B * g.n_pad * sizeof(float) + (size_t)B * sizeof(int32_t) + 1024;
+}
+
+int launch_eig_jacobi(const float* G, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan,
+                      void* ws, cudaStream_t stream) {
+  if (B == 0) return 0;
+  if (n > 512) return -1;
+  const JacobiGeom g = jacobi_geom(n);
+  char* w = static_cast<char*>(ws);
+  float* Ucols = reinterpret_cast<float*>(w);
+  w += (size_t)B * g.n_pad * g.n_pad * sizeof(float);
+  float* lam_raw = reinterpret_cast<float*>(w);
+  w += (((size_t)B * g.n_pad * sizeof(float)) + 255) & ~(size_t)255;
+  int32_t* jstatus = reinterpret_cast<int32_t*>(w);
+  JacobiArgs a{G, n, g.n_pad, g.cb, g.cl, plan, skip_converged, Ucols, lam_raw, jstatus};
+#ifdef SPECGPU_EMULATE
+  SPECGPU_LAUNCH_CLUSTER(eig_jacobi_kernel, (unsigned)(B * g.cl), kJacThreads, g.smem, stream, g.cl, a);
+#else
+  cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(B * g.cl));
+  cfg.blockDim = dim3(kJacThreads);
+  cfg.dynamicSmemBytes = g.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)g.cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, eig_jacobi_kernel, a);
+  if (e != cudaSuccess) return (int)e;
+#endif
+  SPECGPU_LAUNCH(eig_sort_kernel, (unsigned)B, 512, 0, stream, (const float*)Ucols, (const float*)lam_raw,
+                 (const int32_t*)jstatus, n, g.n_pad, skip_converged, U, lam, plan);
+  return (int)cudaGetLastError();
+}
+
+// ======================================================================================================
+// Plan: singular values, median, optimal hard threshold count, start/stop with the reference's clamps and
+// Python slice semantics.  kind 0: explicit (start, stop); 1: use_optimal; 2: computeSignal (1, 2*num_sing).
+// ======================================================================================================
+__global__ void svd_plan_kernel(const float* lam, int n, int kind, int start, int stop, float omega_f, int32_t* plan,
+                                float* s_out) {
+  const int64_t b = blockIdx.x;
+  __shared__ float s_s[512];
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  if (kind != 0 || s_out != nullptr) {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      const float s = sqrtf(fmaxf(lam[b * n + k], 0.f));
+      s_s[k] = s;
+      if (s_out != nullptr) s_out[b * n + k] = s;
+    }
+  }
+  __syncthreads();
+  int a = start, e = stop, num_sing = -1;
+  if (kind != 0) {
+    // np.median of the descending s: mean of the two middle values for even n
+    const float med = (n & 1) ? s_s[n / 2] : __fdiv_rn(__fadd_rn(s_s[n / 2 - 1], s_s[n / 2]), 2.0f);
+    const float t_star = __fmul_rn(omega_f, med);
+    int cnt = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) cnt += (s_s[k] > t_star) ? 1 : 0;
+    atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    num_sing = s_cnt;
+    if (kind == 1) {
+      a = 0;
+      e = num_sing - 1;
+    } else {
+      a = 1;
+      e = 2 * num_sing;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (a < 0) a = 0;          // "prevent some bad values from being used"
+    if (e > n) e = n;
+    // python slice u[:, a:e]
+    if (e < 0) e = (e + n > 0) ? e + n : 0;
+    if (a > n) a = n;
+    plan[b * 4 + 0] = a;
+    plan[b * 4 + 1] = e;
+    plan[b * 4 + 2] = num_sing;
+  }
+}
+
+int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int stop, float omega_f, int32_t* plan,
+                    float* s_out, cudaStream_t stream) {
+  if (B == 0) return 0;
+  if (n > 512) return -1;
+  SPECGPU_LAUNCH(svd_plan_kernel, (unsigned)B, 256, 0, stream, lam, n, kind, start, stop, omega_f, plan, s_out);
+  return (int)cudaGetLastError();
+}
+
+// ======================================================================================================
+// Projection: out = sum_{k in [a,e)} u_k (u_k^T S), or S minus the complementary sum when that is the
+// shorter one.  A CTA owns a [rows x 32] column tile of S in shared memory; each warp takes one vector
+// of a chunk of 8 for the coefficient pass (lane = column) and rows warp, warp+8, ... for the update.
+// ======================================================================================================
+constexpr int kRecThreads = 256, kRecCols = 32, kRecChunk = 8;
+
+template <class OutT, int RPW>   // RPW = rows per warp-thread = ceil(rows / 8)
+__global__ void __launch_bounds__(kRecThreads) svd_project_kernel(const float* S, int rows, int64_t cols, int64_t ld,
+                                                                  const float* U, const int32_t* plan, int clip,
+                                                                  OutT* out, int64_t ldo) {
+  SPECGPU_DYN_SMEM(smem);
+  float* tile = reinterpret_cast<float*>(smem);                   // [rows][33]
+  float* s_u = tile + (size_t)rows * (kRecCols + 1);               // [kRecChunk][rows]
+  float* s_w = s_u + (size_t)kRecChunk * rows;                     // [kRecChunk][32]
+  const int64_t b = blockIdx.y;
+  const int64_t c0 = (int64_t)blockIdx.x * kRecCols;
+  const int ncol = (int)((cols - c0 < kRecCols) ? (cols - c0) : kRecCols);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* Sb = S + b * rows * ld;
+  const float* Ub = U + b * (int64_t)rows * rows;
+  int a = plan[b * 4 + 0], e = plan[b * 4 + 1];
+  if (e < a) e = a;
+  const int nk = e - a;
+  const bool complement = (rows - nk) < nk;   // subtract the vectors outside [a, e)
+  const int nvec = complement ? rows - nk : nk;
+
+  for (int r = warp; r < rows; r += kRecThreads / 32)
+    tile[r * (kRecCols + 1) + lane] = (lane < ncol) ? Sb[(int64_t)r * ld + c0 + lane] : 0.f;
+
+  float acc[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) acc[i] = 0.f;
+
+  for (int v0 = 0; v0 < nvec; v0 += kRecChunk) {
+    __syncthreads();   // tile ready / previous chunk consumed
+    // stage up to 8 vectors: index v -> eigen-column k
+    for (int i = tid; i < kRecChunk * rows; i += kRecThreads) {
+      const int vv = i / rows, r = i % rows;
+      const int v = v0 + vv;
+      float val = 0.f;
+      if (v < nvec) {
+        const int k = complement ? (v < a ? v : v + nk) : a + v;
+        val = Ub[(int64_t)r * rows + k];
+      }
+      s_u[vv * rows + r] = val;
+    }
+    __syncthreads();
+    {  // coefficients w[vv][col] = u^T tile[:, col]
+      const float* u = s_u + warp * rows;
+      float w = 0.f;
+      if (v0 + warp < nvec)
+        for (int r = 0; r < rows; ++r) w += u[r] * tile[r * (kRecCols + 1) + lane];
+      s_w[warp * 32 + lane] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = warp + 8 * i;
+      if (r < rows) {
+        float s = 0.f;
+#pragma unroll
+        for (int vv = 0; vv < kRecChunk; ++vv) s += s_u[vv * rows + r] * s_w[vv * 32 + lane];
+        acc[i] += s;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = warp + 8 * i;
+    if (r < rows && lane < ncol) {
+      float v = complement ? tile[r * (kRecCols + 1) + lane] - acc[i] : acc[i];
+      if (clip && v < 0.f) v = 0.f;
+      out[(b * rows + r) * ldo + c0 + lane] = (OutT)v;
+    }
+  }
+}
+
+template <class OutT>
+static int launch_project_t(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U,
+                            const int32_t* plan, int clip, OutT* out, int64_t ldo, cudaStream_t stream) {
+  const size_t smem = ((size_t)rows * (kRecCols + 1) + (size_t)kRecChunk * rows + kRecChunk * 32) * sizeof(float);
+  const dim3 grid((unsigned)ceil_div(cols, kRecCols), (unsigned)B);
+#define SPECGPU_PROJECT_CASE(RPW)                                                                             \
+  {                                                                                                           \
+    auto kern = svd_project_kernel<OutT, RPW>;                                                                \
+    if (smem > 48 * 1024) {                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      if (e != cudaSuccess) return (int)e;                                                                    \
+    }                                                                                                         \
+    SPECGPU_LAUNCH(kern, grid, kRecThreads, smem, stream, S, rows, cols, ld, U, plan, clip, out, ldo);        \
+  }
+  if (rows <= 64) SPECGPU_PROJECT_CASE(8)
+  else if (rows <= 128) SPECGPU_PROJECT_CASE(16)
+  else if (rows <= 256) SPECGPU_PROJECT_CASE(32)
+  else if (rows <= 512) SPECGPU_PROJECT_CASE(64)
+  else return -1;
+#undef SPECGPU_PROJECT_CASE
+  return (int)cudaGetLastError();
+}
+
+int launch_svd_project(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U,
+                       const int32_t* plan, int clip, void* out, int out_f64, int64_t ldo, cudaStream_t stream) {
+  if (B == 0 || rows == 0 || cols == 0) return 0;
+  if (out_f64) return launch_project_t<double>(S, B, rows, cols, ld, U, plan, clip, (double*)out, ldo, stream);
+  return launch_project_t<float>(S, B, rows, cols, ld, U, plan, clip, (float*)out, ldo, stream);
+}
+
+}  // namespace specgpu

@@ -30,7 +30,7 @@
 #define __noinline__ __attribute__((noinline))
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 #define __constant__ static
 
