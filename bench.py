@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: input samples/s from raw ECE signal to denoised spectrogram (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one pass of the whole hot path (STFT -> |X|^2 -> log -> min-max -> Nyquist drop -> SVD
+denoise -> clip) over one synthetic shot of 40 ECE channels x 1 000 000 float32 samples with the
+reference's spec_params (BASELINE config 2).  With N > 1 (torchrun, one rank per GPU) every rank
+processes its own shots (config 4's shot sharding: no data-path collective, weak scaling) and the
+value is the whole-job aggregate over the max-over-ranks device time.
+
+Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` goes through the
+public host API with pinned HOST buffers, H2D of the shot and D2H of the denoised spectrogram inside
+the timed region; `roofline` is for the dominant kernel, timed live with CUDA events recorded by the
+library around each launch during the timed steps; `cpu_baseline` is the reference's per-channel
+arithmetic (scipy.signal.spectrogram + numpy SVD, oracle.reference_channel) on a bounded sample of
+the same workload on this host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_CH = 40
+N_SAMP = 1_000_000
+SP = {"nperseg": 512, "noverlap": 256, "fs": 500000, "window": "hamm", "scaling": "density", "detrend": "linear",
+      "eps": 1e-11}
+ROWS = SP["nperseg"] // 2
+NSEG = (N_SAMP - SP["noverlap"]) // (SP["nperseg"] - SP["noverlap"])
+METRIC = "input samples/sec -> denoised spectrogram"
+UNIT = "samples/s"
+WORKLOAD = ("config2: one shot, 40 ECE channels x 1M samples @500 kHz, nperseg=512 noverlap=256 hamm linear-detrend "
+            "density; STFT+log+min-max+SVD(top-1 removed)+clip")
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.ok:
+            self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.th.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# ---------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    shot, ch = args
+    from oracle import spec_oracle as oc
+    try:
+        from threadpoolctl import threadpool_limits
+        ctxm = threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover
+        import contextlib
+        ctxm = contextlib.nullcontext()
+    x = oc.synth_ece(shot, ch, n=N_SAMP)
+    t0 = time.perf_counter()
+    with ctxm:
+        S, D = oc.reference_channel(x, SP)
+    return time.perf_counter() - t0, float(D.sum())
+
+
+def cpu_serial_baseline(nch):
+    """The reference as it runs: one process, serial channel loop (pipeline_data.py:92-95), BLAS threads as found."""
+    from oracle import spec_oracle as oc
+    xs = [oc.synth_ece(0, c, n=N_SAMP) for c in range(nch)]
+    t0 = time.perf_counter()
+    for x in xs:
+        oc.reference_channel(x, SP)
+    dt = time.perf_counter() - t0
+    return nch * N_SAMP / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU arithmetic on all host cores (one channel per worker process,
+    BLAS pinned to 1 thread per worker); each step is a bounded sample of `workers` channels."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    per_step = workers
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        for w in range(args.warmup):
+            pool.map(_ref_worker, [(100 + w, c) for c in range(min(per_step, workers))])
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_ref_worker, [(s, c) for c in range(per_step)])
+        dt = time.perf_counter() - t0
+    value = args.steps * per_step * N_SAMP / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "channels_per_step": per_step, "samples_per_channel": N_SAMP},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"{per_step} channels x 1M samples per step ({workers} worker processes, 1 BLAS thread "
+                                   "each): scipy.signal.spectrogram + log/min-max + np.linalg.svd truncation + clip, "
+                                   "exactly the reference's calls (oracle.reference_channel)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+ALGO_BYTES = {   # algorithmic HBM bytes of one launch over B channels (DESIGN.md "kernels")
+    "stft_kernel": lambda B: B * (4 * N_SAMP + 4 * ROWS * NSEG),          # read x, write log-PSD (Nyquist dropped)
+    "lognorm": lambda B: B * 8 * ROWS * NSEG,                              # read + write the image
+    "gram_tc": lambda B: B * 4 * ROWS * NSEG,                              # read the image once
+    "gram_simt": lambda B: B * 4 * ROWS * NSEG,
+    "svd_project": lambda B: B * 8 * ROWS * NSEG,                          # read S, write D
+    "patch": lambda B: B * 8 * ROWS * (NSEG // 128) * 128,
+}
+
+
+def synth_on_device(torch, device, shot, gen):
+    """Device-side synthetic shot with the oracle's signal model (0.5*chirp + N(0,1)); parity on these exact
+    bytes is checked in run_ours() by reading a channel back."""
+    t = torch.arange(N_SAMP, device=device, dtype=torch.float64) / SP["fs"]
+    f0, f1 = 20e3, 120e3
+    base = 2 * np.pi * (f0 * t + 0.5 * (f1 - f0) / float(t[-1]) * t * t)
+    ph = 2 * np.pi * torch.arange(N_CH, device=device, dtype=torch.float64)[:, None] / N_CH
+    x = 0.5 * torch.cos(base[None, :] + ph).to(torch.float32)
+    x += torch.randn((N_CH, N_SAMP), device=device, dtype=torch.float32, generator=gen)
+    return x.contiguous()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from spectrogram_enhancement_b200 import api
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libspecgpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rt = api.Runtime(device=device)
+    plan = rt.plan_from_params(SP)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1234 + rank)
+    nbuf = 3   # rotate over 3 resident shots (3 x 160 MB in, 2 x 160 MB out each) so no step finds its data in L2
+    xs = [synth_on_device(torch, device, rank * 1000 + i, gen) for i in range(nbuf)]
+    S = [rt.empty((N_CH, ROWS, NSEG)) for _ in range(nbuf)]
+    D = [rt.empty((N_CH, ROWS, NSEG)) for _ in range(nbuf)]
+    info = torch.zeros((N_CH, 4), dtype=torch.int32, device=device)
+
+    def step(i):
+        b = i % nbuf
+        rt.pipeline_dev(plan, xs[b], S[b], D[b], clip=True, info=info)
+
+    # ---- correctness on these exact bytes (rank 0, untimed): one channel against the oracle ----
+    step(0)
+    torch.cuda.synchronize()
+    parity = None
+    if rank == 0:
+        from oracle import spec_oracle as oc
+        xc = xs[0][3].cpu().numpy()
+        Sr, _, _ = oc.specgr_array(xc.astype(np.float64), SP)
+        Sg = S[0][3].cpu().numpy()
+        Dg = D[0][3].cpu().numpy()
+        Dr = oc.clip(oc.denoiseSignal(Sg.astype(np.float64)))
+        parity = {"spec_max_abs_err": float(np.abs(Sg - Sr).max()),
+                  "denoise_max_err_rel_to_max": float(np.abs(Dg - Dr).max() / np.abs(Dr).max())}
+        assert parity["spec_max_abs_err"] < 1e-4 and parity["denoise_max_err_rel_to_max"] < 1e-3, parity
+
+    # ---- device-resident timing ----
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    rt.profile(True)
+    l0 = rt.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = rt.launch_count() - l0
+    prof = rt.profile_read()
+    rt.profile(False)
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    lt = torch.tensor([launches], device=device, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    value = world * args.steps * N_CH * N_SAMP / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with host buffers ----
+    xh = [torch.empty((N_CH, N_SAMP), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for i in range(2):
+        xh[i].copy_(xs[i])
+    dh = torch.empty((N_CH, ROWS, NSEG), dtype=torch.float32).pin_memory()
+    xd = torch.empty((N_CH, N_SAMP), dtype=torch.float32, device=device)
+
+    def e2e_step(i):
+        xd.copy_(xh[i % 2], non_blocking=True)                        # H2D of the step's input
+        _, Dd = api.pipeline(xd, SP, clip=True, runtime=rt)          # public API on the staged tensor
+        dh.copy_(Dd, non_blocking=True)                               # D2H of the denoised spectrogram
+        torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(2, min(args.steps, 10))
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * N_CH * N_SAMP / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    kernels = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1], "share": v[0] / max(sum(x[0] for x in prof.values()), 1e-9)}
+               for k, v in prof.items()}
+    dom = max((k for k in prof if k in ALGO_BYTES), key=lambda k: prof[k][0], default=None)
+    roof = None
+    if dom is not None:
+        dur_s = prof[dom][0] / max(prof[dom][1], 1) * 1e-3
+        ach = ALGO_BYTES[dom](N_CH) / dur_s / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALGO_BYTES[dom](N_CH), "ms_per_launch": dur_s * 1e3}
+    pipeline_gbs = 12.0 * N_CH * N_SAMP * args.steps / (ms * 1e-3) / 1e9      # 12 B/sample
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        nch = 8
+        v, dt = cpu_serial_baseline(nch)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{nch} of the 40 channels x 1M samples, one process, serial channel loop as the reference runs "
+                         f"(scipy.signal.spectrogram + np.linalg.svd, BLAS threads as found; {dt:.1f} s)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "channels": N_CH, "samples_per_channel": N_SAMP, "shots_per_step_per_gpu": 1,
+                   "sharding": "by shot, no data-path collective" if world > 1 else "single GPU",
+                   "l2": f"inputs larger than L2: {nbuf} resident shots rotated (160 MB in + 320 MB out per step)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_CH * N_SAMP * 4,
+                "d2h_bytes_per_step": N_CH * ROWS * NSEG * 4, "steps": e2e_steps},
+        "gpu_launches": int(lt.item()),
+        "clocks": clk.summary(),
+        "roofline": roof,
+        "pipeline_hbm": {"algorithmic_gbs": pipeline_gbs, "frac_of_peak": pipeline_gbs / peak, "bytes_per_sample": 12},
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "parity_on_bench_bytes": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

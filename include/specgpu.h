@@ -164,6 +164,16 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
  * gpu_launches claim). */
 int64_t specgpu_launch_count(const specgpu_ctx* ctx);
 
+/* Optional per-kernel timing for bench.py's roofline line: while enabled, every launch group the
+ * library enqueues is bracketed by CUDA events on the caller's stream.  specgpu_profile_count
+ * synchronises on the recorded events and returns the number of distinct kernel names seen since
+ * the last enable; name / total milliseconds / number of timed launches are then read per index. */
+int specgpu_profile_enable(specgpu_ctx* ctx, int enable);
+int specgpu_profile_count(specgpu_ctx* ctx);
+const char* specgpu_profile_name(const specgpu_ctx* ctx, int i);
+double specgpu_profile_ms(const specgpu_ctx* ctx, int i);
+int64_t specgpu_profile_calls(const specgpu_ctx* ctx, int i);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,11 @@ PROTOTYPES = {
     "specgpu_csd_allpairs": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "specgpu_pipeline": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp]),
     "specgpu_launch_count": (_i64, [_vp]),
+    "specgpu_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "specgpu_profile_count": (C.c_int, [_vp]),
+    "specgpu_profile_name": (C.c_char_p, [_vp, C.c_int]),
+    "specgpu_profile_ms": (C.c_double, [_vp, C.c_int]),
+    "specgpu_profile_calls": (_i64, [_vp, C.c_int]),
 }
 
 

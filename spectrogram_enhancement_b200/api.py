@@ -43,6 +43,11 @@ def _is_torch(x):
     return isinstance(x, torch.Tensor)
 
 
+def _ld(t):
+    """Leading dimension (elements between consecutive rows) of a row-major tensor view."""
+    return max(int(t.stride(-2)), int(t.shape[-1]), 1) if t.shape[-2] > 1 else max(int(t.shape[-1]), 1)
+
+
 class Runtime:
     """One libspecgpu context on one device, with a plan cache.
 
@@ -94,6 +99,17 @@ class Runtime:
 
     def launch_count(self) -> int:
         return int(self.lib.launch_count(self._ctx))
+
+    def profile(self, enable: bool):
+        """Bracket every kernel launch group with CUDA events (bench.py's roofline leg)."""
+        self.check(self.lib.profile_enable(self._ctx, 1 if enable else 0))
+
+    def profile_read(self):
+        """{kernel name: (total ms, timed launches)} since profile(True); synchronises."""
+        n = self.lib.profile_count(self._ctx)
+        return {self.lib.profile_name(self._ctx, i).decode(): (float(self.lib.profile_ms(self._ctx, i)),
+                                                               int(self.lib.profile_calls(self._ctx, i)))
+                for i in range(n)}
 
     def reserve(self, nbytes: int):
         self.check(self.lib.workspace_reserve(self._ctx, int(nbytes)))
@@ -172,7 +188,7 @@ class Runtime:
         if S is None:
             S = self.empty((B, F - 1, T))
         mmp = minmax.data_ptr() if minmax is not None else None
-        self.check(self.lib.specgr(self._ctx, plan, x2d.data_ptr(), B, n, x2d.stride(0), S.data_ptr(), S.stride(1), mmp,
+        self.check(self.lib.specgr(self._ctx, plan, x2d.data_ptr(), B, n, _ld(x2d), S.data_ptr(), _ld(S), mmp,
                                    self.stream()))
         return S
 
@@ -182,8 +198,8 @@ class Runtime:
         F = self.lib.plan_num_freqs(plan)
         if Sxx is None:
             Sxx = self.empty((B, F, T))
-        self.check(self.lib.spectrogram(self._ctx, plan, x2d.data_ptr(), B, n, x2d.stride(0), Sxx.data_ptr(),
-                                        Sxx.stride(1) if T else 1, self.stream()))
+        self.check(self.lib.spectrogram(self._ctx, plan, x2d.data_ptr(), B, n, _ld(x2d), Sxx.data_ptr(),
+                                        _ld(Sxx), self.stream()))
         return Sxx
 
     def pipeline_dev(self, plan, x2d, S=None, D=None, clip=True, tiles=None, tile_w=128, ntiles=0, info=None):
@@ -194,8 +210,8 @@ class Runtime:
             S = self.empty((B, F - 1, T))
         if D is None:
             D = self.empty((B, F - 1, T))
-        self.check(self.lib.pipeline(self._ctx, plan, x2d.data_ptr(), B, n, x2d.stride(0), S.data_ptr(), D.data_ptr(),
-                                     S.stride(1), 1 if clip else 0, tiles.data_ptr() if tiles is not None else None,
+        self.check(self.lib.pipeline(self._ctx, plan, x2d.data_ptr(), B, n, _ld(x2d), S.data_ptr(), D.data_ptr(),
+                                     _ld(S), 1 if clip else 0, tiles.data_ptr() if tiles is not None else None,
                                      tile_w, ntiles, info.data_ptr() if info is not None else None, self.stream()))
         return S, D
 
@@ -260,7 +276,7 @@ def stft(x, fs=1.0, window="hann", nperseg=256, noverlap=None, detrend=False, bo
     T = rt.lib.stft_num_segments(plan, n, bz, pd)
     F = rt.lib.plan_num_freqs(plan)
     Z = rt.empty((B, F, T, 2))
-    rt.check(rt.lib.stft(rt._ctx, plan, x2.data_ptr(), B, n, x2.stride(0), bz, pd, Z.data_ptr(), T if T else 1, rt.stream()))
+    rt.check(rt.lib.stft(rt._ctx, plan, x2.data_ptr(), B, n, _ld(x2), bz, pd, Z.data_ptr(), T if T else 1, rt.stream()))
     Zc = torch.view_as_complex(Z).reshape(lead + (F, T))
     hop = int(nperseg) - int(noverlap)
     f = np.fft.rfftfreq(int(nperseg), 1.0 / fs)
@@ -286,7 +302,7 @@ def csd_allpairs(x, fs=1.0, window="hann", nperseg=256, noverlap=None, detrend="
     Cn, n = xd.shape
     F = rt.lib.plan_num_freqs(plan)
     P = rt.empty((Cn, Cn, F, 2))
-    rt.check(rt.lib.csd_allpairs(rt._ctx, plan, xd.data_ptr(), Cn, n, xd.stride(0), P.data_ptr(), rt.stream()))
+    rt.check(rt.lib.csd_allpairs(rt._ctx, plan, xd.data_ptr(), Cn, n, _ld(xd), P.data_ptr(), rt.stream()))
     f = np.fft.rfftfreq(int(nperseg), 1.0 / fs)
     return f, rt.ret(torch.view_as_complex(P), as_torch)
 
@@ -509,7 +525,7 @@ def patch(arr, tile=128, ntiles=30, dtype=np.float64, runtime=None):
         raise ValueError(f"could not broadcast input array: need at least {tile * ntiles} columns, got {ld}")
     f64 = np.dtype(dtype) == np.float64
     out = torch.empty((n * ntiles, rows, tile), dtype=torch.float64 if f64 else torch.float32, device=rt.device)
-    rt.check(rt.lib.patch(rt._ctx, d.data_ptr(), n, rows, d.stride(1), tile, ntiles, out.data_ptr(), 1 if f64 else 0,
+    rt.check(rt.lib.patch(rt._ctx, d.data_ptr(), n, rows, _ld(d), tile, ntiles, out.data_ptr(), 1 if f64 else 0,
                           rt.stream()))
     return rt.ret(out, as_torch)
 
@@ -593,7 +609,7 @@ def ae_co2(signal1, signal2, t, nperseg=1024, noverlap=None, navg=8, window="han
     P = rt.empty((2, 2, F, 2))
     for k in range(nframes):            # frames are independent all-pairs problems of C = 2
         xk = torch.stack([s1[k * frame:(k + 1) * frame], s2[k * frame:(k + 1) * frame]])
-        rt.check(rt.lib.csd_allpairs(rt._ctx, plan, xk.data_ptr(), 2, frame, xk.stride(0), P.data_ptr(), rt.stream()))
+        rt.check(rt.lib.csd_allpairs(rt._ctx, plan, xk.data_ptr(), 2, frame, _ld(xk), P.data_ptr(), rt.stream()))
         amps[k] = torch.view_as_complex(P)[0, 1].abs()
     freq = np.fft.rfftfreq(nperseg, 1.0 / fs) / 1e3
     time = tt[0] + (np.arange(nframes) * frame + frame / 2.0) / fs * 1e3

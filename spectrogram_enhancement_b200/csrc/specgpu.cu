@@ -17,6 +17,16 @@ struct specgpu_ctx {
   int64_t launches = 0;
   int num_sms = 148;
   size_t ws_csd_off = 0;   // offset of the pair partials inside ws (set by specgpu_csd_allpairs)
+  // optional per-kernel timing (specgpu_profile_*): CUDA events recorded around every launch group
+  bool prof_on = false;
+  std::vector<std::string> prof_names;
+  std::vector<double> prof_ms;
+  std::vector<int64_t> prof_calls;
+#ifndef SPECGPU_EMULATE
+  struct ProfRec { int name; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_open;
+  std::vector<cudaEvent_t> prof_pool;
+#endif
 };
 
 struct specgpu_plan {
@@ -48,11 +58,71 @@ int cuda_fail(specgpu_ctx* ctx, int e, const char* what) {
   return fail(ctx, SPECGPU_ERR_CUDA, "%s: CUDA error %d (%s)", what, e, cudaGetErrorString((cudaError_t)e));
 }
 
-#define CHECK_LAUNCH(ctx, expr, what, nlaunch)         \
-  do {                                                 \
-    int e__ = (expr);                                  \
-    if (e__ != 0) return cuda_fail(ctx, e__, what);    \
-    (ctx)->launches += (nlaunch);                      \
+#ifndef SPECGPU_EMULATE
+int prof_name_id(specgpu_ctx* ctx, const char* what) {
+  for (size_t i = 0; i < ctx->prof_names.size(); ++i)
+    if (ctx->prof_names[i] == what) return (int)i;
+  ctx->prof_names.push_back(what);
+  ctx->prof_ms.push_back(0.0);
+  ctx->prof_calls.push_back(0);
+  return (int)ctx->prof_names.size() - 1;
+}
+cudaEvent_t prof_event(specgpu_ctx* ctx) {
+  if (!ctx->prof_pool.empty()) {
+    cudaEvent_t e = ctx->prof_pool.back();
+    ctx->prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+// Fold finished event pairs into the per-name totals (synchronises on the last recorded event).
+void prof_collect(specgpu_ctx* ctx) {
+  for (auto& r : ctx->prof_open) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      ctx->prof_ms[r.name] += ms;
+      ctx->prof_calls[r.name] += 1;
+    }
+    ctx->prof_pool.push_back(r.e0);
+    ctx->prof_pool.push_back(r.e1);
+  }
+  ctx->prof_open.clear();
+}
+struct ProfScope {
+  specgpu_ctx* ctx;
+  cudaStream_t st;
+  cudaEvent_t e1 = nullptr;
+  ProfScope(specgpu_ctx* c, cudaStream_t s, const char* what) : ctx(c), st(s) {
+    if (!ctx->prof_on) return;
+    if (ctx->prof_open.size() >= 8192) prof_collect(ctx);
+    cudaEvent_t e0 = prof_event(ctx);
+    e1 = prof_event(ctx);
+    cudaEventRecord(e0, st);
+    ctx->prof_open.push_back({prof_name_id(ctx, what), e0, e1});
+  }
+  ~ProfScope() {
+    if (e1) cudaEventRecord(e1, st);
+  }
+};
+#else
+struct ProfScope {
+  ProfScope(specgpu_ctx*, cudaStream_t, const char*) {}
+};
+#endif
+
+// `stream` (void*) must be in scope at every use.
+#define CHECK_LAUNCH(ctx, expr, what, nlaunch)                       \
+  do {                                                               \
+    int e__;                                                         \
+    {                                                                \
+      ProfScope prof__((ctx), (cudaStream_t)stream, what);           \
+      e__ = (expr);                                                  \
+    }                                                                \
+    if (e__ != 0) return cuda_fail(ctx, e__, what);                  \
+    (ctx)->launches += (nlaunch);                                    \
   } while (0)
 
 // Grow-on-demand device workspace.  Growing synchronises the device (cudaFree), so production callers
@@ -160,6 +230,10 @@ int specgpu_destroy(specgpu_ctx* ctx) {
   if (!ctx) return SPECGPU_OK;
   cudaSetDevice(ctx->device);
   if (ctx->ws) cudaFree(ctx->ws);
+#ifndef SPECGPU_EMULATE
+  prof_collect(ctx);
+  for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
+#endif
   delete ctx;
   return SPECGPU_OK;
 }
@@ -173,6 +247,40 @@ int specgpu_workspace_reserve(specgpu_ctx* ctx, int64_t bytes) {
 }
 
 int64_t specgpu_launch_count(const specgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int specgpu_profile_enable(specgpu_ctx* ctx, int enable) {
+  if (!ctx) return SPECGPU_ERR_INVALID_ARG;
+#ifndef SPECGPU_EMULATE
+  cudaSetDevice(ctx->device);
+  prof_collect(ctx);
+#endif
+  ctx->prof_on = enable != 0;
+  if (enable) {
+    ctx->prof_names.clear();
+    ctx->prof_ms.clear();
+    ctx->prof_calls.clear();
+  }
+  return SPECGPU_OK;
+}
+
+int specgpu_profile_count(specgpu_ctx* ctx) {
+  if (!ctx) return 0;
+#ifndef SPECGPU_EMULATE
+  cudaSetDevice(ctx->device);
+  prof_collect(ctx);
+#endif
+  return (int)ctx->prof_names.size();
+}
+
+const char* specgpu_profile_name(const specgpu_ctx* ctx, int i) {
+  return (ctx && i >= 0 && i < (int)ctx->prof_names.size()) ? ctx->prof_names[i].c_str() : "";
+}
+double specgpu_profile_ms(const specgpu_ctx* ctx, int i) {
+  return (ctx && i >= 0 && i < (int)ctx->prof_ms.size()) ? ctx->prof_ms[i] : 0.0;
+}
+int64_t specgpu_profile_calls(const specgpu_ctx* ctx, int i) {
+  return (ctx && i >= 0 && i < (int)ctx->prof_calls.size()) ? ctx->prof_calls[i] : 0;
+}
 
 int specgpu_plan_create(specgpu_ctx* ctx, const specgpu_stft_params* p, const double* window_host, specgpu_plan** out) {
   if (!ctx || !p || !out) return SPECGPU_ERR_INVALID_ARG;
@@ -430,6 +538,7 @@ SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
 int svd_run(specgpu_ctx* ctx, void* ws_base, const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, int kind,
             int start, int stop, int clip, bool power_ok, void* out, int out_f64, int64_t ldo, float* s_out,
             int32_t* info, cudaStream_t st) {
+  void* stream = (void*)st;
   const bool tc = power_ok && gram_tc_supported(rows);   // TF32 Gram only feeds the leading-pair route
   const bool full = true;                                // Jacobi scratch is always carved (fallback for power)
   SvdWs w = svd_carve(ws_base, B, rows, tc, full);

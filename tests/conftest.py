@@ -5,8 +5,9 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -35,3 +36,18 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
     return load
+
+
+@pytest.fixture(scope="session")
+def emu_rt():
+    """Runtime over the CPU-emulation build of the kernel sources (test infrastructure only)."""
+    from spectrogram_enhancement_b200 import _ffi, api, build
+    path = build.build_emu()
+    return api.Runtime(_ffi.Library(path), "cpu")
+
+
+@pytest.fixture(scope="session")
+def cuda_rt():
+    """The product runtime: libspecgpu.so on cuda:0.  Fails (does not skip) if the library is missing."""
+    from spectrogram_enhancement_b200 import api
+    return api.Runtime()

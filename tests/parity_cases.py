@@ -1,0 +1,192 @@
+"""Parity cases shared by the CPU-emulation suite (tests/test_emulated.py, tiny sizes) and the GPU
+suite (tests/test_gpu_parity.py, -m gpu, through the real libspecgpu.so).  Each case drives the
+product host API (spectrogram_enhancement_b200.api) on a Runtime and checks it against the CPU
+oracle (oracle/spec_oracle.py) run in float64 on the same float32 input.
+
+Tolerances (BASELINE.json north_star; SURVEY.md section 7.2 "precision contract"):
+  * linear spectra (PSD, STFT, CSD):    rtol 1e-4, atol 1e-6 * max|oracle|
+  * log/min-max normalised image:       atol 1e-4 on the [0, 1] image
+  * denoised reconstruction:            rtol 1e-3, atol 1e-3 * max|oracle|
+  * integer outputs (segment counts, axes, masks, start/stop/num_sing, tile copies): bit-exact
+"""
+import numpy as np
+
+from oracle import spec_oracle as oc
+from spectrogram_enhancement_b200 import api
+
+RTOL_SPEC = 1e-4
+ATOL_SPEC_REL = 1e-6
+ATOL_IMAGE = 1e-4
+RTOL_DENOISE = 1e-3
+ATOL_DENOISE_REL = 1e-3
+
+
+def assert_spec_close(got, ref):
+    ref = np.asarray(ref)
+    np.testing.assert_allclose(got, ref, rtol=RTOL_SPEC, atol=ATOL_SPEC_REL * float(np.abs(ref).max()))
+
+
+def assert_denoise_close(got, ref):
+    ref = np.asarray(ref)
+    np.testing.assert_allclose(got, ref, rtol=RTOL_DENOISE, atol=ATOL_DENOISE_REL * float(np.abs(ref).max()))
+
+
+def signals(B, n, shot=1, fs=500000.0, offset=0.0):
+    return np.stack([oc.synth_ece(shot, c, n=n, fs=fs) for c in range(B)]) + np.float32(offset)
+
+
+# ---- spectrogram front-end ---------------------------------------------------------------------
+def case_spectrogram(rt, nperseg, noverlap, n, detrend, window, scaling, B=2):
+    x = signals(B, n, offset=0.7)
+    f, t, P = api.spectrogram(x, fs=500000, window=window, nperseg=nperseg, noverlap=noverlap, detrend=detrend,
+                              scaling=scaling, runtime=rt)
+    fr, tr, Pr = oc.spectrogram(x.astype(np.float64), fs=500000, window=window, nperseg=nperseg, noverlap=noverlap,
+                                detrend=detrend, scaling=scaling)
+    assert P.shape == Pr.shape and P.dtype == np.float32
+    assert np.array_equal(f, fr) and np.array_equal(t, tr)          # index-derived: exact
+    assert_spec_close(P, Pr)
+
+
+def case_specgr(rt, sp, n, B=2):
+    x = signals(B, n)
+    S, f, t = api.spectrogram_batch(x, sp, runtime=rt)
+    Sr, fr, tr = oc.specgr_array(x.astype(np.float64), sp)
+    assert S.shape == Sr.shape
+    assert np.array_equal(f, fr) and np.array_equal(t, tr)
+    np.testing.assert_allclose(S, Sr, rtol=0, atol=ATOL_IMAGE)
+    assert S.min() >= 0.0 and S.max() <= 1.0
+    return S, Sr
+
+
+def case_stft(rt, nperseg, noverlap, n, boundary, padded, window="hann", B=1):
+    x = signals(B, n)
+    f, t, Z = api.stft(x, fs=500000, window=window, nperseg=nperseg, noverlap=noverlap, boundary=boundary, padded=padded,
+                       runtime=rt)
+    fr, tr, Zr = oc.stft(x.astype(np.float64), fs=500000, window=window, nperseg=nperseg, noverlap=noverlap,
+                         boundary=boundary, padded=padded)
+    assert Z.shape == Zr.shape and Z.dtype == np.complex64
+    assert np.array_equal(f, fr)
+    np.testing.assert_allclose(t, tr, rtol=0, atol=1e-12)
+    assert_spec_close(Z, Zr)
+
+
+# ---- helpers -------------------------------------------------------------------------------------
+def case_rescale_norm(rt, shape, seed=0):
+    a = (np.random.default_rng(seed).standard_normal(shape) * 3 + 1).astype(np.float32)
+    np.testing.assert_allclose(api.rescale(a, runtime=rt), oc.rescale(a.astype(np.float64)), rtol=0, atol=2e-7)
+    np.testing.assert_allclose(api.norm(a, runtime=rt), oc.norm(a.astype(np.float64)), rtol=1e-5, atol=1e-5)
+
+
+def case_quantfilt(rt, rows, cols, thr, seed=0, ties=False):
+    a = np.random.default_rng(seed).random((rows, cols)).astype(np.float32)
+    if ties:
+        a = np.round(a * 8).astype(np.float32) / 8      # heavy ties: many equal order statistics
+    out, q, mask = api.quantfilt_mask(a, thr, runtime=rt)
+    qr = np.quantile(a, thr, axis=0)
+    assert q.dtype == np.float32 and np.array_equal(q, qr)                    # bit-exact threshold
+    assert np.array_equal(out, oc.quantfilt(a, thr))                          # bit-exact image
+    assert np.array_equal(mask.astype(bool), ~(a < qr))                       # bit-exact mask
+    assert np.array_equal(api.quantfilt(a, thr, runtime=rt), out)
+
+
+def case_quantfilt_3d(rt, rows, cols, chans, seed=0):
+    a = np.random.default_rng(seed).random((rows, cols, chans)).astype(np.float32)
+    assert np.array_equal(api.quantfilt(a, 0.9, runtime=rt), oc.quantfilt(a, 0.9))
+
+
+def case_patch(rt, n, rows, cols, tile, ntiles, seed=0):
+    arr = [np.random.default_rng(seed + i).random((rows, cols)).astype(np.float32) for i in range(n)]
+    p = api.patch(arr, tile=tile, ntiles=ntiles, runtime=rt)
+    pr = oc.patch(arr, tile=tile, ntiles=ntiles)
+    assert p.dtype == np.float64 and np.array_equal(p, pr)
+    p32 = api.patch(np.stack(arr), tile=tile, ntiles=ntiles, dtype=np.float32, runtime=rt)
+    assert p32.dtype == np.float32 and np.array_equal(p32, pr.astype(np.float32))
+    u = api.unpatch(p, ntiles=ntiles, runtime=rt)
+    assert np.array_equal(u, oc.unpatch(pr, ntiles=ntiles))
+    assert np.array_equal(u, np.stack(arr)[:, :, :tile * ntiles])             # round trip
+
+
+# ---- SVD denoise -----------------------------------------------------------------------------------
+def case_svd_default(rt, rows, cols, sv, noise=0.05, seed=3, method="auto", clip=False):
+    m = oc.synth_lowrank(rows, cols, sv, noise, seed)
+    d = api.denoiseSignal(m, clip=clip, method=method, runtime=rt)
+    dr = oc.denoiseSignal(m.astype(np.float64))
+    if clip:
+        dr = oc.clip(dr)
+    assert d.shape == dr.shape and d.dtype == np.float32
+    assert_denoise_close(d, dr)
+
+
+def case_svd_range(rt, rows, cols, sv, start, stop, noise=0.05, seed=4):
+    m = oc.synth_lowrank(rows, cols, sv, noise, seed)
+    d, s, info = api.denoiseSignal(m, start=start, stop=stop, return_info=True, runtime=rt)
+    m64 = m.astype(np.float64)
+    dr = oc.denoiseSignal(m64, start=start, stop=stop)
+    sr = np.linalg.svd(m64, compute_uv=False)
+    a, b, _ = oc.svd_plan(m.shape, sr, start, stop)
+    ea, eb, _ = slice(a, b).indices(len(sr))            # what the python slice u[:, a:b] resolves to
+    assert (int(info[0]), int(info[1])) == (ea, eb) and int(info[2]) == -1
+    np.testing.assert_allclose(s, sr, rtol=1e-4, atol=1e-5 * sr[0])
+    assert_denoise_close(d, dr)
+
+
+def case_svd_optimal(rt, rows, cols, sv, noise=0.05, seed=5):
+    m = oc.synth_lowrank(rows, cols, sv, noise, seed)
+    d, s, info = api.denoiseSignal(m, use_optimal=True, return_info=True, runtime=rt)
+    m64 = m.astype(np.float64)
+    dr = oc.denoiseSignal(m64, use_optimal=True)
+    sr = np.linalg.svd(m64, compute_uv=False)
+    a, b, num_sing = oc.svd_plan(m.shape, sr, use_optimal=True)
+    assert int(info[2]) == num_sing                                           # integer: exact
+    ea, eb, _ = slice(a, b).indices(len(sr))
+    assert (int(info[0]), int(info[1])) == (ea, eb)
+    np.testing.assert_allclose(s, sr, rtol=1e-4, atol=1e-5 * sr[0])
+    assert_denoise_close(d, dr)
+
+
+def case_compute_signal(rt, rows, cols, sv, noise=0.05, seed=6):
+    m = oc.synth_lowrank(rows, cols, sv, noise, seed)
+    out, s, info = api.computeSignal(m, return_info=True, runtime=rt)
+    ref = oc.computeSignal(m.astype(np.float64))
+    assert out.dtype == np.float64
+    assert_denoise_close(out, ref)
+
+
+# ---- cross-power spectrum ----------------------------------------------------------------------------
+def case_csd(rt, C, n, nperseg, fs=1.6e6, detrend="constant", window="hann", scaling="density"):
+    x = signals(C, n, shot=2, fs=fs, offset=0.3)
+    f, P = api.csd_allpairs(x, fs=fs, window=window, nperseg=nperseg, noverlap=nperseg // 2, detrend=detrend,
+                            scaling=scaling, runtime=rt)
+    fr, Pr = oc.csd_allpairs(x.astype(np.float64), fs=fs, window=window, nperseg=nperseg, noverlap=nperseg // 2,
+                             detrend=detrend, scaling=scaling)
+    assert np.array_equal(f, fr) and P.shape == Pr.shape
+    assert_spec_close(P, Pr)
+    # Hermitian in the pair index, real diagonal
+    np.testing.assert_allclose(P, np.conj(np.swapaxes(P, 0, 1)), rtol=1e-5, atol=1e-7 * np.abs(Pr).max())
+    f2, P01 = api.csd(x[0], x[1], fs=fs, window=window, nperseg=nperseg, noverlap=nperseg // 2, detrend=detrend,
+                      scaling=scaling, runtime=rt)
+    assert_spec_close(P01, Pr[0, 1])
+
+
+# ---- whole path ------------------------------------------------------------------------------------
+def case_pipeline(rt, sp, n, B=2, tile=None):
+    x = signals(B, n)
+    T = oc.segment_count(n, sp["nperseg"], sp["noverlap"])
+    if tile:
+        S, D, tiles, info = api.pipeline(x, sp, clip=True, tiles=True, tile=tile, return_info=True, runtime=rt)
+    else:
+        S, D, info = api.pipeline(x, sp, clip=True, return_info=True, runtime=rt)
+    Sr, _, _ = oc.specgr_array(x.astype(np.float64), sp)
+    np.testing.assert_allclose(S, Sr, rtol=0, atol=ATOL_IMAGE)
+    # stage-isolated: denoise OUR S with the oracle, so the SVD stage is judged on identical input
+    Dr = np.stack([oc.clip(oc.denoiseSignal(s.astype(np.float64))) for s in S])
+    assert_denoise_close(D, Dr)
+    assert (D >= 0).all()
+    rows = sp["nperseg"] // 2
+    assert np.array_equal(info[:, :2], np.tile([1, rows], (B, 1)))
+    if tile:
+        nt = T // tile
+        assert np.array_equal(tiles, oc.patch(list(D), tile=tile, ntiles=nt).astype(np.float32))
+    # end to end against the pure oracle chain
+    De = np.stack([oc.clip(oc.denoiseSignal(s)) for s in Sr])
+    np.testing.assert_allclose(D, De, rtol=0, atol=5e-3 * np.abs(De).max())

@@ -1,0 +1,149 @@
+"""Host logic + kernel index arithmetic on the CPU: the product kernel sources compiled with
+-DSPECGPU_EMULATE (tests/emu/cuda_emu.h: CUDA threads -> OS threads) and driven through the same
+ctypes/C-ABI/host-API stack as on the GPU, at sizes the emulation finishes in seconds.  The parity
+tests proper are tests/test_gpu_parity.py (-m gpu); this suite exists so that indexing, tiling and
+host bookkeeping bugs are caught without a device.  tcgen05 PTX is not emulated (gram_tc.cu carries a
+numerically equivalent scalar stand-in under SPECGPU_EMULATE)."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from oracle import spec_oracle as oc
+from spectrogram_enhancement_b200 import api
+
+
+@pytest.mark.parametrize("nperseg", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_spectrogram_every_size(emu_rt, nperseg):
+    n = max(5 * nperseg, 3000) if nperseg < 4096 else 3 * nperseg
+    pc.case_spectrogram(emu_rt, nperseg, nperseg // 2, n, "linear", "hamm", "density")
+
+
+@pytest.mark.parametrize("nperseg,noverlap,n,detrend,window,scaling", [
+    (512, 256, 20000, "constant", "hann", "spectrum"),
+    (512, 63, 5001, False, "boxcar", "density"),
+    (64, 63, 700, "linear", "hann", "density"),
+    (256, 0, 2048, "constant", "hamming", "density"),
+])
+def test_spectrogram_variants(emu_rt, nperseg, noverlap, n, detrend, window, scaling):
+    pc.case_spectrogram(emu_rt, nperseg, noverlap, n, detrend, window, scaling)
+
+
+def test_spectrogram_custom_window(emu_rt):
+    w = np.hanning(130)[1:-1]
+    pc.case_spectrogram(emu_rt, 128, 64, 3000, "constant", w, "density")
+
+
+def test_specgr_reference_defaults(emu_rt):
+    pc.case_specgr(emu_rt, oc.DEFAULT_SPEC_PARAMS, 20000)
+
+
+def test_specgr_golden_small(emu_rt, golden):
+    g = golden("specgr_small.npz")
+    S, f, t = api.spectrogram_batch(g["x"], oc.DEFAULT_SPEC_PARAMS, runtime=emu_rt)
+    np.testing.assert_allclose(S, g["S_f64"], rtol=0, atol=pc.ATOL_IMAGE)
+    assert np.array_equal(f, g["f_f64"]) and np.array_equal(t, g["t_f64"])
+
+
+@pytest.mark.parametrize("boundary,padded", [("zeros", True), (None, True), (None, False), ("zeros", False)])
+def test_stft(emu_rt, boundary, padded):
+    pc.case_stft(emu_rt, 256, 128, 3001, boundary, padded)
+
+
+def test_rescale_norm(emu_rt):
+    pc.case_rescale_norm(emu_rt, (37, 101))
+
+
+@pytest.mark.parametrize("rows,thr", [(256, 0.9), (257, 0.9), (100, 0.5), (33, 0.123), (64, 0.0), (64, 1.0), (513, 0.99)])
+def test_quantfilt(emu_rt, rows, thr):
+    pc.case_quantfilt(emu_rt, rows, 45, thr)
+
+
+def test_quantfilt_ties_and_3d(emu_rt):
+    pc.case_quantfilt(emu_rt, 128, 40, 0.9, ties=True)
+    pc.case_quantfilt_3d(emu_rt, 64, 33, 3)
+
+
+def test_patch_roundtrip(emu_rt):
+    pc.case_patch(emu_rt, 3, 16, 70, 8, 8)
+    pc.case_patch(emu_rt, 1, 256, 130, 128, 1)
+
+
+def test_svd_default_power(emu_rt):
+    pc.case_svd_default(emu_rt, 64, 200, [50, 20, 10])
+    pc.case_svd_default(emu_rt, 48, 90, [30, 5], clip=True)
+
+
+def test_svd_default_tf32_gram(emu_rt):
+    # rows = 128 takes the tensor-core Gram route (TF32 operand rounding, emulated bit-for-bit)
+    pc.case_svd_default(emu_rt, 128, 300, [200, 20, 10])
+
+
+def test_svd_jacobi_range_optimal_compute(emu_rt):
+    pc.case_svd_range(emu_rt, 32, 80, [40, 20, 10, 5], 0, 3)
+    pc.case_svd_range(emu_rt, 32, 80, [40, 20, 10, 5], 1, -28)
+    pc.case_svd_optimal(emu_rt, 32, 90, [40, 20, 10])
+    pc.case_compute_signal(emu_rt, 32, 90, [40, 20])
+
+
+def test_svd_tall_matrix_is_transposed(emu_rt):
+    m = oc.synth_lowrank(90, 32, [40, 20, 10], 0.05, 9)
+    d = api.denoiseSignal(m, runtime=emu_rt)
+    pc.assert_denoise_close(d, oc.denoiseSignal(m.astype(np.float64)))
+
+
+def test_csd(emu_rt):
+    pc.case_csd(emu_rt, 4, 6000, 256)
+    pc.case_csd(emu_rt, 5, 3000, 64, detrend="linear", scaling="spectrum")
+
+
+def test_csd_scipy_kat(emu_rt):
+    # scipy/signal/tests/test_spectral.py TestCSD.test_real_onesided_even
+    x = np.zeros(16, np.float32)
+    x[0] = 1
+    x[8] = 1
+    f, p = api.csd(x, x, nperseg=8, runtime=emu_rt)
+    np.testing.assert_allclose(f, np.linspace(0, 0.5, 5))
+    np.testing.assert_allclose(p.real, [0.08333333, 0.15277778, 0.22222222, 0.22222222, 0.11111111], rtol=1e-5)
+    np.testing.assert_allclose(p.imag, 0, atol=1e-7)
+
+
+def test_pipeline_small(emu_rt):
+    sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=32, noverlap=16)
+    pc.case_pipeline(emu_rt, sp, 9000, B=2, tile=64)
+
+
+# ---- host logic / error behaviour ---------------------------------------------------------------
+def test_errors_mirror_scipy(emu_rt):
+    x = np.zeros(100, np.float32)
+    with pytest.raises(ValueError, match="noverlap must be less than nperseg"):
+        api.spectrogram(x, nperseg=8, noverlap=8, runtime=emu_rt)
+    with pytest.raises(ValueError, match="Unknown scaling"):
+        api.spectrogram(x, nperseg=8, noverlap=4, scaling="foo", runtime=emu_rt)
+    with pytest.raises(ValueError, match="power of two"):
+        api.spectrogram(x, nperseg=100, noverlap=4, runtime=emu_rt)
+    with pytest.raises(ValueError, match="Quantiles must be in the range"):
+        api.quantfilt(np.zeros((4, 4), np.float32), 1.5, runtime=emu_rt)
+    with pytest.raises(ValueError):
+        api.stft(x, nperseg=8, boundary="even", runtime=emu_rt)
+
+
+def test_empty_and_short_inputs(emu_rt):
+    f, t, P = api.spectrogram(np.zeros((2, 100), np.float32), nperseg=256, noverlap=128, runtime=emu_rt)
+    assert P.shape == (2, 129, 0) and t.shape == (0,)
+    f, t, P = api.spectrogram(np.zeros((0, 1000), np.float32), nperseg=256, noverlap=128, runtime=emu_rt)
+    assert P.shape == (0, 129, 6)
+    out = api.patch([], runtime=emu_rt)
+    assert out.shape[0] == 0
+
+
+def test_torch_in_torch_out(emu_rt):
+    import torch
+    x = torch.from_numpy(pc.signals(1, 3000))
+    f, t, P = api.spectrogram(x, fs=500000, nperseg=256, noverlap=128, runtime=emu_rt)
+    assert isinstance(P, torch.Tensor) and P.shape == (1, 129, 22)
+
+
+def test_launch_counter(emu_rt):
+    before = emu_rt.launch_count()
+    api.spectrogram(np.zeros(1000, np.float32), nperseg=64, noverlap=32, runtime=emu_rt)
+    assert emu_rt.launch_count() == before + 1

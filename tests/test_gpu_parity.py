@@ -1,0 +1,224 @@
+"""Parity tests proper: libspecgpu.so (CUDA, sm_100a) through the C ABI / host API on cuda:0 versus the
+CPU oracle on the same seeded inputs, the committed golden vectors produced by the reference's own
+functions, and size-independent properties at BASELINE.json's full sizes.  Run with `-m gpu`."""
+import zlib
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from oracle import spec_oracle as oc
+from spectrogram_enhancement_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+SP = oc.DEFAULT_SPEC_PARAMS
+
+
+# ---- K1/K2a: spectrogram front-end -----------------------------------------------------------------
+@pytest.mark.parametrize("nperseg", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_spectrogram_every_size(cuda_rt, nperseg):
+    pc.case_spectrogram(cuda_rt, nperseg, nperseg // 2, max(40 * nperseg, 50_000), "linear", "hamm", "density", B=3)
+
+
+@pytest.mark.parametrize("nperseg,noverlap,n,detrend,window,scaling", [
+    (512, 256, 100_000, "constant", "hann", "spectrum"),
+    (512, 63, 50_001, False, "boxcar", "density"),
+    (64, 63, 7_000, "linear", "hann", "density"),
+    (256, 0, 20_480, "constant", "hamming", "density"),
+    (1024, 1000, 30_001, "linear", "hann", "density"),
+])
+def test_spectrogram_variants(cuda_rt, nperseg, noverlap, n, detrend, window, scaling):
+    pc.case_spectrogram(cuda_rt, nperseg, noverlap, n, detrend, window, scaling)
+
+
+def test_spectrogram_custom_window(cuda_rt):
+    pc.case_spectrogram(cuda_rt, 128, 64, 30_000, "constant", np.hanning(130)[1:-1], "density")
+
+
+def test_specgr_golden_small(cuda_rt, golden):
+    """specgr() of the reference itself (pipeline_data.py:28-36) on 20 000 samples."""
+    g = golden("specgr_small.npz")
+    S, f, t = api.spectrogram_batch(g["x"], SP, runtime=cuda_rt)
+    np.testing.assert_allclose(S, g["S_f64"], rtol=0, atol=pc.ATOL_IMAGE)
+    np.testing.assert_allclose(S, g["S_f32"], rtol=0, atol=pc.ATOL_IMAGE)
+    assert np.array_equal(f, g["f_f64"]) and np.array_equal(t, g["t_f64"])
+    # quantfilt of the reference on its own float32 spectrogram: integer mask bit-exact
+    out, thr, mask = api.quantfilt_mask(g["S_f32"], 0.9, runtime=cuda_rt)
+    assert np.array_equal(thr, g["quant_thr_f32"]) and np.array_equal(out, g["quant_f32"])
+    np.testing.assert_allclose(api.norm(g["S_f32"], runtime=cuda_rt), g["norm_f32"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(api.rescale(g["S_f32"] * 3 - 1, runtime=cuda_rt), g["rescale_f32"], rtol=0, atol=1e-6)
+
+
+def test_specgr_golden_full_channel(cuda_rt, golden):
+    """Config 1/2 size: the reference's specgr on the full 1 000 000-sample synthetic channel (shot 0, ch 0)."""
+    g = golden("specgr_full_cols.npz")
+    x = oc.synth_ece(0, 0)
+    assert np.uint32(zlib.crc32(x.tobytes())) == g["x_crc"]
+    S, f, t = api.spectrogram_batch(x, SP, runtime=cuda_rt)
+    assert S.shape == tuple(g["shape"]) == (256, 3905)
+    assert np.array_equal(f, g["f"]) and np.array_equal(t, g["t"])
+    np.testing.assert_allclose(S[:, g["cols"]], g["S_f64"], rtol=0, atol=pc.ATOL_IMAGE)
+    np.testing.assert_allclose(S.astype(np.float64).sum(axis=1), g["rowsum_f64"], rtol=1e-5)
+
+
+def test_config1_stft_and_spectrogram(cuda_rt):
+    """BASELINE config 1: single channel, 1M samples @500 kHz, nperseg=1024 hann 50% overlap."""
+    x = oc.synth_ece(1, 0)
+    f, t, Z = api.stft(x, fs=500000, window="hann", nperseg=1024, noverlap=512, runtime=cuda_rt)
+    fr, tr, Zr = oc.stft(x.astype(np.float64), fs=500000, window="hann", nperseg=1024, noverlap=512)
+    assert Z.shape == (513, 1955) and np.array_equal(f, fr)
+    np.testing.assert_allclose(t, tr, rtol=0, atol=1e-12)
+    pc.assert_spec_close(Z, Zr)
+    f, t, P = api.spectrogram(x, fs=500000, window="hann", nperseg=1024, noverlap=512, runtime=cuda_rt)
+    _, _, Pr = oc.spectrogram(x.astype(np.float64), fs=500000, window="hann", nperseg=1024, noverlap=512)
+    assert P.shape == (513, 1952)
+    pc.assert_spec_close(P, Pr)
+
+
+def test_config1_rank_k_denoise_512_rows(cuda_rt):
+    """Config 1's SVD leg: rank-k truncation of a 512-row image with a planted gap (cluster-of-8 Jacobi)."""
+    pc.case_svd_range(cuda_rt, 512, 1952, [900.0, 300.0, 120.0], 0, 3, noise=0.05, seed=11)
+
+
+@pytest.mark.parametrize("boundary,padded", [("zeros", True), (None, True), (None, False), ("zeros", False)])
+def test_stft_boundaries(cuda_rt, boundary, padded):
+    pc.case_stft(cuda_rt, 256, 128, 30_001, boundary, padded, B=2)
+
+
+def test_spectrogram_linearity_and_welch_identity(cuda_rt):
+    """Size-independent properties at full size: PSD(2x) = 4 PSD(x); mean over segments == csd diagonal."""
+    x = pc.signals(2, 1_000_000)
+    f, t, P1 = api.spectrogram(x, fs=500000, window="hann", nperseg=512, noverlap=256, detrend="constant", runtime=cuda_rt)
+    _, _, P2 = api.spectrogram(2 * x, fs=500000, window="hann", nperseg=512, noverlap=256, detrend="constant", runtime=cuda_rt)
+    np.testing.assert_allclose(P2, 4 * P1, rtol=2e-6, atol=1e-12)
+    _, C = api.csd_allpairs(x, fs=500000, window="hann", nperseg=512, noverlap=256, runtime=cuda_rt)
+    np.testing.assert_allclose(np.stack([C[0, 0].real, C[1, 1].real]), P1.astype(np.float64).mean(axis=-1), rtol=2e-5)
+
+
+# ---- helpers, K4 ------------------------------------------------------------------------------------
+def test_rescale_norm(cuda_rt):
+    pc.case_rescale_norm(cuda_rt, (256, 3905))
+    pc.case_rescale_norm(cuda_rt, (7,))
+
+
+@pytest.mark.parametrize("rows,cols,thr", [(256, 3905, 0.9), (257, 1000, 0.9), (100, 333, 0.5), (33, 65, 0.123),
+                                           (64, 64, 0.0), (64, 64, 1.0), (513, 700, 0.99), (1024, 129, 0.75)])
+def test_quantfilt(cuda_rt, rows, cols, thr):
+    pc.case_quantfilt(cuda_rt, rows, cols, thr)
+
+
+def test_quantfilt_ties_and_3d(cuda_rt):
+    pc.case_quantfilt(cuda_rt, 256, 500, 0.9, ties=True)
+    pc.case_quantfilt_3d(cuda_rt, 256, 3905, 8)          # denoising_spectrogram.ipynb:115 layout [F, T, C]
+
+
+def test_patch_roundtrip(cuda_rt):
+    pc.case_patch(cuda_rt, 4, 256, 3905, 128, 30)        # the reference's hard-wired 30 x (256, 128)
+    pc.case_patch(cuda_rt, 3, 16, 70, 8, 8)
+
+
+# ---- K3: SVD denoise --------------------------------------------------------------------------------
+def test_svd_golden(cuda_rt, golden):
+    """denoiseSignal / computeSignal / omega of the reference notebook on a planted-gap matrix."""
+    g = golden("svd_small.npz")
+    M = g["M"]
+    np.testing.assert_allclose([api.omega(b) for b in g["omega_beta"]], g["omega"], rtol=1e-15)
+    pc.assert_denoise_close(api.denoiseSignal(M, runtime=cuda_rt), g["M64_default"])
+    pc.assert_denoise_close(api.denoiseSignal(M, method="jacobi", runtime=cuda_rt), g["M64_default"])
+    d, s, info = api.denoiseSignal(M, use_optimal=True, return_info=True, runtime=cuda_rt)
+    pc.assert_denoise_close(d, g["M64_optimal"])
+    np.testing.assert_allclose(s, g["M64_s"], rtol=1e-4, atol=1e-5 * g["M64_s"][0])
+    pc.assert_denoise_close(api.denoiseSignal(M, 0, 4, runtime=cuda_rt), g["M64_0_4"])
+    pc.assert_denoise_close(api.denoiseSignal(M, 2, 9, runtime=cuda_rt), g["M64_2_9"])
+    pc.assert_denoise_close(api.denoiseSignal(M, -3, 1000, runtime=cuda_rt), g["M64_m3_1000"])
+    pc.assert_denoise_close(api.computeSignal(M, runtime=cuda_rt), g["M64_compute"])
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 200), (128, 1000), (256, 3905), (200, 777)])
+def test_svd_default(cuda_rt, rows, cols):
+    pc.case_svd_default(cuda_rt, rows, cols, [50.0 * rows ** 0.5, 20.0, 10.0])
+    pc.case_svd_default(cuda_rt, rows, cols, [50.0 * rows ** 0.5, 20.0, 10.0], clip=True)
+
+
+def test_svd_tensor_core_gram_matches_simt(cuda_rt):
+    """The tcgen05 TF32 Gram route (method='auto', rows 256) and the fp32 SIMT + Jacobi route agree."""
+    m = oc.synth_lowrank(256, 3905, [700.0, 9.0, 8.0], 0.1, 21) + np.float32(0.4)
+    a = api.denoiseSignal(m, runtime=cuda_rt)
+    b = api.denoiseSignal(m, method="jacobi", runtime=cuda_rt)
+    ref = oc.denoiseSignal(m.astype(np.float64))
+    pc.assert_denoise_close(a, ref)
+    pc.assert_denoise_close(b, ref)
+
+
+def test_svd_range_optimal_compute(cuda_rt):
+    pc.case_svd_range(cuda_rt, 256, 3905, [400.0, 200.0, 100.0, 50.0], 0, 3)
+    pc.case_svd_range(cuda_rt, 32, 80, [40, 20, 10, 5], 1, -28)
+    pc.case_svd_optimal(cuda_rt, 256, 3905, [400.0, 200.0, 100.0], noise=0.05)
+    pc.case_svd_optimal(cuda_rt, 100, 333, [40, 20, 10])
+    pc.case_compute_signal(cuda_rt, 64, 300, [40, 20])
+
+
+def test_svd_batched_and_tall(cuda_rt):
+    ms = np.stack([oc.synth_lowrank(128, 500, [300.0, 20.0], 0.05, 30 + i) for i in range(5)])
+    d = api.denoiseSignal(ms, runtime=cuda_rt)
+    for i in range(5):
+        pc.assert_denoise_close(d[i], oc.denoiseSignal(ms[i].astype(np.float64)))
+    m = oc.synth_lowrank(300, 64, [40, 20, 10], 0.05, 9)
+    pc.assert_denoise_close(api.denoiseSignal(m, runtime=cuda_rt), oc.denoiseSignal(m.astype(np.float64)))
+
+
+# ---- K2b: cross-power spectrum -------------------------------------------------------------------------
+def test_config3_co2_csd(cuda_rt):
+    """BASELINE config 3: 4 chords, 2 s @ 1.6 MHz, nperseg 4096, all pairs."""
+    pc.case_csd(cuda_rt, 4, 3_200_000, 4096)
+
+
+@pytest.mark.parametrize("nperseg", [256, 512, 1024, 2048, 4096, 8192])
+def test_config5_nperseg_sweep_40ch(cuda_rt, nperseg):
+    """BASELINE config 5 (single-GPU leg): 40-channel all-pairs CSD across the nperseg sweep."""
+    pc.case_csd(cuda_rt, 40, 120_000, nperseg, fs=500000.0)
+
+
+def test_csd_variants_and_kat(cuda_rt):
+    pc.case_csd(cuda_rt, 5, 30_000, 64, detrend="linear", scaling="spectrum")
+    pc.case_csd(cuda_rt, 3, 30_000, 512, detrend=False, window="hamm")
+    x = np.zeros(16, np.float32)
+    x[0] = 1
+    x[8] = 1
+    f, p = api.csd(x, x, nperseg=8, runtime=cuda_rt)     # scipy TestCSD.test_real_onesided_even
+    np.testing.assert_allclose(p.real, [0.08333333, 0.15277778, 0.22222222, 0.22222222, 0.11111111], rtol=1e-5)
+
+
+# ---- whole path ----------------------------------------------------------------------------------------
+def test_pipeline_small(cuda_rt):
+    pc.case_pipeline(cuda_rt, dict(SP, nperseg=32, noverlap=16), 9000, B=2, tile=64)
+    pc.case_pipeline(cuda_rt, dict(SP, nperseg=256, noverlap=128), 60_000, B=3, tile=128)
+
+
+def test_config2_pipeline_40ch(cuda_rt):
+    """BASELINE config 2: one shot, 40 ECE channels x 1M samples, reference defaults.  Oracle on 6 of
+    the 40 channels (seconds each); invariants on all 40."""
+    x = pc.signals(40, 1_000_000, shot=7)
+    S, D, tiles, info = api.pipeline(x, SP, clip=True, tiles=True, return_info=True, runtime=cuda_rt)
+    assert S.shape == D.shape == (40, 256, 3905) and tiles.shape == (40 * 30, 256, 128)
+    assert np.array_equal(info[:, :2], np.tile([1, 256], (40, 1))) and (info[:, 3] == 0).all()
+    assert (D >= 0).all() and S.min() >= 0 and S.max() <= 1
+    assert np.array_equal(tiles, oc.patch(list(D), 128, 30).astype(np.float32))
+    for c in (0, 1, 13, 26, 38, 39):
+        Sr, _, _ = oc.specgr_array(x[c].astype(np.float64), SP)
+        np.testing.assert_allclose(S[c], Sr, rtol=0, atol=pc.ATOL_IMAGE)
+        pc.assert_denoise_close(D[c], oc.clip(oc.denoiseSignal(S[c].astype(np.float64))))
+    # batch invariance: channel 5 alone gives the same bits as inside the batch of 40
+    S5, D5 = api.pipeline(x[5:6], SP, clip=True, runtime=cuda_rt)
+    assert np.array_equal(S5[0], S[5])
+    np.testing.assert_allclose(D5[0], D[5], rtol=0, atol=2e-5)
+
+
+def test_torch_cuda_zero_copy(cuda_rt):
+    import torch
+    x = torch.from_numpy(pc.signals(2, 100_000)).cuda()
+    S, f, t = api.spectrogram_batch(x, SP, runtime=cuda_rt)
+    assert isinstance(S, torch.Tensor) and S.is_cuda and S.shape == (2, 256, 389)
+    Sr, _, _ = oc.specgr_array(x.cpu().numpy().astype(np.float64), SP)
+    np.testing.assert_allclose(S.cpu().numpy(), Sr, rtol=0, atol=pc.ATOL_IMAGE)
