@@ -150,16 +150,19 @@ struct Carver {
   explicit Carver(void* b) : base(static_cast<char*>(b)) {}
   template <class T>
   T* take(size_t count) {
-    off = (off + 255) & ~(size_t)255;
+    // 256-byte aligned ABSOLUTE addresses (vector loads/stores in the kernels rely on it)
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(base) + off + 255) & ~(uintptr_t)255;
+    off = a - reinterpret_cast<uintptr_t>(base);
     T* p = reinterpret_cast<T*>(base + off);
     off += count * sizeof(T);
     return p;
   }
 };
+// Upper bound of what a Carver consumes for these parts from any base address; a multiple of 256.
 inline size_t carve_size(std::initializer_list<size_t> parts) {
   size_t off = 0;
   for (size_t b : parts) off = ((off + 255) & ~(size_t)255) + b;
-  return off + 256;
+  return ((off + 255) & ~(size_t)255) + 256;
 }
 
 int64_t num_segments(int64_t n, int nperseg, int noverlap) {
