@@ -2,7 +2,9 @@
 // accumulators in tensor memory) for rows in {128, 256} -- the one dense contraction of the path.
 //
 // Work unit = (matrix b, split s): a contiguous range of 32-column chunks of S[b].  Per chunk the
-// producer warps read the [rows x 32] fp32 slab (row-contiguous 128 B runs), round it to TF32
+// producer warps read the [rows x 32] fp32 slab (row-contiguous 128 B runs, a whole slab in flight in
+// registers before the first store), optionally apply the min-max normalisation of the log image
+// (so that the pipeline needs no separate normalise pass), round it to TF32
 // (cvt.rna) and store it to shared memory in the UMMA canonical K-major SWIZZLE_128B layout
 // (row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))); a 4-deep mbarrier ring hands slabs to one
 // elected thread that issues tcgen05.mma.kind::tf32 with BOTH operands described on the same slab:
@@ -20,14 +22,14 @@ namespace specgpu {
 
 constexpr int kGtcStages = 4;
 constexpr int kGtcChunk = 32;            // K elements per slab (128 bytes of tf32 per row)
-constexpr int kGtcProducerWarps = 4;
+constexpr int kGtcProducerWarps = 8;
 constexpr int kGtcThreads = (kGtcProducerWarps + 1) * 32;
 
 struct GramTcArgs {
   const float* S;
   int64_t cols, ld;
   int nsplit;
-  int vec4_ok;
+  const unsigned* minmax;   // optional [B][2] ordered-uint (min, max): operands are (x - min) / (max - min)
   float* partial;   // [B][nsplit][128][PW] with PW = rows + (rows == 256 ? 128 : 0)
 };
 
@@ -131,13 +133,24 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 
 #if defined(SPECGPU_EMULATE)
   // scalar stand-in with identical operand rounding and output layout
+  float e_mn = 0.f, e_den = 1.f;
+  if (a.minmax != nullptr) {
+    e_mn = ordered_to_float(a.minmax[2 * b]);
+    e_den = ordered_to_float(a.minmax[2 * b + 1]) - e_mn;
+  }
   for (int i = tid; i < 128 * PW; i += kGtcThreads) {
     const int r = i / PW, c = i % PW;
     const int ra = (c < ROWS) ? r : 128 + r;
     const int rb = (c < ROWS) ? c : c - ROWS + 128;
     float acc = 0.f;
-    for (int64_t k = c0 * kGtcChunk; k < c1 * kGtcChunk && k < a.cols; ++k)
-      acc += round_tf32(Sb[(int64_t)ra * a.ld + k]) * round_tf32(Sb[(int64_t)rb * a.ld + k]);
+    for (int64_t k = c0 * kGtcChunk; k < c1 * kGtcChunk && k < a.cols; ++k) {
+      float xa = Sb[(int64_t)ra * a.ld + k], xb = Sb[(int64_t)rb * a.ld + k];
+      if (a.minmax != nullptr) {
+        xa = __fdiv_rn(xa - e_mn, e_den);
+        xb = __fdiv_rn(xb - e_mn, e_den);
+      }
+      acc += round_tf32(xa) * round_tf32(xb);
+    }
     part[i] = acc;
   }
 #else
@@ -171,32 +184,37 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
   unsigned char* slabs = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-byte aligned
 
   if (warp < kGtcProducerWarps) {
-    // ================= producers: global fp32 -> TF32 -> swizzled shared slab =================
+    // ================= producers: global fp32 -> (normalise) -> TF32 -> swizzled shared slab =================
+    float mn = 0.f, den = 1.f;
+    const bool do_norm = a.minmax != nullptr;
+    if (do_norm) {
+      mn = ordered_to_float(a.minmax[2 * b]);
+      den = ordered_to_float(a.minmax[2 * b + 1]) - mn;
+    }
+    constexpr int RPW = ROWS / kGtcProducerWarps;   // rows per warp per chunk (lane = column)
+    constexpr int BATCH = 16;                        // loads in flight per thread
     for (int64_t ci = 0; ci < nch; ++ci) {
       const int stage = (int)(ci % kGtcStages);
       const uint32_t use = (uint32_t)(ci / kGtcStages);
-      if (use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);
       unsigned char* slab = slabs + stage * SLAB;
-      const int64_t k0 = (c0 + ci) * kGtcChunk;
-      if (a.vec4_ok && k0 + kGtcChunk <= a.cols) {
-        // 8 lanes per row (float4 each): a warp covers 4 rows per step
-        const int sub = lane >> 3, c4 = lane & 7;
-#pragma unroll 4
-        for (int r0 = warp * 4; r0 < ROWS; r0 += kGtcProducerWarps * 4) {
-          const int r = r0 + sub;
-          float4 v = __ldg(reinterpret_cast<const float4*>(Sb + (int64_t)r * a.ld + k0) + c4);
-          v.x = round_tf32(v.x);
-          v.y = round_tf32(v.y);
-          v.z = round_tf32(v.z);
-          v.w = round_tf32(v.w);
-          *reinterpret_cast<float4*>(slab + r * 128 + ((c4 ^ (r & 7)) << 4)) = v;
+      const int64_t k = (c0 + ci) * kGtcChunk + lane;
+      const bool kok = k < a.cols;
+      const float* src = Sb + k;
+#pragma unroll
+      for (int r0 = 0; r0 < RPW; r0 += BATCH) {
+        float v[BATCH];
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+          const int r = warp + (r0 + i) * kGtcProducerWarps;
+          v[i] = kok ? __ldg(src + (int64_t)r * a.ld) : 0.f;
         }
-      } else {
-#pragma unroll 4
-        for (int r = warp; r < ROWS; r += kGtcProducerWarps) {
-          const int64_t k = k0 + lane;
-          const float v = (k < a.cols) ? round_tf32(__ldg(Sb + (int64_t)r * a.ld + k)) : 0.f;
-          *reinterpret_cast<float*>(slab + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) = v;
+        if (r0 == 0 && use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);   // loads already in flight
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+          const int r = warp + (r0 + i) * kGtcProducerWarps;
+          float x = v[i];
+          if (do_norm) x = kok ? __fdiv_rn(x - mn, den) : 0.f;
+          *reinterpret_cast<float*>(slab + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) = round_tf32(x);
         }
       }
       fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -207,11 +225,14 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
       mbar_wait(smem_u32(&s_accum), 0);
       tc_fence_after();
     }
-    const int row = warp * 32 + lane;   // TMEM lane == accumulator row
-    for (int c = 0; c < PW; c += 32) {
+    const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    const int row = q * 32 + lane;          // TMEM lane == accumulator row
+    constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the two warps of a quarter
+    for (int cg = warp >> 2; cg < NCG; cg += kGtcProducerWarps / 4) {
+      const int c = cg * 32;
       uint32_t v[32];
       if (nch > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0u;
@@ -300,15 +321,15 @@ size_t gram_tc_workspace_bytes(int64_t B, int64_t rows) {
 
 bool gram_tc_supported(int64_t rows) { return rows == 128 || rows == 256; }
 
-int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* partial_ws, float* G,
-                   int num_sms, cudaStream_t stream) {
+int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* minmax,
+                   float* partial_ws, float* G, int num_sms, cudaStream_t stream) {
   if (B == 0) return 0;
   GramTcArgs a{};
   a.S = S;
   a.cols = cols;
   a.ld = ld;
   a.nsplit = gram_tc_pick_split(B, cols, num_sms);
-  a.vec4_ok = ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (ld % 4 == 0);
+  a.minmax = minmax;
   a.partial = partial_ws;
   const size_t smem = (size_t)kGtcStages * rows * 128 + 1024;
   if (rows == 256) {

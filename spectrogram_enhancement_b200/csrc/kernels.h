@@ -55,14 +55,18 @@ int launch_eig_jacobi(const float* G, int64_t B, int n, int skip_converged, floa
 // kind 0: explicit (start, stop); 1: use_optimal; 2: computeSignal.  plan[b] = {a, e, num_sing, status}
 int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int stop, float omega_f, int32_t* plan,
                     float* s_out, cudaStream_t stream);
+// Leading-component removal fused with the min-max normalisation: L (log image) -> S = (L-min)/(max-min) and
+// D = S - u0 (u0^T S) [clipped]; S may alias L.  minmax == nullptr: L is already normalised (S not written if null).
+int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const unsigned* minmax, const float* U,
+                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream);
 int launch_svd_project(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U, const int32_t* plan,
                        int clip, void* out, int out_f64, int64_t ldo, cudaStream_t stream);
 
 // gram_tc.cu
 bool gram_tc_supported(int64_t rows);
 size_t gram_tc_workspace_bytes(int64_t B, int64_t rows);
-int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* partial_ws, float* G,
-                   int num_sms, cudaStream_t stream);
+int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* minmax,
+                   float* partial_ws, float* G, int num_sms, cudaStream_t stream);
 
 // csd.cu
 int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t ldf, int nfreq, int64_t i0, int64_t ni,

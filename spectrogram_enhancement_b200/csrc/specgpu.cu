@@ -538,16 +538,24 @@ SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
 
 // Shared body of svd_denoise / compute_signal / pipeline.  kind: 0 explicit range, 1 use_optimal,
 // 2 computeSignal.  `ws_base` lets the pipeline place the SVD scratch behind its own.
-int svd_run(specgpu_ctx* ctx, void* ws_base, const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, int kind,
-            int start, int stop, int clip, bool power_ok, void* out, int out_f64, int64_t ldo, float* s_out,
-            int32_t* info, cudaStream_t st) {
+//
+// `raw_mm` != nullptr (pipeline only): S holds the un-normalised log image and raw_mm its per-matrix
+// (min, max); the normalisation is then fused into the Gram producer and the rank-1 projection, which
+// also writes the normalised image back over S.
+int svd_run(specgpu_ctx* ctx, void* ws_base, float* S, const unsigned* raw_mm, int64_t B, int64_t rows, int64_t cols,
+            int64_t ld, int kind, int start, int stop, int clip, bool power_ok, void* out, int out_f64, int64_t ldo,
+            float* s_out, int32_t* info, cudaStream_t st) {
   void* stream = (void*)st;
   const bool tc = power_ok && gram_tc_supported(rows);   // TF32 Gram only feeds the leading-pair route
   const bool full = true;                                // Jacobi scratch is always carved (fallback for power)
   SvdWs w = svd_carve(ws_base, B, rows, tc, full);
   if (tc) {
-    CHECK_LAUNCH(ctx, launch_gram_tc(S, B, rows, cols, ld, w.gram_partial, w.G, ctx->num_sms, st), "gram_tc", 2);
+    CHECK_LAUNCH(ctx, launch_gram_tc(S, B, rows, cols, ld, raw_mm, w.gram_partial, w.G, ctx->num_sms, st), "gram_tc", 2);
   } else {
+    if (raw_mm) {   // no fused route for this shape: normalise in place first
+      CHECK_LAUNCH(ctx, launch_lognorm(S, B, rows, cols, ld, raw_mm, nullptr, st), "lognorm", 1);
+      raw_mm = nullptr;
+    }
     CHECK_LAUNCH(ctx, launch_gram_simt(S, B, rows, cols, ld, w.G, st), "gram_simt", 1);
   }
   if (power_ok) {
@@ -560,7 +568,13 @@ int svd_run(specgpu_ctx* ctx, void* ws_base, const float* S, int64_t B, int64_t 
   const double beta = (double)std::min(rows, cols) / (double)std::max(rows, cols);
   CHECK_LAUNCH(ctx, launch_svd_plan(w.lam, B, (int)rows, kind, start, stop, (float)omega_of(beta), w.plan, s_out, st),
                "svd_plan", 1);
-  CHECK_LAUNCH(ctx, launch_svd_project(S, B, (int)rows, cols, ld, w.U, w.plan, clip, out, out_f64, ldo, st), "svd_project", 1);
+  if (power_ok && !out_f64) {
+    // power_ok implies the range [1, rows): only the leading component is removed
+    CHECK_LAUNCH(ctx, launch_svd_rank1(S, B, (int)rows, cols, ld, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st),
+                 "svd_rank1", 1);
+  } else {
+    CHECK_LAUNCH(ctx, launch_svd_project(S, B, (int)rows, cols, ld, w.U, w.plan, clip, out, out_f64, ldo, st), "svd_project", 1);
+  }
   if (info) {
     cudaError_t e = cudaMemcpyAsync(info, w.plan, (size_t)B * 16, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return cuda_fail(ctx, (int)e, "info copy");
@@ -589,8 +603,8 @@ int specgpu_svd_denoise(specgpu_ctx* ctx, const float* S, int64_t B, int64_t row
   cudaSetDevice(ctx->device);
   const bool power_ok = (mode == 0) && !use_optimal && start == 1 && stop >= rows && s_out == nullptr && rows <= 256;
   if ((rc = ensure_ws(ctx, svd_ws_bytes(B, rows, power_ok && gram_tc_supported(rows), true)))) return rc;
-  return svd_run(ctx, ctx->ws, S, B, rows, cols, ld, use_optimal ? 1 : 0, start, stop, clip, power_ok, out, 0, ldo, s_out,
-                 info, (cudaStream_t)stream);
+  return svd_run(ctx, ctx->ws, const_cast<float*>(S), nullptr, B, rows, cols, ld, use_optimal ? 1 : 0, start, stop, clip,
+                 power_ok, out, 0, ldo, s_out, info, (cudaStream_t)stream);
 }
 
 int specgpu_compute_signal(specgpu_ctx* ctx, const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, double* out,
@@ -600,7 +614,8 @@ int specgpu_compute_signal(specgpu_ctx* ctx, const float* S, int64_t B, int64_t 
   if (B * rows * cols == 0) return SPECGPU_OK;
   cudaSetDevice(ctx->device);
   if ((rc = ensure_ws(ctx, svd_ws_bytes(B, rows, false, true)))) return rc;
-  return svd_run(ctx, ctx->ws, S, B, rows, cols, ld, 2, 0, 0, 0, false, out, 1, ldo, s_out, info, (cudaStream_t)stream);
+  return svd_run(ctx, ctx->ws, const_cast<float*>(S), nullptr, B, rows, cols, ld, 2, 0, 0, 0, false, out, 1, ldo, s_out,
+                 info, (cudaStream_t)stream);
 }
 
 // ---- tiles -----------------------------------------------------------------------------------------
@@ -710,8 +725,9 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
   CHECK_LAUNCH(ctx, launch_minmax_init(mm, B, st), "minmax_init", 1);
   StftArgs a = make_args(plan, x, n, ldx, 0, nseg, (float)plan->scale, S, ldt, mm);
   CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, B, st), "stft_kernel", 1);
-  CHECK_LAUNCH(ctx, launch_lognorm(S, B, rows, nseg, ldt, mm, nullptr, st), "lognorm", 1);
-  if ((rc = svd_run(ctx, svd_ws, S, B, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, D, 0, ldt, nullptr, info, st))) return rc;
+  // S holds the raw log image until the rank-1 projection normalises it in place (see svd_run)
+  if ((rc = svd_run(ctx, svd_ws, S, mm, B, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, D, 0, ldt, nullptr, info, st)))
+    return rc;
   if (tiles && ntiles > 0) CHECK_LAUNCH(ctx, launch_patch(D, B, rows, ldt, tile_w, ntiles, tiles, 0, st), "patch", 1);
   return SPECGPU_OK;
 }

@@ -89,7 +89,7 @@ __device__ __forceinline__ void group_sum2(float& a, float& b, float* red, int t
 }
 
 template <int LOG2N, int MODE>
-__global__ void __launch_bounds__(kStftThreads) stft_kernel(StftArgs a) {
+__global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE_COMPLEX) ? 3 : 1) stft_kernel(StftArgs a) {
   using C = StftCfg<LOG2N>;
   constexpr int N = C::N, M = C::M, F = C::F, R0 = C::R0, G = C::G, NG = C::NG;
   constexpr int TT = (MODE == STFT_MODE_COMPLEX) ? C::tile_w(8) : C::tile_w(4);
@@ -198,8 +198,9 @@ __global__ void __launch_bounds__(kStftThreads) stft_kernel(StftArgs a) {
         if (k != 0) pk *= 2.0f;      // k in 1..M/2 (k == M/2 < M is doubled as well)
         if (k != 0) pm *= 2.0f;      // km in M/2..M-1
         if (MODE == STFT_MODE_LOGPSD) {
-          pk = logf(pk + a.eps);
-          pm = logf(pm + a.eps);
+          // lg2.approx * ln2: absolute error ~1e-6 on values in [-26, 10], i.e. < 1e-7 of the normalised image
+          pk = __logf(pk + a.eps);
+          pm = __logf(pm + a.eps);
           if (live) {
             vmin = fminf(vmin, pk);
             vmax = fmaxf(vmax, pk);

@@ -587,6 +587,83 @@ __global__ void __launch_bounds__(kRecThreads) svd_project_kernel(const float* S
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// The default denoiseSignal range (start = 1, stop = len(s)) removes only the leading component:
+//   D = S - u0 (u0^T S).
+// This streaming kernel fuses it with the min-max normalisation of the log image and the clip, so the
+// pipeline reads the log image once and writes S and D once.  A CTA owns a [rows x 32] column tile in
+// shared memory; warp w reduces rows w, w+8, ... for the 32 coefficients, then updates the same rows.
+// ------------------------------------------------------------------------------------------------------
+template <int RPW>
+__global__ void __launch_bounds__(kRecThreads) svd_rank1_kernel(const float* L, int rows, int64_t cols, int64_t ld,
+                                                                const unsigned* minmax, const float* U, int clip,
+                                                                float* S, float* D, int64_t ldo) {
+  SPECGPU_DYN_SMEM(smem);
+  float* s_u = reinterpret_cast<float*>(smem);          // [rows]
+  float* s_w = s_u + rows;                              // [8][32] partial coefficients
+  const int64_t b = blockIdx.y;
+  const int64_t c0 = (int64_t)blockIdx.x * kRecCols;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool col_ok = c0 + lane < cols;
+  const float* Lb = L + b * rows * ld + c0 + lane;
+  float mn = 0.f, den = 1.f;
+  const bool do_norm = minmax != nullptr;
+  if (do_norm) {
+    mn = ordered_to_float(minmax[2 * b]);
+    den = ordered_to_float(minmax[2 * b + 1]) - mn;
+  }
+  for (int r = tid; r < rows; r += kRecThreads) s_u[r] = U[b * (int64_t)rows * rows + (int64_t)r * rows];
+  float x[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = warp + 8 * i;
+    x[i] = (r < rows && col_ok) ? __ldg(Lb + (int64_t)r * ld) : 0.f;
+  }
+  __syncthreads();
+  float w = 0.f;
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = warp + 8 * i;
+    if (do_norm) x[i] = (r < rows && col_ok) ? __fdiv_rn(x[i] - mn, den) : 0.f;
+    if (r < rows) w = fmaf(s_u[r], x[i], w);
+  }
+  s_w[warp * 32 + lane] = w;
+  if (S != nullptr && (do_norm || S != L)) {
+    float* Sb = S + b * rows * ldo + c0 + lane;
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = warp + 8 * i;
+      if (r < rows && col_ok) Sb[(int64_t)r * ldo] = x[i];
+    }
+  }
+  __syncthreads();
+  w = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w += s_w[k * 32 + lane];
+  float* Db = D + b * rows * ldo + c0 + lane;
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = warp + 8 * i;
+    if (r < rows && col_ok) {
+      float v = fmaf(-s_u[r], w, x[i]);
+      if (clip && v < 0.f) v = 0.f;
+      Db[(int64_t)r * ldo] = v;
+    }
+  }
+}
+
+int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const unsigned* minmax, const float* U,
+                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream) {
+  if (B == 0 || rows == 0 || cols == 0) return 0;
+  const size_t smem = ((size_t)rows + 8 * 32) * sizeof(float);
+  const dim3 grid((unsigned)ceil_div(cols, kRecCols), (unsigned)B);
+  if (rows <= 64) SPECGPU_LAUNCH(svd_rank1_kernel<8>, grid, kRecThreads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  else if (rows <= 128) SPECGPU_LAUNCH(svd_rank1_kernel<16>, grid, kRecThreads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  else if (rows <= 256) SPECGPU_LAUNCH(svd_rank1_kernel<32>, grid, kRecThreads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  else return -1;
+  return (int)cudaGetLastError();
+}
+
 template <class OutT>
 static int launch_project_t(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U,
                             const int32_t* plan, int clip, OutT* out, int64_t ldo, cudaStream_t stream) {

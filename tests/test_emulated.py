@@ -112,6 +112,12 @@ def test_pipeline_small(emu_rt):
     pc.case_pipeline(emu_rt, sp, 9000, B=2, tile=64)
 
 
+def test_pipeline_fused_normalise_route(emu_rt):
+    # 128 frequency rows: the tensor-core Gram + rank-1 projection route with the min-max normalisation fused
+    sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=256, noverlap=128)
+    pc.case_pipeline(emu_rt, sp, 20000, B=3, tile=64)
+
+
 # ---- host logic / error behaviour ---------------------------------------------------------------
 def test_errors_mirror_scipy(emu_rt):
     x = np.zeros(100, np.float32)
