@@ -1,7 +1,8 @@
 // K3a: Gram matrix G = S S^T on the 5th-generation tensor cores (tcgen05, TF32 operands, FP32
 // accumulators in tensor memory) for rows in {128, 256} -- the one dense contraction of the path.
 //
-// Work unit = (matrix b, split s): a contiguous range of 32-column chunks of S[b].  Per chunk the
+// The batch is cut into 32-column chunks, numbered g = b * nchunk + c; CTA i of a persistent grid owns
+// the contiguous range [i*per, (i+1)*per), which touches at most two matrices ("segments").  Per chunk the
 // producer warps read the [rows x 32] fp32 slab (row-contiguous 128 B runs, a whole slab in flight in
 // registers before the first store), optionally apply the min-max normalisation of the log image
 // (so that the pipeline needs no separate normalise pass), round it to TF32
@@ -11,8 +12,9 @@
 //     D1[128 x rows] += slab[0:128]   . slab[0:rows]^T     (G00 | G01)
 //     D2[128 x 128 ] += slab[128:256] . slab[128:256]^T    (G11; rows == 256 only; G10 = G01^T)
 // so the symmetric product costs 3/4 of the MMA work.  tcgen05.commit releases the slab; after the
-// last chunk the accumulators are read back with tcgen05.ld and written as a per-unit partial.
-// gram_reduce_kernel sums the split partials in a fixed order (deterministic) and mirrors G10.
+// last chunk of a segment the accumulators are read back with tcgen05.ld and written as that
+// (CTA, segment) partial.  gram_reduce_kernel sums the partials of a matrix in a fixed order
+// (deterministic) and mirrors G10.
 //
 // The emulation build (tests only, no tensor cores on a CPU) replaces the kernel body by a scalar
 // loop with the same TF32 operand rounding and the same partial layout.
@@ -27,21 +29,14 @@ constexpr int kGtcThreads = (kGtcProducerWarps + 1) * 32;
 
 struct GramTcArgs {
   const float* S;
-  int64_t cols, ld;
-  int nsplit;
+  int64_t B, cols, ld;
+  int64_t nchunk;           // chunks per matrix
+  int64_t per;              // chunks per CTA
   const unsigned* minmax;   // optional [B][2] ordered-uint (min, max): operands are (x - min) / (max - min)
-  float* partial;   // [B][nsplit][128][PW] with PW = rows + (rows == 256 ? 128 : 0)
+  float* partial;           // [grid][2][128][PW] with PW = rows + (rows == 256 ? 128 : 0)
 };
 
 __host__ __device__ inline int gram_tc_partial_width(int rows) { return rows == 256 ? 384 : rows; }
-
-__host__ __device__ inline void gram_tc_range(int64_t cols, int nsplit, int s, int64_t* c0, int64_t* c1) {
-  const int64_t nchunk = (cols + kGtcChunk - 1) / kGtcChunk;
-  const int64_t per = (nchunk + nsplit - 1) / nsplit;
-  *c0 = (int64_t)s * per;
-  *c1 = (*c0 + per < nchunk) ? *c0 + per : nchunk;
-  if (*c0 > nchunk) *c0 = nchunk;
-}
 
 __device__ __forceinline__ float round_tf32(float x) {
 #if defined(SPECGPU_EMULATE)
@@ -123,38 +118,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 template <int ROWS>
 __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
   constexpr int PW = (ROWS == 256) ? 384 : ROWS;
-  const int64_t b = blockIdx.x / a.nsplit;
-  const int s = blockIdx.x % a.nsplit;
-  int64_t c0, c1;
-  gram_tc_range(a.cols, a.nsplit, s, &c0, &c1);
-  const float* Sb = a.S + b * ROWS * a.ld;
-  float* part = a.partial + ((size_t)b * a.nsplit + s) * 128 * PW;
   const int tid = threadIdx.x;
+  const int64_t total = a.B * a.nchunk;
+  const int64_t g0 = (int64_t)blockIdx.x * a.per;
+  const int64_t g1 = (g0 + a.per < total) ? g0 + a.per : total;
+  if (g0 >= g1) return;                          // uniform over the CTA
+  const int64_t b_first = g0 / a.nchunk;
+  const int nsegs = (int)((g1 - 1) / a.nchunk - b_first) + 1;     // 1 or 2 (per <= nchunk)
+  float* part0 = a.partial + (size_t)blockIdx.x * 2 * 128 * PW;
 
 #if defined(SPECGPU_EMULATE)
-  // scalar stand-in with identical operand rounding and output layout
-  float e_mn = 0.f, e_den = 1.f;
-  if (a.minmax != nullptr) {
-    e_mn = ordered_to_float(a.minmax[2 * b]);
-    e_den = ordered_to_float(a.minmax[2 * b + 1]) - e_mn;
-  }
-  for (int i = tid; i < 128 * PW; i += kGtcThreads) {
-    const int r = i / PW, c = i % PW;
-    const int ra = (c < ROWS) ? r : 128 + r;
-    const int rb = (c < ROWS) ? c : c - ROWS + 128;
-    float acc = 0.f;
-    for (int64_t k = c0 * kGtcChunk; k < c1 * kGtcChunk && k < a.cols; ++k) {
-      float xa = Sb[(int64_t)ra * a.ld + k], xb = Sb[(int64_t)rb * a.ld + k];
-      if (a.minmax != nullptr) {
-        xa = __fdiv_rn(xa - e_mn, e_den);
-        xb = __fdiv_rn(xb - e_mn, e_den);
-      }
-      acc += round_tf32(xa) * round_tf32(xb);
+  // scalar stand-in with identical operand rounding, work split and partial layout
+  for (int sg = 0; sg < nsegs; ++sg) {
+    const int64_t b = b_first + sg;
+    const int64_t lo = (g0 > b * a.nchunk ? g0 : b * a.nchunk) - b * a.nchunk;
+    const int64_t hi = (g1 < (b + 1) * a.nchunk ? g1 : (b + 1) * a.nchunk) - b * a.nchunk;
+    const float* Sb = a.S + b * ROWS * a.ld;
+    float e_mn = 0.f, e_den = 1.f;
+    if (a.minmax != nullptr) {
+      e_mn = ordered_to_float(a.minmax[2 * b]);
+      e_den = ordered_to_float(a.minmax[2 * b + 1]) - e_mn;
     }
-    part[i] = acc;
+    for (int i = tid; i < 128 * PW; i += kGtcThreads) {
+      const int r = i / PW, c = i % PW;
+      const int ra = (c < ROWS) ? r : 128 + r;
+      const int rb = (c < ROWS) ? c : c - ROWS + 128;
+      float acc = 0.f;
+      for (int64_t k = lo * kGtcChunk; k < hi * kGtcChunk && k < a.cols; ++k) {
+        float xa = Sb[(int64_t)ra * a.ld + k], xb = Sb[(int64_t)rb * a.ld + k];
+        if (a.minmax != nullptr) {
+          xa = div_by(xa - e_mn, e_den, 1.0f / e_den);
+          xb = div_by(xb - e_mn, e_den, 1.0f / e_den);
+        }
+        acc += round_tf32(xa) * round_tf32(xb);
+      }
+      part0[(size_t)sg * 128 * PW + i] = acc;
+    }
   }
 #else
-  SPECGPU_DYN_SMEM(smem);   // 1024-byte aligned: required by SWIZZLE_128B
+  SPECGPU_DYN_SMEM(smem);   // SWIZZLE_128B atoms need 1024-byte alignment (re-aligned below)
   constexpr int SLAB = ROWS * 128;  // bytes per stage
   __shared__ __align__(8) uint64_t s_full[kGtcStages];
   __shared__ __align__(8) uint64_t s_empty[kGtcStages];
@@ -180,91 +182,115 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
-  const int64_t nch = c1 - c0;
-  unsigned char* slabs = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-byte aligned
+  unsigned char* slabs = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
 
   if (warp < kGtcProducerWarps) {
     // ================= producers: global fp32 -> (normalise) -> TF32 -> swizzled shared slab =================
-    float mn = 0.f, den = 1.f;
-    const bool do_norm = a.minmax != nullptr;
-    if (do_norm) {
-      mn = ordered_to_float(a.minmax[2 * b]);
-      den = ordered_to_float(a.minmax[2 * b + 1]) - mn;
-    }
     constexpr int RPW = ROWS / kGtcProducerWarps;   // rows per warp per chunk (lane = column)
-    constexpr int BATCH = 16;                        // loads in flight per thread
-    for (int64_t ci = 0; ci < nch; ++ci) {
-      const int stage = (int)(ci % kGtcStages);
-      const uint32_t use = (uint32_t)(ci / kGtcStages);
-      unsigned char* slab = slabs + stage * SLAB;
-      const int64_t k = (c0 + ci) * kGtcChunk + lane;
-      const bool kok = k < a.cols;
-      const float* src = Sb + k;
+    constexpr int BATCH = 16;                        // rows per register batch
+    constexpr int NBATCH = RPW / BATCH;              // batches per chunk
+    const bool do_norm = a.minmax != nullptr;
+    int64_t g = g0;                                  // next chunk to produce
+    for (int sg = 0; sg < nsegs; ++sg) {
+      const int64_t b = b_first + sg;
+      const int64_t gend = (g1 < (b + 1) * a.nchunk) ? g1 : (b + 1) * a.nchunk;
+      const float* Sb = a.S + b * ROWS * a.ld;
+      float mn = 0.f, den = 1.f;
+      if (do_norm) {
+        mn = ordered_to_float(a.minmax[2 * b]);
+        den = ordered_to_float(a.minmax[2 * b + 1]) - mn;
+      }
+      const float inv = 1.0f / den;
+      // batch t of this segment = (chunk g + t / NBATCH, rows warp + (t % NBATCH * BATCH + i) * 8)
+      const int64_t nbt = (gend - g) * NBATCH;
+      auto load_batch = [&](float (&v)[BATCH], int64_t t) {
+        const int64_t k = ((g + t / NBATCH) - b * a.nchunk) * kGtcChunk + lane;
+        const bool kok = k < a.cols;
+        const float* src = Sb + k + (int64_t)(warp + (int)(t % NBATCH) * BATCH * kGtcProducerWarps) * a.ld;
 #pragma unroll
-      for (int r0 = 0; r0 < RPW; r0 += BATCH) {
-        float v[BATCH];
+        for (int i = 0; i < BATCH; ++i) v[i] = kok ? __ldg(src + (int64_t)i * kGtcProducerWarps * a.ld) : 0.f;
+      };
+      auto store_batch = [&](const float (&v)[BATCH], int64_t t) {
+        const int64_t ci = (g + t / NBATCH) - g0;    // chunk index within this CTA: ring position
+        const int h = (int)(t % NBATCH);
+        const int stage = (int)(ci % kGtcStages);
+        const uint32_t use = (uint32_t)(ci / kGtcStages);
+        if (h == 0 && use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);
+        unsigned char* slab = slabs + stage * SLAB;
+        const bool kok = ((g + t / NBATCH) - b * a.nchunk) * kGtcChunk + lane < a.cols;
 #pragma unroll
         for (int i = 0; i < BATCH; ++i) {
-          const int r = warp + (r0 + i) * kGtcProducerWarps;
-          v[i] = kok ? __ldg(src + (int64_t)r * a.ld) : 0.f;
-        }
-        if (r0 == 0 && use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);   // loads already in flight
-#pragma unroll
-        for (int i = 0; i < BATCH; ++i) {
-          const int r = warp + (r0 + i) * kGtcProducerWarps;
+          const int r = warp + (h * BATCH + i) * kGtcProducerWarps;
           float x = v[i];
-          if (do_norm) x = kok ? __fdiv_rn(x - mn, den) : 0.f;
+          if (do_norm) x = kok ? div_by(x - mn, den, inv) : 0.f;
           *reinterpret_cast<float*>(slab + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) = round_tf32(x);
         }
+        if (h == NBATCH - 1) {
+          fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbar_arrive(smem_u32(&s_full[stage]));
+        }
+      };
+      // software pipeline: the next batch's loads are in flight while this one is converted and stored
+      float va[BATCH], vb[BATCH];
+      load_batch(va, 0);
+      for (int64_t t = 0; t < nbt; t += 2) {
+        if (t + 1 < nbt) load_batch(vb, t + 1);
+        store_batch(va, t);
+        if (t + 1 < nbt) {
+          if (t + 2 < nbt) load_batch(va, t + 2);
+          store_batch(vb, t + 1);
+        }
       }
-      fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(smem_u32(&s_full[stage]));
-    }
-    // ================= epilogue: TMEM -> registers -> partial[128][PW] =================
-    if (nch > 0) {
-      mbar_wait(smem_u32(&s_accum), 0);
+      g = gend;
+      // ================= epilogue: TMEM -> registers -> partial[sg][128][PW] =================
+      mbar_wait(smem_u32(&s_accum), (uint32_t)sg & 1);
       tc_fence_after();
-    }
-    const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    const int row = q * 32 + lane;          // TMEM lane == accumulator row
-    constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the two warps of a quarter
-    for (int cg = warp >> 2; cg < NCG; cg += kGtcProducerWarps / 4) {
-      const int c = cg * 32;
-      uint32_t v[32];
-      if (nch > 0) {
+      float* part = part0 + (size_t)sg * 128 * PW;
+      const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+      const int row = q * 32 + lane;          // TMEM lane == accumulator row
+      constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the two warps of a quarter
+      for (int cg = warp >> 2; cg < NCG; cg += kGtcProducerWarps / 4) {
+        const int c = cg * 32;
+        uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      } else {
+        float4* dst = reinterpret_cast<float4*>(part + (size_t)row * PW + c);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0u;
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                               __uint_as_float(v[4 * i + 3]));
       }
-      float4* dst = reinterpret_cast<float4*>(part + (size_t)row * PW + c);
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                             __uint_as_float(v[4 * i + 3]));
+      tc_fence_before();   // the TMEM reads are ordered before the arrivals that let the next segment's MMAs start
     }
   } else if (lane == 0) {
     // ================= MMA issuer (one thread) =================
     const uint32_t idesc1 = umma_idesc_tf32(128, ROWS);
     const uint32_t idesc2 = umma_idesc_tf32(128, 128);
-    for (int64_t ci = 0; ci < nch; ++ci) {
-      const int stage = (int)(ci % kGtcStages);
-      const uint32_t use = (uint32_t)(ci / kGtcStages);
-      mbar_wait(smem_u32(&s_full[stage]), use & 1);
-      tc_fence_after();
-      const uint32_t base = smem_u32(slabs + stage * SLAB);
+    int64_t g = g0;
+    for (int sg = 0; sg < nsegs; ++sg) {
+      const int64_t b = b_first + sg;
+      const int64_t gend = (g1 < (b + 1) * a.nchunk) ? g1 : (b + 1) * a.nchunk;
+      const int64_t gstart = g;
+      for (; g < gend; ++g) {
+        const int64_t ci = g - g0;
+        const int stage = (int)(ci % kGtcStages);
+        const uint32_t use = (uint32_t)(ci / kGtcStages);
+        mbar_wait(smem_u32(&s_full[stage]), use & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(slabs + stage * SLAB);
 #pragma unroll
-      for (int ks = 0; ks < kGtcChunk / 8; ++ks) {   // K = 8 tf32 (32 bytes) per instruction
-        const uint64_t d_lo = umma_desc_k_sw128(base + ks * 32);
-        umma_tf32(tmem_base, d_lo, d_lo, idesc1, (ci > 0 || ks > 0) ? 1u : 0u);
-        if (ROWS == 256) {
-          const uint64_t d_hi = umma_desc_k_sw128(base + 128 * 128 + ks * 32);
-          umma_tf32(tmem_base + 256, d_hi, d_hi, idesc2, (ci > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < kGtcChunk / 8; ++ks) {   // K = 8 tf32 (32 bytes) per instruction
+          const uint32_t accumulate = (g > gstart || ks > 0) ? 1u : 0u;
+          const uint64_t d_lo = umma_desc_k_sw128(base + ks * 32);
+          umma_tf32(tmem_base, d_lo, d_lo, idesc1, accumulate);
+          if (ROWS == 256) {
+            const uint64_t d_hi = umma_desc_k_sw128(base + 128 * 128 + ks * 32);
+            umma_tf32(tmem_base + 256, d_hi, d_hi, idesc2, accumulate);
+          }
         }
+        umma_commit(smem_u32(&s_empty[stage]));   // slab may be refilled once these MMAs retire
       }
-      umma_commit(smem_u32(&s_empty[stage]));   // slab may be refilled once these MMAs retire
+      umma_commit(smem_u32(&s_accum));            // accumulators of this segment complete
     }
-    if (nch > 0) umma_commit(smem_u32(&s_accum));
   }
   tc_fence_before();
   __syncthreads();
@@ -274,11 +300,11 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 #endif
 }
 
-// G[b] = sum over splits of the unit partials; G10 mirrored from G01.
-__global__ void gram_reduce_kernel(const float* partial, int rows, int nsplit, float* G) {
+// G[b] = sum of the (CTA, segment) partials that cover matrix b, in CTA order; G10 mirrored from G01.
+__global__ void gram_reduce_kernel(const float* partial, int rows, int64_t nchunk, int64_t per, float* G) {
   const int PW = gram_tc_partial_width(rows);
   const int64_t b = blockIdx.y;
-  const float* pb = partial + (size_t)b * nsplit * 128 * PW;
+  const int64_t i0 = (b * nchunk) / per, i1 = ((b + 1) * nchunk - 1) / per;
   float* Gb = G + b * (int64_t)rows * rows;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * rows; i += gridDim.x * blockDim.x) {
     const int r = i / rows, c = i % rows;
@@ -294,29 +320,30 @@ __global__ void gram_reduce_kernel(const float* partial, int rows, int nsplit, f
       pc = r;                       // G10 = G01^T
     }
     float s = 0.f;
-    for (int k = 0; k < nsplit; ++k) s += pb[((size_t)k * 128 + pr) * PW + pc];
+    for (int64_t cta = i0; cta <= i1; ++cta) {
+      const int64_t sg = b - (cta * per) / nchunk;      // which of the CTA's segments is matrix b
+      s += partial[((size_t)(cta * 2 + sg) * 128 + pr) * PW + pc];
+    }
     Gb[i] = s;
   }
 }
 
-static int gram_tc_pick_split(int64_t B, int64_t cols, int num_sms) {
-  const int64_t nchunk = ceil_div(cols, kGtcChunk);
-  int best = 1;
-  double best_cost = 1e300;
-  for (int ns = 1; ns <= 8 && ns <= nchunk; ++ns) {
-    const int64_t per = ceil_div(nchunk, ns);
-    const int64_t waves = ceil_div(B * ns, num_sms);
-    const double cost = (double)waves * ((double)per + 6.0);   // ~6 chunk-times of prologue/epilogue per unit
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = ns;
-    }
-  }
-  return best;
+struct GramTcGeom {
+  int64_t nchunk, per, grid;
+};
+
+static GramTcGeom gram_tc_geom(int64_t B, int64_t cols, int num_sms) {
+  GramTcGeom g;
+  g.nchunk = ceil_div(cols, kGtcChunk);
+  const int64_t total = B * g.nchunk;
+  g.per = std::min<int64_t>(std::max<int64_t>(ceil_div(total, num_sms), 1), g.nchunk);   // <= nchunk: at most 2 segments per CTA
+  g.grid = ceil_div(total, g.per);
+  return g;
 }
 
 size_t gram_tc_workspace_bytes(int64_t B, int64_t rows) {
-  return (size_t)B * 8 * 128 * gram_tc_partial_width((int)rows) * sizeof(float) + 256;
+  // grid <= max(B, num_sms) + 1 CTAs, two partial slots each
+  return (size_t)(std::max<int64_t>(B, 160) + 1) * 2 * 128 * gram_tc_partial_width((int)rows) * sizeof(float) + 256;
 }
 
 bool gram_tc_supported(int64_t rows) { return rows == 128 || rows == 256; }
@@ -324,27 +351,30 @@ bool gram_tc_supported(int64_t rows) { return rows == 128 || rows == 256; }
 int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* minmax,
                    float* partial_ws, float* G, int num_sms, cudaStream_t stream) {
   if (B == 0) return 0;
+  const GramTcGeom g = gram_tc_geom(B, cols, std::min(num_sms, 160));
   GramTcArgs a{};
   a.S = S;
+  a.B = B;
   a.cols = cols;
   a.ld = ld;
-  a.nsplit = gram_tc_pick_split(B, cols, num_sms);
+  a.nchunk = g.nchunk;
+  a.per = g.per;
   a.minmax = minmax;
   a.partial = partial_ws;
   const size_t smem = (size_t)kGtcStages * rows * 128 + 1024;
   if (rows == 256) {
     cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    SPECGPU_LAUNCH(gram_tc_kernel<256>, (unsigned)(B * a.nsplit), kGtcThreads, smem, stream, a);
+    SPECGPU_LAUNCH(gram_tc_kernel<256>, (unsigned)g.grid, kGtcThreads, smem, stream, a);
   } else {
     cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    SPECGPU_LAUNCH(gram_tc_kernel<128>, (unsigned)(B * a.nsplit), kGtcThreads, smem, stream, a);
+    SPECGPU_LAUNCH(gram_tc_kernel<128>, (unsigned)g.grid, kGtcThreads, smem, stream, a);
   }
   int e = (int)cudaGetLastError();
   if (e) return e;
   SPECGPU_LAUNCH(gram_reduce_kernel, dim3((unsigned)ceil_div(rows * rows, 256 * 4), (unsigned)B), 256, 0, stream,
-                 (const float*)partial_ws, (int)rows, a.nsplit, G);
+                 (const float*)partial_ws, (int)rows, g.nchunk, g.per, G);
   return (int)cudaGetLastError();
 }
 

@@ -269,6 +269,7 @@ __global__ void lognorm_kernel(float* S, int64_t rows, int64_t cols, int64_t ld,
   const float mn = ordered_to_float(mm[2 * b]);
   const float mx = ordered_to_float(mm[2 * b + 1]);
   const float den = mx - mn;
+  const float inv = 1.0f / den;
   if (mm_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     mm_out[2 * b] = mn;
     mm_out[2 * b + 1] = mx;
@@ -276,7 +277,7 @@ __global__ void lognorm_kernel(float* S, int64_t rows, int64_t cols, int64_t ld,
   const int64_t r = blockIdx.y;
   float* row = S + (b * rows + r) * ld;
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += (int64_t)gridDim.x * blockDim.x)
-    row[c] = __fdiv_rn(row[c] - mn, den);
+    row[c] = div_by(row[c] - mn, den, inv);
 }
 
 template <int LOG2N, int MODE>

@@ -605,49 +605,52 @@ __global__ void __launch_bounds__(kRecThreads) svd_rank1_kernel(const float* L, 
   const int64_t c0 = (int64_t)blockIdx.x * kRecCols;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool col_ok = c0 + lane < cols;
-  const float* Lb = L + b * rows * ld + c0 + lane;
   float mn = 0.f, den = 1.f;
   const bool do_norm = minmax != nullptr;
   if (do_norm) {
     mn = ordered_to_float(minmax[2 * b]);
     den = ordered_to_float(minmax[2 * b + 1]) - mn;
   }
+  const float inv = 1.0f / den;
   for (int r = tid; r < rows; r += kRecThreads) s_u[r] = U[b * (int64_t)rows * rows + (int64_t)r * rows];
+  // this thread's rows are warp, warp+8, ...: nr of them are inside the matrix (warp-uniform)
+  const int nr = col_ok ? ((rows - warp + 7) >> 3) : 0;
   float x[RPW];
+  {
+    const float* p = L + (b * rows + warp) * ld + c0 + lane;
+    const int64_t step = 8 * ld;
 #pragma unroll
-  for (int i = 0; i < RPW; ++i) {
-    const int r = warp + 8 * i;
-    x[i] = (r < rows && col_ok) ? __ldg(Lb + (int64_t)r * ld) : 0.f;
+    for (int i = 0; i < RPW; ++i, p += step) x[i] = (i < nr) ? __ldg(p) : 0.f;
   }
   __syncthreads();
   float w = 0.f;
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
-    const int r = warp + 8 * i;
-    if (do_norm) x[i] = (r < rows && col_ok) ? __fdiv_rn(x[i] - mn, den) : 0.f;
-    if (r < rows) w = fmaf(s_u[r], x[i], w);
+    if (do_norm) x[i] = (i < nr) ? div_by(x[i] - mn, den, inv) : 0.f;
+    if (i < nr) w = fmaf(s_u[warp + 8 * i], x[i], w);
   }
   s_w[warp * 32 + lane] = w;
   if (S != nullptr && (do_norm || S != L)) {
-    float* Sb = S + b * rows * ldo + c0 + lane;
+    float* p = S + (b * rows + warp) * ldo + c0 + lane;
+    const int64_t step = 8 * ldo;
 #pragma unroll
-    for (int i = 0; i < RPW; ++i) {
-      const int r = warp + 8 * i;
-      if (r < rows && col_ok) Sb[(int64_t)r * ldo] = x[i];
-    }
+    for (int i = 0; i < RPW; ++i, p += step)
+      if (i < nr) *p = x[i];
   }
   __syncthreads();
   w = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) w += s_w[k * 32 + lane];
-  float* Db = D + b * rows * ldo + c0 + lane;
+  {
+    float* p = D + (b * rows + warp) * ldo + c0 + lane;
+    const int64_t step = 8 * ldo;
 #pragma unroll
-  for (int i = 0; i < RPW; ++i) {
-    const int r = warp + 8 * i;
-    if (r < rows && col_ok) {
-      float v = fmaf(-s_u[r], w, x[i]);
-      if (clip && v < 0.f) v = 0.f;
-      Db[(int64_t)r * ldo] = v;
+    for (int i = 0; i < RPW; ++i, p += step) {
+      if (i < nr) {
+        float v = fmaf(-s_u[warp + 8 * i], w, x[i]);
+        if (clip) v = (v < 0.f) ? 0.f : v;   // NaN stays NaN, like hacked[hacked < 0] = 0
+        *p = v;
+      }
     }
   }
 }
