@@ -24,7 +24,7 @@ namespace specgpu {
 
 constexpr int kGtcStages = 4;
 constexpr int kGtcChunk = 32;            // K elements per slab (128 bytes of tf32 per row)
-constexpr int kGtcProducerWarps = 8;
+constexpr int kGtcProducerWarps = 16;
 constexpr int kGtcThreads = (kGtcProducerWarps + 1) * 32;
 
 struct GramTcArgs {
@@ -186,59 +186,61 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 
   if (warp < kGtcProducerWarps) {
     // ================= producers: global fp32 -> (normalise) -> TF32 -> swizzled shared slab =================
-    constexpr int RPW = ROWS / kGtcProducerWarps;   // rows per warp per chunk (lane = column)
-    constexpr int BATCH = 16;                        // rows per register batch
-    constexpr int NBATCH = RPW / BATCH;              // batches per chunk
+    constexpr int RPW = ROWS / kGtcProducerWarps;   // rows per warp per chunk (lane = column): one register batch
     const bool do_norm = a.minmax != nullptr;
+    const int64_t stride = (int64_t)kGtcProducerWarps * a.ld;     // between this thread's consecutive rows
+    // row r = warp + i*16 of a slab lives at r*128 + ((chunk16 ^ (r & 7)) << 4): r & 7 == warp & 7 for every i
+    const uint32_t sw_off = (uint32_t)(warp * 128 + (((lane >> 2) ^ (warp & 7)) << 4) + ((lane & 3) << 2));
     int64_t g = g0;                                  // next chunk to produce
     for (int sg = 0; sg < nsegs; ++sg) {
       const int64_t b = b_first + sg;
       const int64_t gend = (g1 < (b + 1) * a.nchunk) ? g1 : (b + 1) * a.nchunk;
-      const float* Sb = a.S + b * ROWS * a.ld;
       float mn = 0.f, den = 1.f;
       if (do_norm) {
         mn = ordered_to_float(a.minmax[2 * b]);
         den = ordered_to_float(a.minmax[2 * b + 1]) - mn;
       }
       const float inv = 1.0f / den;
-      // batch t of this segment = (chunk g + t / NBATCH, rows warp + (t % NBATCH * BATCH + i) * 8)
-      const int64_t nbt = (gend - g) * NBATCH;
-      auto load_batch = [&](float (&v)[BATCH], int64_t t) {
-        const int64_t k = ((g + t / NBATCH) - b * a.nchunk) * kGtcChunk + lane;
-        const bool kok = k < a.cols;
-        const float* src = Sb + k + (int64_t)(warp + (int)(t % NBATCH) * BATCH * kGtcProducerWarps) * a.ld;
+      int c = (int)(g - b * a.nchunk);               // chunk inside the matrix
+      const int cend = (int)(gend - b * a.nchunk);
+      int ci = (int)(g - g0);                        // chunk inside this CTA: ring position
+      const float* p = a.S + (b * ROWS + warp) * a.ld + (int64_t)c * kGtcChunk + lane;
+      int kcol = c * kGtcChunk + lane;
+      const int ncols = (int)a.cols;
+
+      auto load_chunk = [&](float (&v)[RPW]) {
+        const bool kok = kcol < ncols;
+        const float* q = p;
 #pragma unroll
-        for (int i = 0; i < BATCH; ++i) v[i] = kok ? __ldg(src + (int64_t)i * kGtcProducerWarps * a.ld) : 0.f;
+        for (int i = 0; i < RPW; ++i, q += stride) v[i] = kok ? __ldg(q) : 0.f;
+        p += kGtcChunk;
+        kcol += kGtcChunk;
       };
-      auto store_batch = [&](const float (&v)[BATCH], int64_t t) {
-        const int64_t ci = (g + t / NBATCH) - g0;    // chunk index within this CTA: ring position
-        const int h = (int)(t % NBATCH);
-        const int stage = (int)(ci % kGtcStages);
+      auto store_chunk = [&](const float (&v)[RPW], bool kok) {
+        const int stage = ci % kGtcStages;
         const uint32_t use = (uint32_t)(ci / kGtcStages);
-        if (h == 0 && use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);
-        unsigned char* slab = slabs + stage * SLAB;
-        const bool kok = ((g + t / NBATCH) - b * a.nchunk) * kGtcChunk + lane < a.cols;
+        if (use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);
+        unsigned char* dst = slabs + stage * SLAB + sw_off;
 #pragma unroll
-        for (int i = 0; i < BATCH; ++i) {
-          const int r = warp + (h * BATCH + i) * kGtcProducerWarps;
+        for (int i = 0; i < RPW; ++i) {
           float x = v[i];
           if (do_norm) x = kok ? div_by(x - mn, den, inv) : 0.f;
-          *reinterpret_cast<float*>(slab + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2)) = round_tf32(x);
+          *reinterpret_cast<float*>(dst + i * (kGtcProducerWarps * 128)) = round_tf32(x);
         }
-        if (h == NBATCH - 1) {
-          fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
-          mbar_arrive(smem_u32(&s_full[stage]));
-        }
+        fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(smem_u32(&s_full[stage]));
+        ++ci;
       };
-      // software pipeline: the next batch's loads are in flight while this one is converted and stored
-      float va[BATCH], vb[BATCH];
-      load_batch(va, 0);
-      for (int64_t t = 0; t < nbt; t += 2) {
-        if (t + 1 < nbt) load_batch(vb, t + 1);
-        store_batch(va, t);
-        if (t + 1 < nbt) {
-          if (t + 2 < nbt) load_batch(va, t + 2);
-          store_batch(vb, t + 1);
+      // software pipeline: the next chunk's loads are in flight while this one is converted and stored
+      float va[RPW], vb[RPW];
+      load_chunk(va);
+      for (; c < cend; c += 2) {
+        const bool ok0 = c * kGtcChunk + lane < ncols, ok1 = (c + 1) * kGtcChunk + lane < ncols;
+        if (c + 1 < cend) load_chunk(vb);
+        store_chunk(va, ok0);
+        if (c + 1 < cend) {
+          if (c + 2 < cend) load_chunk(va);
+          store_chunk(vb, ok1);
         }
       }
       g = gend;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
       float* part = part0 + (size_t)sg * 128 * PW;
       const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
       const int row = q * 32 + lane;          // TMEM lane == accumulator row
-      constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the two warps of a quarter
+      constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the warps of a quarter
       for (int cg = warp >> 2; cg < NCG; cg += kGtcProducerWarps / 4) {
         const int c = cg * 32;
         uint32_t v[32];
