@@ -1,0 +1,82 @@
+"""world-size-2 tests of the sharded paths on CPU (gloo): shot sharding has no collective; the channel-block
+CSD has one all-gather.  The kernels run through the CPU-emulation build (tests/emu); on the GPU box the same
+host code runs over NCCL (bench.py --gpus N, tests/test_gpu_parity.py for the single-GPU legs)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, emu_path, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import spec_oracle as oc
+        from spectrogram_enhancement_b200 import _ffi, api, parallel
+        rt = api.Runtime(_ffi.Library(emu_path), "cpu")
+        C, n = 4, 3000
+        x = np.stack([oc.synth_ece(2, c, n=n, fs=1.6e6) for c in range(C)])
+        lo, hi = parallel.channel_block(rank, world, C)
+        f, P = parallel.csd_allpairs_sharded(x[lo:hi], fs=1.6e6, nperseg=128, noverlap=64, runtime=rt)
+        np.save(os.path.join(outdir, f"P{rank}.npy"), P)
+        # shot sharding: every rank runs the pipeline on its own shots, no communication
+        sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=32, noverlap=16)
+        got = {}
+        for i, (S, D) in parallel.pipeline_sharded(lambda i: np.stack([oc.synth_ece(i, c, n=2000) for c in range(2)]), 5,
+                                                   sp, runtime=rt):
+            got[i] = D
+        np.savez(os.path.join(outdir, f"D{rank}.npz"), **{str(k): v for k, v in got.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shot_range_partitions():
+    from spectrogram_enhancement_b200 import parallel
+    for world in (1, 2, 3, 8):
+        for n in (0, 1, 7, 1000):
+            rs = [parallel.shot_range(r, world, n) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.channel_block(0, 3, 40)
+
+
+def test_world2_csd_and_shot_sharding(tmp_path, emu_rt):
+    from oracle import spec_oracle as oc
+    from spectrogram_enhancement_b200 import build
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), build.EMU_LIB, str(tmp_path)), nprocs=world, join=True)
+    C, n = 4, 3000
+    x = np.stack([oc.synth_ece(2, c, n=n, fs=1.6e6) for c in range(C)])
+    _, Pr = oc.csd_allpairs(x.astype(np.float64), fs=1.6e6, nperseg=128, noverlap=64)
+    P = np.concatenate([np.load(tmp_path / f"P{r}.npy") for r in range(world)])
+    np.testing.assert_allclose(P, Pr, rtol=1e-4, atol=1e-6 * np.abs(Pr).max())
+    # sharded == unsharded (single process, same emulated kernels): bit-identical
+    from spectrogram_enhancement_b200 import api
+    _, P1 = api.csd_allpairs(x, fs=1.6e6, nperseg=128, noverlap=64, runtime=emu_rt)
+    assert np.array_equal(P, P1)
+    d0, d1 = np.load(tmp_path / "D0.npz"), np.load(tmp_path / "D1.npz")
+    assert sorted(d0.files) == ["0", "1", "2"] and sorted(d1.files) == ["3", "4"]
+    sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=32, noverlap=16)
+    for i in range(5):
+        xs = np.stack([oc.synth_ece(i, c, n=2000) for c in range(2)])
+        _, D = api.pipeline(xs, sp, runtime=emu_rt)
+        assert np.array_equal((d0 if i < 3 else d1)[str(i)], D)
