@@ -155,7 +155,9 @@ int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float
 /* ---- the whole path for one batch of channels (bench / production entry) -------------------- */
 /* specgr -> denoiseSignal(default: drop the leading component) -> clip, for x[B][ldx]:
  * S[B][nfreq-1][ldt] (normalised spectrogram) and D[B][nfreq-1][ldt] (denoised, clipped if clip != 0).
- * Optional tiles (NULL to skip): float32 [B*ntiles][nfreq-1][tile_w] cut from D. */
+ * Optional tiles (NULL to skip): float32 [B*ntiles][nfreq-1][tile_w] cut from D.
+ * info[B][4] (optional) = {1, nfreq-1, -1, status}; status 1 = the leading pair of that channel is (nearly) degenerate
+ * and its power iteration hit the cap -- re-run that channel through specgpu_svd_denoise(mode = 1). */
 int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t B, int64_t n, int64_t ldx,
                      float* S, float* D, int64_t ldt, int32_t clip, float* tiles, int32_t tile_w, int32_t ntiles,
                      int32_t* info, void* stream);

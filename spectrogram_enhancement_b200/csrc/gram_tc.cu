@@ -303,30 +303,26 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 }
 
 // G[b] = sum of the (CTA, segment) partials that cover matrix b, in CTA order; G10 mirrored from G01.
+// One thread per partial element (pr, pc): reads are contiguous along pc, the mirrored block is the only
+// scattered write (1/4 of a 256 KB matrix).
 __global__ void gram_reduce_kernel(const float* partial, int rows, int64_t nchunk, int64_t per, float* G) {
   const int PW = gram_tc_partial_width(rows);
   const int64_t b = blockIdx.y;
-  const int64_t i0 = (b * nchunk) / per, i1 = ((b + 1) * nchunk - 1) / per;
+  const int i0 = (int)((b * nchunk) / per), i1 = (int)(((b + 1) * nchunk - 1) / per);
   float* Gb = G + b * (int64_t)rows * rows;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * rows; i += gridDim.x * blockDim.x) {
-    const int r = i / rows, c = i % rows;
-    int pr, pc;
-    if (r < 128) {
-      pr = r;
-      pc = c;                       // D1 = [G00 | G01]
-    } else if (c >= 128) {
-      pr = r - 128;
-      pc = rows + (c - 128);        // D2 = G11
-    } else {
-      pr = c;
-      pc = r;                       // G10 = G01^T
-    }
-    float s = 0.f;
-    for (int64_t cta = i0; cta <= i1; ++cta) {
-      const int64_t sg = b - (cta * per) / nchunk;      // which of the CTA's segments is matrix b
-      s += partial[((size_t)(cta * 2 + sg) * 128 + pr) * PW + pc];
-    }
-    Gb[i] = s;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 128 * PW) return;
+  const int pr = e / PW, pc = e - pr * PW;
+  float s = 0.f;
+  for (int cta = i0; cta <= i1; ++cta) {
+    const int sg = (int)(b - ((int64_t)cta * per) / nchunk);      // which of the CTA's segments is matrix b
+    s += partial[((size_t)(cta * 2 + sg) * 128) * PW + e];
+  }
+  if (pc < rows) {
+    Gb[pr * rows + pc] = s;                                   // D1 = [G00 | G01]
+    if (pc >= 128) Gb[pc * rows + pr] = s;                    // G10 = G01^T
+  } else {
+    Gb[(128 + pr) * rows + 128 + (pc - rows)] = s;            // D2 = G11
   }
 }
 
@@ -375,8 +371,8 @@ int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_
   }
   int e = (int)cudaGetLastError();
   if (e) return e;
-  SPECGPU_LAUNCH(gram_reduce_kernel, dim3((unsigned)ceil_div(rows * rows, 256 * 4), (unsigned)B), 256, 0, stream,
-                 (const float*)partial_ws, (int)rows, g.nchunk, g.per, G);
+  SPECGPU_LAUNCH(gram_reduce_kernel, dim3((unsigned)ceil_div(128 * gram_tc_partial_width((int)rows), 256), (unsigned)B), 256,
+                 0, stream, (const float*)partial_ws, (int)rows, g.nchunk, g.per, G);
   return (int)cudaGetLastError();
 }
 

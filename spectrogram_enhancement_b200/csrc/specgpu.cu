@@ -542,9 +542,12 @@ SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
 // `raw_mm` != nullptr (pipeline only): S holds the un-normalised log image and raw_mm its per-matrix
 // (min, max); the normalisation is then fused into the Gram producer and the rank-1 projection, which
 // also writes the normalised image back over S.
+// `fallback`: after the power iteration also enqueue the full solver for matrices whose iteration hit its cap
+// (a degenerate leading pair).  The pipeline leaves it out (two launches on the critical path for a case in which the
+// reference's own answer is ill-conditioned) and reports info[3] = 1 instead.
 int svd_run(specgpu_ctx* ctx, void* ws_base, float* S, const unsigned* raw_mm, int64_t B, int64_t rows, int64_t cols,
-            int64_t ld, int kind, int start, int stop, int clip, bool power_ok, void* out, int out_f64, int64_t ldo,
-            float* s_out, int32_t* info, cudaStream_t st) {
+            int64_t ld, int kind, int start, int stop, int clip, bool power_ok, bool fallback, void* out, int out_f64,
+            int64_t ldo, float* s_out, int32_t* info, cudaStream_t st) {
   void* stream = (void*)st;
   const bool tc = power_ok && gram_tc_supported(rows);   // TF32 Gram only feeds the leading-pair route
   const bool full = true;                                // Jacobi scratch is always carved (fallback for power)
@@ -561,13 +564,15 @@ int svd_run(specgpu_ctx* ctx, void* ws_base, float* S, const unsigned* raw_mm, i
   if (power_ok) {
     CHECK_LAUNCH(ctx, launch_eig_power(w.G, B, (int)rows, w.U, w.lam, w.plan, st), "eig_power", 1);
     // matrices whose iteration hit its cap are redone by the full solver (it skips the others)
-    CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+    if (fallback)
+      CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
   } else {
     CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, B, (int)rows, 0, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
   }
   const double beta = (double)std::min(rows, cols) / (double)std::max(rows, cols);
-  CHECK_LAUNCH(ctx, launch_svd_plan(w.lam, B, (int)rows, kind, start, stop, (float)omega_of(beta), w.plan, s_out, st),
-               "svd_plan", 1);
+  if (!power_ok)   // the power kernel writes the (fixed) default plan itself
+    CHECK_LAUNCH(ctx, launch_svd_plan(w.lam, B, (int)rows, kind, start, stop, (float)omega_of(beta), w.plan, s_out, st),
+                 "svd_plan", 1);
   if (power_ok && !out_f64) {
     // power_ok implies the range [1, rows): only the leading component is removed
     CHECK_LAUNCH(ctx, launch_svd_rank1(S, B, (int)rows, cols, ld, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st),
@@ -604,7 +609,7 @@ int specgpu_svd_denoise(specgpu_ctx* ctx, const float* S, int64_t B, int64_t row
   const bool power_ok = (mode == 0) && !use_optimal && start == 1 && stop >= rows && s_out == nullptr && rows <= 256;
   if ((rc = ensure_ws(ctx, svd_ws_bytes(B, rows, power_ok && gram_tc_supported(rows), true)))) return rc;
   return svd_run(ctx, ctx->ws, const_cast<float*>(S), nullptr, B, rows, cols, ld, use_optimal ? 1 : 0, start, stop, clip,
-                 power_ok, out, 0, ldo, s_out, info, (cudaStream_t)stream);
+                 power_ok, true, out, 0, ldo, s_out, info, (cudaStream_t)stream);
 }
 
 int specgpu_compute_signal(specgpu_ctx* ctx, const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, double* out,
@@ -614,8 +619,8 @@ int specgpu_compute_signal(specgpu_ctx* ctx, const float* S, int64_t B, int64_t 
   if (B * rows * cols == 0) return SPECGPU_OK;
   cudaSetDevice(ctx->device);
   if ((rc = ensure_ws(ctx, svd_ws_bytes(B, rows, false, true)))) return rc;
-  return svd_run(ctx, ctx->ws, const_cast<float*>(S), nullptr, B, rows, cols, ld, 2, 0, 0, 0, false, out, 1, ldo, s_out,
-                 info, (cudaStream_t)stream);
+  return svd_run(ctx, ctx->ws, const_cast<float*>(S), nullptr, B, rows, cols, ld, 2, 0, 0, 0, false, false, out, 1, ldo,
+                 s_out, info, (cudaStream_t)stream);
 }
 
 // ---- tiles -----------------------------------------------------------------------------------------
@@ -726,7 +731,8 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
   StftArgs a = make_args(plan, x, n, ldx, 0, nseg, (float)plan->scale, S, ldt, mm);
   CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, B, st), "stft_kernel", 1);
   // S holds the raw log image until the rank-1 projection normalises it in place (see svd_run)
-  if ((rc = svd_run(ctx, svd_ws, S, mm, B, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, D, 0, ldt, nullptr, info, st)))
+  if ((rc = svd_run(ctx, svd_ws, S, mm, B, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, false, D, 0, ldt, nullptr, info,
+                    st)))
     return rc;
   if (tiles && ntiles > 0) CHECK_LAUNCH(ctx, launch_patch(D, B, rows, ldt, tile_w, ntiles, tiles, 0, st), "patch", 1);
   return SPECGPU_OK;

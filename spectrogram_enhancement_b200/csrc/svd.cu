@@ -101,7 +101,7 @@ int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int6
 
 // ======================================================================================================
 // Leading eigenpair by power iteration: one CTA per matrix, G held in registers (n <= 256) so that an
-// iteration costs one pass over shared memory only.  Writes U[:,0], lam[0] and status (plan[3]).
+// iteration costs one pass over shared memory only.  Writes U[:,0], lam[0] and plan = {1, n, -1, status}.
 // ======================================================================================================
 constexpr int kPowThreads = 1024;
 constexpr int kPowMaxIter = 200;
@@ -114,18 +114,27 @@ __global__ void __launch_bounds__(kPowThreads) eig_power_kernel(const float* G, 
   const int tid = threadIdx.x, lane = tid & 31;
   const int row = tid >> 2, q = tid & 3;  // 4 threads per row; thread q holds columns q*4 + 16*i + {0..3}
   float4 g[16];
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(Gb) & 15) == 0) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = q * 4 + 16 * i;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < n) {
-      const float* p = Gb + (int64_t)row * n + c;
-      if (c + 0 < n) v.x = p[0];
-      if (c + 1 < n) v.y = p[1];
-      if (c + 2 < n) v.z = p[2];
-      if (c + 3 < n) v.w = p[3];
+    for (int i = 0; i < 16; ++i) {
+      const int c = q * 4 + 16 * i;
+      g[i] = (row < n && c < n) ? __ldg(reinterpret_cast<const float4*>(Gb + (int64_t)row * n + c))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    g[i] = v;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = q * 4 + 16 * i;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < n) {
+        const float* p = Gb + (int64_t)row * n + c;
+        if (c + 0 < n) v.x = p[0];
+        if (c + 1 < n) v.y = p[1];
+        if (c + 2 < n) v.z = p[2];
+        if (c + 3 < n) v.w = p[3];
+      }
+      g[i] = v;
+    }
   }
   if (tid < 256) sx[tid] = (tid < n) ? rsqrtf((float)n) : 0.f;
   __syncthreads();
@@ -173,6 +182,10 @@ __global__ void __launch_bounds__(kPowThreads) eig_power_kernel(const float* G, 
   if (tid < n) U[b * (int64_t)n * n + (int64_t)tid * n] = sx[tid];
   if (tid == 0) {
     lam[b * n] = lambda;
+    // the leading-pair route always serves the default range [1, n): plan = {start, stop, num_sing, status}
+    plan[b * 4 + 0] = 1;
+    plan[b * 4 + 1] = n;
+    plan[b * 4 + 2] = -1;
     plan[b * 4 + 3] = status;
   }
 }
@@ -591,16 +604,18 @@ __global__ void __launch_bounds__(kRecThreads) svd_project_kernel(const float* S
 // The default denoiseSignal range (start = 1, stop = len(s)) removes only the leading component:
 //   D = S - u0 (u0^T S).
 // This streaming kernel fuses it with the min-max normalisation of the log image and the clip, so the
-// pipeline reads the log image once and writes S and D once.  A CTA owns a [rows x 32] column tile in
-// shared memory; warp w reduces rows w, w+8, ... for the 32 coefficients, then updates the same rows.
+// pipeline reads the log image once and writes S and D once.  A CTA owns a [rows x 32] column tile held in
+// registers; warp w reduces rows w, w+16, ... for the 32 coefficients, then updates the same rows.
 // ------------------------------------------------------------------------------------------------------
-template <int RPW>
-__global__ void __launch_bounds__(kRecThreads) svd_rank1_kernel(const float* L, int rows, int64_t cols, int64_t ld,
-                                                                const unsigned* minmax, const float* U, int clip,
-                                                                float* S, float* D, int64_t ldo) {
+constexpr int kR1Warps = 16, kR1Threads = kR1Warps * 32;
+
+template <int RPW>   // rows per thread = ceil(rows / 16)
+__global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L, int rows, int64_t cols, int64_t ld,
+                                                                  const unsigned* minmax, const float* U, int clip,
+                                                                  float* S, float* D, int64_t ldo) {
   SPECGPU_DYN_SMEM(smem);
   float* s_u = reinterpret_cast<float*>(smem);          // [rows]
-  float* s_w = s_u + rows;                              // [8][32] partial coefficients
+  float* s_w = s_u + rows;                              // [16][32] partial coefficients
   const int64_t b = blockIdx.y;
   const int64_t c0 = (int64_t)blockIdx.x * kRecCols;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -612,13 +627,13 @@ __global__ void __launch_bounds__(kRecThreads) svd_rank1_kernel(const float* L, 
     den = ordered_to_float(minmax[2 * b + 1]) - mn;
   }
   const float inv = 1.0f / den;
-  for (int r = tid; r < rows; r += kRecThreads) s_u[r] = U[b * (int64_t)rows * rows + (int64_t)r * rows];
-  // this thread's rows are warp, warp+8, ...: nr of them are inside the matrix (warp-uniform)
-  const int nr = col_ok ? ((rows - warp + 7) >> 3) : 0;
+  for (int r = tid; r < rows; r += kR1Threads) s_u[r] = U[b * (int64_t)rows * rows + (int64_t)r * rows];
+  // this thread's rows are warp, warp+16, ...: nr of them are inside the matrix (warp-uniform)
+  const int nr = col_ok ? ((rows - warp + kR1Warps - 1) / kR1Warps) : 0;
   float x[RPW];
   {
     const float* p = L + (b * rows + warp) * ld + c0 + lane;
-    const int64_t step = 8 * ld;
+    const int64_t step = kR1Warps * ld;
 #pragma unroll
     for (int i = 0; i < RPW; ++i, p += step) x[i] = (i < nr) ? __ldg(p) : 0.f;
   }
@@ -627,12 +642,12 @@ __global__ void __launch_bounds__(kRecThreads) svd_rank1_kernel(const float* L, 
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
     if (do_norm) x[i] = (i < nr) ? div_by(x[i] - mn, den, inv) : 0.f;
-    if (i < nr) w = fmaf(s_u[warp + 8 * i], x[i], w);
+    if (i < nr) w = fmaf(s_u[warp + kR1Warps * i], x[i], w);
   }
   s_w[warp * 32 + lane] = w;
   if (S != nullptr && (do_norm || S != L)) {
     float* p = S + (b * rows + warp) * ldo + c0 + lane;
-    const int64_t step = 8 * ldo;
+    const int64_t step = kR1Warps * ldo;
 #pragma unroll
     for (int i = 0; i < RPW; ++i, p += step)
       if (i < nr) *p = x[i];
@@ -640,14 +655,14 @@ __global__ void __launch_bounds__(kRecThreads) svd_rank1_kernel(const float* L, 
   __syncthreads();
   w = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) w += s_w[k * 32 + lane];
+  for (int k = 0; k < kR1Warps; ++k) w += s_w[k * 32 + lane];
   {
     float* p = D + (b * rows + warp) * ldo + c0 + lane;
-    const int64_t step = 8 * ldo;
+    const int64_t step = kR1Warps * ldo;
 #pragma unroll
     for (int i = 0; i < RPW; ++i, p += step) {
       if (i < nr) {
-        float v = fmaf(-s_u[warp + 8 * i], w, x[i]);
+        float v = fmaf(-s_u[warp + kR1Warps * i], w, x[i]);
         if (clip) v = (v < 0.f) ? 0.f : v;   // NaN stays NaN, like hacked[hacked < 0] = 0
         *p = v;
       }
@@ -658,11 +673,11 @@ __global__ void __launch_bounds__(kRecThreads) svd_rank1_kernel(const float* L, 
 int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const unsigned* minmax, const float* U,
                      int clip, float* S, float* D, int64_t ldo, cudaStream_t stream) {
   if (B == 0 || rows == 0 || cols == 0) return 0;
-  const size_t smem = ((size_t)rows + 8 * 32) * sizeof(float);
+  const size_t smem = ((size_t)rows + kR1Warps * 32) * sizeof(float);
   const dim3 grid((unsigned)ceil_div(cols, kRecCols), (unsigned)B);
-  if (rows <= 64) SPECGPU_LAUNCH(svd_rank1_kernel<8>, grid, kRecThreads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
-  else if (rows <= 128) SPECGPU_LAUNCH(svd_rank1_kernel<16>, grid, kRecThreads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
-  else if (rows <= 256) SPECGPU_LAUNCH(svd_rank1_kernel<32>, grid, kRecThreads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  if (rows <= 64) SPECGPU_LAUNCH(svd_rank1_kernel<4>, grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  else if (rows <= 128) SPECGPU_LAUNCH(svd_rank1_kernel<8>, grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  else if (rows <= 256) SPECGPU_LAUNCH(svd_rank1_kernel<16>, grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
   else return -1;
   return (int)cudaGetLastError();
 }
