@@ -117,32 +117,42 @@ struct FftPass {
   }
 };
 
+// Barrier among the threads that share one FFT line.  A group of G <= 32 threads lives inside one warp (G divides
+// 32 and groups are warp-aligned), so a warp barrier is enough and the other warps of the CTA keep running;
+// larger groups span warps and need the CTA barrier.
+template <int G>
+__device__ __forceinline__ void fft_group_sync() {
+  if constexpr (G <= 32) __syncwarp();
+  else __syncthreads();
+}
+
 // Full transform.  On entry v holds the first-pass inputs of thread tg (element r = z[tg + r*G]);
-// on exit line[fft_pad(k)] = Z[k], k < M, and every thread of the CTA has passed a barrier.
-// All threads of the CTA must call this together (it uses __syncthreads()).
+// on exit line[fft_pad(k)] = Z[k], k < M, and every thread of the group has passed a group barrier.
+// All threads of the CTA must call this together (groups of more than 32 threads use __syncthreads()).
 template <int LOG2M>
 __device__ __forceinline__ void fft_group(float2 (&v)[fft_radix_at(LOG2M, 0)], float2* line, const float2* twM, int tg) {
   constexpr int M = 1 << LOG2M;
   constexpr int R0 = fft_radix_at(LOG2M, 0);
   constexpr int R1 = fft_radix_at(LOG2M, 1);
   constexpr int R2 = fft_radix_at(LOG2M, 2);
+  constexpr int G = M / R0;
   // pass 0: a single radix-R0 butterfly straight from registers
   FftPass<M, R0, R0, 1>::butterflies(v);
   FftPass<M, R0, R0, 1>::store(v, line, tg);
-  __syncthreads();
+  fft_group_sync<G>();
   if constexpr (R1 > 1) {
     FftPass<M, R0, R1, R0>::load(v, line, twM, tg);
     FftPass<M, R0, R1, R0>::butterflies(v);
-    __syncthreads();
+    fft_group_sync<G>();
     FftPass<M, R0, R1, R0>::store(v, line, tg);
-    __syncthreads();
+    fft_group_sync<G>();
   }
   if constexpr (R2 > 1) {
     FftPass<M, R0, R2, R0 * R1>::load(v, line, twM, tg);
     FftPass<M, R0, R2, R0 * R1>::butterflies(v);
-    __syncthreads();
+    fft_group_sync<G>();
     FftPass<M, R0, R2, R0 * R1>::store(v, line, tg);
-    __syncthreads();
+    fft_group_sync<G>();
   }
 }
 

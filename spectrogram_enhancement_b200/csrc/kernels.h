@@ -23,6 +23,7 @@ struct StftArgs {
   void* out;
   int64_t ld_out;
   unsigned* minmax;      // [B][2] ordered-uint min / max (STFT_MODE_LOGPSD)
+  int64_t tiles_per_signal, ntiles;   // filled by the launcher (persistent tile loop)
 };
 
 // stft.cu

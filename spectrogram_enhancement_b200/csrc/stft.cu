@@ -107,9 +107,6 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
   const int tid = threadIdx.x;
   const int grp = tid / G;  // which in-flight segment
   const int tg = tid % G;   // thread within the segment group
-  const int64_t b = blockIdx.y;
-  const int64_t seg0 = (int64_t)blockIdx.x * TT;
-  const float* xb = a.x + b * a.ldx;
 
   for (int i = tid; i < N; i += kStftThreads) s_win[i] = a.window[i];
   for (int i = tid; i < M; i += kStftThreads) s_twm[i] = a.twM[i];
@@ -117,6 +114,11 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
   __syncthreads();
 
   float2* line = s_line + grp * C::LINE;
+  // persistent CTAs: the tables above are loaded once, then the CTA walks tiles (signal b, TT segments)
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+  const int64_t b = tile / a.tiles_per_signal;
+  const int64_t seg0 = (tile - b * a.tiles_per_signal) * TT;
+  const float* xb = a.x + b * a.ldx;
   float vmin = INFINITY, vmax = -INFINITY;
 
   for (int round = 0; round < TT / NG; ++round) {
@@ -214,10 +216,11 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
         if (km != k) s_tile[km * PITCH + tl] = pm;
       }
     }
-    __syncthreads();  // line is reused by the next round
+    fft_group_sync<G>();  // line is reused by the next round
   }
 
-  if (MODE == STFT_MODE_SPECTRA) return;
+  if (MODE == STFT_MODE_SPECTRA) continue;
+  __syncthreads();   // the tile is complete
 
   // ---- write the tile: rows = frequency, runs of up to TT consecutive segments ----
   const int64_t ncol = (a.nseg - seg0 < TT) ? (a.nseg - seg0) : TT;
@@ -237,7 +240,6 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
   if (MODE == STFT_MODE_LOGPSD) {
     vmin = warp_min(vmin);
     vmax = warp_max(vmax);
-    __syncthreads();
     if (lane == 0) {
       s_red[2 * warp] = vmin;
       s_red[2 * warp + 1] = vmax;
@@ -252,6 +254,8 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
       atomicMax(a.minmax + 2 * b + 1, float_to_ordered(vmax));
     }
   }
+  __syncthreads();   // tile and reduction scratch are reused by the next tile
+  }  // tile loop
 }
 
 // minmax[b] = {0xffffffff, 0}
@@ -280,6 +284,16 @@ __global__ void lognorm_kernel(float* S, int64_t rows, int64_t cols, int64_t ld,
     row[c] = div_by(row[c] - mn, den, inv);
 }
 
+static int stft_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    n = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
+  }
+  return n;
+}
+
 template <int LOG2N, int MODE>
 static int launch_stft_t(const StftArgs& a, int64_t B, cudaStream_t stream) {
   using C = StftCfg<LOG2N>;
@@ -292,7 +306,14 @@ static int launch_stft_t(const StftArgs& a, int64_t B, cudaStream_t stream) {
   }
   const int64_t tiles = ceil_div(a.nseg, TT);
   if (tiles == 0 || B == 0) return 0;
-  SPECGPU_LAUNCH(kern, dim3((unsigned)tiles, (unsigned)B), kStftThreads, L.total, stream, a);
+  StftArgs args = a;
+  args.tiles_per_signal = tiles;
+  args.ntiles = tiles * B;
+  // persistent grid: as many CTAs as can be resident (the kernel is smem/register limited to 1-3 per SM)
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStftThreads, L.total) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int64_t grid = std::min<int64_t>(args.ntiles, (int64_t)per_sm * stft_num_sms());
+  SPECGPU_LAUNCH(kern, (unsigned)grid, kStftThreads, L.total, stream, args);
   return (int)cudaGetLastError();
 }
 

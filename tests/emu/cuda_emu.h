@@ -347,4 +347,5 @@ static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) 
   return cudaSuccess;
 }
 template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 2; return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
