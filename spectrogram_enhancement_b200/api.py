@@ -31,7 +31,7 @@ from . import _ffi
 __all__ = [
     "Runtime", "default_runtime", "DEFAULT_SPEC_PARAMS", "spectrogram", "stft", "csd", "csd_allpairs",
     "spectrogram_batch", "specgr_array", "specgr", "norm", "rescale", "quantfilt", "quantfilt_mask", "omega",
-    "computeSignal", "denoiseSignal", "clip", "patch", "unpatch", "reshape", "pipeline", "ae_co2",
+    "computeSignal", "denoiseSignal", "clip", "patch", "unpatch", "reshape", "pipeline", "HostPipeline", "ae_co2",
 ]
 
 # spec_denoising/pipeline_data.py:77-84
@@ -577,6 +577,68 @@ def pipeline(x, spec_params=DEFAULT_SPEC_PARAMS, clip=True, tiles=False, tile=12
     if return_info:
         res.append(info.cpu().numpy())
     return tuple(res)
+
+
+class HostPipeline:
+    """The whole path for shots that live in HOST memory: x[C, N] (pinned) -> D[C, rows, T] (pinned), optionally S.
+
+    The channels of a shot are cut into `groups`; group g runs on CUDA stream g % streams as
+    H2D(x_g) -> specgpu_pipeline -> D2H(D_g), so the uploads of one group overlap the kernels and the downloads of
+    the others (PCIe is full duplex).  Every stream owns a libspecgpu context (its own workspace) and its own
+    device staging buffers; nothing is allocated after construction."""
+
+    def __init__(self, spec_params=DEFAULT_SPEC_PARAMS, channels=40, samples=1_000_000, groups=8, streams=3, clip=True,
+                 want_S=False, device=None, lib=None):
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("libspecgpu needs a CUDA device (sm_100a); there is no CPU fallback")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.clip, self.want_S = clip, want_S
+        groups = max(1, min(groups, channels))
+        streams = max(1, min(streams, groups))
+        bounds = np.linspace(0, channels, groups + 1).astype(int)
+        self.ranges = [(int(bounds[i]), int(bounds[i + 1])) for i in range(groups) if bounds[i + 1] > bounds[i]]
+        gmax = max(b - a for a, b in self.ranges)
+        self.rts = [Runtime(lib=lib, device=self.device) for _ in range(streams)]
+        self.plans = [rt.plan_from_params(spec_params) for rt in self.rts]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(streams)]
+        rt0 = self.rts[0]
+        self.T = int(rt0.lib.plan_num_segments(self.plans[0], samples))
+        self.rows = int(rt0.lib.plan_num_freqs(self.plans[0])) - 1
+        self.xd = [rt0.empty((gmax, samples)) for _ in range(streams)]
+        self.Sd = [rt0.empty((gmax, self.rows, self.T)) for _ in range(streams)]
+        self.Dd = [rt0.empty((gmax, self.rows, self.T)) for _ in range(streams)]
+        self.channels, self.samples = channels, samples
+        for i, rt in enumerate(self.rts):      # grow the workspaces now (growing synchronises the device)
+            with torch.cuda.stream(self.streams[i]):
+                rt.pipeline_dev(self.plans[i], self.xd[i].zero_(), self.Sd[i], self.Dd[i], clip=clip)
+        torch.cuda.synchronize(self.device)
+
+    def launch_count(self):
+        return sum(rt.launch_count() for rt in self.rts)
+
+    def run(self, x_host, D_host, S_host=None):
+        """x_host [C, N] float32 (pinned for real overlap), D_host [C, rows, T] float32 pinned; returns after the
+        last download has completed."""
+        if tuple(x_host.shape) != (self.channels, self.samples):
+            raise ValueError(f"expected x[{self.channels}, {self.samples}], got {tuple(x_host.shape)}")
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+        for g, (a, b) in enumerate(self.ranges):
+            i = g % len(self.streams)
+            n = b - a
+            with torch.cuda.stream(self.streams[i]):
+                self.xd[i][:n].copy_(x_host[a:b], non_blocking=True)
+                self.rts[i].pipeline_dev(self.plans[i], self.xd[i][:n], self.Sd[i][:n], self.Dd[i][:n], clip=self.clip)
+                D_host[a:b].copy_(self.Dd[i][:n], non_blocking=True)
+                if S_host is not None:
+                    S_host[a:b].copy_(self.Sd[i][:n], non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+        cur.synchronize()
+        return D_host
 
 
 # ================================================================================================
