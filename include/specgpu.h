@@ -149,6 +149,12 @@ int specgpu_csd_spectra(specgpu_ctx* ctx, const specgpu_plan* plan, const float*
                         int64_t ldx, float* X, int64_t ldf, void* stream);
 int specgpu_csd_pairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg,
                       int64_t ldf, int64_t i0, int64_t ni, float* P, void* stream);
+/* One block of `nseg` consecutive segments of an average over `nseg_total`: P (+)= sum_t conj(X_i) X_j * scale /
+ * nseg_total.  Lets a channel-sharded caller exchange and consume the spectra block by block (the all-gather of
+ * block n+1 overlaps the pair products of block n); accumulate = 0 on the first block. */
+int specgpu_csd_pairs_block(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg,
+                            int64_t nseg_total, int64_t ldf, int64_t i0, int64_t ni, int32_t accumulate, float* P,
+                            void* stream);
 int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n,
                          int64_t ldx, float* P, void* stream);
 

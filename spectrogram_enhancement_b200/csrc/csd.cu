@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kCsdThreads) csd_pairs_kernel(const float2* X,
   }
 }
 
-__global__ void csd_reduce_kernel(const float2* partial, int nchunk, int64_t count, int nfreq, float scale, float2* P) {
+__global__ void csd_reduce_kernel(const float2* partial, int nchunk, int64_t count, int nfreq, float scale, int accumulate,
+                                  float2* P) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     float2 s = make_float2(0.f, 0.f);
     for (int c = 0; c < nchunk; ++c) {
@@ -77,7 +78,13 @@ __global__ void csd_reduce_kernel(const float2* partial, int nchunk, int64_t cou
     }
     const int f = (int)(i % nfreq);
     const float sc = (f == 0 || f == nfreq - 1) ? scale : 2.0f * scale;
-    P[i] = make_float2(s.x * sc, s.y * sc);
+    float2 r = make_float2(s.x * sc, s.y * sc);
+    if (accumulate) {            // a later block of segments of the same average (channel-sharded, chunked exchange)
+      const float2 p = P[i];
+      r.x += p.x;
+      r.y += p.y;
+    }
+    P[i] = r;
   }
 }
 
@@ -107,8 +114,8 @@ static int launch_pairs_t(const float2* X, int C, int64_t nseg, int64_t ldf, int
   return (int)cudaGetLastError();
 }
 
-int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t ldf, int nfreq, int64_t i0, int64_t ni, float scale,
-                     float* partial_ws, float* P, cudaStream_t stream) {
+int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t nseg_total, int64_t ldf, int nfreq, int64_t i0,
+                     int64_t ni, float scale, int accumulate, float* partial_ws, float* P, cudaStream_t stream) {
   if (C == 0 || ni == 0 || nfreq == 0) return 0;
   if (C > 64) return -1;
   const int nchunk = csd_num_chunks(nseg, ni, nfreq);
@@ -123,7 +130,7 @@ int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t ldf, int n
   if (e) return e;
   const int64_t count = ni * C * nfreq;
   SPECGPU_LAUNCH(csd_reduce_kernel, (unsigned)std::min<int64_t>(ceil_div(count, 256), 148 * 8), 256, 0, stream,
-                 (const float2*)part, nchunk, count, nfreq, scale / (float)nseg, reinterpret_cast<float2*>(P));
+                 (const float2*)part, nchunk, count, nfreq, scale / (float)nseg_total, accumulate, reinterpret_cast<float2*>(P));
   return (int)cudaGetLastError();
 }
 

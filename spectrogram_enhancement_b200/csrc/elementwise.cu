@@ -100,29 +100,34 @@ __global__ void norm_apply_kernel(const float* src, int64_t rows, int64_t cols, 
 }
 
 // ---- VAE tiles ---------------------------------------------------------------------------------------
-// out[(i*ntiles + x)][r][c] = src[i][r][x*tile_w + c]
+// out[(i*ntiles + x)][r][c] = src[i][r][x*tile_w + c].  One CTA per (image i, row r): the row is read once,
+// contiguously, and leaves as ntiles runs of tile_w contiguous elements.
 template <class OutT>
 __global__ void patch_kernel(const float* src, int64_t rows, int64_t ld, int tile_w, int ntiles, OutT* out) {
-  const int64_t i = blockIdx.z;
-  const int64_t r = blockIdx.y;
+  const int64_t i = blockIdx.y;
+  const int64_t r = blockIdx.x;
   const float* row = src + (i * rows + r) * ld;
-  const int64_t width = (int64_t)tile_w * ntiles;
-  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < width; col += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t x = col / tile_w, c = col - x * tile_w;
-    out[((i * ntiles + x) * rows + r) * tile_w + c] = (OutT)row[col];
+  OutT* obase = out + (i * ntiles * rows + r) * tile_w;           // tile x of this row starts at obase + x*rows*tile_w
+  const int64_t tstride = rows * tile_w;
+  const unsigned width = (unsigned)tile_w * (unsigned)ntiles;
+  for (unsigned col = threadIdx.x; col < width; col += blockDim.x) {
+    const unsigned x = col / (unsigned)tile_w, c = col - x * (unsigned)tile_w;
+    obase[x * tstride + c] = (OutT)__ldg(row + col);
   }
 }
 
 // dst[i][r][x*tile_w + c] = tiles[(i*ntiles + x)][r][c]
 template <class InT, class OutT>
 __global__ void unpatch_kernel(const InT* tiles, int64_t rows, int tile_w, int ntiles, OutT* dst, int64_t ld) {
-  const int64_t i = blockIdx.z;
-  const int64_t r = blockIdx.y;
+  const int64_t i = blockIdx.y;
+  const int64_t r = blockIdx.x;
   OutT* row = dst + (i * rows + r) * ld;
-  const int64_t width = (int64_t)tile_w * ntiles;
-  for (int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; col < width; col += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t x = col / tile_w, c = col - x * tile_w;
-    row[col] = (OutT)tiles[((i * ntiles + x) * rows + r) * tile_w + c];
+  const InT* ibase = tiles + (i * ntiles * rows + r) * tile_w;
+  const int64_t tstride = rows * tile_w;
+  const unsigned width = (unsigned)tile_w * (unsigned)ntiles;
+  for (unsigned col = threadIdx.x; col < width; col += blockDim.x) {
+    const unsigned x = col / (unsigned)tile_w, c = col - x * (unsigned)tile_w;
+    row[col] = (OutT)ibase[x * tstride + c];
   }
 }
 
@@ -157,7 +162,7 @@ int launch_norm(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t
 int launch_patch(const float* src, int64_t n, int64_t rows, int64_t ld, int tile_w, int ntiles, void* out, int out_f64,
                  cudaStream_t stream) {
   if (n == 0 || rows == 0 || ntiles == 0) return 0;
-  const dim3 grid((unsigned)ceil_div((int64_t)tile_w * ntiles, kEwThreads * 2), (unsigned)rows, (unsigned)n);
+  const dim3 grid((unsigned)rows, (unsigned)n);
   if (out_f64) SPECGPU_LAUNCH(patch_kernel<double>, grid, kEwThreads, 0, stream, src, rows, ld, tile_w, ntiles, (double*)out);
   else SPECGPU_LAUNCH(patch_kernel<float>, grid, kEwThreads, 0, stream, src, rows, ld, tile_w, ntiles, (float*)out);
   return (int)cudaGetLastError();
@@ -166,7 +171,7 @@ int launch_patch(const float* src, int64_t n, int64_t rows, int64_t ld, int tile
 int launch_unpatch(const void* tiles, int in_f64, int64_t n, int64_t rows, int tile_w, int ntiles, void* dst,
                    int out_f64, int64_t ld, cudaStream_t stream) {
   if (n == 0 || rows == 0 || ntiles == 0) return 0;
-  const dim3 grid((unsigned)ceil_div((int64_t)tile_w * ntiles, kEwThreads * 2), (unsigned)rows, (unsigned)n);
+  const dim3 grid((unsigned)rows, (unsigned)n);
   if (in_f64 && out_f64)
     SPECGPU_LAUNCH((unpatch_kernel<double, double>), grid, kEwThreads, 0, stream, (const double*)tiles, rows, tile_w, ntiles, (double*)dst, ld);
   else if (in_f64)

@@ -70,8 +70,8 @@ int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_
                    float* partial_ws, float* G, int num_sms, cudaStream_t stream);
 
 // csd.cu
-int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t ldf, int nfreq, int64_t i0, int64_t ni,
-                     float scale, float* partial_ws, float* P, cudaStream_t stream);
+int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t nseg_total, int64_t ldf, int nfreq, int64_t i0,
+                     int64_t ni, float scale, int accumulate, float* partial_ws, float* P, cudaStream_t stream);
 size_t csd_pairs_workspace_bytes(int64_t C, int64_t ni, int nfreq, int64_t nseg);
 
 }  // namespace specgpu

@@ -662,13 +662,14 @@ int specgpu_csd_spectra(specgpu_ctx* ctx, const specgpu_plan* plan, const float*
   return SPECGPU_OK;
 }
 
-int specgpu_csd_pairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg, int64_t ldf,
-                      int64_t i0, int64_t ni, float* P, void* stream) {
+int specgpu_csd_pairs_block(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg,
+                            int64_t nseg_total, int64_t ldf, int64_t i0, int64_t ni, int32_t accumulate, float* P,
+                            void* stream) {
   if (!ctx || !plan) return SPECGPU_ERR_INVALID_ARG;
   const int nfreq = plan->p.nperseg / 2 + 1;
-  if (C < 0 || nseg < 0 || ldf < nfreq || i0 < 0 || ni < 0 || i0 + ni > C)
-    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_pairs: bad shape C=%lld nseg=%lld ldf=%lld i0=%lld ni=%lld", (long long)C,
-                (long long)nseg, (long long)ldf, (long long)i0, (long long)ni);
+  if (C < 0 || nseg < 0 || nseg_total < nseg || ldf < nfreq || i0 < 0 || ni < 0 || i0 + ni > C)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_pairs: bad shape C=%lld nseg=%lld/%lld ldf=%lld i0=%lld ni=%lld", (long long)C,
+                (long long)nseg, (long long)nseg_total, (long long)ldf, (long long)i0, (long long)ni);
   if (C > 64) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "csd_pairs: C=%lld > 64 channels", (long long)C);
   if (C == 0 || ni == 0) return SPECGPU_OK;
   if (nseg == 0) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_pairs: no segments to average");
@@ -679,9 +680,15 @@ int specgpu_csd_pairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X
   int rc = ensure_ws(ctx, need);
   if (rc) return rc;
   float* partial = reinterpret_cast<float*>(static_cast<char*>(ctx->ws) + ctx->ws_csd_off);
-  CHECK_LAUNCH(ctx, launch_csd_pairs(X, C, nseg, ldf, nfreq, i0, ni, (float)plan->scale, partial, P, (cudaStream_t)stream),
+  CHECK_LAUNCH(ctx, launch_csd_pairs(X, C, nseg, nseg_total, ldf, nfreq, i0, ni, (float)plan->scale, accumulate ? 1 : 0, partial,
+                                     P, (cudaStream_t)stream),
                "csd_pairs", 2);
   return SPECGPU_OK;
+}
+
+int specgpu_csd_pairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg, int64_t ldf,
+                      int64_t i0, int64_t ni, float* P, void* stream) {
+  return specgpu_csd_pairs_block(ctx, plan, X, C, nseg, nseg, ldf, i0, ni, 0, P, stream);
 }
 
 int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n, int64_t ldx,

@@ -267,21 +267,21 @@ __global__ void minmax_init_kernel(unsigned* mm, int64_t B) {
   }
 }
 
-// S = (L - min) / (max - min) in place; optionally export (min, max) as floats.
+// S = (L - min) / (max - min) in place; optionally export (min, max) as floats.  One CTA per (signal, row).
 __global__ void lognorm_kernel(float* S, int64_t rows, int64_t cols, int64_t ld, const unsigned* mm, float* mm_out) {
-  const int64_t b = blockIdx.z;
+  const int64_t b = blockIdx.y;
+  const int64_t r = blockIdx.x;
   const float mn = ordered_to_float(mm[2 * b]);
   const float mx = ordered_to_float(mm[2 * b + 1]);
   const float den = mx - mn;
   const float inv = 1.0f / den;
-  if (mm_out != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+  if (mm_out != nullptr && r == 0 && threadIdx.x == 0) {
     mm_out[2 * b] = mn;
     mm_out[2 * b + 1] = mx;
   }
-  const int64_t r = blockIdx.y;
   float* row = S + (b * rows + r) * ld;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += (int64_t)gridDim.x * blockDim.x)
-    row[c] = div_by(row[c] - mn, den, inv);
+  const unsigned n = (unsigned)cols;
+  for (unsigned c = threadIdx.x; c < n; c += blockDim.x) row[c] = div_by(row[c] - mn, den, inv);
 }
 
 static int stft_num_sms() {
@@ -353,8 +353,7 @@ int launch_minmax_init(unsigned* mm, int64_t B, cudaStream_t stream) {
 int launch_lognorm(float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* mm, float* mm_out,
                    cudaStream_t stream) {
   if (B == 0 || rows == 0 || cols == 0) return 0;
-  unsigned gx = (unsigned)std::min<int64_t>(ceil_div(cols, 256), 64);
-  SPECGPU_LAUNCH(lognorm_kernel, dim3(gx, (unsigned)rows, (unsigned)B), 256, 0, stream, S, rows, cols, ld, mm, mm_out);
+  SPECGPU_LAUNCH(lognorm_kernel, dim3((unsigned)rows, (unsigned)B), 256, 0, stream, S, rows, cols, ld, mm, mm_out);
   return (int)cudaGetLastError();
 }
 

@@ -35,9 +35,12 @@ def channel_block(rank: int, world: int, n_channels: int):
 
 
 def csd_allpairs_sharded(x_local, fs=1.0, window="hann", nperseg=256, noverlap=None, detrend="constant",
-                         scaling="density", group=None, runtime=None):
+                         scaling="density", blocks=4, group=None, runtime=None):
     """Rows [rank*Cl, (rank+1)*Cl) of the all-pairs Welch CSD of the channel stack whose block `x_local[Cl, N]`
-    this rank holds.  Returns (f, P_rows[Cl, C, F]) with C = world * Cl; P_rows[i, j] = csd(x_i, x_j)."""
+    this rank holds.  Returns (f, P_rows[Cl, C, F]) with C = world * Cl; P_rows[i, j] = csd(x_i, x_j).
+
+    The segment axis is cut into `blocks`: block n's spectra are transformed and all-gathered on a side stream
+    while the pair products of block n-1 run on the caller's stream (specgpu_csd_pairs_block accumulates)."""
     rt = runtime if runtime is not None else api.default_runtime()
     if noverlap is None:
         noverlap = int(nperseg) // 2
@@ -48,20 +51,56 @@ def csd_allpairs_sharded(x_local, fs=1.0, window="hann", nperseg=256, noverlap=N
     if xd.dim() != 2:
         raise ValueError("csd_allpairs_sharded expects x_local[Cl, N]")
     Cl, n = xd.shape
+    C = world * Cl
     F = rt.lib.plan_num_freqs(plan)
     T = rt.lib.plan_num_segments(plan, n)
     if T == 0:
         raise ValueError("record shorter than nperseg")
+    hop = int(nperseg) - int(noverlap)
     ldf = (F + 1) & ~1
-    X_all = rt.empty((world * Cl, T, ldf, 2))
-    X_loc = X_all[rank * Cl:(rank + 1) * Cl]          # transform straight into this rank's slot
-    rt.check(rt.lib.csd_spectra(rt._ctx, plan, xd.data_ptr(), Cl, n, api._ld(xd), X_loc.data_ptr(), ldf, rt.stream()))
-    if world > 1:
-        dist.all_gather_into_tensor(X_all, X_loc.clone(), group=group)
-    P = rt.empty((Cl, world * Cl, F, 2))
-    rt.check(rt.lib.csd_pairs(rt._ctx, plan, X_all.data_ptr(), world * Cl, T, ldf, rank * Cl, Cl, P.data_ptr(), rt.stream()))
+    nb = max(1, min(int(blocks), T))
+    edges = [T * i // nb for i in range(nb + 1)]
+    P = rt.empty((Cl, C, F, 2))
+    cuda = rt.device.type == "cuda"
+    main = torch.cuda.current_stream(rt.device) if cuda else None
+    side = torch.cuda.Stream(device=rt.device) if cuda else None
+    if cuda:
+        side.wait_stream(main)
+    ready, bufs = [], []
+    for bi in range(nb):                      # producer: spectra of this rank's channels for block bi, then the exchange
+        t0, t1 = edges[bi], edges[bi + 1]
+        tb = t1 - t0
+        X_all = rt.empty((C, tb, ldf, 2))
+        X_loc = X_all[rank * Cl:(rank + 1) * Cl]
+        xs = xd[:, t0 * hop:(t1 - 1) * hop + int(nperseg)]      # exactly segments t0 .. t1-1
+        ctxm = torch.cuda.stream(side) if cuda else _null()
+        with ctxm:
+            rt.check(rt.lib.csd_spectra(rt._ctx, plan, xs.data_ptr(), Cl, xs.shape[1], api._ld(xd), X_loc.data_ptr(), ldf,
+                                        rt.stream()))
+            if world > 1:
+                dist.all_gather_into_tensor(X_all, X_loc.clone(), group=group)
+            if cuda:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                ready.append(ev)
+        bufs.append((X_all, tb))
+    for bi, (X_all, tb) in enumerate(bufs):   # consumer: pair products of block bi on the caller's stream
+        if cuda:
+            main.wait_event(ready[bi])
+        rt.check(rt.lib.csd_pairs_block(rt._ctx, plan, X_all.data_ptr(), C, tb, T, ldf, rank * Cl, Cl, 1 if bi else 0,
+                                        P.data_ptr(), rt.stream()))
+        if cuda:
+            X_all.record_stream(main)
     f = np.fft.rfftfreq(int(nperseg), 1.0 / fs)
     return f, rt.ret(torch.view_as_complex(P), as_torch)
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def pipeline_sharded(load_shot, n_shots, spec_params=api.DEFAULT_SPEC_PARAMS, clip=True, tiles=False, runtime=None):

@@ -69,10 +69,10 @@ def test_world2_csd_and_shot_sharding(tmp_path, emu_rt):
     _, Pr = oc.csd_allpairs(x.astype(np.float64), fs=1.6e6, nperseg=128, noverlap=64)
     P = np.concatenate([np.load(tmp_path / f"P{r}.npy") for r in range(world)])
     np.testing.assert_allclose(P, Pr, rtol=1e-4, atol=1e-6 * np.abs(Pr).max())
-    # sharded == unsharded (single process, same emulated kernels): bit-identical
+    # sharded (segment blocks exchanged and accumulated one by one) vs unsharded: same sums in another order
     from spectrogram_enhancement_b200 import api
     _, P1 = api.csd_allpairs(x, fs=1.6e6, nperseg=128, noverlap=64, runtime=emu_rt)
-    assert np.array_equal(P, P1)
+    np.testing.assert_allclose(P, P1, rtol=1e-5, atol=1e-7 * np.abs(P1).max())
     d0, d1 = np.load(tmp_path / "D0.npz"), np.load(tmp_path / "D1.npz")
     assert sorted(d0.files) == ["0", "1", "2"] and sorted(d1.files) == ["3", "4"]
     sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=32, noverlap=16)
