@@ -113,6 +113,20 @@ int specgpu_norm(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, in
 int specgpu_quantfilt(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld,
                       float thr, float* dst, float* thr_out, uint8_t* mask, void* stream);
 
+/* ---- cv2 image chain (spec_denoising/pipeline_data.py:52-72) -------------------------------------------------------- */
+/* gaussblr (:52-55): (rescale(src)*255).astype('uint8') -> cv2.GaussianBlur(ksize = (kw, kh), sigma 0; kw taps along the
+ * contiguous/time axis, kh along rows; OpenCV's CV_8U fixed-point path, BORDER_REFLECT_101) -> rescale -> float64.
+ * src is float32 (in_f64 = 0) or float64; u8_out (optional) receives the blurred uint8 image [B][rows][cols] (bit-exact). */
+int specgpu_gaussblr(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld,
+                     int32_t kw, int32_t kh, double* dst, int64_t ldo, uint8_t* u8_out, void* stream);
+/* meansub (:58-61): rescale(|src - mean over the contiguous axis of each row|), float64 in and out. */
+int specgpu_meansub(specgpu_ctx* ctx, const double* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, double* dst,
+                    int64_t ldo, void* stream);
+/* morph (:64-72): uint8-quantise -> MORPH_CLOSE rect(4,4) -> MORPH_OPEN rect(3,1) -> rescale -> float64; u8_out (optional)
+ * receives the uint8 mask before the final rescale (bit-exact). */
+int specgpu_morph(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld,
+                  double* dst, int64_t ldo, uint8_t* u8_out, void* stream);
+
 /* ---- SVD denoise (denoising_by_svd.ipynb:155-229, 280-281) --------------------------------- */
 /* out = U[:,a:b] diag(s[a:b]) Vh[a:b,:] of each S[b] (rows x cols, rows <= cols, rows <= 512), where
  *   use_optimal == 0: a = start, b = stop (pass start = 1, stop = rows for the reference defaults)

@@ -30,7 +30,8 @@ from . import _ffi
 
 __all__ = [
     "Runtime", "default_runtime", "DEFAULT_SPEC_PARAMS", "spectrogram", "stft", "csd", "csd_allpairs",
-    "spectrogram_batch", "specgr_array", "specgr", "norm", "rescale", "quantfilt", "quantfilt_mask", "omega",
+    "spectrogram_batch", "specgr_array", "specgr", "norm", "rescale", "quantfilt", "quantfilt_mask", "gaussblr", "meansub", "morph",
+    "filter_chain", "omega",
     "computeSignal", "denoiseSignal", "clip", "patch", "unpatch", "reshape", "pipeline", "HostPipeline", "ae_co2",
 ]
 
@@ -422,6 +423,73 @@ def quantfilt_mask(src, thr=0.9, runtime=None):
         raise ValueError("Quantiles must be in the range [0, 1]")
     out, thr_out, mask, as_torch = _quantfilt_impl(rt, src, thr, True)
     return rt.ret(out, as_torch), rt.ret(thr_out, as_torch), rt.ret(mask, as_torch)
+
+
+def _img_batch(rt, src):
+    """[rows, cols] or [B, rows, cols], float32 or float64 -> (device tensor [B, rows, cols], as_torch, squeeze)."""
+    as_torch = _is_torch(src)
+    a = src if as_torch else np.asarray(src)
+    f64 = (a.dtype == torch.float64) if as_torch else (a.dtype == np.float64)
+    d, _ = rt.to_device(a, torch.float64 if f64 else torch.float32)
+    if d.dim() == 2:
+        return d.unsqueeze(0), as_torch, True
+    if d.dim() == 3:
+        return d, as_torch, False
+    raise ValueError("expected a 2-D image or a [B, rows, cols] stack")
+
+
+def gaussblr(src, filt=(31, 3), return_uint8=False, runtime=None):
+    """pipeline_data.py:52-55: uint8-quantise, cv2.GaussianBlur(src, filt, 0), rescale -> float64.
+    `filt` is cv2's ksize = (width along the last axis, height along rows).  The uint8 blur is bit-exact."""
+    rt = _rt(runtime)
+    d, as_torch, squeeze = _img_batch(rt, src)
+    B, rows, cols = d.shape
+    out = torch.empty((B, rows, cols), dtype=torch.float64, device=rt.device)
+    u8 = torch.empty((B, rows, cols), dtype=torch.uint8, device=rt.device) if return_uint8 else None
+    rt.check(rt.lib.gaussblr(rt._ctx, d.data_ptr(), 1 if d.dtype == torch.float64 else 0, B, rows, cols, _ld(d), int(filt[0]),
+                             int(filt[1]), out.data_ptr(), cols, u8.data_ptr() if return_uint8 else None, rt.stream()))
+    if squeeze:
+        out, u8 = out[0], (u8[0] if return_uint8 else None)
+    return (rt.ret(out, as_torch), rt.ret(u8, as_torch)) if return_uint8 else rt.ret(out, as_torch)
+
+
+def meansub(src, runtime=None):
+    """pipeline_data.py:58-61: rescale(|src - mean over time of each frequency row|) -> float64."""
+    rt = _rt(runtime)
+    as_torch = _is_torch(src)
+    d, _ = rt.to_device(src, torch.float64)
+    squeeze = d.dim() == 2
+    if squeeze:
+        d = d.unsqueeze(0)
+    B, rows, cols = d.shape
+    out = torch.empty_like(d)
+    rt.check(rt.lib.meansub(rt._ctx, d.data_ptr(), B, rows, cols, _ld(d), out.data_ptr(), cols, rt.stream()))
+    return rt.ret(out[0] if squeeze else out, as_torch)
+
+
+def morph(src, return_uint8=False, runtime=None):
+    """pipeline_data.py:64-72: uint8-quantise, MORPH_CLOSE rect(4,4), MORPH_OPEN rect(3,1), rescale -> float64."""
+    rt = _rt(runtime)
+    d, as_torch, squeeze = _img_batch(rt, src)
+    B, rows, cols = d.shape
+    out = torch.empty((B, rows, cols), dtype=torch.float64, device=rt.device)
+    u8 = torch.empty((B, rows, cols), dtype=torch.uint8, device=rt.device) if return_uint8 else None
+    rt.check(rt.lib.morph(rt._ctx, d.data_ptr(), 1 if d.dtype == torch.float64 else 0, B, rows, cols, _ld(d), out.data_ptr(),
+                          cols, u8.data_ptr() if return_uint8 else None, rt.stream()))
+    if squeeze:
+        out, u8 = out[0], (u8[0] if return_uint8 else None)
+    return (rt.ret(out, as_torch), rt.ret(u8, as_torch)) if return_uint8 else rt.ret(out, as_torch)
+
+
+def filter_chain(Sxx, thr=0.9, filt=(31, 3), runtime=None):
+    """The denoising pipeline of pipeline_data.py:101-110 on a spectrogram (or a [B, F, T] stack), kept on the device
+    between stages: quantfilt -> gaussblr -> meansub -> morph -> meansub.  Returns `pipeline_out` (float64)."""
+    rt = _rt(runtime)
+    as_torch = _is_torch(Sxx)
+    d, _ = rt.to_device(Sxx)
+    q = quantfilt(d, thr, runtime=rt) if d.dim() == 2 else torch.stack([quantfilt(x, thr, runtime=rt) for x in d])
+    out = meansub(morph(meansub(gaussblr(q, filt, runtime=rt), runtime=rt), runtime=rt), runtime=rt)
+    return rt.ret(out, as_torch)
 
 
 # ================================================================================================

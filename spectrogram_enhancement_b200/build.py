@@ -24,7 +24,7 @@ LIB = os.path.join(PKG, "libspecgpu.so")
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_LIB = os.path.join(EMU_DIR, "libspecgpu_emu.so")
 
-SOURCES = ["specgpu.cu", "stft.cu", "elementwise.cu", "quantile.cu", "svd.cu", "gram_tc.cu", "csd.cu"]
+SOURCES = ["specgpu.cu", "stft.cu", "elementwise.cu", "quantile.cu", "svd.cu", "gram_tc.cu", "csd.cu", "imgchain.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",

@@ -69,6 +69,15 @@ size_t gram_tc_workspace_bytes(int64_t B, int64_t rows);
 int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* minmax,
                    float* partial_ws, float* G, int num_sms, cudaStream_t stream);
 
+// imgchain.cu (the cv2 chain: gaussblr / meansub / morph)
+size_t imgchain_workspace_bytes(int64_t B, int64_t rows, int64_t cols);
+int launch_gaussblr(const void* src, int in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld, const uint16_t* taps_host,
+                    int kw, int kh, void* ws, double* dst, int64_t ldo, uint8_t* u8_out, cudaStream_t st);
+int launch_meansub(const double* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* ws, double* dst, int64_t ldo,
+                   cudaStream_t st);
+int launch_morph(const void* src, int in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* ws, double* dst,
+                 int64_t ldo, uint8_t* u8_out, cudaStream_t st);
+
 // csd.cu
 int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t nseg_total, int64_t ldf, int nfreq, int64_t i0,
                      int64_t ni, float scale, int accumulate, float* partial_ws, float* P, cudaStream_t stream);

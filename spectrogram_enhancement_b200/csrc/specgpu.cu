@@ -648,6 +648,85 @@ int specgpu_unpatch(specgpu_ctx* ctx, const void* tiles, int32_t in_f64, int64_t
   return SPECGPU_OK;
 }
 
+// ---- cv2 image chain (pipeline_data.py:52-72) --------------------------------------------------------------------
+namespace {
+// OpenCV's Q8.8 Gaussian taps for CV_8U (getGaussianKernel + fixed-point error-diffusion rounding): the double kernel
+// (small_gaussian_tab for n <= 7 when sigma <= 0, else exp(-x^2 / (2 sigma^2)) normalised, sigma = 0.3((n-1)/2 - 1) + 0.8)
+// is rounded tap by tap from the outside in, carrying the rounding error; the centre tap takes what is left of 256.
+void gaussian_taps_q8(int n, double sigma, uint16_t* out) {
+  std::vector<double> k(n);
+  static const double small[4][7] = {{1.0}, {0.25, 0.5, 0.25}, {0.0625, 0.25, 0.375, 0.25, 0.0625},
+                                     {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125}};
+  if (n <= 7 && sigma <= 0) {
+    for (int i = 0; i < n; ++i) k[i] = small[n / 2][i];
+  } else {
+    const double s = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
+    double sum = 0;
+    for (int i = 0; i < n; ++i) {
+      const double x = i - (n - 1) * 0.5;
+      k[i] = std::exp(-0.5 * x * x / (s * s));
+      sum += k[i];
+    }
+    for (int i = 0; i < n; ++i) k[i] /= sum;
+  }
+  double err = 0.0;
+  long total = 0;
+  for (int i = 0; i < n / 2; ++i) {
+    const double adj = k[i] * 256.0 + err;
+    const long v = std::lrint(adj);
+    err = adj - (double)v;
+    out[i] = out[n - 1 - i] = (uint16_t)v;
+    total += 2 * v;
+  }
+  out[n / 2] = (uint16_t)(256 - total);
+}
+}  // namespace
+
+int specgpu_gaussblr(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld,
+                     int32_t kw, int32_t kh, double* dst, int64_t ldo, uint8_t* u8_out, void* stream) {
+  int rc = check_matrix_args(ctx, src, B, rows, cols, ld);
+  if (rc) return rc;
+  if (kw < 1 || kh < 1 || !(kw & 1) || !(kh & 1) || kw > 255 || kh > 255)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "ksize (%d, %d): both must be odd and in [1, 255]", kw, kh);
+  if (B * rows * cols == 0) return SPECGPU_OK;
+  if (cols > (1 << 30) || rows > 65535) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "image too large");
+  if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
+  cudaSetDevice(ctx->device);
+  if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
+  uint16_t taps[512];
+  gaussian_taps_q8(kw, 0.0, taps);
+  gaussian_taps_q8(kh, 0.0, taps + kw);
+  CHECK_LAUNCH(ctx, launch_gaussblr(src, in_f64, B, rows, cols, ld, taps, kw, kh, ctx->ws, dst, ldo, u8_out, (cudaStream_t)stream),
+               "gaussblr", 6);
+  return SPECGPU_OK;
+}
+
+int specgpu_meansub(specgpu_ctx* ctx, const double* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, double* dst,
+                    int64_t ldo, void* stream) {
+  int rc = check_matrix_args(ctx, src, B, rows, cols, ld);
+  if (rc) return rc;
+  if (B * rows * cols == 0) return SPECGPU_OK;
+  if (rows > 65535) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "image too large");
+  if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
+  cudaSetDevice(ctx->device);
+  if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
+  CHECK_LAUNCH(ctx, launch_meansub(src, B, rows, cols, ld, ctx->ws, dst, ldo, (cudaStream_t)stream), "meansub", 3);
+  return SPECGPU_OK;
+}
+
+int specgpu_morph(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld,
+                  double* dst, int64_t ldo, uint8_t* u8_out, void* stream) {
+  int rc = check_matrix_args(ctx, src, B, rows, cols, ld);
+  if (rc) return rc;
+  if (B * rows * cols == 0) return SPECGPU_OK;
+  if (cols > (1 << 30) || rows > 65535) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "image too large");
+  if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
+  cudaSetDevice(ctx->device);
+  if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
+  CHECK_LAUNCH(ctx, launch_morph(src, in_f64, B, rows, cols, ld, ctx->ws, dst, ldo, u8_out, (cudaStream_t)stream), "morph", 8);
+  return SPECGPU_OK;
+}
+
 // ---- cross-power spectrum ----------------------------------------------------------------------------
 int specgpu_csd_spectra(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n, int64_t ldx,
                         float* X, int64_t ldf, void* stream) {

@@ -268,6 +268,10 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float emu_fast_logf(float a) { return std::log(a); }

@@ -190,3 +190,25 @@ def case_pipeline(rt, sp, n, B=2, tile=None):
     # end to end against the pure oracle chain
     De = np.stack([oc.clip(oc.denoiseSignal(s)) for s in Sr])
     np.testing.assert_allclose(D, De, rtol=0, atol=5e-3 * np.abs(De).max())
+
+
+# ---- cv2 image chain ---------------------------------------------------------------------------------
+def case_filter_chain(rt, S):
+    """Stage-isolated and chained parity of gaussblr / meansub / morph: uint8 intermediates bit-exact, float64
+    outputs to 1e-12 (the row means are summed in another order than numpy's pairwise sum)."""
+    q = oc.quantfilt(S, 0.9)
+    g_ref = oc.gaussblr(q, (31, 3))
+    g, g8 = api.gaussblr(q, (31, 3), return_uint8=True, runtime=rt)
+    assert g.dtype == np.float64
+    assert np.array_equal(g8, oc.gaussian_blur_u8((oc.rescale(q) * 255).astype("uint8"), (31, 3)))
+    assert np.array_equal(g, g_ref)
+    m_ref = oc.meansub(g_ref)
+    m = api.meansub(g_ref, runtime=rt)
+    np.testing.assert_allclose(m, m_ref, rtol=1e-12, atol=1e-13)
+    mo_ref = oc.morph(m_ref)
+    mo, mo8 = api.morph(m_ref, return_uint8=True, runtime=rt)
+    assert np.array_equal(mo8, oc.morph_close_open_u8((oc.rescale(m_ref) * 255).astype("uint8")))
+    assert np.array_equal(mo, mo_ref)
+    fin = api.filter_chain(S, runtime=rt)
+    np.testing.assert_allclose(fin, oc.filter_chain(S), rtol=1e-12, atol=1e-13)
+    return g, fin

@@ -118,6 +118,25 @@ def test_patch_roundtrip(cuda_rt):
     pc.case_patch(cuda_rt, 3, 16, 70, 8, 8)
 
 
+# ---- K5: cv2 image chain --------------------------------------------------------------------------------
+def test_cv2_chain_golden(cuda_rt, golden):
+    """quantfilt -> gaussblr -> meansub -> morph -> meansub of the reference itself (pipeline_data.py:101-110)."""
+    g = golden("specgr_small.npz")
+    pc.case_filter_chain(cuda_rt, g["S_f32"])
+    assert np.array_equal(api.gaussblr(g["quant_f32"], (31, 3), runtime=cuda_rt), g["gauss"])
+    np.testing.assert_allclose(api.meansub(g["gauss"], runtime=cuda_rt), g["mean"], rtol=1e-12, atol=1e-13)
+    assert np.array_equal(api.morph(g["mean"], runtime=cuda_rt), g["morph"])
+    np.testing.assert_allclose(api.filter_chain(g["S_f32"], runtime=cuda_rt), g["final"], rtol=1e-12, atol=1e-13)
+
+
+def test_cv2_chain_full_size(cuda_rt):
+    S, _, _ = api.spectrogram_batch(oc.synth_ece(3, 1), SP, runtime=cuda_rt)       # [256, 3905]
+    pc.case_filter_chain(cuda_rt, S)
+    Sb = np.stack([S, S[::-1].copy()])
+    out = api.gaussblr(Sb, (31, 3), runtime=cuda_rt)
+    assert np.array_equal(out[1], oc.gaussblr(Sb[1], (31, 3)))
+
+
 # ---- K3: SVD denoise --------------------------------------------------------------------------------
 def test_svd_golden(cuda_rt, golden):
     """denoiseSignal / computeSignal / omega of the reference notebook on a planted-gap matrix."""

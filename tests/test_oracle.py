@@ -219,3 +219,36 @@ def test_against_reference_functions():
         np.testing.assert_allclose(oc.denoiseSignal(M, **kw), nbk["denoiseSignal"](M, **kw), atol=1e-10)
     np.testing.assert_allclose(oc.computeSignal(M), nbk["computeSignal"](M), atol=1e-10)
     assert oc.omega(0.3) == nbk["omega"](0.3) or abs(oc.omega(0.3) - nbk["omega"](0.3)) < 1e-15
+
+
+# ---- cv2 chain restatement vs OpenCV itself and vs the reference's golden outputs ----------------
+def test_cv2_chain_restatement_matches_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for n in (3, 5, 7, 9, 15, 31, 41):          # Q8.8 taps: read them off a constant-column probe image
+        img = np.zeros((9, 4 * n + 1), np.uint8)
+        img[:, 2 * n] = 255
+        taps = cv2.GaussianBlur(img, (n, 3), 0)[4, 2 * n - n // 2: 2 * n + n // 2 + 1].astype(int)
+        assert np.array_equal(taps, oc.gaussian_taps_q8(n))
+    se1 = cv2.getStructuringElement(cv2.MORPH_RECT, (4, 4))
+    se2 = cv2.getStructuringElement(cv2.MORPH_RECT, (3, 1))
+    for shape in ((256, 390), (17, 40), (5, 33), (9, 9)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        for ks in ((31, 3), (5, 5), (9, 3)):
+            if shape[1] >= ks[0]:
+                assert np.array_equal(cv2.GaussianBlur(img, ks, 0), oc.gaussian_blur_u8(img, ks))
+        m = cv2.morphologyEx(cv2.morphologyEx(img, cv2.MORPH_CLOSE, se1), cv2.MORPH_OPEN, se2)
+        assert np.array_equal(m, oc.morph_close_open_u8(img))
+
+
+def test_cv2_chain_golden(golden):
+    """quantfilt -> gaussblr -> meansub -> morph -> meansub of the reference itself (pipeline_data.py:101-110)."""
+    g = golden("specgr_small.npz")
+    gauss = oc.gaussblr(g["quant_f32"], (31, 3))
+    assert np.array_equal(gauss, g["gauss"])
+    mean = oc.meansub(gauss)
+    assert np.array_equal(mean, g["mean"])
+    mo = oc.morph(mean)
+    assert np.array_equal(mo, g["morph"])
+    assert np.array_equal(oc.meansub(mo), g["final"])
+    assert np.array_equal(oc.filter_chain(g["S_f32"]), g["final"])
