@@ -217,8 +217,10 @@ def run_ours(args):
     gen.manual_seed(1234 + rank)
     nbuf = 3   # rotate over 3 resident shots (3 x 160 MB in, 2 x 160 MB out each) so no step finds its data in L2
     xs = [synth_on_device(torch, device, rank * 1000 + i, gen) for i in range(nbuf)]
-    S = [rt.empty((N_CH, ROWS, NSEG)) for _ in range(nbuf)]
-    D = [rt.empty((N_CH, ROWS, NSEG)) for _ in range(nbuf)]
+    # image rows are pitched to a multiple of 32 floats so every row starts on a 128-byte line (the C ABI takes any ld)
+    ldt = int(os.environ.get("SPECGPU_BENCH_LDT", (NSEG + 31) // 32 * 32))
+    S = [rt.empty((N_CH, ROWS, ldt))[:, :, :NSEG] for _ in range(nbuf)]
+    D = [rt.empty((N_CH, ROWS, ldt))[:, :, :NSEG] for _ in range(nbuf)]
     info = torch.zeros((N_CH, 4), dtype=torch.int32, device=device)
 
     def step(i):
@@ -233,8 +235,8 @@ def run_ours(args):
         from oracle import spec_oracle as oc
         xc = xs[0][3].cpu().numpy()
         Sr, _, _ = oc.specgr_array(xc.astype(np.float64), SP)
-        Sg = S[0][3].cpu().numpy()
-        Dg = D[0][3].cpu().numpy()
+        Sg = S[0][3].contiguous().cpu().numpy()
+        Dg = D[0][3].contiguous().cpu().numpy()
         Dr = oc.clip(oc.denoiseSignal(Sg.astype(np.float64)))
         parity = {"spec_max_abs_err": float(np.abs(Sg - Sr).max()),
                   "denoise_max_err_rel_to_max": float(np.abs(Dg - Dr).max() / np.abs(Dr).max())}
@@ -329,7 +331,8 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "channels": N_CH, "samples_per_channel": N_SAMP, "shots_per_step_per_gpu": 1,
                    "sharding": "by shot, no data-path collective" if world > 1 else "single GPU",
-                   "l2": f"inputs larger than L2: {nbuf} resident shots rotated (160 MB in + 320 MB out per step)"},
+                   "l2": f"inputs larger than L2: {nbuf} resident shots rotated (160 MB in + 320 MB out per step)",
+                   "image_row_pitch_floats": ldt},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_CH * N_SAMP * 4,
                 "d2h_bytes_per_step": N_CH * ROWS * NSEG * 4, "steps": e2e_steps, "api": "HostPipeline(groups=8, streams=3)",
                 "gpu_launches": int(e2e_launches), "matches_device_path": e2e_ok},

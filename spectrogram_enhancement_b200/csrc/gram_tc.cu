@@ -314,8 +314,10 @@ __global__ void gram_reduce_kernel(const float* partial, int rows, int64_t nchun
   if (e >= 128 * PW) return;
   const int pr = e / PW, pc = e - pr * PW;
   float s = 0.f;
+  const int64_t bstart = b * nchunk;
   for (int cta = i0; cta <= i1; ++cta) {
-    const int sg = (int)(b - ((int64_t)cta * per) / nchunk);      // which of the CTA's segments is matrix b
+    // a CTA whose range starts before this matrix began in matrix b-1: matrix b is its second segment
+    const int sg = ((int64_t)cta * per < bstart) ? 1 : 0;
     s += partial[((size_t)(cta * 2 + sg) * 128) * PW + e];
   }
   if (pc < rows) {
