@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libspecgpu.so")
+LIB_PATH = os.environ.get("SPECGPU_LIB") or os.path.join(_PKG, "libspecgpu.so")   # SPECGPU_LIB: another build of the CUDA library
 
 OK = 0
 ERR_INVALID_ARG = -1

@@ -115,9 +115,11 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
 
   float2* line = s_line + grp * C::LINE;
   // persistent CTAs: the tables above are loaded once, then the CTA walks tiles (signal b, TT segments)
-  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-  const int64_t b = tile / a.tiles_per_signal;
-  const int64_t seg0 = (tile - b * a.tiles_per_signal) * TT;
+  const unsigned tps = (unsigned)a.tiles_per_signal;      // ntiles < 2^31 is checked by the launcher
+  for (unsigned tile = blockIdx.x; tile < (unsigned)a.ntiles; tile += gridDim.x) {
+  const unsigned b32 = tile / tps;
+  const int64_t b = b32;
+  const int64_t seg0 = (int64_t)(tile - b32 * tps) * TT;
   const float* xb = a.x + b * a.ldx;
   float vmin = INFINITY, vmax = -INFINITY;
 
@@ -173,12 +175,16 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
     // ---- M-point complex FFT of the packed segment ----
     fft_group<C::LOG2M>(v, line, s_twm, tg);
 
-    // ---- untangle: X[k] = E + W_N^k O, X[M-k] = conj(E - W_N^k O) ----
+    // ---- untangle: 2 X[k] = E + W_N^k O, 2 X[M-k] = conj(E - W_N^k O) with E = Z[k] + conj(Z[M-k]),
+    //      O = -i (Z[k] - conj(Z[M-k])); the factor 2 is folded into the output scales ----
+    const float cscale = 0.5f * a.scale;             // complex / spectra outputs
+    const float pscale1 = 0.25f * a.scale;           // |2X|^2 -> PSD, bins 0 and Nyquist
+    const float pscale2 = 0.5f * a.scale;            // one-sided doubling for every other bin
     for (int k = tg; k <= M / 2; k += G) {
       const float2 zk = line[fft_pad(k)];
       const float2 zm = line[fft_pad((M - k) & (M - 1))];
-      const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-      const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+      const float2 e = make_float2(zk.x + zm.x, zk.y - zm.y);
+      const float2 o = make_float2(zk.y + zm.y, zm.x - zk.x);
       const float2 wo = cmul(s_twn[k], o);
       const float2 xk = cadd(e, wo);
       float2 xm = csub(e, wo);
@@ -187,29 +193,24 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
       if (MODE == STFT_MODE_SPECTRA) {
         if (live) {
           float2* o2 = reinterpret_cast<float2*>(a.out) + (b * a.nseg + seg) * a.ld_out;
-          o2[k] = xk;
-          if (km != k) o2[km] = xm;
+          o2[k] = make_float2(0.5f * xk.x, 0.5f * xk.y);
+          if (km != k) o2[km] = make_float2(0.5f * xm.x, 0.5f * xm.y);
         }
       } else if (MODE == STFT_MODE_COMPLEX) {
-        s_tile2[k * PITCH + tl] = make_float2(xk.x * a.scale, xk.y * a.scale);
-        if (km != k) s_tile2[km * PITCH + tl] = make_float2(xm.x * a.scale, xm.y * a.scale);
+        s_tile2[k * PITCH + tl] = make_float2(xk.x * cscale, xk.y * cscale);
+        if (km != k) s_tile2[km * PITCH + tl] = make_float2(xm.x * cscale, xm.y * cscale);
       } else {
-        // conj(X) X scale, doubled on 1..M-1 (one-sided, even nfft)
-        float pk = (xk.x * xk.x + xk.y * xk.y) * a.scale;
-        float pm = (xm.x * xm.x + xm.y * xm.y) * a.scale;
-        if (k != 0) pk *= 2.0f;      // k in 1..M/2 (k == M/2 < M is doubled as well)
-        if (k != 0) pm *= 2.0f;      // km in M/2..M-1
+        // conj(X) X scale, doubled on 1..M-1 (one-sided, even nfft): only k == 0 (bins 0 and M) is not doubled
+        const float ps = (k != 0) ? pscale2 : pscale1;
+        float pk = (xk.x * xk.x + xk.y * xk.y) * ps;
+        float pm = (xm.x * xm.x + xm.y * xm.y) * ps;
         if (MODE == STFT_MODE_LOGPSD) {
           // lg2.approx * ln2: absolute error ~1e-6 on values in [-26, 10], i.e. < 1e-7 of the normalised image
           pk = __logf(pk + a.eps);
           pm = __logf(pm + a.eps);
           if (live) {
-            vmin = fminf(vmin, pk);
-            vmax = fmaxf(vmax, pk);
-            if (km != k) {
-              vmin = fminf(vmin, pm);
-              vmax = fmaxf(vmax, pm);
-            }
+            vmin = fminf(vmin, fminf(pk, pm));       // k == km (k = M/2) gives pk == pm: harmless
+            vmax = fmaxf(vmax, fmaxf(pk, pm));
           }
         }
         s_tile[k * PITCH + tl] = pk;
@@ -309,6 +310,7 @@ static int launch_stft_t(const StftArgs& a, int64_t B, cudaStream_t stream) {
   StftArgs args = a;
   args.tiles_per_signal = tiles;
   args.ntiles = tiles * B;
+  if (args.ntiles >= ((int64_t)1 << 31)) return (int)cudaErrorInvalidValue;
   // persistent grid: as many CTAs as can be resident (the kernel is smem/register limited to 1-3 per SM)
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStftThreads, L.total) != cudaSuccess || per_sm < 1) per_sm = 1;
