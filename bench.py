@@ -276,24 +276,28 @@ def run_ours(args):
     for i in range(2):
         xh[i].copy_(xs[i])
     dh = torch.empty((N_CH, ROWS, NSEG), dtype=torch.float32).pin_memory()
-    hp = api.HostPipeline(SP, channels=N_CH, samples=N_SAMP, groups=8, streams=3, clip=True, device=device)
     e2e_steps = max(2, min(args.steps, 10))
-    for i in range(2):
-        hp.run(xh[i % 2], dh)
-    e2e_ok = bool(torch.allclose(dh[3], D[1][3].cpu(), rtol=0, atol=2e-5))   # dh now holds shot xs[1], as D[1] does
-    barrier()
-    l0e = hp.launch_count()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        hp.run(xh[i % 2], dh)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    if args.no_e2e:
+        e2e_steps = 0
+    hp = api.HostPipeline(SP, channels=N_CH, samples=N_SAMP, groups=8, streams=3, clip=True, device=device) if e2e_steps else None
+    e2e_ok, e2e_launches, e2e_value = None, 0, None
+    if hp is not None:
+        for i in range(2):
+            hp.run(xh[i % 2], dh)
+        e2e_ok = bool(torch.allclose(dh[3], D[1][3].cpu(), rtol=0, atol=2e-5))   # dh now holds shot xs[1], as D[1] does
+        barrier()
+        l0e = hp.launch_count()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            hp.run(xh[i % 2], dh)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_launches = hp.launch_count() - l0e
+        te = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = world * e2e_steps * N_CH * N_SAMP / float(te.item())
     clk.__exit__()
-    e2e_launches = hp.launch_count() - l0e
-    te = torch.tensor([e2e_s], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * N_CH * N_SAMP / float(te.item())
 
     if rank != 0:
         if world > 1:
@@ -358,6 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-to-host leg (e2e is then null)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

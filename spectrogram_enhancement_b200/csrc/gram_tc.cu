@@ -303,28 +303,38 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 }
 
 // G[b] = sum of the (CTA, segment) partials that cover matrix b, in CTA order; G10 mirrored from G01.
-// One thread per partial element (pr, pc): reads are contiguous along pc, the mirrored block is the only
-// scattered write (1/4 of a 256 KB matrix).
+// One thread per four consecutive partial elements (pr, pc..pc+3): float4 reads along pc, float4 writes of the
+// direct blocks; the mirrored block is the only scattered write (1/4 of a 256 KB matrix).
 __global__ void gram_reduce_kernel(const float* partial, int rows, int64_t nchunk, int64_t per, float* G) {
   const int PW = gram_tc_partial_width(rows);
+  const int PW4 = PW / 4;
   const int64_t b = blockIdx.y;
   const int i0 = (int)((b * nchunk) / per), i1 = (int)(((b + 1) * nchunk - 1) / per);
   float* Gb = G + b * (int64_t)rows * rows;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 128 * PW) return;
-  const int pr = e / PW, pc = e - pr * PW;
-  float s = 0.f;
+  const int e4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e4 >= 128 * PW4) return;
+  const int pr = e4 / PW4, pc = (e4 - pr * PW4) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t bstart = b * nchunk;
   for (int cta = i0; cta <= i1; ++cta) {
     // a CTA whose range starts before this matrix began in matrix b-1: matrix b is its second segment
     const int sg = ((int64_t)cta * per < bstart) ? 1 : 0;
-    s += partial[((size_t)(cta * 2 + sg) * 128) * PW + e];
+    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)(cta * 2 + sg) * 128 + pr) * PW + pc));
+    s.x += v.x;
+    s.y += v.y;
+    s.z += v.z;
+    s.w += v.w;
   }
   if (pc < rows) {
-    Gb[pr * rows + pc] = s;                                   // D1 = [G00 | G01]
-    if (pc >= 128) Gb[pc * rows + pr] = s;                    // G10 = G01^T
+    *reinterpret_cast<float4*>(Gb + pr * rows + pc) = s;          // D1 = [G00 | G01]
+    if (pc >= 128) {                                              // G10 = G01^T
+      Gb[(pc + 0) * rows + pr] = s.x;
+      Gb[(pc + 1) * rows + pr] = s.y;
+      Gb[(pc + 2) * rows + pr] = s.z;
+      Gb[(pc + 3) * rows + pr] = s.w;
+    }
   } else {
-    Gb[(128 + pr) * rows + 128 + (pc - rows)] = s;            // D2 = G11
+    *reinterpret_cast<float4*>(Gb + (128 + pr) * rows + 128 + (pc - rows)) = s;   // D2 = G11
   }
 }
 
@@ -373,7 +383,7 @@ int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_
   }
   int e = (int)cudaGetLastError();
   if (e) return e;
-  SPECGPU_LAUNCH(gram_reduce_kernel, dim3((unsigned)ceil_div(128 * gram_tc_partial_width((int)rows), 256), (unsigned)B), 256,
+  SPECGPU_LAUNCH(gram_reduce_kernel, dim3((unsigned)ceil_div(32 * gram_tc_partial_width((int)rows), 256), (unsigned)B), 256,
                  0, stream, (const float*)partial_ws, (int)rows, g.nchunk, g.per, G);
   return (int)cudaGetLastError();
 }

@@ -65,7 +65,7 @@ if benchlog != "-":
     bench = json.loads([l for l in open(benchlog).read().strip().split("\n") if l.startswith("{")][-1])
 with open(os.path.join(out, f"{tag}_summary.md"), "w") as f:
     f.write(f"# {tag}: ncu launch list + full capture summary\n\n{note}\n\n")
-    f.write("Command: `python bench.py --steps 3 --warmup 3 --no-cpu-baseline` on one B200 (gpurun); launch list from\n"
+    f.write("Command: `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e` on one B200 (gpurun); launch list from\n"
             "`ncu --metrics gpu__time_duration.sum --clock-control none`, per-kernel metrics from `ncu --set full "
             "--clock-control none --import-source on`.\nncu launch times are cold-cache and serialised: compare SHARES.\n\n")
     f.write("## Launch list (our kernels; setup kernels of torch's synthetic-input generation excluded: "
@@ -75,7 +75,7 @@ with open(os.path.join(out, f"{tag}_summary.md"), "w") as f:
     if bench is not None:
       f.write("\n## bench.py (same build, not under ncu)\n\n")
       f.write(f"* {bench['ms_per_step']:.4f} ms per 40-channel shot = {bench['value'] / 1e9:.1f} G samples/s; e2e "
-            f"{bench['e2e']['value'] / 1e9:.2f} G samples/s\n")
+            f"{(bench['e2e']['value'] or 0) / 1e9:.2f} G samples/s\n")
       ks = bench.get("kernels", {})
       ktot = sum(v["ms_per_launch"] for v in ks.values()) or 1.0
       f.write("\n| kernel group (CUDA events in bench.py) | ms / launch | share |\n|---|---|---|\n")
