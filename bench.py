@@ -168,6 +168,9 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+NCU_TRAFFIC = {   # dram__bytes_read.sum + dram__bytes_write.sum per 40-channel launch, profiles/r01b_ncu_raw.csv
+    "stft_kernel": 275.3e6, "gram_tc": 168.5e6, "svd_rank1": 426.9e6,
+}
 ALGO_BYTES = {   # algorithmic HBM bytes of one launch over B channels (DESIGN.md "kernels")
     "stft_kernel": lambda B: B * (4 * N_SAMP + 4 * ROWS * NSEG),          # read x, write log-PSD (Nyquist dropped)
     "lognorm": lambda B: B * 8 * ROWS * NSEG,                              # read + write the image
@@ -246,7 +249,6 @@ def run_ours(args):
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
-    rt.profile(True)
     l0 = rt.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clk = ClockSampler(local)
@@ -259,6 +261,11 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = rt.launch_count() - l0
+    # per-kernel durations: the same K steps once more with the library's per-launch CUDA events switched on
+    # (the event pairs cost ~8 % of a step, so the timed region above runs without them)
+    rt.profile(True)
+    for i in range(args.steps):
+        step(i)
     prof = rt.profile_read()
     rt.profile(False)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
@@ -318,7 +325,8 @@ def run_ours(args):
         dur_s = prof[dom][0] / max(prof[dom][1], 1) * 1e-3
         ach = ALGO_BYTES[dom](N_CH) / dur_s / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC.get(dom), "traffic_source": "ncu --set full capture in profiles/r01b_ncu_raw.csv",
+                "peak_source": peak_src, "timing": "CUDA events around each launch, second pass of the same K steps",
                 "algorithmic_bytes_per_launch": ALGO_BYTES[dom](N_CH), "ms_per_launch": dur_s * 1e3}
     pipeline_gbs = 12.0 * N_CH * N_SAMP * args.steps / (ms * 1e-3) / 1e9      # 12 B/sample
 
