@@ -48,10 +48,11 @@ int launch_quantfilt(const float* src, int64_t B, int64_t rows, int64_t cols, in
                      float* thr_out, uint8_t* mask, cudaStream_t stream);
 
 // svd.cu
-int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* G, cudaStream_t stream);
+int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* G, int g_f64, cudaStream_t stream);
 int launch_eig_power(const float* G, int64_t B, int n, float* U, float* lam, int32_t* plan, cudaStream_t stream);
 size_t jacobi_workspace_bytes(int64_t B, int n);
-int launch_eig_jacobi(const float* G, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan, void* ws,
+bool eig_jacobi_f64_supported(int n);
+int launch_eig_jacobi(const void* G, int g_f64, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan, void* ws,
                       cudaStream_t stream);
 // kind 0: explicit (start, stop); 1: use_optimal; 2: computeSignal.  plan[b] = {a, e, num_sing, status}
 int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int stop, float omega_f, int32_t* plan,

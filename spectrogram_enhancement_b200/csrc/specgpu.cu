@@ -520,14 +520,14 @@ struct SvdWs {
 };
 
 size_t svd_ws_bytes(int64_t B, int64_t rows, bool tc, bool full) {
-  return carve_size({(size_t)B * rows * rows * 4, (size_t)B * rows * rows * 4, (size_t)B * rows * 4, (size_t)B * 16,
+  return carve_size({(size_t)B * rows * rows * 8, (size_t)B * rows * rows * 4, (size_t)B * rows * 4, (size_t)B * 16,
                      tc ? gram_tc_workspace_bytes(B, rows) : 0, full ? jacobi_workspace_bytes(B, (int)rows) : 0});
 }
 
 SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
   Carver cv(ws);
   SvdWs w{};
-  w.G = cv.take<float>(B * rows * rows);
+  w.G = reinterpret_cast<float*>(cv.take<double>(B * rows * rows));   // float or double Gram (see svd_run)
   w.U = cv.take<float>(B * rows * rows);
   w.lam = cv.take<float>(B * rows);
   w.plan = cv.take<int32_t>(B * 4);
@@ -550,6 +550,8 @@ int svd_run(specgpu_ctx* ctx, void* ws_base, float* S, const unsigned* raw_mm, i
             int64_t ldo, float* s_out, int32_t* info, cudaStream_t st) {
   void* stream = (void*)st;
   const bool tc = power_ok && gram_tc_supported(rows);   // TF32 Gram only feeds the leading-pair route
+  // full decomposition: Gram and Jacobi in double (float would square the condition number into the noise floor)
+  const int g_f64 = (!power_ok && eig_jacobi_f64_supported((int)rows)) ? 1 : 0;
   const bool full = true;                                // Jacobi scratch is always carved (fallback for power)
   SvdWs w = svd_carve(ws_base, B, rows, tc, full);
   if (tc) {
@@ -559,15 +561,15 @@ int svd_run(specgpu_ctx* ctx, void* ws_base, float* S, const unsigned* raw_mm, i
       CHECK_LAUNCH(ctx, launch_lognorm(S, B, rows, cols, ld, raw_mm, nullptr, st), "lognorm", 1);
       raw_mm = nullptr;
     }
-    CHECK_LAUNCH(ctx, launch_gram_simt(S, B, rows, cols, ld, w.G, st), "gram_simt", 1);
+    CHECK_LAUNCH(ctx, launch_gram_simt(S, B, rows, cols, ld, w.G, g_f64, st), "gram_simt", 1);
   }
   if (power_ok) {
     CHECK_LAUNCH(ctx, launch_eig_power(w.G, B, (int)rows, w.U, w.lam, w.plan, st), "eig_power", 1);
     // matrices whose iteration hit its cap are redone by the full solver (it skips the others)
     if (fallback)
-      CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+      CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 0, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
   } else {
-    CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, B, (int)rows, 0, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+    CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, g_f64, B, (int)rows, 0, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
   }
   const double beta = (double)std::min(rows, cols) / (double)std::max(rows, cols);
   if (!power_ok)   // the power kernel writes the (fixed) default plan itself

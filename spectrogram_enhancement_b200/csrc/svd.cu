@@ -29,8 +29,9 @@ namespace specgpu {
 // ======================================================================================================
 constexpr int kGramTile = 64, kGramKB = 32, kGramThreads = 256;
 
+template <class T>
 __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S, int rows, int64_t cols, int64_t ld,
-                                                                 int ksplit, float* G) {
+                                                                 int ksplit, T* G) {
   __shared__ float sa[kGramTile][kGramKB + 1];
   __shared__ float sb[kGramTile][kGramKB + 1];
   const int64_t b = blockIdx.z;
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
   const float* Sb = S + b * rows * ld;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4 x 4 outputs each
-  float acc[4][4] = {};
+  T acc[4][4] = {};
   for (int64_t k = k0; k < k1; k += kGramKB) {
     for (int i = tid; i < kGramTile * kGramKB; i += kGramThreads) {
       const int r = i / kGramKB, c = i % kGramKB;
@@ -59,11 +60,11 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
     __syncthreads();
 #pragma unroll 8
     for (int c = 0; c < kGramKB; ++c) {
-      float av[4], bv[4];
+      T av[4], bv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        av[i] = sa[ty + 16 * i][c];
-        bv[i] = sb[tx + 16 * i][c];
+        av[i] = (T)sa[ty + 16 * i][c];
+        bv[i] = (T)sb[tx + 16 * i][c];
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
     }
     __syncthreads();
   }
-  float* Gb = G + b * (int64_t)rows * rows;
+  T* Gb = G + b * (int64_t)rows * rows;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -87,15 +88,18 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
     }
 }
 
-int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* G, cudaStream_t stream) {
+// g_f64: accumulate and store G in double (the full-decomposition route; squaring the condition number in fp32 would
+// blur cuts between close singular values), else float.
+int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* G, int g_f64, cudaStream_t stream) {
   if (B == 0 || rows == 0) return 0;
-  cudaError_t e = cudaMemsetAsync(G, 0, (size_t)B * rows * rows * sizeof(float), stream);
+  cudaError_t e = cudaMemsetAsync(G, 0, (size_t)B * rows * rows * (g_f64 ? sizeof(double) : sizeof(float)), stream);
   if (e != cudaSuccess) return (int)e;
   const int nt = (int)ceil_div(rows, kGramTile);
   const int npairs = nt * (nt + 1) / 2;
   int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(cols, 512), 16));
-  SPECGPU_LAUNCH(gram_simt_kernel, dim3((unsigned)npairs, (unsigned)ksplit, (unsigned)B), kGramThreads, 0, stream, S,
-                 (int)rows, cols, ld, ksplit, G);
+  const dim3 grid((unsigned)npairs, (unsigned)ksplit, (unsigned)B);
+  if (g_f64) SPECGPU_LAUNCH(gram_simt_kernel<double>, grid, kGramThreads, 0, stream, S, (int)rows, cols, ld, ksplit, (double*)G);
+  else SPECGPU_LAUNCH(gram_simt_kernel<float>, grid, kGramThreads, 0, stream, S, (int)rows, cols, ld, ksplit, (float*)G);
   return (int)cudaGetLastError();
 }
 
@@ -209,23 +213,32 @@ int launch_eig_power(const float* G, int64_t B, int n, float* U, float* lam, int
 // ======================================================================================================
 constexpr int kJacThreads = 1024;
 constexpr int kJacMaxSweeps = 40;
-constexpr float kJacTol = 1e-6f;
+template <class T>
+struct JacTol {
+  static constexpr float value = 1e-6f;
+};
+template <>
+struct JacTol<double> {
+  static constexpr double value = 1e-14;
+};
 
+template <class T>
 struct JacobiArgs {
-  const float* G;     // [B][n][n]
+  const T* G;         // [B][n][n]
   int n, n_pad, cb, cl;
   const int32_t* plan;  // skip matrices whose plan[b][3] == 0 when skip_converged
   int skip_converged;
-  float* Ucols;       // [B][n_pad][n_pad] : row k = (unsorted) eigenvector k (contiguous)
-  float* lam_raw;     // [B][n_pad]
+  T* Ucols;           // [B][n_pad][n_pad] : row k = (unsorted) eigenvector k (contiguous)
+  T* lam_raw;         // [B][n_pad]
   int32_t* status;    // [B] sweeps used (negative: hit the cap)
 };
 
 // Orthogonalise columns x, y (length n, one warp).  Returns true if a rotation was applied.
-__device__ __forceinline__ bool jacobi_pair(float* x, float* y, int n, int lane) {
-  float a = 0.f, bq = 0.f, g = 0.f;
+template <class T>
+__device__ __forceinline__ bool jacobi_pair(T* x, T* y, int n, int lane) {
+  T a = 0, bq = 0, g = 0;
   for (int i = lane; i < n; i += 32) {
-    const float xv = x[i], yv = y[i];
+    const T xv = x[i], yv = y[i];
     a += xv * xv;
     bq += yv * yv;
     g += xv * yv;
@@ -233,19 +246,22 @@ __device__ __forceinline__ bool jacobi_pair(float* x, float* y, int n, int lane)
   a = warp_sum(a);
   bq = warp_sum(bq);
   g = warp_sum(g);
-  if (!(fabsf(g) > kJacTol * sqrtf(a * bq))) return false;
-  const float zeta = (bq - a) / (2.0f * g);
-  const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
-  const float c = rsqrtf(1.0f + t * t), s = c * t;
+  const T ag = g < 0 ? -g : g;
+  if (!(ag > (T)JacTol<T>::value * (T)sqrt((double)(a * bq)))) return false;
+  const T zeta = (bq - a) / ((T)2 * g);
+  const T az = zeta < 0 ? -zeta : zeta;
+  const T t = (zeta < 0 ? (T)-1 : (T)1) / (az + (T)sqrt((double)((T)1 + zeta * zeta)));
+  const T c = (T)1 / (T)sqrt((double)((T)1 + t * t)), s = c * t;
   for (int i = lane; i < n; i += 32) {
-    const float xv = x[i], yv = y[i];
+    const T xv = x[i], yv = y[i];
     x[i] = c * xv - s * yv;
     y[i] = s * xv + c * yv;
   }
   return true;
 }
 
-__global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
+template <class T>
+__global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs<T> a) {
   SPECGPU_DYN_SMEM(smem);
   const int n = a.n, np = a.n_pad, cb = a.cb, CL = a.cl;
   const int rank = SPECGPU_CLUSTER_RANK();
@@ -253,7 +269,7 @@ __global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kJacThreads / 32;
   const size_t slot_floats = (size_t)cb * np;
-  float* slots = reinterpret_cast<float*>(smem);
+  T* slots = reinterpret_cast<T*>(smem);
   int* s_flag = reinterpret_cast<int*>(slots + 3 * slot_floats);  // [CL] per-rank "rotated" flags + [1] local
   // Slot roles.  Rank 0 never re-labels (top 0, bot 1, spare 2); every rank >= 1 applies the same
   // permutation after each ring step, so all of them share (p_top, p_bot, p_spare), which every rank
@@ -263,13 +279,13 @@ __global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
 
   if (!skip) {
     // block ids: rank r starts with blocks 2r (top) and 2r+1 (bot); column j of G == row j (symmetric)
-    const float* Gb = a.G + b * (int64_t)n * n;
+    const T* Gb = a.G + b * (int64_t)n * n;
     for (int s = 0; s < 2; ++s) {
-      float* dst = slots + (size_t)s * slot_floats;   // initially top = slot 0, bot = slot 1 everywhere
+      T* dst = slots + (size_t)s * slot_floats;   // initially top = slot 0, bot = slot 1 everywhere
       const int col0 = (2 * rank + s) * cb;
       for (int i = tid; i < cb * np; i += kJacThreads) {
         const int c = col0 + i / np, r = i % np;
-        dst[i] = (c < n && r < n) ? Gb[(int64_t)c * n + r] : 0.f;
+        dst[i] = (c < n && r < n) ? Gb[(int64_t)c * n + r] : (T)0;
       }
     }
   }
@@ -283,8 +299,8 @@ __global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
       bool rotated = false;
       for (int br = 0; br < 2 * CL - 1; ++br) {
         const int top = (rank == 0) ? 0 : p_top, bot = (rank == 0) ? 1 : p_bot;
-        float* T = slots + top * slot_floats;
-        float* Bt = slots + bot * slot_floats;
+        T* Tp = slots + top * slot_floats;
+        T* Bt = slots + bot * slot_floats;
         if (br == 0) {
           // full tournament over the m = 2*cb local columns (player m-1 fixed)
           const int m = 2 * cb;
@@ -298,8 +314,8 @@ __global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
                 p = (r + i) % (m - 1);
                 q = (r - i + (m - 1)) % (m - 1);
               }
-              float* x = (p < cb) ? T + (size_t)p * np : Bt + (size_t)(p - cb) * np;
-              float* y = (q < cb) ? T + (size_t)q * np : Bt + (size_t)(q - cb) * np;
+              T* x = (p < cb) ? Tp + (size_t)p * np : Bt + (size_t)(p - cb) * np;
+              T* y = (q < cb) ? Tp + (size_t)q * np : Bt + (size_t)(q - cb) * np;
               rotated |= jacobi_pair(x, y, np, lane);
             }
             __syncthreads();
@@ -307,8 +323,8 @@ __global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
         } else {
           for (int r = 0; r < cb; ++r) {
             for (int i = warp; i < cb; i += NW) {
-              float* x = T + (size_t)i * np;
-              float* y = Bt + (size_t)((i + r) % cb) * np;
+              T* x = Tp + (size_t)i * np;
+              T* y = Bt + (size_t)((i + r) % cb) * np;
               rotated |= jacobi_pair(x, y, np, lane);
             }
             __syncthreads();
@@ -318,17 +334,17 @@ __global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
           // ---- move the blocks one step round the ring (see header comment) ----
           // phase 1: rank 0 sends bot, ranks 1..CL-2 send top, to the right neighbour's spare slot
           if (rank < CL - 1) {
-            const float* srcp = slots + (rank == 0 ? bot : top) * slot_floats;
-            float* dstp = SPECGPU_MAP_SHARED(slots + p_spare * slot_floats, rank + 1);
+            const T* srcp = slots + (rank == 0 ? bot : top) * slot_floats;
+            T* dstp = SPECGPU_MAP_SHARED(slots + p_spare * slot_floats, rank + 1);
             for (size_t i = tid; i < slot_floats; i += kJacThreads) dstp[i] = srcp[i];
           }
           SPECGPU_CLUSTER_SYNC();
           // phase 2: ranks 1..CL-1 send their old bot to the left neighbour's freed slot
           //          (rank 0: its old bot slot; rank i-1 >= 1: its old top slot)
           if (rank >= 1) {
-            const float* srcp = slots + bot * slot_floats;
+            const T* srcp = slots + bot * slot_floats;
             const int left_free = (rank - 1 == 0) ? 1 : p_top;
-            float* dstp = SPECGPU_MAP_SHARED(slots + left_free * slot_floats, rank - 1);
+            T* dstp = SPECGPU_MAP_SHARED(slots + left_free * slot_floats, rank - 1);
             for (size_t i = tid; i < slot_floats; i += kJacThreads) dstp[i] = srcp[i];
           }
           SPECGPU_CLUSTER_SYNC();
@@ -362,17 +378,17 @@ __global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
     // ---- write lambda_k = |a_k|, u_k = a_k / |a_k| for the 2*cb local columns ----
     for (int s = 0; s < 2; ++s) {
       const int slot = (rank == 0) ? s : (s == 0 ? p_top : p_bot);
-      const float* src = slots + slot * slot_floats;
+      const T* src = slots + slot * slot_floats;
       for (int i = warp; i < cb; i += NW) {
-        const float* x = src + (size_t)i * np;
-        float nn = 0.f;
+        const T* x = src + (size_t)i * np;
+        T nn = 0;
         for (int r = lane; r < np; r += 32) nn += x[r] * x[r];
         nn = warp_sum(nn);
-        const float nrm = sqrtf(nn);
-        const float inv = nrm > 0.f ? 1.0f / nrm : 0.f;
+        const T nrm = (T)sqrt((double)nn);
+        const T inv = nrm > 0 ? (T)1 / nrm : (T)0;
         // any slot order is fine: eig_sort_kernel orders by lambda
         const int64_t k = (int64_t)(2 * rank + s) * cb + i;
-        float* u = a.Ucols + (b * np + k) * np;
+        T* u = a.Ucols + (b * np + k) * np;
         for (int r = lane; r < np; r += 32) u[r] = x[r] * inv;
         if (lane == 0) a.lam_raw[b * np + k] = nrm;
       }
@@ -383,27 +399,28 @@ __global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs a) {
 
 // Order eigenpairs by descending lambda (rank by counting; ties by index) and lay U out as
 // U[b][i][k] (row-major n x n, column k = k-th largest).  One CTA per matrix.
-__global__ void eig_sort_kernel(const float* Ucols, const float* lam_raw, const int32_t* jstatus, int n, int n_pad,
+template <class T>
+__global__ void eig_sort_kernel(const T* Ucols, const T* lam_raw, const int32_t* jstatus, int n, int n_pad,
                                 int skip_converged, float* U, float* lam, int32_t* plan) {
   const int64_t b = blockIdx.x;
   if (skip_converged && plan[b * 4 + 3] == 0) return;
   __shared__ int s_rank[512];
-  const float* lr = lam_raw + b * n_pad;
+  const T* lr = lam_raw + b * n_pad;
   for (int k = threadIdx.x; k < n_pad; k += blockDim.x) {
-    const float v = lr[k];
+    const T v = lr[k];
     int rk = 0;
     for (int j = 0; j < n_pad; ++j) {
-      const float w = lr[j];
+      const T w = lr[j];
       rk += (w > v || (w == v && j < k)) ? 1 : 0;
     }
     s_rank[k] = rk;
-    if (rk < n) lam[b * n + rk] = v;
+    if (rk < n) lam[b * n + rk] = (float)v;
   }
   __syncthreads();
   for (int64_t i = threadIdx.x; i < (int64_t)n_pad * n; i += blockDim.x) {
     const int k = (int)(i / n), r = (int)(i % n);
     const int rk = s_rank[k];
-    if (rk < n) U[b * (int64_t)n * n + (int64_t)r * n + rk] = Ucols[(b * n_pad + k) * n_pad + r];
+    if (rk < n) U[b * (int64_t)n * n + (int64_t)r * n + rk] = (float)Ucols[(b * n_pad + k) * n_pad + r];
   }
   if (threadIdx.x == 0) plan[b * 4 + 3] = (jstatus[b] > 0) ? 0 : 1;
 }
@@ -413,37 +430,43 @@ struct JacobiGeom {
   size_t smem;
 };
 
-static JacobiGeom jacobi_geom(int n) {
+// fp64 columns are twice as large: twice the cluster size keeps the three slots of a CTA under 227 KB.
+// (n > 256 in double would need a non-portable cluster of 16: that size stays in float.)
+static bool jacobi_f64_supported(int n) { return n <= 256; }
+
+static JacobiGeom jacobi_geom(int n, int f64) {
   JacobiGeom g;
-  g.cl = (n <= 128) ? 1 : (n <= 256 ? 2 : 8);
+  if (f64) g.cl = (n <= 64) ? 1 : (n <= 128 ? 2 : 4);
+  else g.cl = (n <= 128) ? 1 : (n <= 256 ? 2 : 8);
   const int nb = 2 * g.cl;
   g.cb = (n + nb - 1) / nb;
   g.n_pad = g.cb * nb;
-  g.smem = 3 * (size_t)g.cb * g.n_pad * sizeof(float) + (g.cl + 2) * sizeof(int) + 16;
+  g.smem = 3 * (size_t)g.cb * g.n_pad * (f64 ? sizeof(double) : sizeof(float)) + (g.cl + 2) * sizeof(int) + 16;
   return g;
 }
 
 size_t jacobi_workspace_bytes(int64_t B, int n) {
-  const JacobiGeom g = jacobi_geom(n);
-  return (size_t)B * g.n_pad * g.n_pad * sizeof(float) + (size_t)B * g.n_pad * sizeof(float) + (size_t)B * sizeof(int32_t) + 1024;
+  const JacobiGeom g = jacobi_geom(n, 0);
+  const JacobiGeom g2 = jacobi_geom(std::min(n, 256), 1);
+  const size_t np = (size_t)std::max(g.n_pad, g2.n_pad);
+  return (size_t)B * np * np * sizeof(double) + (size_t)B * np * sizeof(double) + (size_t)B * sizeof(int32_t) + 1024;
 }
 
-int launch_eig_jacobi(const float* G, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan,
-                      void* ws, cudaStream_t stream) {
-  if (B == 0) return 0;
-  if (n > 512) return -1;
-  const JacobiGeom g = jacobi_geom(n);
+template <class T>
+static int launch_eig_jacobi_t(const T* G, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan,
+                               void* ws, cudaStream_t stream) {
+  const JacobiGeom g = jacobi_geom(n, sizeof(T) == 8);
   char* w = static_cast<char*>(ws);
-  float* Ucols = reinterpret_cast<float*>(w);
-  w += (size_t)B * g.n_pad * g.n_pad * sizeof(float);
-  float* lam_raw = reinterpret_cast<float*>(w);
-  w += (((size_t)B * g.n_pad * sizeof(float)) + 255) & ~(size_t)255;
+  T* Ucols = reinterpret_cast<T*>(w);
+  w += (size_t)B * g.n_pad * g.n_pad * sizeof(T);
+  T* lam_raw = reinterpret_cast<T*>(w);
+  w += (((size_t)B * g.n_pad * sizeof(T)) + 255) & ~(size_t)255;
   int32_t* jstatus = reinterpret_cast<int32_t*>(w);
-  JacobiArgs a{G, n, g.n_pad, g.cb, g.cl, plan, skip_converged, Ucols, lam_raw, jstatus};
+  JacobiArgs<T> a{G, n, g.n_pad, g.cb, g.cl, plan, skip_converged, Ucols, lam_raw, jstatus};
 #ifdef SPECGPU_EMULATE
-  SPECGPU_LAUNCH_CLUSTER(eig_jacobi_kernel, (unsigned)(B * g.cl), kJacThreads, g.smem, stream, g.cl, a);
+  SPECGPU_LAUNCH_CLUSTER(eig_jacobi_kernel<T>, (unsigned)(B * g.cl), kJacThreads, g.smem, stream, g.cl, a);
 #else
-  cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(B * g.cl));
@@ -457,12 +480,25 @@ int launch_eig_jacobi(const float* G, int64_t B, int n, int skip_converged, floa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, eig_jacobi_kernel, a);
+  e = cudaLaunchKernelEx(&cfg, eig_jacobi_kernel<T>, a);
   if (e != cudaSuccess) return (int)e;
 #endif
-  SPECGPU_LAUNCH(eig_sort_kernel, (unsigned)B, 512, 0, stream, (const float*)Ucols, (const float*)lam_raw,
-                 (const int32_t*)jstatus, n, g.n_pad, skip_converged, U, lam, plan);
+  SPECGPU_LAUNCH(eig_sort_kernel<T>, (unsigned)B, 512, 0, stream, (const T*)Ucols, (const T*)lam_raw, (const int32_t*)jstatus, n,
+                 g.n_pad, skip_converged, U, lam, plan);
   return (int)cudaGetLastError();
+}
+
+bool eig_jacobi_f64_supported(int n) { return jacobi_f64_supported(n); }
+
+int launch_eig_jacobi(const void* G, int g_f64, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan,
+                      void* ws, cudaStream_t stream) {
+  if (B == 0) return 0;
+  if (n > 512) return -1;
+  if (g_f64) {
+    if (!jacobi_f64_supported(n)) return -1;
+    return launch_eig_jacobi_t<double>((const double*)G, B, n, skip_converged, U, lam, plan, ws, stream);
+  }
+  return launch_eig_jacobi_t<float>((const float*)G, B, n, skip_converged, U, lam, plan, ws, stream);
 }
 
 // ======================================================================================================

@@ -236,6 +236,18 @@ static inline float atomicAdd(float* p, float v) {
   std::memcpy(&f, &old, 4);
   return f;
 }
+static inline double atomicAdd(double* p, double v) {
+  uint64_t* u = reinterpret_cast<uint64_t*>(p);
+  uint64_t old = __atomic_load_n(u, __ATOMIC_SEQ_CST), nw;
+  double f;
+  do {
+    std::memcpy(&f, &old, 8);
+    f += v;
+    std::memcpy(&nw, &f, 8);
+  } while (!__atomic_compare_exchange_n(u, &old, nw, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  std::memcpy(&f, &old, 8);
+  return f;
+}
 static inline int atomicMax(int* p, int v) {
   int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}

@@ -28,6 +28,22 @@ def test_spectrogram_variants(emu_rt, nperseg, noverlap, n, detrend, window, sca
     pc.case_spectrogram(emu_rt, nperseg, noverlap, n, detrend, window, scaling)
 
 
+def test_spectrogram_property_random_parameters(emu_rt):
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=8, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(log2n=st.integers(3, 9), ov=st.floats(0.0, 0.9), nseg=st.integers(1, 12),
+           window=st.sampled_from(["hann", "hamm", "boxcar"]), detrend=st.sampled_from([False, "constant", "linear"]),
+           scaling=st.sampled_from(["density", "spectrum"]))
+    def run(log2n, ov, nseg, window, detrend, scaling):
+        nperseg = 1 << log2n
+        noverlap = min(int(ov * nperseg), nperseg - 1)
+        n = nperseg + (nseg - 1) * (nperseg - noverlap) + 3
+        pc.case_spectrogram(emu_rt, nperseg, noverlap, n, detrend, window, scaling, B=1)
+
+    run()
+
+
 def test_spectrogram_custom_window(emu_rt):
     w = np.hanning(130)[1:-1]
     pc.case_spectrogram(emu_rt, 128, 64, 3000, "constant", w, "density")

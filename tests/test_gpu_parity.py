@@ -32,6 +32,23 @@ def test_spectrogram_variants(cuda_rt, nperseg, noverlap, n, detrend, window, sc
     pc.case_spectrogram(cuda_rt, nperseg, noverlap, n, detrend, window, scaling)
 
 
+def test_spectrogram_property_random_parameters(cuda_rt):
+    """random (n, nperseg, noverlap, window, detrend, scaling, batch) against the oracle."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(log2n=st.integers(3, 13), ov=st.floats(0.0, 0.97), extra=st.integers(0, 5000), nseg=st.integers(1, 40),
+           window=st.sampled_from(["hann", "hamm", "boxcar"]), detrend=st.sampled_from([False, "constant", "linear"]),
+           scaling=st.sampled_from(["density", "spectrum"]), B=st.integers(1, 3))
+    def run(log2n, ov, extra, nseg, window, detrend, scaling, B):
+        nperseg = 1 << log2n
+        noverlap = min(int(ov * nperseg), nperseg - 1)
+        n = nperseg + (nseg - 1) * (nperseg - noverlap) + extra % (nperseg - noverlap)
+        pc.case_spectrogram(cuda_rt, nperseg, noverlap, n, detrend, window, scaling, B=B)
+
+    run()
+
+
 def test_spectrogram_custom_window(cuda_rt):
     pc.case_spectrogram(cuda_rt, 128, 64, 30_000, "constant", np.hanning(130)[1:-1], "density")
 
@@ -151,11 +168,18 @@ def test_svd_golden(cuda_rt, golden):
     pc.assert_denoise_close(api.denoiseSignal(M, 0, 4, runtime=cuda_rt), g["M64_0_4"])
     pc.assert_denoise_close(api.denoiseSignal(M, 2, 9, runtime=cuda_rt), g["M64_2_9"])
     pc.assert_denoise_close(api.denoiseSignal(M, -3, 1000, runtime=cuda_rt), g["M64_m3_1000"])
-    # computeSignal sums idx in range(1, 2*num_sing) = 1..7: the cut falls INSIDE the noise bulk
-    # (s[7] - s[8] = 2e-3 on s[0] = 300), where the result is ill-conditioned for any Gram-based
-    # solver in float32 (SURVEY.md 7.2 "conditioning of rank-k"): gap-scaled tolerance 5e-3 of max.
-    cs = api.computeSignal(M, runtime=cuda_rt)
-    np.testing.assert_allclose(cs, g["M64_compute"], rtol=0, atol=5e-3 * np.abs(g["M64_compute"]).max())
+    # computeSignal sums idx in range(1, 2*num_sing) = 1..7: the cut falls INSIDE the noise bulk (s[7] - s[8] = 2e-3 on
+    # s[0] = 300).  The full route forms the Gram matrix and runs the Jacobi sweeps in float64 for exactly this case.
+    cs, s2, info2 = api.computeSignal(M, return_info=True, runtime=cuda_rt)
+    pc.assert_denoise_close(cs, g["M64_compute"])
+    np.testing.assert_allclose(s2, g["M64_s"], rtol=2e-6)
+    # the reference's own spectrogram (256 x 77: taller than wide, handled through the transpose)
+    S = golden("specgr_small.npz")["S_f32"]
+    pc.assert_denoise_close(api.denoiseSignal(S, runtime=cuda_rt), g["S64_default"])
+    pc.assert_denoise_close(api.denoiseSignal(S, method="jacobi", runtime=cuda_rt), g["S64_default"])
+    d, s3, info3 = api.denoiseSignal(S, use_optimal=True, return_info=True, runtime=cuda_rt)
+    np.testing.assert_allclose(s3, g["S64_s"], rtol=1e-5, atol=1e-6 * g["S64_s"][0])
+    pc.assert_denoise_close(d, g["S64_optimal"])
 
 
 @pytest.mark.parametrize("rows,cols", [(64, 200), (128, 1000), (256, 3905), (200, 777)])
