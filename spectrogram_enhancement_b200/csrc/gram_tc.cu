@@ -3,8 +3,8 @@
 //
 // The batch is cut into 32-column chunks, numbered g = b * nchunk + c; CTA i of a persistent grid owns
 // the contiguous range [i*per, (i+1)*per), which touches at most two matrices ("segments").  Per chunk the
-// producer warps read the [rows x 32] fp32 slab (row-contiguous 128 B runs, a whole slab in flight in
-// registers before the first store), optionally apply the min-max normalisation of the log image
+// producer warps read the [rows x 32] fp32 slab (row-contiguous 128 B runs, three slabs in flight in
+// registers), optionally apply the min-max normalisation of the log image
 // (so that the pipeline needs no separate normalise pass), round it to TF32
 // (cvt.rna) and store it to shared memory in the UMMA canonical K-major SWIZZLE_128B layout
 // (row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))); a 4-deep mbarrier ring hands slabs to one
@@ -231,16 +231,23 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
         mbar_arrive(smem_u32(&s_full[stage]));
         ++ci;
       };
-      // software pipeline: the next chunk's loads are in flight while this one is converted and stored
-      float va[RPW], vb[RPW];
-      load_chunk(va);
-      for (; c < cend; c += 2) {
-        const bool ok0 = c * kGtcChunk + lane < ncols, ok1 = (c + 1) * kGtcChunk + lane < ncols;
-        if (c + 1 < cend) load_chunk(vb);
-        store_chunk(va, ok0);
+      // software pipeline, three register buffers: the loads of the next TWO chunks are in flight while this one is
+      // converted and stored (one CTA per SM: bytes in flight per SM are what bounds this kernel)
+      float v0[RPW], v1[RPW], v2[RPW];
+      load_chunk(v0);
+      if (c + 1 < cend) load_chunk(v1);
+      for (; c < cend; c += 3) {
+        const bool ok0 = c * kGtcChunk + lane < ncols, ok1 = (c + 1) * kGtcChunk + lane < ncols,
+                   ok2 = (c + 2) * kGtcChunk + lane < ncols;
+        if (c + 2 < cend) load_chunk(v2);
+        store_chunk(v0, ok0);
         if (c + 1 < cend) {
-          if (c + 2 < cend) load_chunk(va);
-          store_chunk(vb, ok1);
+          if (c + 3 < cend) load_chunk(v0);
+          store_chunk(v1, ok1);
+        }
+        if (c + 2 < cend) {
+          if (c + 4 < cend) load_chunk(v1);
+          store_chunk(v2, ok2);
         }
       }
       g = gend;
