@@ -169,6 +169,11 @@ int specgpu_csd_pairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X
 int specgpu_csd_pairs_block(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg,
                             int64_t nseg_total, int64_t ldf, int64_t i0, int64_t ni, int32_t accumulate, float* P,
                             void* stream);
+/* Time-resolved cross-power amplitude for the `ampsp[n_time, n_freq]` image of interferometer/crosspowerspec.py:39-50:
+ * amp[k][f] = | mean over segments [k*seg_stride, k*seg_stride + navg) of conj(X_i) X_j | * scale (one-sided doubled),
+ * from the spectra of specgpu_csd_spectra.  amp is [nframes][nfreq] float32. */
+int specgpu_csd_frames(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg, int64_t ldf,
+                       int64_t i, int64_t j, int64_t seg_stride, int32_t navg, int64_t nframes, float* amp, void* stream);
 int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n,
                          int64_t ldx, float* P, void* stream);
 

@@ -730,17 +730,25 @@ def ae_co2(signal1, signal2, t, nperseg=1024, noverlap=None, navg=8, window="han
     tt = np.asarray(t.cpu() if _is_torch(t) else t, dtype=np.float64)
     fs = 1000.0 / float(np.mean(np.diff(tt)))        # t in ms -> Hz
     frame = nperseg + (navg - 1) * hop
-    nframes = s1.shape[-1] // frame
+    if frame % hop != 0:
+        raise ValueError("ae_co2: nperseg must be a multiple of nperseg - noverlap")
+    seg_stride = frame // hop          # frame k = segments [k*seg_stride, k*seg_stride + navg) of the whole record
+    n = int(s1.shape[-1])
+    nframes = n // frame
     if nframes == 0:
         raise ValueError("record shorter than one averaging frame")
+    if s2.shape != s1.shape or s1.dim() != 1:
+        raise ValueError("ae_co2 expects two 1-D records of equal length")
     F = nperseg // 2 + 1
-    amps = rt.empty((nframes, F))
     plan = rt.plan(nperseg, noverlap, fs, window, "density", detrend)
-    P = rt.empty((2, 2, F, 2))
-    for k in range(nframes):            # frames are independent all-pairs problems of C = 2
-        xk = torch.stack([s1[k * frame:(k + 1) * frame], s2[k * frame:(k + 1) * frame]])
-        rt.check(rt.lib.csd_allpairs(rt._ctx, plan, xk.data_ptr(), 2, frame, _ld(xk), P.data_ptr(), rt.stream()))
-        amps[k] = torch.view_as_complex(P)[0, 1].abs()
+    x = torch.stack([s1, s2])
+    T = rt.lib.plan_num_segments(plan, n)
+    ldf = (F + 1) & ~1
+    X = rt.empty((2, T, ldf, 2))
+    rt.check(rt.lib.csd_spectra(rt._ctx, plan, x.data_ptr(), 2, n, _ld(x), X.data_ptr(), ldf, rt.stream()))
+    amps = rt.empty((nframes, F))
+    rt.check(rt.lib.csd_frames(rt._ctx, plan, X.data_ptr(), 2, T, ldf, 0, 1, seg_stride, navg, nframes, amps.data_ptr(),
+                               rt.stream()))
     freq = np.fft.rfftfreq(nperseg, 1.0 / fs) / 1e3
     time = tt[0] + (np.arange(nframes) * frame + frame / 2.0) / fs * 1e3
     return rt.ret(amps, as_torch), freq, time

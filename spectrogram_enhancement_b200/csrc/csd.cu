@@ -164,6 +164,34 @@ __global__ void csd_reduce_kernel(const float2* partial, int nchunk, int ni, int
   }
 }
 
+// Time-resolved cross-power amplitude (the `ampsp[n_time, n_freq]` the interferometer script plots,
+// interferometer/crosspowerspec.py:39-50): frame k averages segments [k*seg_stride, k*seg_stride + navg) of the
+// record's spectra, amp[k][f] = | mean_t conj(X_i) X_j | * scale (one-sided doubled).  One thread per (frame, bin).
+__global__ void csd_frames_kernel(const float2* X, int64_t nseg, int64_t ldf, int nfreq, int ci, int cj, int64_t seg_stride,
+                                  int navg, int64_t nframes, float scale, float* amp) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t k = blockIdx.y;
+  if (f >= nfreq || k >= nframes) return;
+  const float2* xi = X + ((int64_t)ci * nseg + k * seg_stride) * ldf + f;
+  const float2* xj = X + ((int64_t)cj * nseg + k * seg_stride) * ldf + f;
+  float re = 0.f, im = 0.f;
+  for (int t = 0; t < navg; ++t) {
+    const float2 a = __ldg(xi + (int64_t)t * ldf), b = __ldg(xj + (int64_t)t * ldf);
+    re = fmaf(a.x, b.x, fmaf(a.y, b.y, re));
+    im = fmaf(a.x, b.y, fmaf(-a.y, b.x, im));
+  }
+  const float sc = ((f == 0 || f == nfreq - 1) ? scale : 2.0f * scale) / (float)navg;
+  amp[k * nfreq + f] = sqrtf(re * re + im * im) * sc;
+}
+
+int launch_csd_frames(const float* X, int64_t nseg, int64_t ldf, int nfreq, int ci, int cj, int64_t seg_stride, int navg,
+                      int64_t nframes, float scale, float* amp, cudaStream_t stream) {
+  if (nframes == 0 || nfreq == 0) return 0;
+  SPECGPU_LAUNCH(csd_frames_kernel, dim3((unsigned)ceil_div(nfreq, 128), (unsigned)nframes), 128, 0, stream,
+                 reinterpret_cast<const float2*>(X), nseg, ldf, nfreq, ci, cj, seg_stride, navg, nframes, scale, amp);
+  return (int)cudaGetLastError();
+}
+
 struct CsdGeom {
   int sym, nbi, nbj, ntiles, ngroups, nchunk;
   int64_t seg_per_chunk;

@@ -82,6 +82,8 @@ int launch_morph(const void* src, int in_f64, int64_t B, int64_t rows, int64_t c
 // csd.cu
 int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t nseg_total, int64_t ldf, int nfreq, int64_t i0,
                      int64_t ni, float scale, int accumulate, float* partial_ws, float* P, cudaStream_t stream);
+int launch_csd_frames(const float* X, int64_t nseg, int64_t ldf, int nfreq, int ci, int cj, int64_t seg_stride, int navg,
+                      int64_t nframes, float scale, float* amp, cudaStream_t stream);
 size_t csd_pairs_workspace_bytes(int64_t C, int64_t ni, int nfreq, int64_t nseg);
 
 }  // namespace specgpu

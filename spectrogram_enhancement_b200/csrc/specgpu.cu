@@ -772,6 +772,22 @@ int specgpu_csd_pairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X
   return specgpu_csd_pairs_block(ctx, plan, X, C, nseg, nseg, ldf, i0, ni, 0, P, stream);
 }
 
+int specgpu_csd_frames(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg, int64_t ldf,
+                       int64_t i, int64_t j, int64_t seg_stride, int32_t navg, int64_t nframes, float* amp, void* stream) {
+  if (!ctx || !plan) return SPECGPU_ERR_INVALID_ARG;
+  const int nfreq = plan->p.nperseg / 2 + 1;
+  if (C <= 0 || i < 0 || j < 0 || i >= C || j >= C || ldf < nfreq || navg < 1 || seg_stride < 1 || nframes < 0 ||
+      (nframes > 0 && (nframes - 1) * seg_stride + navg > nseg))
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_frames: frames (%lld x stride %lld + %d) exceed the %lld segments", (long long)nframes,
+                (long long)seg_stride, navg, (long long)nseg);
+  if (nframes == 0) return SPECGPU_OK;
+  if (nframes > 65535) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "csd_frames: more than 65535 frames");
+  if (!X || !amp) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null pointer");
+  CHECK_LAUNCH(ctx, launch_csd_frames(X, nseg, ldf, nfreq, (int)i, (int)j, seg_stride, navg, nframes, (float)plan->scale, amp,
+                                      (cudaStream_t)stream), "csd_frames", 1);
+  return SPECGPU_OK;
+}
+
 int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n, int64_t ldx,
                          float* P, void* stream) {
   int rc = check_signal_args(ctx, plan, x, C, n, ldx);

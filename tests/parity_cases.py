@@ -212,3 +212,20 @@ def case_filter_chain(rt, S):
     fin = api.filter_chain(S, runtime=rt)
     np.testing.assert_allclose(fin, oc.filter_chain(S), rtol=1e-12, atol=1e-13)
     return g, fin
+
+
+# ---- time-resolved cross-power amplitude (ae_co2; PARITY-UNPINNED upstream: defined as frame-wise scipy.signal.csd) ----
+def case_ae_co2(rt, n, nperseg, navg, fs=1.6e6):
+    x = signals(2, n, shot=4, fs=fs, offset=0.2)
+    t_ms = np.arange(n) / fs * 1e3 + 5.0
+    amp, freq, time = api.ae_co2(x[0], x[1], t_ms, nperseg=nperseg, navg=navg, runtime=rt)
+    hop = nperseg // 2
+    frame = nperseg + (navg - 1) * hop
+    nframes = n // frame
+    assert amp.shape == (nframes, nperseg // 2 + 1) and amp.dtype == np.float32
+    ref = np.stack([np.abs(oc.csd(x[0, k * frame:(k + 1) * frame].astype(np.float64),
+                                  x[1, k * frame:(k + 1) * frame].astype(np.float64), fs=fs, nperseg=nperseg)[1])
+                    for k in range(nframes)])
+    assert_spec_close(amp, ref)
+    np.testing.assert_allclose(freq, np.fft.rfftfreq(nperseg, 1 / fs) / 1e3, rtol=1e-9)      # kHz
+    np.testing.assert_allclose(time, 5.0 + (np.arange(nframes) * frame + frame / 2) / fs * 1e3, rtol=1e-9)   # ms

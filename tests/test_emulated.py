@@ -123,6 +123,10 @@ def test_csd_scipy_kat(emu_rt):
     np.testing.assert_allclose(p.imag, 0, atol=1e-7)
 
 
+def test_ae_co2_time_resolved(emu_rt):
+    pc.case_ae_co2(emu_rt, 6000, 128, 4)
+
+
 def test_pipeline_small(emu_rt):
     sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=32, noverlap=16)
     pc.case_pipeline(emu_rt, sp, 9000, B=2, tile=64)

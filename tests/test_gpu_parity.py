@@ -237,6 +237,12 @@ def test_csd_variants_and_kat(cuda_rt):
     np.testing.assert_allclose(p.real, [0.08333333, 0.15277778, 0.22222222, 0.22222222, 0.11111111], rtol=1e-5)
 
 
+def test_ae_co2_time_resolved(cuda_rt):
+    """interferometer/crosspowerspec.py:39 call shape: 2 s @ 1.6 MHz, frames of 8 half-overlapped 1024-sample segments."""
+    pc.case_ae_co2(cuda_rt, 3_200_000, 1024, 8)
+    pc.case_ae_co2(cuda_rt, 100_000, 4096, 3)
+
+
 # ---- whole path ----------------------------------------------------------------------------------------
 def test_pipeline_small(cuda_rt):
     pc.case_pipeline(cuda_rt, dict(SP, nperseg=32, noverlap=16), 9000, B=2, tile=64)
