@@ -7,8 +7,8 @@
 // registers), optionally apply the min-max normalisation of the log image
 // (so that the pipeline needs no separate normalise pass), round it to TF32
 // (cvt.rna) and store it to shared memory in the UMMA canonical K-major SWIZZLE_128B layout
-// (row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))); a 4-deep mbarrier ring hands slabs to one
-// elected thread that issues tcgen05.mma.kind::tf32 with BOTH operands described on the same slab:
+// (row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))); a 4-deep ring (named barriers producer -> issuer,
+// mbarriers tensor core -> producer) hands slabs to one elected thread that issues tcgen05.mma.kind::tf32 with BOTH operands described on the same slab:
 //     D1[128 x rows] += slab[0:128]   . slab[0:rows]^T     (G00 | G01)
 //     D2[128 x 128 ] += slab[128:256] . slab[128:256]^T    (G11; rows == 256 only; G10 = G01^T)
 // so the symmetric product costs 3/4 of the MMA work.  tcgen05.commit releases the slab; after the
@@ -25,6 +25,7 @@ namespace specgpu {
 constexpr int kGtcStages = 4;
 constexpr int kGtcChunk = 32;            // K elements per slab (128 bytes of tf32 per row)
 constexpr int kGtcProducerWarps = 16;
+constexpr int kGtcGroups = 2;             // producer groups; group k produces the chunks k, k + kGtcGroups, ... of a CTA
 constexpr int kGtcThreads = (kGtcProducerWarps + 1) * 32;
 
 struct GramTcArgs {
@@ -72,6 +73,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+// A load the compiler may not sink towards its first use: asm volatile keeps its program order relative to the other
+// volatile asm statements (mbarrier waits/arrives), so three slabs really are in flight per thread.
+__device__ __forceinline__ float ldg_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+// Hardware named barriers for the producer -> MMA-issuer hand-off.  An mbarrier.arrive has release semantics and
+// compiles to MEMBAR.ALL.CTA, which drains the producers' global loads that are still in flight for the NEXT slabs
+// (measured: it serialised every slab on the memory latency); bar.arrive / bar.sync order shared memory like
+// __syncthreads() without touching outstanding loads.
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -158,7 +176,6 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 #else
   SPECGPU_DYN_SMEM(smem);   // SWIZZLE_128B atoms need 1024-byte alignment (re-aligned below)
   constexpr int SLAB = ROWS * 128;  // bytes per stage
-  __shared__ __align__(8) uint64_t s_full[kGtcStages];
   __shared__ __align__(8) uint64_t s_empty[kGtcStages];
   __shared__ __align__(8) uint64_t s_accum;
   __shared__ uint32_t s_tmem;
@@ -167,7 +184,6 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 
   if (tid == 0) {
     for (int i = 0; i < kGtcStages; ++i) {
-      mbar_init(smem_u32(&s_full[i]), kGtcProducerWarps * 32);
       mbar_init(smem_u32(&s_empty[i]), 1);
     }
     mbar_init(smem_u32(&s_accum), 1);
@@ -186,12 +202,22 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 
   if (warp < kGtcProducerWarps) {
     // ================= producers: global fp32 -> (normalise) -> TF32 -> swizzled shared slab =================
-    constexpr int RPW = ROWS / kGtcProducerWarps;   // rows per warp per chunk (lane = column): one register batch
+    // The 16 producer warps form kGtcStages groups of 4; group k owns ring stage k and produces the chunks
+    // k, k+4, k+8, ... of this CTA.  The proxy fence that must follow the shared-memory stores compiles to
+    // MEMBAR.ALL.CTA, which also drains the thread's global loads in flight, so a thread can only keep the loads
+    // of ONE chunk in flight; with four groups working on four different chunks the SM still has 3-4 slabs
+    // (96-128 KB) in flight, which is what bounds this kernel (one CTA per SM because of TMEM).
+    constexpr int WPG = kGtcProducerWarps / kGtcGroups;   // warps per group
+    constexpr int RPW = ROWS / WPG;                        // rows per warp per chunk (lane = column)
+    const int grp = warp / WPG, wg = warp % WPG;
     const bool do_norm = a.minmax != nullptr;
-    const int64_t stride = (int64_t)kGtcProducerWarps * a.ld;     // between this thread's consecutive rows
-    // row r = warp + i*16 of a slab lives at r*128 + ((chunk16 ^ (r & 7)) << 4): r & 7 == warp & 7 for every i
-    const uint32_t sw_off = (uint32_t)(warp * 128 + (((lane >> 2) ^ (warp & 7)) << 4) + ((lane & 3) << 2));
-    int64_t g = g0;                                  // next chunk to produce
+    const int64_t stride = (int64_t)WPG * a.ld;            // between this thread's consecutive rows (r = wg + WPG*i)
+    // row r of a slab lives at r*128 + ((chunk16 ^ (r & 7)) << 4); r & 7 takes the two values wg and wg + 4
+    // (WPG = 4) or the single value wg & 7 (WPG = 8)
+    const uint32_t sw_even = (uint32_t)((((lane >> 2) ^ (wg & 7)) << 4) + ((lane & 3) << 2));
+    const uint32_t sw_odd = (uint32_t)((((lane >> 2) ^ ((wg + WPG) & 7)) << 4) + ((lane & 3) << 2));
+    const int ncols = (int)a.cols;
+    int64_t g = g0;                                  // first chunk of the current segment
     for (int sg = 0; sg < nsegs; ++sg) {
       const int64_t b = b_first + sg;
       const int64_t gend = (g1 < (b + 1) * a.nchunk) ? g1 : (b + 1) * a.nchunk;
@@ -201,54 +227,28 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
         den = ordered_to_float(a.minmax[2 * b + 1]) - mn;
       }
       const float inv = 1.0f / den;
-      int c = (int)(g - b * a.nchunk);               // chunk inside the matrix
-      const int cend = (int)(gend - b * a.nchunk);
-      int ci = (int)(g - g0);                        // chunk inside this CTA: ring position
-      const float* p = a.S + (b * ROWS + warp) * a.ld + (int64_t)c * kGtcChunk + lane;
-      int kcol = c * kGtcChunk + lane;
-      const int ncols = (int)a.cols;
-
-      auto load_chunk = [&](float (&v)[RPW]) {
+      // this group's chunks of the segment: CTA-relative index ci = grp (mod kGtcGroups)
+      int64_t gg = g + ((grp - (int)((g - g0) % kGtcGroups)) + kGtcGroups) % kGtcGroups;
+      for (; gg < gend; gg += kGtcGroups) {
+        const int c = (int)(gg - b * a.nchunk);           // chunk inside the matrix
+        const int stage = (int)((gg - g0) % kGtcStages);
+        const uint32_t use = (uint32_t)((gg - g0) / kGtcStages);
+        unsigned char* const my_slab = slabs + stage * SLAB + wg * 128;
+        const int kcol = c * kGtcChunk + lane;
         const bool kok = kcol < ncols;
-        const float* q = p;
+        const float* q = a.S + (b * ROWS + wg) * a.ld + kcol;
+        float v[RPW];
 #pragma unroll
         for (int i = 0; i < RPW; ++i, q += stride) v[i] = kok ? __ldg(q) : 0.f;
-        p += kGtcChunk;
-        kcol += kGtcChunk;
-      };
-      auto store_chunk = [&](const float (&v)[RPW], bool kok) {
-        const int stage = ci % kGtcStages;
-        const uint32_t use = (uint32_t)(ci / kGtcStages);
-        if (use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);
-        unsigned char* dst = slabs + stage * SLAB + sw_off;
+        if (use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);     // loads already in flight
 #pragma unroll
         for (int i = 0; i < RPW; ++i) {
           float x = v[i];
           if (do_norm) x = kok ? div_by(x - mn, den, inv) : 0.f;
-          *reinterpret_cast<float*>(dst + i * (kGtcProducerWarps * 128)) = round_tf32(x);
+          *reinterpret_cast<float*>(my_slab + i * (WPG * 128) + ((i & 1) ? sw_odd : sw_even)) = round_tf32(x);
         }
         fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(smem_u32(&s_full[stage]));
-        ++ci;
-      };
-      // software pipeline, three register buffers: the loads of the next TWO chunks are in flight while this one is
-      // converted and stored (one CTA per SM: bytes in flight per SM are what bounds this kernel)
-      float v0[RPW], v1[RPW], v2[RPW];
-      load_chunk(v0);
-      if (c + 1 < cend) load_chunk(v1);
-      for (; c < cend; c += 3) {
-        const bool ok0 = c * kGtcChunk + lane < ncols, ok1 = (c + 1) * kGtcChunk + lane < ncols,
-                   ok2 = (c + 2) * kGtcChunk + lane < ncols;
-        if (c + 2 < cend) load_chunk(v2);
-        store_chunk(v0, ok0);
-        if (c + 1 < cend) {
-          if (c + 3 < cend) load_chunk(v0);
-          store_chunk(v1, ok1);
-        }
-        if (c + 2 < cend) {
-          if (c + 4 < cend) load_chunk(v1);
-          store_chunk(v2, ok2);
-        }
+        named_bar_arrive(1 + stage, WPG * 32 + 32);
       }
       g = gend;
       // ================= epilogue: TMEM -> registers -> partial[sg][128][PW] =================
@@ -256,22 +256,29 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
       tc_fence_after();
       float* part = part0 + (size_t)sg * 128 * PW;
       const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-      const int row = q * 32 + lane;          // TMEM lane == accumulator row
       constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the warps of a quarter
+      // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns); a per-warp [32][33] shared tile
+      // transposes it so that the partial is written as 128-byte rows instead of 32 scattered 16-byte pieces
+      float* tr = reinterpret_cast<float*>(slabs + kGtcStages * SLAB) + warp * (32 * 33);
       for (int cg = warp >> 2; cg < NCG; cg += kGtcProducerWarps / 4) {
         const int c = cg * 32;
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        float4* dst = reinterpret_cast<float4*>(part + (size_t)row * PW + c);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                               __uint_as_float(v[4 * i + 3]));
+        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        float* dst = part + (size_t)(q * 32) * PW + c + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) dst[(size_t)r * PW] = tr[r * 33 + lane];
+        __syncwarp();
       }
-      tc_fence_before();   // the TMEM reads are ordered before the arrivals that let the next segment's MMAs start
+      tc_fence_before();
+      // every producer warp has read its part of TMEM before any slab of the next segment can be completed (the
+      // issuer overwrites the accumulators with its first MMA)
+      if (sg + 1 < nsegs) named_bar_sync(1 + kGtcStages, kGtcProducerWarps * 32);
     }
-  } else if (lane == 0) {
-    // ================= MMA issuer (one thread) =================
+  } else {
+    // ================= MMA issuer warp: all lanes join the named barrier, lane 0 issues =================
     const uint32_t idesc1 = umma_idesc_tf32(128, ROWS);
     const uint32_t idesc2 = umma_idesc_tf32(128, 128);
     int64_t g = g0;
@@ -282,23 +289,26 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
       for (; g < gend; ++g) {
         const int64_t ci = g - g0;
         const int stage = (int)(ci % kGtcStages);
-        const uint32_t use = (uint32_t)(ci / kGtcStages);
-        mbar_wait(smem_u32(&s_full[stage]), use & 1);
-        tc_fence_after();
-        const uint32_t base = smem_u32(slabs + stage * SLAB);
+        named_bar_sync(1 + stage, (kGtcProducerWarps / kGtcGroups) * 32 + 32);   // this stage's producer group has stored and fenced the slab
+        if (lane == 0) {
+          tc_fence_after();
+          const uint32_t base = smem_u32(slabs + stage * SLAB);
 #pragma unroll
-        for (int ks = 0; ks < kGtcChunk / 8; ++ks) {   // K = 8 tf32 (32 bytes) per instruction
-          const uint32_t accumulate = (g > gstart || ks > 0) ? 1u : 0u;
-          const uint64_t d_lo = umma_desc_k_sw128(base + ks * 32);
-          umma_tf32(tmem_base, d_lo, d_lo, idesc1, accumulate);
-          if (ROWS == 256) {
-            const uint64_t d_hi = umma_desc_k_sw128(base + 128 * 128 + ks * 32);
-            umma_tf32(tmem_base + 256, d_hi, d_hi, idesc2, accumulate);
+          for (int ks = 0; ks < kGtcChunk / 8; ++ks) {   // K = 8 tf32 (32 bytes) per instruction
+            const uint32_t accumulate = (g > gstart || ks > 0) ? 1u : 0u;
+            const uint64_t d_lo = umma_desc_k_sw128(base + ks * 32);
+            umma_tf32(tmem_base, d_lo, d_lo, idesc1, accumulate);
+            if (ROWS == 256) {
+              const uint64_t d_hi = umma_desc_k_sw128(base + 128 * 128 + ks * 32);
+              umma_tf32(tmem_base + 256, d_hi, d_hi, idesc2, accumulate);
+            }
           }
+          umma_commit(smem_u32(&s_empty[stage]));   // slab may be refilled once these MMAs retire
         }
-        umma_commit(smem_u32(&s_empty[stage]));   // slab may be refilled once these MMAs retire
+        __syncwarp();
       }
-      umma_commit(smem_u32(&s_accum));            // accumulators of this segment complete
+      if (lane == 0) umma_commit(smem_u32(&s_accum));            // accumulators of this segment complete
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -378,7 +388,7 @@ int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_
   a.per = g.per;
   a.minmax = minmax;
   a.partial = partial_ws;
-  const size_t smem = (size_t)kGtcStages * rows * 128 + 1024;
+  const size_t smem = (size_t)kGtcStages * rows * 128 + 1024 + (size_t)kGtcProducerWarps * 32 * 33 * sizeof(float);
   if (rows == 256) {
     cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
