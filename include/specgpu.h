@@ -107,6 +107,10 @@ int specgpu_rescale(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows,
 int specgpu_norm(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld,
                  float* dst, void* stream);
 
+/* clip: dst = src with negatives set to 0 (denoising_by_svd.ipynb:280-281), n contiguous elements; in place allowed.
+ * (specgpu_svd_denoise / specgpu_pipeline fuse this through their `clip` argument.) */
+int specgpu_clip(specgpu_ctx* ctx, const float* src, int64_t n, float* dst, void* stream);
+
 /* quantfilt (pipeline_data.py:46-49): per column, q = np.quantile(src[:,j], thr) over the `rows`
  * axis with numpy's float32 'linear' arithmetic (bit-exact), dst = src < q ? 0 : src.
  * thr_out[B][cols] and mask[B][rows][ld] (uint8, 1 = kept) are optional (NULL to skip). rows <= 1024. */

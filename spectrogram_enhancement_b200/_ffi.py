@@ -51,6 +51,7 @@ PROTOTYPES = {
     "specgpu_stft": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int, _vp, _i64, _vp]),
     "specgpu_rescale": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "specgpu_norm": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "specgpu_clip": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "specgpu_quantfilt": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp]),
     "specgpu_gaussblr": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
     "specgpu_meansub": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp]),

@@ -564,10 +564,12 @@ def computeSignal(matrix, return_info=False, runtime=None):
 
 def clip(x, runtime=None):
     """denoising_by_svd.ipynb:280-281: copy with negatives set to 0 (fused into denoiseSignal(clip=True)
-    and `pipeline` on the hot path; this standalone form is a device elementwise op)."""
+    and `pipeline` on the hot path)."""
     rt = _rt(runtime)
     d, as_torch = rt.to_device(x)
-    return rt.ret(torch.where(d < 0, torch.zeros_like(d), d), as_torch)
+    out = torch.empty_like(d)
+    rt.check(rt.lib.clip(rt._ctx, d.data_ptr(), d.numel(), out.data_ptr(), rt.stream()))
+    return rt.ret(out, as_torch)
 
 
 # ================================================================================================

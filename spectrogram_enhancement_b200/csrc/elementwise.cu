@@ -131,6 +131,14 @@ __global__ void unpatch_kernel(const InT* tiles, int64_t rows, int tile_w, int n
   }
 }
 
+// hacked = svd.copy(); hacked[hacked < 0] = 0   (denoising_by_svd.ipynb:280-281); NaN stays NaN
+__global__ void clip_neg_kernel(const float* src, int64_t n, float* dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    dst[i] = (v < 0.f) ? 0.f : v;
+  }
+}
+
 static unsigned stream_blocks(int64_t total) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, kEwThreads * 4), 148 * 8));
 }
@@ -144,6 +152,12 @@ int launch_rescale(const float* src, int64_t B, int64_t rows, int64_t cols, int6
   SPECGPU_LAUNCH(minmax_reduce_kernel, dim3(gx, (unsigned)B), kEwThreads, 0, stream, src, rows, cols, ld, mm_ws);
   SPECGPU_LAUNCH(rescale_apply_kernel, dim3(gx, (unsigned)B), kEwThreads, 0, stream, src, rows, cols, ld,
                  (const unsigned*)mm_ws, dst);
+  return (int)cudaGetLastError();
+}
+
+int launch_clip_neg(const float* src, int64_t n, float* dst, cudaStream_t stream) {
+  if (n == 0) return 0;
+  SPECGPU_LAUNCH(clip_neg_kernel, stream_blocks(n), kEwThreads, 0, stream, src, n, dst);
   return (int)cudaGetLastError();
 }
 

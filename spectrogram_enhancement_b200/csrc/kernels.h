@@ -35,6 +35,7 @@ int launch_lognorm(float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, 
 // elementwise.cu
 int launch_rescale(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst, unsigned* mm_ws,
                    cudaStream_t stream);
+int launch_clip_neg(const float* src, int64_t n, float* dst, cudaStream_t stream);
 int norm_num_parts(int64_t rows, int64_t cols);
 int launch_norm(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst, double* sums_ws,
                 cudaStream_t stream);

@@ -483,6 +483,14 @@ int specgpu_norm(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, in
   return SPECGPU_OK;
 }
 
+int specgpu_clip(specgpu_ctx* ctx, const float* src, int64_t n, float* dst, void* stream) {
+  if (!ctx || n < 0) return SPECGPU_ERR_INVALID_ARG;
+  if (n == 0) return SPECGPU_OK;
+  if (!src || !dst) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null pointer");
+  CHECK_LAUNCH(ctx, launch_clip_neg(src, n, dst, (cudaStream_t)stream), "clip", 1);
+  return SPECGPU_OK;
+}
+
 int specgpu_quantfilt(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float thr,
                       float* dst, float* thr_out, uint8_t* mask, void* stream) {
   int rc = check_matrix_args(ctx, src, B, rows, cols, ld);

@@ -79,6 +79,12 @@ def test_quantfilt_ties_and_3d(emu_rt):
     pc.case_quantfilt_3d(emu_rt, 64, 33, 3)
 
 
+def test_clip(emu_rt):
+    a = np.array([[-1.0, 0.0, 2.5], [np.nan, -0.0, -3.0]], np.float32)
+    out = api.clip(a, runtime=emu_rt)
+    assert np.array_equal(out, oc.clip(a), equal_nan=True) and np.signbit(out[1, 1])
+
+
 def test_patch_roundtrip(emu_rt):
     pc.case_patch(emu_rt, 3, 16, 70, 8, 8)
     pc.case_patch(emu_rt, 1, 256, 130, 128, 1)
