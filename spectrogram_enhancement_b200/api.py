@@ -487,7 +487,12 @@ def filter_chain(Sxx, thr=0.9, filt=(31, 3), runtime=None):
     rt = _rt(runtime)
     as_torch = _is_torch(Sxx)
     d, _ = rt.to_device(Sxx)
-    q = quantfilt(d, thr, runtime=rt) if d.dim() == 2 else torch.stack([quantfilt(x, thr, runtime=rt) for x in d])
+    if d.dim() == 2:
+        q = quantfilt(d, thr, runtime=rt)
+    else:                                   # [B, F, T] stack: one batched launch
+        B, rows, cols = d.shape
+        q = torch.empty_like(d)
+        rt.check(rt.lib.quantfilt(rt._ctx, d.data_ptr(), B, rows, cols, cols, float(thr), q.data_ptr(), None, None, rt.stream()))
     out = meansub(morph(meansub(gaussblr(q, filt, runtime=rt), runtime=rt), runtime=rt), runtime=rt)
     return rt.ret(out, as_torch)
 
