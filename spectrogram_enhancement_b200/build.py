@@ -1,11 +1,10 @@
 """Build libspecgpu.so (sm_100a) in-tree with nvcc.
 
-    python -m spectrogram_enhancement_b200.build           # the product library
-    python -m spectrogram_enhancement_b200.build --emu     # CPU emulation build (tests only)
+    python -m spectrogram_enhancement_b200.build [--force] [--verbose]
 
-The product library is CUDA-only (`-gencode arch=compute_100a,code=sm_100a`); the emulation build
-compiles the same kernel sources as plain C++ against tests/emu/cuda_emu.h and is loaded only by the
-CPU test-suite.
+The library is CUDA-only (`-gencode arch=compute_100a,code=sm_100a -lineinfo`).  (The CPU test-suite has its own
+builder, tests/emu/build_emu.py, which compiles the same kernel sources against a CUDA-execution-model emulator;
+nothing in this package builds or loads it.)
 """
 from __future__ import annotations
 
@@ -21,8 +20,6 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(ROOT, "build")
 LIB = os.path.join(PKG, "libspecgpu.so")
-EMU_DIR = os.path.join(ROOT, "tests", "emu")
-EMU_LIB = os.path.join(EMU_DIR, "libspecgpu_emu.so")
 
 SOURCES = ["specgpu.cu", "stft.cu", "elementwise.cu", "quantile.cu", "svd.cu", "gram_tc.cu", "csd.cu", "imgchain.cu"]
 
@@ -30,8 +27,6 @@ NVCC_FLAGS = [
     "-std=c++17", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-Xcompiler", "-fPIC",
 ]
-GXX_FLAGS = ["-std=c++20", "-O2", "-fPIC", "-pthread", "-DSPECGPU_EMULATE", "-x", "c++", "-I", EMU_DIR,
-             "-Wno-unknown-pragmas", "-Wno-attributes"]
 
 
 def _nvcc() -> str:
@@ -91,29 +86,5 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_emu(force: bool = False) -> str:
-    emu_files = [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "cuda_emu.cpp")]
-    digest = _deps_digest(emu_files) + "|" + " ".join(GXX_FLAGS)
-    if not force and _up_to_date(EMU_LIB, digest):
-        return EMU_LIB
-    os.makedirs(os.path.join(BUILD, "emu"), exist_ok=True)
-
-    def one(path):
-        obj = os.path.join(BUILD, "emu", os.path.basename(path).rsplit(".", 1)[0] + ".o")
-        _run(["g++"] + GXX_FLAGS + ["-c", path, "-o", obj])
-        return obj
-
-    srcs = [os.path.join(CSRC, s) for s in _sources()] + [emu_files[1]]
-    with ThreadPoolExecutor(max_workers=8) as ex:
-        objs = list(ex.map(one, srcs))
-    _run(["g++", "-shared", "-pthread", "-o", EMU_LIB] + objs)
-    open(EMU_LIB + ".digest", "w").write(digest)
-    return EMU_LIB
-
-
 if __name__ == "__main__":
-    force = "--force" in sys.argv
-    if "--emu" in sys.argv:
-        print(build_emu(force))
-    else:
-        print(build_cuda(force, verbose="--verbose" in sys.argv))
+    print(build_cuda("--force" in sys.argv, verbose="--verbose" in sys.argv))

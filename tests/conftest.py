@@ -41,9 +41,9 @@ def golden():
 @pytest.fixture(scope="session")
 def emu_rt():
     """Runtime over the CPU-emulation build of the kernel sources (test infrastructure only)."""
-    from spectrogram_enhancement_b200 import _ffi, api, build
-    path = build.build_emu()
-    return api.Runtime(_ffi.Library(path), "cpu")
+    from emu.build_emu import build_emu
+    from spectrogram_enhancement_b200 import _ffi, api
+    return api.Runtime(_ffi.Library(build_emu()), "cpu")
 
 
 @pytest.fixture(scope="session")
