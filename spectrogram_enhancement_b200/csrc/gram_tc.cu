@@ -2,19 +2,23 @@
 // accumulators in tensor memory) for rows in {128, 256} -- the one dense contraction of the path.
 //
 // The batch is cut into 32-column chunks, numbered g = b * nchunk + c; CTA i of a persistent grid owns
-// the contiguous range [i*per, (i+1)*per), which touches at most two matrices ("segments").  Per chunk the
-// producer warps read the [rows x 32] fp32 slab (row-contiguous 128 B runs, three slabs in flight in
-// registers), optionally apply the min-max normalisation of the log image
-// (so that the pipeline needs no separate normalise pass), round it to TF32
-// (cvt.rna) and store it to shared memory in the UMMA canonical K-major SWIZZLE_128B layout
-// (row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))); a 4-deep ring (named barriers producer -> issuer,
-// mbarriers tensor core -> producer) hands slabs to one elected thread that issues tcgen05.mma.kind::tf32 with BOTH operands described on the same slab:
+// the contiguous range [i*per, (i+1)*per), which touches at most two matrices ("segments").  Warp roles:
+//   4 loader warps     cp.async (LDGSTS) the [rows x 32] fp32 slab of a chunk straight into a shared-memory ring stage
+//                      in the UMMA canonical K-major SWIZZLE_128B layout (row r at r*128 B, 16-byte chunk c at
+//                      c ^ (r & 7)), zero-filling columns past the end, and signal an mbarrier through
+//                      cp.async.mbarrier.arrive; they hold nothing in registers and never fence, so the whole ring
+//                      (6 x 32 KB) is in flight per SM -- the kernel runs one CTA per SM because of TMEM;
+//   12 transform warps apply the min-max normalisation of the log image (so the pipeline needs no separate normalise
+//                      pass) and cvt.rna.tf32 IN PLACE, fence.proxy.async, and arrive on a named barrier (an
+//                      mbarrier.arrive.release or the proxy fence compile to MEMBAR.ALL.CTA; that is harmless here
+//                      because these threads have no global loads in flight);
+//   1 issuer warp      one elected thread issues tcgen05.mma.kind::tf32 with BOTH operands described on the same slab:
 //     D1[128 x rows] += slab[0:128]   . slab[0:rows]^T     (G00 | G01)
 //     D2[128 x 128 ] += slab[128:256] . slab[128:256]^T    (G11; rows == 256 only; G10 = G01^T)
-// so the symmetric product costs 3/4 of the MMA work.  tcgen05.commit releases the slab; after the
-// last chunk of a segment the accumulators are read back with tcgen05.ld and written as that
-// (CTA, segment) partial.  gram_reduce_kernel sums the partials of a matrix in a fixed order
-// (deterministic) and mirrors G10.
+//                      so the symmetric product costs 3/4 of the MMA work; tcgen05.commit releases the stage.
+// After the last chunk of a segment all 16 worker warps read the accumulators back with tcgen05.ld, transpose them
+// through per-warp shared tiles and write the (CTA, segment) partial as 128-byte rows.  gram_reduce_kernel sums the
+// partials of a matrix in a fixed order (deterministic) and mirrors G10.
 //
 // The emulation build (tests only, no tensor cores on a CPU) replaces the kernel body by a scalar
 // loop with the same TF32 operand rounding and the same partial layout.
@@ -22,11 +26,11 @@
 
 namespace specgpu {
 
-constexpr int kGtcStages = 4;
+constexpr int kGtcStages = 6;             // 32 KB slabs in the ring (rows = 256): 192 KB of loads in flight per SM
 constexpr int kGtcChunk = 32;            // K elements per slab (128 bytes of tf32 per row)
-constexpr int kGtcProducerWarps = 16;
-constexpr int kGtcGroups = 2;             // producer groups; group k produces the chunks k, k + kGtcGroups, ... of a CTA
-constexpr int kGtcThreads = (kGtcProducerWarps + 1) * 32;
+constexpr int kGtcWarps = 16;             // worker warps: loaders + transformers (all of them run the epilogue)
+constexpr int kGtcLoadWarps = 4;
+constexpr int kGtcThreads = (kGtcWarps + 1) * 32;   // + the MMA issuer warp
 
 struct GramTcArgs {
   const float* S;
@@ -34,22 +38,18 @@ struct GramTcArgs {
   int64_t nchunk;           // chunks per matrix
   int64_t per;              // chunks per CTA
   const unsigned* minmax;   // optional [B][2] ordered-uint (min, max): operands are (x - min) / (max - min)
+  int vec16;                // base and pitch allow 16-byte copies
   float* partial;           // [grid][2][128][PW] with PW = rows + (rows == 256 ? 128 : 0)
 };
 
 __host__ __device__ inline int gram_tc_partial_width(int rows) { return rows == 256 ? 384 : rows; }
 
+// Round to TF32 (10 mantissa bits), nearest with ties away from zero -- what cvt.rna.tf32.f32 does -- as two integer
+// instructions on the sign-magnitude bit pattern (the cvt expands to about four).
 __device__ __forceinline__ float round_tf32(float x) {
-#if defined(SPECGPU_EMULATE)
-  // cvt.rna.tf32.f32: round to nearest, ties away from zero, keep 10 mantissa bits
   unsigned u = __float_as_uint(x);
   u = (u + 0x1000u) & 0xffffe000u;
   return __uint_as_float(u);
-#else
-  unsigned u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-#endif
 }
 
 #if !defined(SPECGPU_EMULATE)
@@ -66,20 +66,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"     // suspend-time hint: do not spin on issue slots
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(1000000u)
       : "memory");
-}
-// A load the compiler may not sink towards its first use: asm volatile keeps its program order relative to the other
-// volatile asm statements (mbarrier waits/arrives), so three slabs really are in flight per thread.
-__device__ __forceinline__ float ldg_pinned(const float* p) {
-  float v;
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
 }
 // Hardware named barriers for the producer -> MMA-issuer hand-off.  An mbarrier.arrive has release semantics and
 // compiles to MEMBAR.ALL.CTA, which drains the producers' global loads that are still in flight for the NEXT slabs
@@ -164,9 +157,9 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
       float acc = 0.f;
       for (int64_t k = lo * kGtcChunk; k < hi * kGtcChunk && k < a.cols; ++k) {
         float xa = Sb[(int64_t)ra * a.ld + k], xb = Sb[(int64_t)rb * a.ld + k];
-        if (a.minmax != nullptr) {
-          xa = div_by(xa - e_mn, e_den, 1.0f / e_den);
-          xb = div_by(xb - e_mn, e_den, 1.0f / e_den);
+        if (a.minmax != nullptr) {       // same single-FMA normalisation as the device path
+          xa = fmaf(xa, 1.0f / e_den, -e_mn / e_den);
+          xb = fmaf(xb, 1.0f / e_den, -e_mn / e_den);
         }
         acc += round_tf32(xa) * round_tf32(xb);
       }
@@ -176,20 +169,24 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 #else
   SPECGPU_DYN_SMEM(smem);   // SWIZZLE_128B atoms need 1024-byte alignment (re-aligned below)
   constexpr int SLAB = ROWS * 128;  // bytes per stage
-  __shared__ __align__(8) uint64_t s_empty[kGtcStages];
+  __shared__ __align__(8) uint64_t s_loaded[kGtcStages];   // the loader threads' cp.async copies have landed
+  __shared__ __align__(8) uint64_t s_empty[kGtcStages];    // the tensor core has consumed the slab
   __shared__ __align__(8) uint64_t s_accum;
   __shared__ uint32_t s_tmem;
   const int warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t TMEM_COLS = (ROWS == 256) ? 512 : 128;
+  constexpr int kLoadThreads = kGtcLoadWarps * 32, kXformThreads = (kGtcWarps - kGtcLoadWarps) * 32;
+  constexpr int kSegBarrier = 1 + kGtcStages;       // named barrier: every worker warp is done with a segment
 
   if (tid == 0) {
     for (int i = 0; i < kGtcStages; ++i) {
+      mbar_init(smem_u32(&s_loaded[i]), kLoadThreads);
       mbar_init(smem_u32(&s_empty[i]), 1);
     }
     mbar_init(smem_u32(&s_accum), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kGtcProducerWarps) {
+  if (warp == kGtcWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -199,103 +196,120 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
   unsigned char* slabs = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  const int ncols = (int)a.cols;
+  const bool do_norm = a.minmax != nullptr;
 
-  if (warp < kGtcProducerWarps) {
-    // ================= producers: global fp32 -> (normalise) -> TF32 -> swizzled shared slab =================
-    // The 16 producer warps form kGtcStages groups of 4; group k owns ring stage k and produces the chunks
-    // k, k+4, k+8, ... of this CTA.  The proxy fence that must follow the shared-memory stores compiles to
-    // MEMBAR.ALL.CTA, which also drains the thread's global loads in flight, so a thread can only keep the loads
-    // of ONE chunk in flight; with four groups working on four different chunks the SM still has 3-4 slabs
-    // (96-128 KB) in flight, which is what bounds this kernel (one CTA per SM because of TMEM).
-    constexpr int WPG = kGtcProducerWarps / kGtcGroups;   // warps per group
-    constexpr int RPW = ROWS / WPG;                        // rows per warp per chunk (lane = column)
-    const int grp = warp / WPG, wg = warp % WPG;
-    const bool do_norm = a.minmax != nullptr;
-    const int64_t stride = (int64_t)WPG * a.ld;            // between this thread's consecutive rows (r = wg + WPG*i)
-    // row r of a slab lives at r*128 + ((chunk16 ^ (r & 7)) << 4); r & 7 takes the two values wg and wg + 4
-    // (WPG = 4) or the single value wg & 7 (WPG = 8)
-    const uint32_t sw_even = (uint32_t)((((lane >> 2) ^ (wg & 7)) << 4) + ((lane & 3) << 2));
-    const uint32_t sw_odd = (uint32_t)((((lane >> 2) ^ ((wg + WPG) & 7)) << 4) + ((lane & 3) << 2));
-    const int ncols = (int)a.cols;
-    int64_t g = g0;                                  // first chunk of the current segment
-    for (int sg = 0; sg < nsegs; ++sg) {
-      const int64_t b = b_first + sg;
-      const int64_t gend = (g1 < (b + 1) * a.nchunk) ? g1 : (b + 1) * a.nchunk;
+  int64_t g = g0;                                   // first chunk of the current segment
+  for (int sg = 0; sg < nsegs; ++sg) {
+    const int64_t b = b_first + sg;
+    const int64_t gend = (g1 < (b + 1) * a.nchunk) ? g1 : (b + 1) * a.nchunk;
+    if (warp < kGtcLoadWarps) {
+      // ================= loaders: global fp32 -> cp.async -> swizzled shared slab (raw values) =================
+      // Nothing is held in registers and these warps never execute a fence (a fence is a MEMBAR.ALL.CTA that would
+      // drain the copies in flight), so the whole ring can be in flight.  Row r of a slab lives at
+      // r*128 + ((chunk16 ^ (r & 7)) << 4); this thread copies column `lane` of the rows warp, warp + 4, ...
+      if (a.vec16) {
+        // 16-byte copies (base and pitch are multiples of 4 floats): a warp instruction covers 4 rows x 128 bytes, lane =
+        // (row sub-index, 16-byte chunk); a quarter of the copy instructions.  The padded tail of a row may be read
+        // (ld >= round_up(cols, 4)); whatever it holds is zeroed by the transform warps.
+        const int sub = lane >> 3, c16 = lane & 7;
+        const int r0 = 4 * warp + sub;                        // rows r0 + 16 i; (r0 + 16 i) & 7 == r0 & 7
+        const uint32_t voff = (uint32_t)(r0 * 128 + ((c16 ^ (r0 & 7)) << 4));
+        const int64_t vstride = 16 * a.ld;
+        for (int64_t gg = g; gg < gend; ++gg) {
+          const int64_t ci = gg - g0;
+          const int stage = (int)(ci % kGtcStages);
+          const uint32_t use = (uint32_t)(ci / kGtcStages);
+          if (use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);
+          const int kcol = (int)(gg - b * a.nchunk) * kGtcChunk + 4 * c16;
+          const int nbytes = kcol < ncols ? 16 : 0;
+          const float* q = a.S + (b * ROWS + r0) * a.ld + (kcol < ncols ? kcol : 0);
+          const uint32_t dst = smem_u32(slabs + stage * SLAB) + voff;
+#pragma unroll 8
+          for (int i = 0; i < ROWS / 16; ++i, q += vstride)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * (16 * 128)), "l"(q), "r"(nbytes) : "memory");
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_loaded[stage])) : "memory");
+        }
+      } else {
+      const uint32_t sw0 = (uint32_t)((((lane >> 2) ^ (warp & 7)) << 4) + ((lane & 3) << 2));
+      const uint32_t sw1 = (uint32_t)((((lane >> 2) ^ ((warp + kGtcLoadWarps) & 7)) << 4) + ((lane & 3) << 2));
+      const int64_t stride = (int64_t)kGtcLoadWarps * a.ld;
+      for (int64_t gg = g; gg < gend; ++gg) {
+        const int64_t ci = gg - g0;
+        const int stage = (int)(ci % kGtcStages);
+        const uint32_t use = (uint32_t)(ci / kGtcStages);
+        if (use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);
+        const int kcol = (int)(gg - b * a.nchunk) * kGtcChunk + lane;
+        const int nbytes = kcol < ncols ? 4 : 0;            // src-size 0: the destination is zero-filled
+        const float* q = a.S + (b * ROWS + warp) * a.ld + (kcol < ncols ? kcol : 0);
+        const uint32_t dst = smem_u32(slabs + stage * SLAB + warp * 128);
+#pragma unroll 8
+        for (int i = 0; i < ROWS / kGtcLoadWarps; ++i, q += stride)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + i * (kGtcLoadWarps * 128) + ((i & 1) ? sw1 : sw0)),
+                       "l"(q), "r"(nbytes)
+                       : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_loaded[stage])) : "memory");
+      }
+      }
+    } else if (warp < kGtcWarps) {
+      // ================= transform warps: (normalise) + round to TF32, in place =================
+      const int t = tid - kLoadThreads;
       float mn = 0.f, den = 1.f;
       if (do_norm) {
         mn = ordered_to_float(a.minmax[2 * b]);
         den = ordered_to_float(a.minmax[2 * b + 1]) - mn;
       }
-      const float inv = 1.0f / den;
-      // this group's chunks of the segment: CTA-relative index ci = grp (mod kGtcGroups)
-      int64_t gg = g + ((grp - (int)((g - g0) % kGtcGroups)) + kGtcGroups) % kGtcGroups;
-      for (; gg < gend; gg += kGtcGroups) {
-        const int c = (int)(gg - b * a.nchunk);           // chunk inside the matrix
-        const int stage = (int)((gg - g0) % kGtcStages);
-        const uint32_t use = (uint32_t)((gg - g0) / kGtcStages);
-        unsigned char* const my_slab = slabs + stage * SLAB + wg * 128;
-        const int kcol = c * kGtcChunk + lane;
-        const bool kok = kcol < ncols;
-        const float* q = a.S + (b * ROWS + wg) * a.ld + kcol;
-        float v[RPW];
-#pragma unroll
-        for (int i = 0; i < RPW; ++i, q += stride) v[i] = kok ? __ldg(q) : 0.f;
-        if (use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);     // loads already in flight
-#pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-          float x = v[i];
-          if (do_norm) x = kok ? div_by(x - mn, den, inv) : 0.f;
-          *reinterpret_cast<float*>(my_slab + i * (WPG * 128) + ((i & 1) ? sw_odd : sw_even)) = round_tf32(x);
+      const float nscale = do_norm ? 1.0f / den : 1.0f;        // x -> (x - mn) / den as x * nscale + noff
+      const float noff = do_norm ? -mn / den : 0.0f;
+      for (int64_t gg = g; gg < gend; ++gg) {
+        const int64_t ci = gg - g0;
+        const int stage = (int)(ci % kGtcStages);
+        const uint32_t use = (uint32_t)(ci / kGtcStages);
+        mbar_wait(smem_u32(&s_loaded[stage]), use & 1);
+        unsigned char* slab = slabs + stage * SLAB;
+        const int k0 = (int)(gg - b * a.nchunk) * kGtcChunk;
+        // 16-byte pieces: piece e = (row e / 8, physical chunk e % 8); its logical chunk is (e % 8) ^ (row & 7).
+        // The operands are rounded to 10 mantissa bits, so the normalisation is a single FMA here (the exactly
+        // rounded division is kept for the image the pipeline writes, not for the Gram operands).
+        if (k0 + kGtcChunk <= ncols) {
+#pragma unroll 2
+          for (int e = t; e < ROWS * 8; e += kXformThreads) {
+            float4 x = *reinterpret_cast<float4*>(slab + e * 16);
+            x.x = round_tf32(fmaf(x.x, nscale, noff));
+            x.y = round_tf32(fmaf(x.y, nscale, noff));
+            x.z = round_tf32(fmaf(x.z, nscale, noff));
+            x.w = round_tf32(fmaf(x.w, nscale, noff));
+            *reinterpret_cast<float4*>(slab + e * 16) = x;
+          }
+        } else {   // last chunk of a matrix: columns past the end were zero-filled and must stay zero
+          for (int e = t; e < ROWS * 8; e += kXformThreads) {
+            const int row = e >> 3, pc = e & 7;
+            const int k = k0 + ((pc ^ (row & 7)) << 2);
+            float4 x = *reinterpret_cast<float4*>(slab + e * 16);
+            x.x = (k + 0 < ncols) ? round_tf32(fmaf(x.x, nscale, noff)) : 0.f;
+            x.y = (k + 1 < ncols) ? round_tf32(fmaf(x.y, nscale, noff)) : 0.f;
+            x.z = (k + 2 < ncols) ? round_tf32(fmaf(x.z, nscale, noff)) : 0.f;
+            x.w = (k + 3 < ncols) ? round_tf32(fmaf(x.w, nscale, noff)) : 0.f;
+            *reinterpret_cast<float4*>(slab + e * 16) = x;
+          }
         }
         fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
-        named_bar_arrive(1 + stage, WPG * 32 + 32);
+        named_bar_arrive(1 + stage, kXformThreads + 32);
       }
-      g = gend;
-      // ================= epilogue: TMEM -> registers -> partial[sg][128][PW] =================
-      mbar_wait(smem_u32(&s_accum), (uint32_t)sg & 1);
-      tc_fence_after();
-      float* part = part0 + (size_t)sg * 128 * PW;
-      const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-      constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the warps of a quarter
-      // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns); a per-warp [32][33] shared tile
-      // transposes it so that the partial is written as 128-byte rows instead of 32 scattered 16-byte pieces
-      float* tr = reinterpret_cast<float*>(slabs + kGtcStages * SLAB) + warp * (32 * 33);
-      for (int cg = warp >> 2; cg < NCG; cg += kGtcProducerWarps / 4) {
-        const int c = cg * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        float* dst = part + (size_t)(q * 32) * PW + c + lane;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) dst[(size_t)r * PW] = tr[r * 33 + lane];
-        __syncwarp();
-      }
-      tc_fence_before();
-      // every producer warp has read its part of TMEM before any slab of the next segment can be completed (the
-      // issuer overwrites the accumulators with its first MMA)
-      if (sg + 1 < nsegs) named_bar_sync(1 + kGtcStages, kGtcProducerWarps * 32);
-    }
-  } else {
-    // ================= MMA issuer warp: all lanes join the named barrier, lane 0 issues =================
-    const uint32_t idesc1 = umma_idesc_tf32(128, ROWS);
-    const uint32_t idesc2 = umma_idesc_tf32(128, 128);
-    int64_t g = g0;
-    for (int sg = 0; sg < nsegs; ++sg) {
-      const int64_t b = b_first + sg;
-      const int64_t gend = (g1 < (b + 1) * a.nchunk) ? g1 : (b + 1) * a.nchunk;
-      const int64_t gstart = g;
-      for (; g < gend; ++g) {
-        const int64_t ci = g - g0;
+    } else {
+      // ================= MMA issuer warp: all lanes join the named barrier, lane 0 issues =================
+      const uint32_t idesc1 = umma_idesc_tf32(128, ROWS);
+      const uint32_t idesc2 = umma_idesc_tf32(128, 128);
+      for (int64_t gg = g; gg < gend; ++gg) {
+        const int64_t ci = gg - g0;
         const int stage = (int)(ci % kGtcStages);
-        named_bar_sync(1 + stage, (kGtcProducerWarps / kGtcGroups) * 32 + 32);   // this stage's producer group has stored and fenced the slab
+        named_bar_sync(1 + stage, kXformThreads + 32);      // the transform warps have rewritten and fenced this slab
         if (lane == 0) {
           tc_fence_after();
           const uint32_t base = smem_u32(slabs + stage * SLAB);
 #pragma unroll
           for (int ks = 0; ks < kGtcChunk / 8; ++ks) {   // K = 8 tf32 (32 bytes) per instruction
-            const uint32_t accumulate = (g > gstart || ks > 0) ? 1u : 0u;
+            const uint32_t accumulate = (gg > g || ks > 0) ? 1u : 0u;
             const uint64_t d_lo = umma_desc_k_sw128(base + ks * 32);
             umma_tf32(tmem_base, d_lo, d_lo, idesc1, accumulate);
             if (ROWS == 256) {
@@ -310,10 +324,39 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
       if (lane == 0) umma_commit(smem_u32(&s_accum));            // accumulators of this segment complete
       __syncwarp();
     }
+    if (warp < kGtcWarps) {
+      // ================= epilogue (all worker warps): TMEM -> registers -> partial[sg][128][PW] =================
+      mbar_wait(smem_u32(&s_accum), (uint32_t)sg & 1);
+      tc_fence_after();
+      float* part = part0 + (size_t)sg * 128 * PW;
+      const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+      constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the warps of a quarter
+      // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns); a per-warp [32][33] tile transposes it so
+      // that the partial is written as 128-byte rows.  The tiles live in the slab ring: every MMA of the segment has
+      // retired and the loaders (which run this epilogue too) have not started on the next segment.
+      float* tr = reinterpret_cast<float*>(slabs) + warp * (32 * 33);
+      for (int cg = warp >> 2; cg < NCG; cg += kGtcWarps / 4) {
+        const int c = cg * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        float* dst = part + (size_t)(q * 32) * PW + c + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) dst[(size_t)r * PW] = tr[r * 33 + lane];
+        __syncwarp();
+      }
+      tc_fence_before();
+      // every worker warp has read its part of TMEM and is done with its transpose tile before the next segment's
+      // copies land in the ring and its first MMA overwrites the accumulators
+      if (sg + 1 < nsegs) named_bar_sync(kSegBarrier, kGtcWarps * 32);
+    }
+    g = gend;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kGtcProducerWarps) {
+  if (warp == kGtcWarps) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 #endif
@@ -387,8 +430,9 @@ int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_
   a.nchunk = g.nchunk;
   a.per = g.per;
   a.minmax = minmax;
+  a.vec16 = (((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (ld % 4 == 0) && (ld >= ((cols + 3) & ~(int64_t)3))) ? 1 : 0;
   a.partial = partial_ws;
-  const size_t smem = (size_t)kGtcStages * rows * 128 + 1024 + (size_t)kGtcProducerWarps * 32 * 33 * sizeof(float);
+  const size_t smem = std::max((size_t)kGtcStages * rows * 128, (size_t)kGtcWarps * 32 * 33 * sizeof(float)) + 1024;
   if (rows == 256) {
     cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
