@@ -645,65 +645,100 @@ __global__ void __launch_bounds__(kRecThreads) svd_project_kernel(const float* S
 // ------------------------------------------------------------------------------------------------------
 constexpr int kR1Warps = 16, kR1Threads = kR1Warps * 32;
 
-template <int RPW>   // rows per thread = ceil(rows / 16)
+template <int RPW, bool NORM, bool CLIP>   // RPW = rows per thread = ceil(rows / 16)
 __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L, int rows, int64_t cols, int64_t ld,
-                                                                  const unsigned* minmax, const float* U, int clip,
-                                                                  float* S, float* D, int64_t ldo) {
+                                                                  const unsigned* minmax, const float* U, float* S,
+                                                                  float* D, int64_t ldo) {
   SPECGPU_DYN_SMEM(smem);
   float* s_u = reinterpret_cast<float*>(smem);          // [rows]
   float* s_w = s_u + rows;                              // [16][32] partial coefficients
   const int64_t b = blockIdx.y;
   const int64_t c0 = (int64_t)blockIdx.x * kRecCols;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool col_ok = c0 + lane < cols;
   float mn = 0.f, den = 1.f;
-  const bool do_norm = minmax != nullptr;
-  if (do_norm) {
+  if (NORM) {
     mn = ordered_to_float(minmax[2 * b]);
     den = ordered_to_float(minmax[2 * b + 1]) - mn;
   }
   const float inv = 1.0f / den;
   for (int r = tid; r < rows; r += kR1Threads) s_u[r] = U[b * (int64_t)rows * rows + (int64_t)r * rows];
-  // this thread's rows are warp, warp+16, ...: nr of them are inside the matrix (warp-uniform)
-  const int nr = col_ok ? ((rows - warp + kR1Warps - 1) / kR1Warps) : 0;
+  const float* pl = L + (b * rows + warp) * ld + c0 + lane;
+  float* ps = S + (b * rows + warp) * ldo + c0 + lane;
+  float* pd = D + (b * rows + warp) * ldo + c0 + lane;
+  const int64_t stepl = kR1Warps * ld, stepo = kR1Warps * ldo;
+  const bool write_s = S != nullptr && (NORM || S != L);
   float x[RPW];
-  {
-    const float* p = L + (b * rows + warp) * ld + c0 + lane;
-    const int64_t step = kR1Warps * ld;
+  if (c0 + kRecCols <= cols && rows == kR1Warps * RPW) {
+    // ---- full tile: no per-element predicates ----
 #pragma unroll
-    for (int i = 0; i < RPW; ++i, p += step) x[i] = (i < nr) ? __ldg(p) : 0.f;
+    for (int i = 0; i < RPW; ++i) x[i] = __ldg(pl + i * stepl);
+    __syncthreads();
+    float u[RPW];
+    float w = 0.f;
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      u[i] = s_u[warp + kR1Warps * i];
+      if (NORM) x[i] = div_by(x[i] - mn, den, inv);
+      w = fmaf(u[i], x[i], w);
+    }
+    s_w[warp * 32 + lane] = w;
+    if (write_s) {
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) ps[i * stepo] = x[i];
+    }
+    __syncthreads();
+    w = 0.f;
+#pragma unroll
+    for (int k = 0; k < kR1Warps; ++k) w += s_w[k * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      float v = fmaf(-u[i], w, x[i]);
+      if (CLIP) v = (v < 0.f) ? 0.f : v;   // NaN stays NaN, like hacked[hacked < 0] = 0
+      pd[i * stepo] = v;
+    }
+    return;
   }
+  // ---- ragged tile (last columns / rows not a multiple of 16): this thread's rows are warp, warp+16, ...; nr of them
+  //      are inside the matrix (warp-uniform) ----
+  const bool col_ok = c0 + lane < cols;
+  const int nr = col_ok ? ((rows - warp + kR1Warps - 1) / kR1Warps) : 0;
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) x[i] = (i < nr) ? __ldg(pl + i * stepl) : 0.f;
   __syncthreads();
   float w = 0.f;
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
-    if (do_norm) x[i] = (i < nr) ? div_by(x[i] - mn, den, inv) : 0.f;
+    if (NORM) x[i] = (i < nr) ? div_by(x[i] - mn, den, inv) : 0.f;
     if (i < nr) w = fmaf(s_u[warp + kR1Warps * i], x[i], w);
   }
   s_w[warp * 32 + lane] = w;
-  if (S != nullptr && (do_norm || S != L)) {
-    float* p = S + (b * rows + warp) * ldo + c0 + lane;
-    const int64_t step = kR1Warps * ldo;
+  if (write_s) {
 #pragma unroll
-    for (int i = 0; i < RPW; ++i, p += step)
-      if (i < nr) *p = x[i];
+    for (int i = 0; i < RPW; ++i)
+      if (i < nr) ps[i * stepo] = x[i];
   }
   __syncthreads();
   w = 0.f;
 #pragma unroll
   for (int k = 0; k < kR1Warps; ++k) w += s_w[k * 32 + lane];
-  {
-    float* p = D + (b * rows + warp) * ldo + c0 + lane;
-    const int64_t step = kR1Warps * ldo;
 #pragma unroll
-    for (int i = 0; i < RPW; ++i, p += step) {
-      if (i < nr) {
-        float v = fmaf(-s_u[warp + kR1Warps * i], w, x[i]);
-        if (clip) v = (v < 0.f) ? 0.f : v;   // NaN stays NaN, like hacked[hacked < 0] = 0
-        *p = v;
-      }
+  for (int i = 0; i < RPW; ++i) {
+    if (i < nr) {
+      float v = fmaf(-s_u[warp + kR1Warps * i], w, x[i]);
+      if (CLIP) v = (v < 0.f) ? 0.f : v;
+      pd[i * stepo] = v;
     }
   }
+}
+
+template <int RPW>
+static void launch_rank1_t(dim3 grid, size_t smem, cudaStream_t stream, const float* L, int rows, int64_t cols, int64_t ld,
+                           const unsigned* minmax, const float* U, int clip, float* S, float* D, int64_t ldo) {
+  const bool nrm = minmax != nullptr;
+  if (nrm && clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, true>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
+  else if (nrm) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, false>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
+  else if (clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, true>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
+  else SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, false>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
 }
 
 int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const unsigned* minmax, const float* U,
@@ -711,9 +746,9 @@ int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t 
   if (B == 0 || rows == 0 || cols == 0) return 0;
   const size_t smem = ((size_t)rows + kR1Warps * 32) * sizeof(float);
   const dim3 grid((unsigned)ceil_div(cols, kRecCols), (unsigned)B);
-  if (rows <= 64) SPECGPU_LAUNCH(svd_rank1_kernel<4>, grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
-  else if (rows <= 128) SPECGPU_LAUNCH(svd_rank1_kernel<8>, grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
-  else if (rows <= 256) SPECGPU_LAUNCH(svd_rank1_kernel<16>, grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  if (rows <= 64) launch_rank1_t<4>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  else if (rows <= 128) launch_rank1_t<8>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  else if (rows <= 256) launch_rank1_t<16>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
   else return -1;
   return (int)cudaGetLastError();
 }
