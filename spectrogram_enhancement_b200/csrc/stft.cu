@@ -6,6 +6,8 @@
 // segment (M = nperseg/2 complex points, see fft.cuh), untangle the packed real transform into the
 // one-sided spectrum, apply the epilogue of the requested mode and stage the result in a shared-
 // memory tile so that the [freq][time] output is written in time-contiguous runs.
+#include <type_traits>
+
 #include "fft.cuh"
 #include "kernels.h"
 
@@ -176,11 +178,14 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
     fft_group<C::LOG2M>(v, line, s_twm, tg);
 
     // ---- untangle: 2 X[k] = E + W_N^k O, 2 X[M-k] = conj(E - W_N^k O) with E = Z[k] + conj(Z[M-k]),
-    //      O = -i (Z[k] - conj(Z[M-k])); the factor 2 is folded into the output scales ----
+    //      O = -i (Z[k] - conj(Z[M-k])); the factor 2 is folded into the output scales.  (Splitting the special bins
+    //      k = 0 and k = M/2 out of the loop was measured 4 % slower: they belong to one thread per group, so the
+    //      warp issues two more, nearly empty iterations.) ----
     const float cscale = 0.5f * a.scale;             // complex / spectra outputs
     const float pscale1 = 0.25f * a.scale;           // |2X|^2 -> PSD, bins 0 and Nyquist
     const float pscale2 = 0.5f * a.scale;            // one-sided doubling for every other bin
-    for (int k = tg; k <= M / 2; k += G) {
+    auto bin_pair = [&](int k, auto generic_c) {
+      constexpr bool GENERIC = decltype(generic_c)::value;     // 0 < k < M/2: two distinct, doubled bins
       const float2 zk = line[fft_pad(k)];
       const float2 zm = line[fft_pad((M - k) & (M - 1))];
       const float2 e = make_float2(zk.x + zm.x, zk.y - zm.y);
@@ -190,33 +195,39 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
       float2 xm = csub(e, wo);
       xm.y = -xm.y;
       const int km = M - k;
+      const bool two = GENERIC || km != k;
       if (MODE == STFT_MODE_SPECTRA) {
         if (live) {
           float2* o2 = reinterpret_cast<float2*>(a.out) + (b * a.nseg + seg) * a.ld_out;
           o2[k] = make_float2(0.5f * xk.x, 0.5f * xk.y);
-          if (km != k) o2[km] = make_float2(0.5f * xm.x, 0.5f * xm.y);
+          if (two) o2[km] = make_float2(0.5f * xm.x, 0.5f * xm.y);
         }
       } else if (MODE == STFT_MODE_COMPLEX) {
         s_tile2[k * PITCH + tl] = make_float2(xk.x * cscale, xk.y * cscale);
-        if (km != k) s_tile2[km * PITCH + tl] = make_float2(xm.x * cscale, xm.y * cscale);
+        if (two) s_tile2[km * PITCH + tl] = make_float2(xm.x * cscale, xm.y * cscale);
       } else {
         // conj(X) X scale, doubled on 1..M-1 (one-sided, even nfft): only k == 0 (bins 0 and M) is not doubled
-        const float ps = (k != 0) ? pscale2 : pscale1;
-        float pk = (xk.x * xk.x + xk.y * xk.y) * ps;
-        float pm = (xm.x * xm.x + xm.y * xm.y) * ps;
+        const float ps = (GENERIC || k != 0) ? pscale2 : pscale1;
+        float pk = xk.x * xk.x + xk.y * xk.y;
+        float pm = xm.x * xm.x + xm.y * xm.y;
         if (MODE == STFT_MODE_LOGPSD) {
-          // lg2.approx * ln2: absolute error ~1e-6 on values in [-26, 10], i.e. < 1e-7 of the normalised image
-          pk = __logf(pk + a.eps);
-          pm = __logf(pm + a.eps);
+          // log2 (one MUFU): the min-max normalisation that follows is invariant to the base of the logarithm, only the
+          // exported (min, max) are converted to natural logs.  lg2.approx: absolute error ~1e-6 on values in [-37, 14].
+          pk = __log2f(fmaf(pk, ps, a.eps));
+          pm = __log2f(fmaf(pm, ps, a.eps));
           if (live) {
             vmin = fminf(vmin, fminf(pk, pm));       // k == km (k = M/2) gives pk == pm: harmless
             vmax = fmaxf(vmax, fmaxf(pk, pm));
           }
+        } else {
+          pk *= ps;
+          pm *= ps;
         }
         s_tile[k * PITCH + tl] = pk;
-        if (km != k) s_tile[km * PITCH + tl] = pm;
+        if (two) s_tile[km * PITCH + tl] = pm;
       }
-    }
+    };
+    for (int k = tg; k <= M / 2; k += G) bin_pair(k, std::false_type{});
     fft_group_sync<G>();  // line is reused by the next round
   }
 
@@ -276,9 +287,9 @@ __global__ void lognorm_kernel(float* S, int64_t rows, int64_t cols, int64_t ld,
   const float mx = ordered_to_float(mm[2 * b + 1]);
   const float den = mx - mn;
   const float inv = 1.0f / den;
-  if (mm_out != nullptr && r == 0 && threadIdx.x == 0) {
-    mm_out[2 * b] = mn;
-    mm_out[2 * b + 1] = mx;
+  if (mm_out != nullptr && r == 0 && threadIdx.x == 0) {   // the log image is kept in base 2 (see stft_kernel)
+    mm_out[2 * b] = mn * 0.69314718055994531f;
+    mm_out[2 * b + 1] = mx * 0.69314718055994531f;
   }
   float* row = S + (b * rows + r) * ld;
   const unsigned n = (unsigned)cols;

@@ -288,6 +288,8 @@ static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float emu_fast_logf(float a) { return std::log(a); }
 static inline float emu_fast_expf(float a) { return std::exp(a); }
+static inline float emu_fast_log2f(float a) { return std::log2(a); }
+#define __log2f emu_fast_log2f
 #define __logf emu_fast_logf
 #define __expf emu_fast_expf
 static inline float __fdividef(float a, float b) { return a / b; }

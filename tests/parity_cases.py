@@ -55,6 +55,15 @@ def case_specgr(rt, sp, n, B=2):
     assert np.array_equal(f, fr) and np.array_equal(t, tr)
     np.testing.assert_allclose(S, Sr, rtol=0, atol=ATOL_IMAGE)
     assert S.min() >= 0.0 and S.max() <= 1.0
+    # the exported (min, max) of the log image are natural logs (the kernel keeps the image in base 2 internally)
+    import torch
+    xd, _ = rt.to_device(x)
+    mm = torch.empty((B, 2), dtype=torch.float32, device=rt.device)
+    rt.specgr_dev(rt.plan_from_params(sp), xd, minmax=mm)
+    _, _, P = oc.spectrogram(x.astype(np.float64), fs=sp["fs"], window=sp["window"], nperseg=sp["nperseg"],
+                             noverlap=sp["noverlap"], detrend=sp["detrend"], scaling=sp["scaling"])
+    Lr = np.log(P + sp["eps"])
+    np.testing.assert_allclose(mm.cpu().numpy(), np.stack([Lr.min(axis=(1, 2)), Lr.max(axis=(1, 2))], axis=1), rtol=0, atol=2e-4)
     return S, Sr
 
 

@@ -53,6 +53,10 @@ def test_spectrogram_custom_window(cuda_rt):
     pc.case_spectrogram(cuda_rt, 128, 64, 30_000, "constant", np.hanning(130)[1:-1], "density")
 
 
+def test_specgr_reference_defaults(cuda_rt):
+    pc.case_specgr(cuda_rt, SP, 200_000, B=3)
+
+
 def test_specgr_golden_small(cuda_rt, golden):
     """specgr() of the reference itself (pipeline_data.py:28-36) on 20 000 samples."""
     g = golden("specgr_small.npz")
