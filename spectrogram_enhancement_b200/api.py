@@ -693,14 +693,23 @@ class HostPipeline:
     def launch_count(self):
         return sum(rt.launch_count() for rt in self.rts)
 
-    def run(self, x_host, D_host, S_host=None):
-        """x_host [C, N] float32 (pinned for real overlap), D_host [C, rows, T] float32 pinned; returns after the
-        last download has completed."""
+    class _Done:
+        """Completion handle of one submitted shot: one CUDA event per worker stream."""
+
+        def __init__(self, events):
+            self.events = events
+
+        def synchronize(self):
+            for e in self.events:
+                e.synchronize()
+
+    def submit(self, x_host, D_host, S_host=None):
+        """Enqueue one shot (uploads, kernels, downloads) on the worker streams and return a handle whose
+        synchronize() returns when its last download has completed.  The shot is ordered only after earlier work on
+        the same worker streams, so shots submitted back to back overlap (the downloads of one run under the uploads
+        of the next); x_host must already be final (host memory), and D_host must not be read before synchronize()."""
         if tuple(x_host.shape) != (self.channels, self.samples):
             raise ValueError(f"expected x[{self.channels}, {self.samples}], got {tuple(x_host.shape)}")
-        cur = torch.cuda.current_stream(self.device)
-        for st in self.streams:
-            st.wait_stream(cur)
         for g, (a, b) in enumerate(self.ranges):
             i = g % len(self.streams)
             n = b - a
@@ -710,9 +719,17 @@ class HostPipeline:
                 D_host[a:b].copy_(self.Dd[i][:n], non_blocking=True)
                 if S_host is not None:
                     S_host[a:b].copy_(self.Sd[i][:n], non_blocking=True)
+        events = []
         for st in self.streams:
-            cur.wait_stream(st)
-        cur.synchronize()
+            e = torch.cuda.Event()
+            e.record(st)
+            events.append(e)
+        return HostPipeline._Done(events)
+
+    def run(self, x_host, D_host, S_host=None):
+        """x_host [C, N] float32 (pinned for real overlap), D_host [C, rows, T] float32 pinned; returns after the
+        last download has completed."""
+        self.submit(x_host, D_host, S_host).synchronize()
         return D_host
 
 

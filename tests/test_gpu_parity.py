@@ -272,6 +272,27 @@ def test_config2_pipeline_40ch(cuda_rt):
     np.testing.assert_allclose(D5[0], D[5], rtol=0, atol=2e-5)
 
 
+def test_host_pipeline_streams(cuda_rt):
+    """HostPipeline (pinned host in/out, channel groups on several streams, shots in flight) == api.pipeline."""
+    import torch
+    n, C = 300_000, 12
+    xs = [torch.from_numpy(pc.signals(C, n, shot=20 + i)).pin_memory() for i in range(3)]
+    hp = api.HostPipeline(SP, channels=C, samples=n, groups=5, streams=3, clip=True, want_S=True)
+    outs = [torch.empty((C, hp.rows, hp.T)).pin_memory() for _ in range(3)]
+    Ss = torch.empty((C, hp.rows, hp.T)).pin_memory()
+    hp.run(xs[0], outs[0], Ss)
+    handles = [hp.submit(xs[i], outs[i]) for i in (1, 2)]
+    for h in handles:
+        h.synchronize()
+    for i in range(3):
+        S, D = api.pipeline(xs[i].numpy(), SP, clip=True, runtime=cuda_rt)
+        np.testing.assert_allclose(outs[i].numpy(), D, rtol=0, atol=2e-5)
+        if i == 0:
+            assert np.array_equal(Ss.numpy(), S)
+    with pytest.raises(ValueError):
+        hp.run(xs[0][:3], outs[0])
+
+
 def test_torch_cuda_zero_copy(cuda_rt):
     import torch
     x = torch.from_numpy(pc.signals(2, 100_000)).cuda()
