@@ -25,6 +25,10 @@ struct StftCfg {
   static constexpr int G = M / R0;                      // threads per segment
   static constexpr int NG = kStftThreads / G;           // segments in flight per CTA
   static constexpr int LINE = M + (M >> 4) + 1;          // padded float2 per FFT line
+  // Extra columns of the transposed output tile.  A warp holds 32/G segment groups (consecutive tile columns) whose
+  // threads store 16 consecutive frequencies each: with a pitch of TT + 32/G (float tiles) the 32 lanes of such a
+  // store fall into 32 different banks (pitch TT + 1 left the groups one bank apart: 2-way conflicts).
+  static constexpr int PAD4 = (G >= 2 && G <= 16) ? 32 / G : 1;
   // tile width (segments per CTA): >= NG, grown towards 32 while the float tile stays <= 72 KB
   __host__ __device__ static constexpr int tile_w(int bytes_per_elem) {
     int tt = NG;
@@ -50,7 +54,7 @@ __host__ __device__ inline StftSmem stft_smem_layout(int mode) {
   s.red_off = off;    off += (kStftThreads / 32) * 2 * 4 + 64;
   off = (off + 15) & ~15;
   s.tile_off = off;
-  if (mode == STFT_MODE_PSD || mode == STFT_MODE_LOGPSD) off += C::F * (C::tile_w(4) + 1) * 4;
+  if (mode == STFT_MODE_PSD || mode == STFT_MODE_LOGPSD) off += C::F * (C::tile_w(4) + C::PAD4) * 4;
   else if (mode == STFT_MODE_COMPLEX) off += C::F * (C::tile_w(8) + 1) * 8;
   s.total = off;
   return s;
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE
   using C = StftCfg<LOG2N>;
   constexpr int N = C::N, M = C::M, F = C::F, R0 = C::R0, G = C::G, NG = C::NG;
   constexpr int TT = (MODE == STFT_MODE_COMPLEX) ? C::tile_w(8) : C::tile_w(4);
-  constexpr int PITCH = TT + 1;
+  constexpr int PITCH = (MODE == STFT_MODE_COMPLEX) ? TT + 1 : TT + C::PAD4;
   SPECGPU_DYN_SMEM(smem);
   const StftSmem L = stft_smem_layout<LOG2N>(MODE);
   float* s_win = reinterpret_cast<float*>(smem + L.window_off);
