@@ -94,8 +94,17 @@ __device__ __forceinline__ void group_sum2(float& a, float& b, float* red, int t
   }
 }
 
+// Resident CTAs per SM the register allocator should aim for: what the shared-memory footprint of the mode allows
+// (the spectra mode has no output tile).  Without it the 3-pass sizes compile to ~195 registers = one CTA per SM.
+__host__ __device__ constexpr int stft_min_blocks(int log2n, int mode) {
+  if (mode == STFT_MODE_COMPLEX) return 1;
+  if (log2n <= 9) return 3;
+  if (mode == STFT_MODE_SPECTRA) return log2n <= 12 ? 3 : 1;
+  return log2n == 10 ? 2 : 1;
+}
+
 template <int LOG2N, int MODE>
-__global__ void __launch_bounds__(kStftThreads, (LOG2N <= 9 && MODE != STFT_MODE_COMPLEX) ? 3 : 1) stft_kernel(StftArgs a) {
+__global__ void __launch_bounds__(kStftThreads, stft_min_blocks(LOG2N, MODE)) stft_kernel(StftArgs a) {
   using C = StftCfg<LOG2N>;
   constexpr int N = C::N, M = C::M, F = C::F, R0 = C::R0, G = C::G, NG = C::NG;
   constexpr int TT = (MODE == STFT_MODE_COMPLEX) ? C::tile_w(8) : C::tile_w(4);

@@ -61,6 +61,16 @@ report("patch f32 tiles 40x30x[256x128]", timeit(lambda i: rt.check(rt.lib.patch
        1200 * 256 * 128 * 8)
 report("patch f64 tiles (reference dtype)", timeit(lambda i: rt.check(rt.lib.patch(rt._ctx, imgs[i % NB].data_ptr(), 40, 256, 3905, 128, 30, t64.data_ptr(), 1, rt.stream()))),
        1200 * 256 * 128 * 12)
+# ---- cv2 chain on 40 x [256, 3905] (quantfilt output as input) ----
+g64 = torch.empty((40, 256, 3905), device=dev, dtype=torch.float64)
+m64 = torch.empty_like(g64)
+o64 = torch.empty_like(g64)
+report("gaussblr (31,3) 40x[256x3905] f32 -> f64", timeit(lambda i: rt.check(rt.lib.gaussblr(rt._ctx, imgs[i % NB].data_ptr(), 0, 40, 256, 3905, 3905, 31, 3, g64.data_ptr(), 3905, None, rt.stream())), iters=5),
+       40 * 256 * 3905 * 12)
+report("meansub 40x[256x3905] f64", timeit(lambda i: rt.check(rt.lib.meansub(rt._ctx, g64.data_ptr(), 40, 256, 3905, 3905, m64.data_ptr(), 3905, rt.stream())), iters=5),
+       40 * 256 * 3905 * 16)
+report("morph 40x[256x3905] f64", timeit(lambda i: rt.check(rt.lib.morph(rt._ctx, m64.data_ptr(), 1, 40, 256, 3905, 3905, o64.data_ptr(), 3905, None, rt.stream())), iters=5),
+       40 * 256 * 3905 * 16)
 # ---- specgr only (spectrogram + log + min-max), 40 channels ----
 xs = [torch.randn((40, 1_000_000), device=dev, generator=g) for _ in range(NB)]
 plan = rt.plan_from_params(api.DEFAULT_SPEC_PARAMS)
