@@ -8,8 +8,9 @@
 //                      c ^ (r & 7)), zero-filling columns past the end, and signal an mbarrier through
 //                      cp.async.mbarrier.arrive; they hold nothing in registers and never fence, so the whole ring
 //                      (6 x 32 KB) is in flight per SM -- the kernel runs one CTA per SM because of TMEM;
-//   12 transform warps apply the min-max normalisation of the log image (so the pipeline needs no separate normalise
-//                      pass) and cvt.rna.tf32 IN PLACE, fence.proxy.async, and arrive on a named barrier (an
+//   12 transform warps apply the min-max normalisation of the log image (one FMA; so the pipeline needs no separate
+//                      normalise pass) and round to TF32 like cvt.rna (two integer ops) IN PLACE, fence.proxy.async,
+//                      and arrive on a named barrier (an
 //                      mbarrier.arrive.release or the proxy fence compile to MEMBAR.ALL.CTA; that is harmless here
 //                      because these threads have no global loads in flight);
 //   1 issuer warp      one elected thread issues tcgen05.mma.kind::tf32 with BOTH operands described on the same slab:
@@ -57,9 +58,6 @@ __device__ __forceinline__ float round_tf32(float x) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
