@@ -213,6 +213,24 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   w.bar->arrive_and_wait();
   return r;
 }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+  emu::WarpState& w = emu::tctx.blk->warps[emu::tctx.warp];
+  w.slot[emu::tctx.lane] = v;
+  w.bar->arrive_and_wait();
+  unsigned r = 0;
+  for (int i = 0; i < w.nlanes; ++i) r = std::max(r, (unsigned)w.slot[i]);
+  w.bar->arrive_and_wait();
+  return r;
+}
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  emu::WarpState& w = emu::tctx.blk->warps[emu::tctx.warp];
+  w.slot[emu::tctx.lane] = v;
+  w.bar->arrive_and_wait();
+  unsigned r = 0xffffffffu;
+  for (int i = 0; i < w.nlanes; ++i) r = std::min(r, (unsigned)w.slot[i]);
+  w.bar->arrive_and_wait();
+  return r;
+}
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __all_sync(unsigned m, int pred) {
   unsigned full = emu::tctx.blk->warps[emu::tctx.warp].nlanes == 32 ? 0xffffffffu
