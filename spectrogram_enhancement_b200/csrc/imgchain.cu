@@ -34,11 +34,14 @@ __global__ void img_minmax_kernel(const T* src, int64_t rows, int64_t cols, int6
     vmin = (T)INFINITY;
     vmax = (T)-INFINITY;
   }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / cols, c = i - r * cols;
-    const T v = src[(b * rows + r) * ld + c];
-    vmin = v < vmin ? v : vmin;      // NaN never wins, like np.min on finite data
-    vmax = v > vmax ? v : vmax;
+  (void)total;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {          // a CTA walks whole rows: no division per element
+    const T* row = src + (b * rows + r) * ld;
+    for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) {
+      const T v = row[c];
+      vmin = v < vmin ? v : vmin;      // NaN never wins, like np.min on finite data
+      vmax = v > vmax ? v : vmax;
+    }
   }
   __shared__ T s_min[kImgThreads], s_max[kImgThreads];
   s_min[threadIdx.x] = vmin;
@@ -58,16 +61,40 @@ __global__ void img_minmax_kernel(const T* src, int64_t rows, int64_t cols, int6
   }
 }
 
+// Fold the kImgParts partial (min, max) pairs of image b: warp 0 reads two per lane and reduces with shuffles, the
+// result is broadcast through shared memory.  Every thread of the CTA must call this (it contains a barrier).
 template <class T>
 __device__ __forceinline__ MinMax<T> fold_minmax(const T* part, int64_t b) {
-  MinMax<T> m;
-  m.mn = part[b * kImgParts * 2];
-  m.mx = part[b * kImgParts * 2 + 1];
-  for (int p = 1; p < kImgParts; ++p) {
-    const T a = part[(b * kImgParts + p) * 2], c = part[(b * kImgParts + p) * 2 + 1];
-    m.mn = a < m.mn ? a : m.mn;
-    m.mx = c > m.mx ? c : m.mx;
+  __shared__ double s_mm[2];     // wide enough for every T
+  static_assert(kImgParts == 64, "two partials per lane");
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    T mn = part[(b * kImgParts + lane) * 2], mx = part[(b * kImgParts + lane) * 2 + 1];
+    const T a = part[(b * kImgParts + 32 + lane) * 2], c = part[(b * kImgParts + 32 + lane) * 2 + 1];
+    mn = a < mn ? a : mn;
+    mx = c > mx ? c : mx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      // shuffles move 32- or 64-bit payloads: widen uint8 to int
+      if constexpr (sizeof(T) == 1) {
+        const int a2 = __shfl_xor_sync(0xffffffffu, (int)mn, o), c2 = __shfl_xor_sync(0xffffffffu, (int)mx, o);
+        mn = (T)a2 < mn ? (T)a2 : mn;
+        mx = (T)c2 > mx ? (T)c2 : mx;
+      } else {
+        const T a2 = __shfl_xor_sync(0xffffffffu, mn, o), c2 = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a2 < mn ? a2 : mn;
+        mx = c2 > mx ? c2 : mx;
+      }
+    }
+    if (lane == 0) {
+      reinterpret_cast<T*>(s_mm)[0] = mn;
+      reinterpret_cast<T*>(s_mm + 1)[0] = mx;
+    }
   }
+  __syncthreads();
+  MinMax<T> m;
+  m.mn = reinterpret_cast<const T*>(s_mm)[0];
+  m.mx = reinterpret_cast<const T*>(s_mm + 1)[0];
   return m;
 }
 
