@@ -63,7 +63,13 @@ def test_world2_csd_and_shot_sharding(tmp_path, emu_rt):
     from oracle import spec_oracle as oc
     from emu.build_emu import EMU_LIB
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), EMU_LIB, str(tmp_path)), nprocs=world, join=True)
+    for attempt in range(3):          # the rendezvous port is picked optimistically: retry on a collision
+        try:
+            mp.spawn(_worker, args=(world, _free_port(), EMU_LIB, str(tmp_path)), nprocs=world, join=True)
+            break
+        except Exception:
+            if attempt == 2:
+                raise
     C, n = 4, 3000
     x = np.stack([oc.synth_ece(2, c, n=n, fs=1.6e6) for c in range(C)])
     _, Pr = oc.csd_allpairs(x.astype(np.float64), fs=1.6e6, nperseg=128, noverlap=64)
