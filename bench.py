@@ -168,8 +168,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-NCU_TRAFFIC = {   # dram__bytes_read.sum + dram__bytes_write.sum per 40-channel launch, profiles/r01d_ncu_raw.csv
-    "stft_kernel": 275.9e6, "gram_tc": 169.5e6 + 36.0e6, "svd_rank1": 423.8e6,      # gram_tc group = kernel + reduce
+NCU_TRAFFIC = {   # dram__bytes_read.sum + dram__bytes_write.sum per 40-channel launch, profiles/r01e_ncu_raw.csv
+    "stft_kernel": 278.1e6, "gram_tc": 169.5e6 + 36.1e6, "svd_rank1": 425.2e6,      # gram_tc group = kernel + reduce
 }
 ALGO_BYTES = {   # algorithmic HBM bytes of one launch over B channels (DESIGN.md "kernels")
     "stft_kernel": lambda B: B * (4 * N_SAMP + 4 * ROWS * NSEG),          # read x, write log-PSD (Nyquist dropped)
@@ -333,7 +333,7 @@ def run_ours(args):
         dur_s = prof[dom][0] / max(prof[dom][1], 1) * 1e-3
         ach = ALGO_BYTES[dom](N_CH) / dur_s / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": NCU_TRAFFIC.get(dom), "traffic_source": "ncu --set full capture in profiles/r01d_ncu_raw.csv",
+                "traffic": NCU_TRAFFIC.get(dom), "traffic_source": "ncu --set full capture in profiles/r01e_ncu_raw.csv",
                 "peak_source": peak_src, "timing": "CUDA events around each launch, second pass of the same K steps",
                 "algorithmic_bytes_per_launch": ALGO_BYTES[dom](N_CH), "ms_per_launch": dur_s * 1e3}
     pipeline_gbs = 12.0 * N_CH * N_SAMP * args.steps / (ms * 1e-3) / 1e9      # 12 B/sample
