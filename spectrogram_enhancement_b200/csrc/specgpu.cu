@@ -806,7 +806,7 @@ int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float
   if (nseg == 0) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_allpairs: record shorter than nperseg");
   if (!P) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null output pointer");
   const int nfreq = plan->p.nperseg / 2 + 1;
-  const int64_t ldf = (nfreq + 1) & ~(int64_t)1;  // 16-byte aligned rows of float2
+  const int64_t ldf = (nfreq + 15) & ~(int64_t)15;  // 128-byte aligned rows of float2
   cudaSetDevice(ctx->device);
   const size_t xbytes = (((size_t)C * nseg * ldf * 8) + 255) & ~(size_t)255;
   if ((rc = ensure_ws(ctx, xbytes + csd_pairs_workspace_bytes(C, C, nfreq, nseg) + 512))) return rc;

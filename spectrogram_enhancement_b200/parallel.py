@@ -5,6 +5,10 @@
 * All-pairs CSD over a channel stack sharded by channel block (config 5) has ONE exchange step: every rank
   transforms its own channels (specgpu_csd_spectra), the spectra are all-gathered (NCCL over NVLink on the
   GPUs; gloo in the CPU tests), and every rank forms its row block of pairs (specgpu_csd_pairs).
+* When every rank can read the whole record (one shot file), the same matrix shards by SEGMENT instead
+  (`csd_allpairs_segment_sharded`): the Welch mean is a sum over segments, so each rank sums its own contiguous range
+  of segments of all channels and the only exchange is an all-reduce of the [C, C, F] result (6.5 MB at 40 channels,
+  nperseg 1024, against 160 MB of spectra per rank for the channel-block form).
 """
 from __future__ import annotations
 
@@ -14,7 +18,8 @@ import torch.distributed as dist
 
 from . import api
 
-__all__ = ["shot_range", "channel_block", "csd_allpairs_sharded", "pipeline_sharded"]
+__all__ = ["shot_range", "channel_block", "segment_range", "csd_allpairs_sharded", "csd_allpairs_segment_sharded",
+           "pipeline_sharded"]
 
 
 def shot_range(rank: int, world: int, n_shots: int):
@@ -57,7 +62,7 @@ def csd_allpairs_sharded(x_local, fs=1.0, window="hann", nperseg=256, noverlap=N
     if T == 0:
         raise ValueError("record shorter than nperseg")
     hop = int(nperseg) - int(noverlap)
-    ldf = (F + 1) & ~1
+    ldf = (F + 15) & ~15                      # 128-byte rows: the pair kernel stages them with 16-byte copies
     nb = max(1, min(int(blocks), T))
     edges = [T * i // nb for i in range(nb + 1)]
     P = rt.empty((Cl, C, F, 2))
@@ -91,6 +96,59 @@ def csd_allpairs_sharded(x_local, fs=1.0, window="hann", nperseg=256, noverlap=N
                                         P.data_ptr(), rt.stream()))
         if cuda:
             X_all.record_stream(main)
+    f = np.fft.rfftfreq(int(nperseg), 1.0 / fs)
+    return f, rt.ret(torch.view_as_complex(P), as_torch)
+
+
+def segment_range(rank: int, world: int, n_segments: int):
+    """Contiguous, balanced range [t0, t1) of Welch segments owned by `rank` (same rule as `shot_range`)."""
+    return shot_range(rank, world, n_segments)
+
+
+def csd_allpairs_segment_sharded(x, fs=1.0, window="hann", nperseg=256, noverlap=None, detrend="constant",
+                                 scaling="density", n_samples=None, n_channels=None, group=None, runtime=None):
+    """All-pairs Welch CSD of the record `x[C, N]` sharded over segments.  `x` is the whole record (numpy or torch,
+    readable by every rank) or a callable `x(lo, hi) -> [C, hi - lo]` that loads a sample range (then `n_samples` and
+    `n_channels` describe the record).  Every rank returns the full (f, P[C, C, F]): rank r transforms and multiplies
+    segments `segment_range(r, world, T)` of all channels, scaled by the total segment count, and the partial
+    matrices are summed with one all-reduce."""
+    rt = runtime if runtime is not None else api.default_runtime()
+    if noverlap is None:
+        noverlap = int(nperseg) // 2
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    plan = rt.plan(nperseg, noverlap, fs, window, scaling, detrend)
+    hop = int(nperseg) - int(noverlap)
+    if callable(x):
+        if n_samples is None or n_channels is None:
+            raise ValueError("a loader needs n_samples and n_channels")
+        n, C = int(n_samples), int(n_channels)
+    else:
+        if x.ndim != 2:
+            raise ValueError("csd_allpairs_segment_sharded expects x[C, N]")
+        C, n = int(x.shape[0]), int(x.shape[1])
+    F = rt.lib.plan_num_freqs(plan)
+    T = rt.lib.plan_num_segments(plan, n)
+    if T == 0:
+        raise ValueError("record shorter than nperseg")
+    t0, t1 = segment_range(rank, world, T)
+    as_torch = (not callable(x)) and api._is_torch(x)
+    P = rt.empty((C, C, F, 2))
+    if t1 > t0:
+        lo, hi = t0 * hop, (t1 - 1) * hop + int(nperseg)          # exactly segments t0 .. t1-1
+        part = x(lo, hi) if callable(x) else x[:, lo:hi]
+        if api._is_torch(part) and part.device == rt.device and part.dtype == torch.float32 and part.stride(-1) == 1:
+            xs = part                                              # a view of the resident record: no copy
+        else:
+            xs, _ = rt.to_device(part)                             # only this rank's samples are uploaded
+        ldf = (F + 15) & ~15
+        X = rt.empty((C, t1 - t0, ldf, 2))
+        rt.check(rt.lib.csd_spectra(rt._ctx, plan, xs.data_ptr(), C, xs.shape[1], api._ld(xs), X.data_ptr(), ldf, rt.stream()))
+        rt.check(rt.lib.csd_pairs_block(rt._ctx, plan, X.data_ptr(), C, t1 - t0, T, ldf, 0, C, 0, P.data_ptr(), rt.stream()))
+    else:
+        P.zero_()
+    if world > 1:
+        dist.all_reduce(P, op=dist.ReduceOp.SUM, group=group)
     f = np.fft.rfftfreq(int(nperseg), 1.0 / fs)
     return f, rt.ret(torch.view_as_complex(P), as_torch)
 

@@ -177,6 +177,31 @@ def case_csd(rt, C, n, nperseg, fs=1.6e6, detrend="constant", window="hann", sca
     assert_spec_close(P01, Pr[0, 1])
 
 
+def case_csd_row_block(rt, C, n, nperseg, i0, ni, nblocks=2, fs=1.6e6):
+    """Rows [i0, i0 + ni) of the pair matrix through specgpu_csd_pairs_block, accumulated over `nblocks` segment blocks
+    (the call pattern of parallel.csd_allpairs_sharded) against the oracle's full matrix."""
+    import torch
+    x = signals(C, n, shot=3, fs=fs, offset=0.1)
+    plan = rt.plan(nperseg, nperseg // 2, fs, "hann", "density", "constant")
+    xd, _ = rt.to_device(x)
+    F = rt.lib.plan_num_freqs(plan)
+    T = rt.lib.plan_num_segments(plan, n)
+    hop = nperseg // 2
+    ldf = (F + 1) & ~1
+    P = rt.empty((ni, C, F, 2))
+    edges = [T * b // nblocks for b in range(nblocks + 1)]
+    for b in range(nblocks):
+        t0, t1 = edges[b], edges[b + 1]
+        X = rt.empty((C, t1 - t0, ldf, 2))
+        xs = xd[:, t0 * hop:(t1 - 1) * hop + nperseg]
+        rt.check(rt.lib.csd_spectra(rt._ctx, plan, xs.data_ptr(), C, xs.shape[1], api._ld(xd), X.data_ptr(), ldf, rt.stream()))
+        rt.check(rt.lib.csd_pairs_block(rt._ctx, plan, X.data_ptr(), C, t1 - t0, T, ldf, i0, ni, 1 if b else 0, P.data_ptr(),
+                                        rt.stream()))
+    got = torch.view_as_complex(P).cpu().numpy()
+    _, Pr = oc.csd_allpairs(x.astype(np.float64), fs=fs, nperseg=nperseg, noverlap=nperseg // 2)
+    assert_spec_close(got, Pr[i0:i0 + ni])
+
+
 # ---- whole path ------------------------------------------------------------------------------------
 def case_pipeline(rt, sp, n, B=2, tile=None):
     x = signals(B, n)

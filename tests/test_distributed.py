@@ -35,6 +35,14 @@ def _worker(rank, world, port, emu_path, outdir):
         lo, hi = parallel.channel_block(rank, world, C)
         f, P = parallel.csd_allpairs_sharded(x[lo:hi], fs=1.6e6, nperseg=128, noverlap=64, runtime=rt)
         np.save(os.path.join(outdir, f"P{rank}.npy"), P)
+        # segment sharding: every rank sees the record, sums its own segments, one all-reduce; odd segment count and
+        # a loader callable on the second call
+        x9 = np.stack([oc.synth_ece(4, c, n=2100, fs=1.6e6) for c in range(9)])
+        f, Pa = parallel.csd_allpairs_segment_sharded(x9, fs=1.6e6, nperseg=64, runtime=rt)
+        f, Pb = parallel.csd_allpairs_segment_sharded(lambda lo, hi: x9[:, lo:hi], fs=1.6e6, nperseg=64, n_samples=2100,
+                                                      n_channels=9, runtime=rt)
+        assert np.array_equal(Pa, Pb)
+        np.save(os.path.join(outdir, f"S{rank}.npy"), Pa)
         # shot sharding: every rank runs the pipeline on its own shots, no communication
         sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=32, noverlap=16)
         got = {}
@@ -57,6 +65,7 @@ def test_shot_range_partitions():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         parallel.channel_block(0, 3, 40)
+    assert [parallel.segment_range(r, 3, 7) for r in range(3)] == [(0, 3), (3, 5), (5, 7)]
 
 
 def test_world2_csd_and_shot_sharding(tmp_path, emu_rt):
@@ -79,6 +88,11 @@ def test_world2_csd_and_shot_sharding(tmp_path, emu_rt):
     from spectrogram_enhancement_b200 import api
     _, P1 = api.csd_allpairs(x, fs=1.6e6, nperseg=128, noverlap=64, runtime=emu_rt)
     np.testing.assert_allclose(P, P1, rtol=1e-5, atol=1e-7 * np.abs(P1).max())
+    x9 = np.stack([oc.synth_ece(4, c, n=2100, fs=1.6e6) for c in range(9)])
+    _, P9 = oc.csd_allpairs(x9.astype(np.float64), fs=1.6e6, nperseg=64, noverlap=32)
+    S0, S1 = np.load(tmp_path / "S0.npy"), np.load(tmp_path / "S1.npy")
+    assert np.array_equal(S0, S1)                       # the all-reduce leaves every rank with the same matrix
+    np.testing.assert_allclose(S0, P9, rtol=1e-4, atol=1e-6 * np.abs(P9).max())
     d0, d1 = np.load(tmp_path / "D0.npz"), np.load(tmp_path / "D1.npz")
     assert sorted(d0.files) == ["0", "1", "2"] and sorted(d1.files) == ["3", "4"]
     sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=32, noverlap=16)

@@ -118,6 +118,18 @@ def test_csd(emu_rt):
     pc.case_csd(emu_rt, 5, 3000, 64, detrend="linear", scaling="spectrum")
 
 
+def test_csd_wide_stacks(emu_rt):
+    # 8x4 tiles: folded interleaved-segment warps (9 and 16 channels), the shared-memory staged kernel (27 and 40
+    # channels, ragged last tiles, odd segment counts) and a non-symmetric row block accumulated over segment blocks
+    pc.case_csd(emu_rt, 9, 3000, 64)
+    pc.case_csd(emu_rt, 16, 2100, 32)
+    pc.case_csd(emu_rt, 27, 2100, 32)
+    pc.case_csd(emu_rt, 40, 2000, 64)
+    pc.case_csd_row_block(emu_rt, 40, 2100, 32, 8, 24, nblocks=3)
+    pc.case_csd_row_block(emu_rt, 40, 1500, 32, 20, 20, nblocks=1)
+    pc.case_csd_row_block(emu_rt, 6, 1500, 32, 2, 3, nblocks=2)
+
+
 def test_csd_scipy_kat(emu_rt):
     # scipy/signal/tests/test_spectral.py TestCSD.test_real_onesided_even
     x = np.zeros(16, np.float32)

@@ -231,6 +231,18 @@ def test_config5_nperseg_sweep_40ch(cuda_rt, nperseg):
     pc.case_csd(cuda_rt, 40, 120_000, nperseg, fs=500000.0)
 
 
+def test_csd_wide_stacks_and_row_blocks(cuda_rt):
+    """8x4 tiles with folded warps (9..20 channels), the staged kernel with ragged tiles (27, 64 channels), and row
+    blocks accumulated over segment blocks (the sharded call pattern)."""
+    pc.case_csd(cuda_rt, 9, 60_000, 256)
+    pc.case_csd(cuda_rt, 20, 60_000, 128)
+    pc.case_csd(cuda_rt, 27, 50_000, 256)
+    pc.case_csd(cuda_rt, 64, 40_000, 512)
+    pc.case_csd_row_block(cuda_rt, 40, 120_000, 1024, 8, 24, nblocks=3)
+    pc.case_csd_row_block(cuda_rt, 40, 120_000, 1024, 20, 20, nblocks=4)
+    pc.case_csd_row_block(cuda_rt, 6, 30_000, 64, 2, 3, nblocks=2)
+
+
 def test_csd_variants_and_kat(cuda_rt):
     pc.case_csd(cuda_rt, 5, 30_000, 64, detrend="linear", scaling="spectrum")
     pc.case_csd(cuda_rt, 3, 30_000, 512, detrend=False, window="hamm")

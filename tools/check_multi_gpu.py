@@ -56,6 +56,36 @@ for blocks in (1, 4):
     t = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     res[f"ms_sharded_blocks{blocks}"] = float(t.item())
+# segment sharding: every rank holds the whole record on its device, one all-reduce of the [C, C, F] matrix
+xt = torch.from_numpy(x).to(dev)
+_, Ps = parallel.csd_allpairs_segment_sharded(xt, fs=500000.0, nperseg=nps, runtime=rt)
+if rank == 0:
+    Ps = Ps.cpu().numpy()
+    res["segment_sharded_max_rel_err_vs_oracle"] = float(np.abs(Ps - Pr).max() / np.abs(Pr).max())
+    np.testing.assert_allclose(Ps, Pr, rtol=1e-4, atol=1e-6 * np.abs(Pr).max())
+g.manual_seed(7)
+xfull = [torch.randn((C, n2), device=dev, generator=g) for _ in range(2)]      # same record on every rank
+
+
+def timed(fn, iters=10):
+    for it in range(3):
+        fn(it)
+    dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for it in range(iters):
+        fn(it)
+    b.record()
+    torch.cuda.synchronize()
+    tt = torch.tensor([a.elapsed_time(b) / iters], device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.item())
+
+
+res["ms_segment_sharded"] = timed(lambda i: parallel.csd_allpairs_segment_sharded(xfull[i % 2], fs=500000.0, nperseg=nps,
+                                                                                   runtime=rt))
+res["ms_single_gpu"] = timed(lambda i: api.csd_allpairs(xfull[i % 2], fs=500000.0, nperseg=nps, runtime=rt))
 if rank == 0:
     res.update(world=world, C=C, nperseg=nps, n_check=n, n_timed=n2)
     print(json.dumps(res), flush=True)
