@@ -9,6 +9,12 @@
 //     BORDER_REFLECT_101;
 //   * morphology on a rectangle with OpenCV's anchor (k/2, k/2) and "ignore outside" borders.
 // Float outputs are float64 like numpy's (uint8 / uint8 true division, float64 means).
+//
+// Layout: the uint8 planes between the stages live in the workspace with rows padded to 16 bytes, so every stage moves
+// 4 pixels per 32-bit word.  The blur is ONE kernel per tile (horizontal Q8.8 pass with IDP.4A on packed taps into
+// shared memory, vertical pass out of it), the four morphology passes are ONE kernel per tile (separable min / max
+// on 16-bit lanes in shared-memory planes, halo 4 + 2 rows and 8 + 8 columns); both fold the image min / max of their uint8
+// result with integer atomics, and the final rescale is a 256-entry float64 table per CTA (uint8 has 256 quotients).
 #include "kernels.h"
 
 namespace specgpu {
@@ -37,10 +43,18 @@ __global__ void img_minmax_kernel(const T* src, int64_t rows, int64_t cols, int6
   (void)total;
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {          // a CTA walks whole rows: no division per element
     const T* row = src + (b * rows + r) * ld;
-    for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) {
-      const T v = row[c];
-      vmin = v < vmin ? v : vmin;      // NaN never wins, like np.min on finite data
-      vmax = v > vmax ? v : vmax;
+    for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kImgThreads) {     // four loads in flight per thread
+      T v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned c = c0 + k * kImgThreads;
+        v[k] = row[c < (unsigned)cols ? c : c0];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        vmin = v[k] < vmin ? v[k] : vmin;      // NaN never wins, like np.min on finite data
+        vmax = v[k] > vmax ? v[k] : vmax;
+      }
     }
   }
   __shared__ T s_min[kImgThreads], s_max[kImgThreads];
@@ -98,44 +112,73 @@ __device__ __forceinline__ MinMax<T> fold_minmax(const T* part, int64_t b) {
   return m;
 }
 
-// (rescale(src) * 255).astype('uint8') in the dtype of src
+// pitch (bytes) of the workspace uint8 planes
+static inline int64_t img_pitch(int64_t cols) { return (cols + 15) & ~(int64_t)15; }
+
+// (rescale(src) * 255).astype('uint8') in the dtype of src, into a pitched plane.  Block (0, b) also resets the
+// {min, max} slot the uint8 producers of image b fold into.
 template <class T>
-__global__ void img_quantise_kernel(const T* src, int64_t rows, int64_t cols, int64_t ld, const T* part, uint8_t* dst) {
+__global__ void img_quantise_kernel(const T* src, int64_t rows, int64_t cols, int64_t ld, const T* part, uint8_t* dst,
+                                    int64_t pitch, unsigned* mm8) {
   const int64_t b = blockIdx.y;
   const int64_t r = blockIdx.x;
   const MinMax<T> m = fold_minmax(part, b);
+  if (r == 0 && threadIdx.x == 0) {
+    mm8[2 * b] = 255u;
+    mm8[2 * b + 1] = 0u;
+  }
   const T den = m.mx - m.mn;
   const T* row = src + (b * rows + r) * ld;
-  uint8_t* out = dst + (b * rows + r) * cols;
-  for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) {
-    T q;
-    if constexpr (sizeof(T) == 4) q = __fmul_rn(__fdiv_rn(__fsub_rn(row[c], m.mn), den), 255.0f);
-    else q = __dmul_rn(__ddiv_rn(__dsub_rn(row[c], m.mn), den), 255.0);
-    out[c] = (uint8_t)(int)q;          // truncation toward zero; inputs are in [0, 255]
+  uint8_t* out = dst + (b * rows + r) * pitch;
+  for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kImgThreads) {
+    T v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned c = c0 + k * kImgThreads;
+      v[k] = row[c < (unsigned)cols ? c : c0];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned c = c0 + k * kImgThreads;
+      T q;
+      if constexpr (sizeof(T) == 4) q = __fmul_rn(__fdiv_rn(__fsub_rn(v[k], m.mn), den), 255.0f);
+      else q = __dmul_rn(__ddiv_rn(__dsub_rn(v[k], m.mn), den), 255.0);
+      if (c < (unsigned)cols) out[c] = (uint8_t)(int)q;          // truncation toward zero; inputs are in [0, 255]
+    }
   }
 }
 
-// (u - min) / (max - min) with numpy's uint8 arithmetic and float64 true division
-__global__ void img_rescale_u8_kernel(const uint8_t* src, int64_t rows, int64_t cols, const uint8_t* part, double* dst,
-                                      int64_t ldo) {
+// (u - min) / (max - min) with numpy's uint8 arithmetic and float64 true division: 256 possible quotients per image
+__global__ void img_rescale_u8_kernel(const uint8_t* src, int64_t rows, int64_t cols, int64_t pitch, const unsigned* mm8,
+                                      double* dst, int64_t ldo) {
+  __shared__ double s_lut[256];
   const int64_t b = blockIdx.y;
   const int64_t r = blockIdx.x;
-  const MinMax<uint8_t> m = fold_minmax(part, b);
-  const double den = (double)(uint8_t)(m.mx - m.mn);
-  const uint8_t* row = src + (b * rows + r) * cols;
+  const uint8_t mn = (uint8_t)mm8[2 * b], mx = (uint8_t)mm8[2 * b + 1];
+  const double den = (double)(uint8_t)(mx - mn);
+  for (int v = threadIdx.x; v < 256; v += blockDim.x) s_lut[v] = __ddiv_rn((double)(uint8_t)((uint8_t)v - mn), den);
+  __syncthreads();
+  const uint8_t* row = src + (b * rows + r) * pitch;
   double* out = dst + (b * rows + r) * ldo;
-  for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) out[c] = __ddiv_rn((double)(uint8_t)(row[c] - m.mn), den);
+  for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kImgThreads) {
+    uint8_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned c = c0 + k * kImgThreads;
+      v[k] = row[c < (unsigned)cols ? c : c0];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned c = c0 + k * kImgThreads;
+      if (c < (unsigned)cols) out[c] = s_lut[v[k]];
+    }
+  }
 }
 
-__global__ void img_rescale_f64_kernel(const double* src, int64_t rows, int64_t cols, int64_t ld, const double* part,
-                                       double* dst, int64_t ldo) {
-  const int64_t b = blockIdx.y;
-  const int64_t r = blockIdx.x;
-  const MinMax<double> m = fold_minmax(part, b);
-  const double den = m.mx - m.mn;
-  const double* row = src + (b * rows + r) * ld;
-  double* out = dst + (b * rows + r) * ldo;
-  for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) out[c] = __ddiv_rn(row[c] - m.mn, den);
+// pitched plane -> dense [B][rows][cols] (only when the caller asks for the uint8 image)
+__global__ void img_unpitch_kernel(const uint8_t* src, int64_t cols, int64_t pitch, uint8_t* dst) {
+  const int64_t row = blockIdx.x;       // over B * rows
+  for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) dst[row * cols + c] = src[row * pitch + c];
 }
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -144,65 +187,347 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
-// horizontal pass: inter[r][c] = sum_d src[r][reflect(c + d - kw/2)] * kx[d]   (Q8.8, <= 255 * 256)
-__global__ void blur_h_kernel(const uint8_t* src, int64_t rows, int cols, const uint16_t* kx, int kw, uint16_t* inter) {
-  SPECGPU_DYN_SMEM(smem);
-  uint8_t* s_row = smem;                                   // [cols + kw - 1] with the border already reflected
-  const int64_t row = blockIdx.x;                           // over B * rows
-  const uint8_t* in = src + row * cols;
-  const int half = kw / 2;
-  for (int i = threadIdx.x; i < cols + kw - 1; i += blockDim.x) s_row[i] = in[reflect101(i - half, cols)];
-  __syncthreads();
-  uint16_t* out = inter + row * cols;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    unsigned acc = 0;
-    for (int d = 0; d < kw; ++d) acc += (unsigned)s_row[c + d] * (unsigned)kx[d];
-    out[c] = (uint16_t)(acc > 65535u ? 65535u : acc);      // ufixedpoint16 saturates (cannot trigger: taps sum to 256)
-  }
-}
-
-// vertical pass: dst[r][c] = (sum_e inter[reflect(r + e - kh/2)][c] * ky[e] + 2^15) >> 16
-__global__ void blur_v_kernel(const uint16_t* inter, int rows, int cols, const uint16_t* ky, int kh, uint8_t* dst) {
-  const int64_t b = blockIdx.z;
-  const int r = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const uint16_t* img = inter + b * (int64_t)rows * cols;
-  unsigned acc = 0;
-  for (int e = 0; e < kh; ++e) acc += (unsigned)img[(int64_t)reflect101(r + e - kh / 2, rows) * cols + c] * (unsigned)ky[e];
-  const unsigned v = (acc + 32768u) >> 16;
-  dst[(b * rows + r) * cols + c] = (uint8_t)(v > 255u ? 255u : v);
-}
-
-// rectangular dilation / erosion, anchor (ay, ax), pixels outside the image are ignored
-__global__ void morph_rect_kernel(const uint8_t* src, int rows, int cols, int kh, int kw, int ay, int ax, int erode,
-                                  uint8_t* dst) {
-  const int64_t b = blockIdx.z;
-  const int r = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  const uint8_t* img = src + b * (int64_t)rows * cols;
-  int v = erode ? 255 : 0;
-  for (int dy = 0; dy < kh; ++dy) {
-    const int y = r + dy - ay;
-    if (y < 0 || y >= rows) continue;
-    for (int dx = 0; dx < kw; ++dx) {
-      const int x = c + dx - ax;
-      if (x < 0 || x >= cols) continue;
-      const int p = img[(int64_t)y * cols + x];
-      v = erode ? (p < v ? p : v) : (p > v ? p : v);
+// fold the valid bytes of a packed word into running min / max
+__device__ __forceinline__ void minmax_bytes(uint32_t w, int nvalid, unsigned& mn, unsigned& mx) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const unsigned v = (w >> (8 * s)) & 255u;
+    if (s < nvalid) {
+      mn = v < mn ? v : mn;
+      mx = v > mx ? v : mx;
     }
   }
-  dst[(b * rows + r) * cols + c] = (uint8_t)v;
 }
 
-// |x - mean over the row| (np.mean(axis=1) in float64), one CTA per row; fixed-order tree => deterministic
-__global__ void meansub_abs_kernel(const double* src, int64_t rows, int64_t cols, int64_t ld, double* dst) {
+// CTA-wide fold of per-thread {min, max} into the image slot: warp shuffles, shared atomics, one global atomic pair
+__device__ __forceinline__ void fold_mm8(unsigned mn, unsigned mx, unsigned* slot) {
+  __shared__ unsigned s_mm8[2];
+  if (threadIdx.x == 0) {
+    s_mm8[0] = 255u;
+    s_mm8[1] = 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned a = __shfl_xor_sync(0xffffffffu, mn, o), c = __shfl_xor_sync(0xffffffffu, mx, o);
+    mn = a < mn ? a : mn;
+    mx = c > mx ? c : mx;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&s_mm8[0], mn);
+    atomicMax(&s_mm8[1], mx);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicMin(&slot[0], s_mm8[0]);
+    atomicMax(&slot[1], s_mm8[1]);
+  }
+}
+
+// ---- GaussianBlur, both passes in one kernel -------------------------------------------------------------------------
+// Tile: kBlurRows x TC output pixels.  Shared memory holds the uint8 tile with its reflected border (kh - 1 extra rows,
+// kw - 1 extra columns; byte i of a row is image column c0 - kw/2 + i, so the window of output column c starts at byte
+// c and 4-pixel groups start on a word), then the Q8.8 horizontal result of all its rows.
+//   horizontal: inter[r][c] = sum_d src[r][c + d - kw/2] * kx[d]        (<= 255 * 256)
+//   vertical:   dst[r][c]   = (sum_e inter[r + e - kh/2][c] * ky[e] + 2^15) >> 16
+// The taps are Q8.8 <= 256; when all horizontal ones fit a byte (always, except kw = 1) four of them are packed per
+// word and the pass runs on IDP.4A with funnel-shifted windows: 4 pixels x 4 taps per 4 + 3 instructions.
+constexpr int kBlurRows = 16;
+
+struct BlurGeom {
+  int tc;                // tile columns (multiple of 4)
+  int in_words;          // words per input-tile row
+  size_t smem;
+};
+
+template <int GT>   // packed tap words known at compile time (0: run-time count)
+__global__ void __launch_bounds__(kImgThreads) blur_fused_kernel(const uint8_t* src, int rows, int cols, int64_t pitch,
+                                                                 const uint16_t* taps, int kw, int kh, int tc, int in_words,
+                                                                 int packed, uint8_t* dst, unsigned* mm8) {
+  SPECGPU_DYN_SMEM(smem);
+  const int rin = kBlurRows + kh - 1;                                        // input rows of the tile
+  uint32_t* s_in = reinterpret_cast<uint32_t*>(smem);                        // [rin][in_words]
+  uint32_t* s_h = s_in + rin * in_words;                                     // [rin][tc / 2]   (two Q8.8 values per word)
+  uint32_t* s_tap = s_h + rin * (tc / 2);                                    // packed kx words, then kx, ky as uint16 pairs
+  const int G = (kw + 3) / 4;
+  uint16_t* s_k16 = reinterpret_cast<uint16_t*>(s_tap + G);                  // [kw + kh]
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.z;
+  const int r0 = blockIdx.y * kBlurRows, c0 = blockIdx.x * tc;
+  const int halfw = kw / 2, halfh = kh / 2;
+  const uint8_t* img = src + b * (int64_t)rows * pitch;
+
+  for (int i = tid; i < kw + kh; i += kImgThreads) s_k16[i] = taps[i];
+  for (int g = tid; g < G; g += kImgThreads) {
+    uint32_t w = 0;
+    for (int s = 0; s < 4; ++s)
+      if (4 * g + s < kw) w |= (uint32_t)(taps[4 * g + s] & 255u) << (8 * s);
+    s_tap[g] = w;
+  }
+  // ---- load the tile: aligned word pairs + funnel shift in the interior, per-byte reflection at the image border ----
+  const int x0 = c0 - halfw;                                                 // image column of byte 0 of a tile row
+  const int sh = (x0 & 3) * 8;
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int j = warp; j < rin; j += kImgThreads / 32) {                       // a warp per tile row: no index division
+    const uint8_t* row = img + (int64_t)reflect101(r0 - halfh + j, rows) * pitch;
+    for (int k = lane; k < in_words; k += 32) {
+      const int x = x0 + 4 * k;
+      uint32_t w;
+      if (x >= 0 && x + 3 < cols) {
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(row) + (x >> 2);
+        const uint32_t lo = rw[0];
+        w = sh ? __funnelshift_r(lo, rw[1], sh) : lo;
+      } else {
+        w = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) w |= (uint32_t)row[reflect101(x + s, cols)] << (8 * s);
+      }
+      s_in[j * in_words + k] = w;
+    }
+  }
+  __syncthreads();
+  // ---- horizontal pass: 4 outputs per item (tc / 4 is a power of two) ----
+  const int tq = tc / 4, lq = 31 - __clz(tq);
+  uint2* s_h2 = reinterpret_cast<uint2*>(s_h);                               // four Q8.8 values per 64-bit slot
+  for (int i = tid; i < rin * tq; i += kImgThreads) {
+    const int j = i >> lq, g = i & (tq - 1);
+    unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (GT > 0) {
+      const uint32_t* rw = s_in + j * in_words + g;
+      uint32_t w0 = rw[0], w1 = rw[1];
+#pragma unroll
+      for (int t = 0; t < GT; ++t) {
+        const uint32_t tap = s_tap[t];
+        a0 = __dp4a(w0, tap, a0);
+        a1 = __dp4a(__funnelshift_r(w0, w1, 8), tap, a1);
+        a2 = __dp4a(__funnelshift_r(w0, w1, 16), tap, a2);
+        a3 = __dp4a(__funnelshift_r(w0, w1, 24), tap, a3);
+        w0 = w1;
+        w1 = rw[t + 2];
+      }
+    } else if (packed) {
+      const uint32_t* rw = s_in + j * in_words + g;
+      uint32_t w0 = rw[0], w1 = rw[1];
+      for (int t = 0; t < G; ++t) {
+        const uint32_t tap = s_tap[t];
+        a0 = __dp4a(w0, tap, a0);
+        a1 = __dp4a(__funnelshift_r(w0, w1, 8), tap, a1);
+        a2 = __dp4a(__funnelshift_r(w0, w1, 16), tap, a2);
+        a3 = __dp4a(__funnelshift_r(w0, w1, 24), tap, a3);
+        w0 = w1;
+        w1 = rw[t + 2];
+      }
+    } else {
+      const uint8_t* rb = reinterpret_cast<const uint8_t*>(s_in + j * in_words) + 4 * g;
+      for (int d = 0; d < kw; ++d) {
+        const unsigned k = s_k16[d];
+        a0 += rb[d] * k;
+        a1 += rb[d + 1] * k;
+        a2 += rb[d + 2] * k;
+        a3 += rb[d + 3] * k;
+      }
+    }
+    a0 = a0 > 65535u ? 65535u : a0;        // ufixedpoint16 saturates (cannot trigger: the taps sum to 256)
+    a1 = a1 > 65535u ? 65535u : a1;
+    a2 = a2 > 65535u ? 65535u : a2;
+    a3 = a3 > 65535u ? 65535u : a3;
+    s_h2[i] = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
+  }
+  __syncthreads();
+  // ---- vertical pass, store, min / max ----
+  unsigned mn = 255u, mx = 0u;
+  const uint16_t* ky = s_k16 + kw;
+  for (int i = tid; i < kBlurRows * tq; i += kImgThreads) {
+    const int j = i >> lq, g = i & (tq - 1);
+    const int r = r0 + j, c = c0 + 4 * g;
+    if (r >= rows || c >= cols) continue;
+    unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int e = 0; e < kh; ++e) {
+      const unsigned k = ky[e];
+      const uint2 pq = s_h2[i + e * tq];
+      a0 += (pq.x & 65535u) * k;
+      a1 += (pq.x >> 16) * k;
+      a2 += (pq.y & 65535u) * k;
+      a3 += (pq.y >> 16) * k;
+    }
+    a0 = (a0 + 32768u) >> 16;
+    a1 = (a1 + 32768u) >> 16;
+    a2 = (a2 + 32768u) >> 16;
+    a3 = (a3 + 32768u) >> 16;
+    a0 = a0 > 255u ? 255u : a0;
+    a1 = a1 > 255u ? 255u : a1;
+    a2 = a2 > 255u ? 255u : a2;
+    a3 = a3 > 255u ? 255u : a3;
+    const uint32_t w = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+    *reinterpret_cast<uint32_t*>(dst + (b * rows + r) * pitch + c) = w;      // pad columns may receive garbage
+    minmax_bytes(w, cols - c, mn, mx);
+  }
+  fold_mm8(mn, mx, mm8 + 2 * b);
+}
+
+static BlurGeom blur_geom(int kw, int kh) {
+  BlurGeom g;
+  const int rin = kBlurRows + kh - 1;
+  for (int tc = 512; tc >= 16; tc >>= 1) {
+    g.tc = tc;
+    g.in_words = (tc / 4 + (kw + 3) / 4 + 2 + 1) & ~1;      // even: the Q8.8 plane behind it is read as 64-bit slots
+    g.smem = (size_t)rin * g.in_words * 4 + (size_t)rin * (tc / 2) * 4 + (size_t)((kw + 3) / 4) * 4 + (size_t)(kw + kh) * 2 + 16;
+    if (g.smem <= (tc > 64 ? 64u : 200u) * 1024u) break;
+  }
+  return g;
+}
+
+// ---- MORPH_CLOSE rect 4x4 then MORPH_OPEN rect 3(time) x 1, one kernel --------------------------------------------------
+// close = dilate, erode with the 4x4 rectangle, anchor (2, 2): offsets -2..+1 in both directions;
+// open  = erode, dilate with 1 row x 3 columns, anchor (0, 1): offsets -1..+1 along the row.
+// Rectangles are separable.  The tile lives in shared memory as 16-bit lanes, two pixels per word, so every min / max
+// is one native VIMNMX(3).U16x2 and a one-pixel shift is a 16-bit funnel shift.  A thread owns one word column and half
+// of the rows: for each 4x4 stage it walks down its rows, forms the horizontal 4-window of a row from shared memory
+// and keeps the last four of them in registers for the vertical window - one shared-memory round trip per 2-D stage.
+// OpenCV ignores pixels outside the image: every stage writes, at positions outside the image, the identity of the
+// stage that reads it next (0 before a max, 255 before a min).  Tile kMorphRows x kMorphCols outputs with halo 4 rows
+// above, 2 below and 8 columns on either side (256 pixels = 128 words per row); results in the halo are garbage
+// that never reaches the interior.
+constexpr int kMorphRows = 26, kMorphCols = 240;
+constexpr int kMorphPR = kMorphRows + 6, kMorphW = (kMorphCols + 16) / 2;
+static_assert(kMorphW == 128 && kImgThreads == 2 * kMorphW, "one thread per word column and row half");
+
+template <bool MAX>
+__device__ __forceinline__ uint32_t pk2(uint32_t a, uint32_t b) {
+  return MAX ? __vmaxs2(a, b) : __vmins2(a, b);           // lanes hold 0..255: signed and unsigned agree
+}
+template <bool MAX>
+__device__ __forceinline__ uint32_t pk3(uint32_t a, uint32_t b, uint32_t c) {
+  return MAX ? __vimax3_s16x2(a, b, c) : __vimin3_s16x2(a, b, c);
+}
+
+// horizontal window -L..+1 (L = 2: four wide, L = 1: three wide) of one word; pm / pc / pp point at the previous, own
+// and next word of the row (clamped at the plane edge by the caller, where the result is halo garbage anyway)
+template <bool MAX, int L>
+__device__ __forceinline__ uint32_t morph_hwin(const uint32_t* pm, const uint32_t* pc, const uint32_t* pp, int row) {
+  const uint32_t wm = pm[row * kMorphW], w = pc[row * kMorphW], wp = pp[row * kMorphW];
+  const uint32_t left = __funnelshift_r(wm, w, 16), right = __funnelshift_r(w, wp, 16);   // offsets -1, +1
+  const uint32_t v = pk3<MAX>(left, w, right);
+  return L == 2 ? pk2<MAX>(v, wm) : v;                                                   // offset -2 = the previous word
+}
+
+// one 4x4 stage: rows [y0, y0 + N) of plane `out` = op over rows y-2..y+1, columns -2..+1 of plane `in`.  N is a
+// compile-time count so the row loop unrolls into immediate-offset shared-memory accesses.
+template <bool MAX, int N>
+__device__ __forceinline__ void morph_stage4(const uint32_t* in, uint32_t* out, int k, int km, int kp, int y0, int r0, int rows,
+                                             uint32_t cm, uint32_t next_ident) {
+  const uint32_t *pm = in + (y0 - 2) * kMorphW + km, *pc = in + (y0 - 2) * kMorphW + k, *pp = in + (y0 - 2) * kMorphW + kp;
+  uint32_t* po = out + y0 * kMorphW + k;
+  uint32_t h0, h1 = morph_hwin<MAX, 2>(pm, pc, pp, 0), h2 = morph_hwin<MAX, 2>(pm, pc, pp, 1),
+               h3 = morph_hwin<MAX, 2>(pm, pc, pp, 2);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    h0 = h1;
+    h1 = h2;
+    h2 = h3;
+    h3 = morph_hwin<MAX, 2>(pm, pc, pp, i + 3);
+    const uint32_t v = pk2<MAX>(pk3<MAX>(h0, h1, h2), h3);
+    const uint32_t m = (unsigned)(r0 - 4 + y0 + i) < (unsigned)rows ? cm : 0u;
+    po[i * kMorphW] = (v & m) | (next_ident & ~m);
+  }
+}
+
+__global__ void __launch_bounds__(kImgThreads) morph_fused_kernel(const uint8_t* src, int rows, int cols, int64_t pitch,
+                                                                  uint8_t* dst, unsigned* mm8) {
+  __shared__ uint32_t s_a[kMorphPR * kMorphW], s_b[kMorphPR * kMorphW];
+  const int64_t b = blockIdx.z;
+  const int r0 = blockIdx.y * kMorphRows, c0 = blockIdx.x * kMorphCols;
+  const uint8_t* img = src + b * (int64_t)rows * pitch;
+  const int k = threadIdx.x & (kMorphW - 1), half = threadIdx.x >> 7;
+  const int km = k > 0 ? k - 1 : 0, kp = k < kMorphW - 1 ? k + 1 : k;
+  const int gx = c0 - 8 + 2 * k;                                             // image column of the word's first pixel
+  const uint32_t cm = ((unsigned)gx < (unsigned)cols ? 0x0000ffffu : 0u) | ((unsigned)(gx + 1) < (unsigned)cols ? 0xffff0000u : 0u);
+  const uint32_t ones = 0x00ff00ffu;                                         // 255 in both lanes
+  // load: outside the image -> 0 (the first stage is a max)
+  {
+    const uint8_t* p = img + (int64_t)(r0 - 4 + half) * pitch + gx;
+#pragma unroll
+    for (int i = 0; i < kMorphPR / 2; ++i) {
+      const int gy = r0 - 4 + half + 2 * i;
+      uint32_t w = 0;
+      if ((unsigned)gy < (unsigned)rows && cm) {
+        const unsigned v = *reinterpret_cast<const uint16_t*>(p + (int64_t)(2 * i) * pitch);
+        w = ((v & 255u) | ((v >> 8) << 16)) & cm;
+      }
+      s_a[(half + 2 * i) * kMorphW + k] = w;
+    }
+  }
+  __syncthreads();
+  // Each half takes N consecutive rows of a stage; when the row count is odd the halves overlap by one row, which both
+  // compute identically.
+  // dilate 4x4 -> rows 2 .. PR-2 of plane b (next: min)
+  {
+    constexpr int ya = 2, yb = kMorphPR - 1, N = (yb - ya + 1) / 2;
+    morph_stage4<true, N>(s_a, s_b, k, km, kp, half ? yb - N : ya, r0, rows, cm, ones);
+  }
+  __syncthreads();
+  // erode 4x4 -> rows 4 .. PR-3 of plane a (next: min)
+  constexpr int ya = 4, yb = kMorphPR - 2, N = (yb - ya + 1) / 2;
+  const int y0 = half ? yb - N : ya;
+  morph_stage4<false, N>(s_b, s_a, k, km, kp, y0, r0, rows, cm, ones);
+  __syncthreads();
+  // erode 1x3 -> plane b (next: max)
+  {
+    const uint32_t *pm = s_a + y0 * kMorphW + km, *pc = s_a + y0 * kMorphW + k, *pp = s_a + y0 * kMorphW + kp;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const uint32_t v = morph_hwin<false, 1>(pm, pc, pp, i);
+      const uint32_t m = (unsigned)(r0 - 4 + y0 + i) < (unsigned)rows ? cm : 0u;
+      s_b[(y0 + i) * kMorphW + k] = v & m;
+    }
+  }
+  __syncthreads();
+  // dilate 1x3 straight to global memory: words 4 .. W-5 are the tile's own columns
+  unsigned mn = 255u, mx = 0u;
+  if (k >= 4 && k < kMorphW - 4 && cm) {
+    const uint32_t *pm = s_b + y0 * kMorphW + km, *pc = s_b + y0 * kMorphW + k, *pp = s_b + y0 * kMorphW + kp;
+    uint8_t* po = dst + (b * rows + (r0 - 4 + y0)) * pitch + gx;
+    uint32_t lo_mn = 0x00ff00ffu, lo_mx = 0u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (r0 - 4 + y0 + i < rows) {
+        const uint32_t v = morph_hwin<true, 1>(pm, pc, pp, i);
+        *reinterpret_cast<uint16_t*>(po + (int64_t)i * pitch) = (uint16_t)((v & 255u) | ((v >> 16) << 8));   // pad may get garbage
+        lo_mn = __vmins2(lo_mn, (v & cm) | (ones & ~cm));                    // lanes outside the image cannot win
+        lo_mx = __vmaxs2(lo_mx, v & cm);
+      }
+    }
+    const unsigned a0 = lo_mn & 0xffffu, a1 = lo_mn >> 16, c0x = lo_mx & 0xffffu, c1x = lo_mx >> 16;
+    mn = a0 < a1 ? a0 : a1;
+    mx = c0x > c1x ? c0x : c1x;
+  }
+  fold_mm8(mn, mx, mm8 + 2 * b);
+}
+
+// ---- meansub: |x - mean over the row| then the image rescale, two passes over the source -------------------------------
+// pass 1: one CTA per row: float64 mean (fixed-order tree => deterministic), then min / max of |x - mean| (from
+// registers for rows up to 4096 columns, else a second read that comes from cache) -> rowstat[row] = {mean, min, max}
+constexpr int kMeanRegs = 16;      // rows up to 16 * 256 = 4096 columns stay in registers between the two sweeps
+
+template <bool INREG>
+__global__ void meansub_stats_kernel(const double* src, int64_t cols, int64_t ld, double* rowstat) {
   const int64_t row = blockIdx.x;       // over B * rows
   const double* in = src + row * ld;
+  double v[INREG ? kMeanRegs : 1];
   double s = 0.0;
-  for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) s += in[c];
-  __shared__ double sh[kImgThreads];
+  if (INREG) {
+#pragma unroll
+    for (int q = 0; q < kMeanRegs; ++q) {
+      const unsigned c = threadIdx.x + q * kImgThreads;
+      v[q] = c < (unsigned)cols ? in[c] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < kMeanRegs; ++q)
+      if (threadIdx.x + q * kImgThreads < (unsigned)cols) s += v[q];          // same order as the strided loop below
+  } else {
+    for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) s += in[c];
+  }
+  __shared__ double sh[kImgThreads], sh2[kImgThreads];
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = kImgThreads / 2; o > 0; o >>= 1) {
@@ -210,27 +535,101 @@ __global__ void meansub_abs_kernel(const double* src, int64_t rows, int64_t cols
     __syncthreads();
   }
   const double mean = __ddiv_rn(sh[0], (double)cols);
-  double* out = dst + row * cols;
-  for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) out[c] = fabs(in[c] - mean);
+  __syncthreads();
+  double mn = INFINITY, mx = -INFINITY;
+  if (INREG) {
+#pragma unroll
+    for (int q = 0; q < kMeanRegs; ++q)
+      if (threadIdx.x + q * kImgThreads < (unsigned)cols) {
+        const double d = fabs(v[q] - mean);
+        mn = d < mn ? d : mn;
+        mx = d > mx ? d : mx;
+      }
+  } else {
+    for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) {
+      const double d = fabs(in[c] - mean);
+      mn = d < mn ? d : mn;
+      mx = d > mx ? d : mx;
+    }
+  }
+  sh[threadIdx.x] = mn;
+  sh2[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = kImgThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const double a = sh[threadIdx.x + o], c = sh2[threadIdx.x + o];
+      if (a < sh[threadIdx.x]) sh[threadIdx.x] = a;
+      if (c > sh2[threadIdx.x]) sh2[threadIdx.x] = c;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    rowstat[row * 3] = mean;
+    rowstat[row * 3 + 1] = sh[0];
+    rowstat[row * 3 + 2] = sh2[0];
+  }
+}
+
+// pass 2: fold the image's row statistics, then (|x - mean| - min) / (max - min)
+__global__ void meansub_apply_kernel(const double* src, int64_t rows, int64_t cols, int64_t ld, const double* rowstat,
+                                     double* dst, int64_t ldo) {
+  const int64_t b = blockIdx.y;
+  const int64_t r = blockIdx.x;
+  __shared__ double sh[kImgThreads], sh2[kImgThreads];
+  double mn = INFINITY, mx = -INFINITY;
+  for (int64_t q = threadIdx.x; q < rows; q += blockDim.x) {
+    const double a = rowstat[(b * rows + q) * 3 + 1], c = rowstat[(b * rows + q) * 3 + 2];
+    mn = a < mn ? a : mn;
+    mx = c > mx ? c : mx;
+  }
+  sh[threadIdx.x] = mn;
+  sh2[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = kImgThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const double a = sh[threadIdx.x + o], c = sh2[threadIdx.x + o];
+      if (a < sh[threadIdx.x]) sh[threadIdx.x] = a;
+      if (c > sh2[threadIdx.x]) sh2[threadIdx.x] = c;
+    }
+    __syncthreads();
+  }
+  mn = sh[0];
+  const double den = sh2[0] - mn;
+  const double mean = rowstat[(b * rows + r) * 3];
+  const double* in = src + (b * rows + r) * ld;
+  double* out = dst + (b * rows + r) * ldo;
+  for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kImgThreads) {
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned c = c0 + k * kImgThreads;
+      v[k] = in[c < (unsigned)cols ? c : c0];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned c = c0 + k * kImgThreads;
+      if (c < (unsigned)cols) out[c] = __ddiv_rn(fabs(v[k] - mean) - mn, den);
+    }
+  }
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------------------
 size_t imgchain_workspace_bytes(int64_t B, int64_t rows, int64_t cols) {
-  const size_t px = (size_t)B * rows * cols;
-  // two uint8 planes, one uint16 plane, one float64 plane, partial min/max slots, kernel taps
-  return 2 * (px + 256) + 2 * px + 256 + 8 * px + 256 + (size_t)B * kImgParts * 2 * 8 + 256 + 4096;
+  const size_t plane = (size_t)B * rows * img_pitch(cols);
+  // two pitched uint8 planes, float/double min-max partials, uint8 min-max slots, row statistics, kernel taps
+  return 2 * (plane + 256) + (size_t)B * kImgParts * 2 * 8 + 256 + (size_t)B * 2 * 4 + 256 + (size_t)B * rows * 3 * 8 + 256 + 4096;
 }
 
 namespace {
 struct ImgWs {
   uint8_t *u8a, *u8b;
-  uint16_t* u16;
-  double* f64;
   void* part;
+  unsigned* mm8;
+  double* rowstat;
   uint16_t* taps;
 };
 ImgWs img_carve(void* ws, int64_t B, int64_t rows, int64_t cols) {
-  const size_t px = (size_t)B * rows * cols;
+  const size_t plane = (size_t)B * rows * img_pitch(cols);
   char* p = static_cast<char*>(ws);
   auto take = [&](size_t bytes) {
     char* q = p;
@@ -238,17 +637,40 @@ ImgWs img_carve(void* ws, int64_t B, int64_t rows, int64_t cols) {
     return q;
   };
   ImgWs w;
-  w.f64 = reinterpret_cast<double*>(take(8 * px));
-  w.u16 = reinterpret_cast<uint16_t*>(take(2 * px));
-  w.u8a = reinterpret_cast<uint8_t*>(take(px));
-  w.u8b = reinterpret_cast<uint8_t*>(take(px));
+  w.u8a = reinterpret_cast<uint8_t*>(take(plane));
+  w.u8b = reinterpret_cast<uint8_t*>(take(plane));
   w.part = take((size_t)B * kImgParts * 2 * 8);
+  w.mm8 = reinterpret_cast<unsigned*>(take((size_t)B * 2 * 4));
+  w.rowstat = reinterpret_cast<double*>(take((size_t)B * rows * 3 * 8));
   w.taps = reinterpret_cast<uint16_t*>(take(4096));
   return w;
 }
 template <class T>
 void run_minmax(const T* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, T* part, cudaStream_t st) {
   SPECGPU_LAUNCH((img_minmax_kernel<T>), dim3(kImgParts, (unsigned)B), kImgThreads, 0, st, src, rows, cols, ld, part);
+}
+// min / max of the source, then its uint8 quantisation into plane `dst`
+void run_quantise(const void* src, int in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld, const ImgWs& w, uint8_t* dst,
+                  cudaStream_t st) {
+  const dim3 rowgrid((unsigned)rows, (unsigned)B);
+  const int64_t pitch = img_pitch(cols);
+  if (in_f64) {
+    run_minmax<double>((const double*)src, B, rows, cols, ld, (double*)w.part, st);
+    SPECGPU_LAUNCH((img_quantise_kernel<double>), rowgrid, kImgThreads, 0, st, (const double*)src, rows, cols, ld,
+                   (const double*)w.part, dst, pitch, w.mm8);
+  } else {
+    run_minmax<float>((const float*)src, B, rows, cols, ld, (float*)w.part, st);
+    SPECGPU_LAUNCH((img_quantise_kernel<float>), rowgrid, kImgThreads, 0, st, (const float*)src, rows, cols, ld,
+                   (const float*)w.part, dst, pitch, w.mm8);
+  }
+}
+// rescale of the uint8 result (+ the dense copy when the caller wants the uint8 image)
+void run_rescale_u8(const uint8_t* plane, int64_t B, int64_t rows, int64_t cols, const ImgWs& w, double* dst, int64_t ldo,
+                    uint8_t* u8_out, cudaStream_t st) {
+  const int64_t pitch = img_pitch(cols);
+  SPECGPU_LAUNCH(img_rescale_u8_kernel, dim3((unsigned)rows, (unsigned)B), kImgThreads, 0, st, plane, rows, cols, pitch,
+                 (const unsigned*)w.mm8, dst, ldo);
+  if (u8_out) SPECGPU_LAUNCH(img_unpitch_kernel, (unsigned)(B * rows), kImgThreads, 0, st, plane, cols, pitch, u8_out);
 }
 }  // namespace
 
@@ -259,25 +681,25 @@ int launch_gaussblr(const void* src, int in_f64, int64_t B, int64_t rows, int64_
   ImgWs w = img_carve(ws, B, rows, cols);
   cudaError_t e = cudaMemcpyAsync(w.taps, taps_host, (size_t)(kw + kh) * sizeof(uint16_t), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return (int)e;
-  const dim3 rowgrid((unsigned)rows, (unsigned)B);
-  if (in_f64) {
-    run_minmax<double>((const double*)src, B, rows, cols, ld, (double*)w.part, st);
-    SPECGPU_LAUNCH((img_quantise_kernel<double>), rowgrid, kImgThreads, 0, st, (const double*)src, rows, cols, ld,
-                   (const double*)w.part, w.u8a);
-  } else {
-    run_minmax<float>((const float*)src, B, rows, cols, ld, (float*)w.part, st);
-    SPECGPU_LAUNCH((img_quantise_kernel<float>), rowgrid, kImgThreads, 0, st, (const float*)src, rows, cols, ld,
-                   (const float*)w.part, w.u8a);
-  }
-  SPECGPU_LAUNCH(blur_h_kernel, (unsigned)(B * rows), kImgThreads, (size_t)(cols + kw), st, (const uint8_t*)w.u8a, rows,
-                 (int)cols, (const uint16_t*)w.taps, kw, w.u16);
-  const dim3 pixgrid((unsigned)ceil_div(cols, kImgThreads), (unsigned)rows, (unsigned)B);
-  uint8_t* blurred = u8_out ? u8_out : w.u8b;
-  SPECGPU_LAUNCH(blur_v_kernel, pixgrid, kImgThreads, 0, st, (const uint16_t*)w.u16, (int)rows, (int)cols,
-                 (const uint16_t*)(w.taps + kw), kh, blurred);
-  run_minmax<uint8_t>(blurred, B, rows, cols, cols, (uint8_t*)w.part, st);
-  SPECGPU_LAUNCH(img_rescale_u8_kernel, rowgrid, kImgThreads, 0, st, (const uint8_t*)blurred, rows, cols,
-                 (const uint8_t*)w.part, dst, ldo);
+  run_quantise(src, in_f64, B, rows, cols, ld, w, w.u8a, st);
+  int packed = 1;
+  for (int d = 0; d < kw; ++d) packed &= taps_host[d] <= 255;
+  const BlurGeom g = blur_geom(kw, kh);
+  const dim3 grid((unsigned)ceil_div(cols, g.tc), (unsigned)ceil_div(rows, kBlurRows), (unsigned)B);
+  const int G = (kw + 3) / 4;
+#define SPECGPU_BLUR(GT)                                                                                                    \
+  do {                                                                                                                      \
+    e = cudaFuncSetAttribute(blur_fused_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                           \
+                             (int)std::max<size_t>(g.smem, 48 * 1024));                                                     \
+    if (e != cudaSuccess) return (int)e;                                                                                    \
+    SPECGPU_LAUNCH(blur_fused_kernel<GT>, grid, kImgThreads, g.smem, st, (const uint8_t*)w.u8a, (int)rows, (int)cols,       \
+                   img_pitch(cols), (const uint16_t*)w.taps, kw, kh, g.tc, g.in_words, packed, w.u8b, w.mm8);               \
+  } while (0)
+  if (packed && G == 8) SPECGPU_BLUR(8);          // ksize 29 / 31 (the reference's (31, 3))
+  else if (packed && G == 2) SPECGPU_BLUR(2);     // ksize 5 / 7
+  else SPECGPU_BLUR(0);
+#undef SPECGPU_BLUR
+  run_rescale_u8(w.u8b, B, rows, cols, w, dst, ldo, u8_out, st);
   return (int)cudaGetLastError();
 }
 
@@ -285,10 +707,12 @@ int launch_meansub(const double* src, int64_t B, int64_t rows, int64_t cols, int
                    cudaStream_t st) {
   if (B * rows * cols == 0) return 0;
   ImgWs w = img_carve(ws, B, rows, cols);
-  SPECGPU_LAUNCH(meansub_abs_kernel, (unsigned)(B * rows), kImgThreads, 0, st, src, rows, cols, ld, w.f64);
-  run_minmax<double>(w.f64, B, rows, cols, cols, (double*)w.part, st);
-  SPECGPU_LAUNCH(img_rescale_f64_kernel, dim3((unsigned)rows, (unsigned)B), kImgThreads, 0, st, (const double*)w.f64, rows,
-                 cols, cols, (const double*)w.part, dst, ldo);
+  if (cols <= kMeanRegs * kImgThreads)
+    SPECGPU_LAUNCH(meansub_stats_kernel<true>, (unsigned)(B * rows), kImgThreads, 0, st, src, cols, ld, w.rowstat);
+  else
+    SPECGPU_LAUNCH(meansub_stats_kernel<false>, (unsigned)(B * rows), kImgThreads, 0, st, src, cols, ld, w.rowstat);
+  SPECGPU_LAUNCH(meansub_apply_kernel, dim3((unsigned)rows, (unsigned)B), kImgThreads, 0, st, src, rows, cols, ld,
+                 (const double*)w.rowstat, dst, ldo);
   return (int)cudaGetLastError();
 }
 
@@ -296,28 +720,11 @@ int launch_morph(const void* src, int in_f64, int64_t B, int64_t rows, int64_t c
                  int64_t ldo, uint8_t* u8_out, cudaStream_t st) {
   if (B * rows * cols == 0) return 0;
   ImgWs w = img_carve(ws, B, rows, cols);
-  const dim3 rowgrid((unsigned)rows, (unsigned)B);
-  if (in_f64) {
-    run_minmax<double>((const double*)src, B, rows, cols, ld, (double*)w.part, st);
-    SPECGPU_LAUNCH((img_quantise_kernel<double>), rowgrid, kImgThreads, 0, st, (const double*)src, rows, cols, ld,
-                   (const double*)w.part, w.u8a);
-  } else {
-    run_minmax<float>((const float*)src, B, rows, cols, ld, (float*)w.part, st);
-    SPECGPU_LAUNCH((img_quantise_kernel<float>), rowgrid, kImgThreads, 0, st, (const float*)src, rows, cols, ld,
-                   (const float*)w.part, w.u8a);
-  }
-  const dim3 pixgrid((unsigned)ceil_div(cols, kImgThreads), (unsigned)rows, (unsigned)B);
-  const int R = (int)rows, Cc = (int)cols;
-  uint8_t* fin = u8_out ? u8_out : w.u8a;
-  // MORPH_CLOSE with rect(4, 4): dilate then erode, anchor (2, 2)
-  SPECGPU_LAUNCH(morph_rect_kernel, pixgrid, kImgThreads, 0, st, (const uint8_t*)w.u8a, R, Cc, 4, 4, 2, 2, 0, w.u8b);
-  SPECGPU_LAUNCH(morph_rect_kernel, pixgrid, kImgThreads, 0, st, (const uint8_t*)w.u8b, R, Cc, 4, 4, 2, 2, 1, w.u8a);
-  // MORPH_OPEN with getStructuringElement(RECT, (3, 1)) = 1 row x 3 columns: erode then dilate, anchor (0, 1)
-  SPECGPU_LAUNCH(morph_rect_kernel, pixgrid, kImgThreads, 0, st, (const uint8_t*)w.u8a, R, Cc, 1, 3, 0, 1, 1, w.u8b);
-  SPECGPU_LAUNCH(morph_rect_kernel, pixgrid, kImgThreads, 0, st, (const uint8_t*)w.u8b, R, Cc, 1, 3, 0, 1, 0, fin);
-  run_minmax<uint8_t>(fin, B, rows, cols, cols, (uint8_t*)w.part, st);
-  SPECGPU_LAUNCH(img_rescale_u8_kernel, rowgrid, kImgThreads, 0, st, (const uint8_t*)fin, rows, cols, (const uint8_t*)w.part,
-                 dst, ldo);
+  run_quantise(src, in_f64, B, rows, cols, ld, w, w.u8a, st);
+  const dim3 grid((unsigned)ceil_div(cols, kMorphCols), (unsigned)ceil_div(rows, kMorphRows), (unsigned)B);
+  SPECGPU_LAUNCH(morph_fused_kernel, grid, kImgThreads, 0, st, (const uint8_t*)w.u8a, (int)rows, (int)cols, img_pitch(cols),
+                 w.u8b, w.mm8);
+  run_rescale_u8(w.u8b, B, rows, cols, w, dst, ldo, u8_out, st);
   return (int)cudaGetLastError();
 }
 

@@ -707,7 +707,7 @@ int specgpu_gaussblr(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t 
   gaussian_taps_q8(kw, 0.0, taps);
   gaussian_taps_q8(kh, 0.0, taps + kw);
   CHECK_LAUNCH(ctx, launch_gaussblr(src, in_f64, B, rows, cols, ld, taps, kw, kh, ctx->ws, dst, ldo, u8_out, (cudaStream_t)stream),
-               "gaussblr", 6);
+               "gaussblr", 4 + (u8_out ? 1 : 0));
   return SPECGPU_OK;
 }
 
@@ -720,7 +720,7 @@ int specgpu_meansub(specgpu_ctx* ctx, const double* src, int64_t B, int64_t rows
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
   cudaSetDevice(ctx->device);
   if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
-  CHECK_LAUNCH(ctx, launch_meansub(src, B, rows, cols, ld, ctx->ws, dst, ldo, (cudaStream_t)stream), "meansub", 3);
+  CHECK_LAUNCH(ctx, launch_meansub(src, B, rows, cols, ld, ctx->ws, dst, ldo, (cudaStream_t)stream), "meansub", 2);
   return SPECGPU_OK;
 }
 
@@ -733,7 +733,7 @@ int specgpu_morph(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, 
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
   cudaSetDevice(ctx->device);
   if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
-  CHECK_LAUNCH(ctx, launch_morph(src, in_f64, B, rows, cols, ld, ctx->ws, dst, ldo, u8_out, (cudaStream_t)stream), "morph", 8);
+  CHECK_LAUNCH(ctx, launch_morph(src, in_f64, B, rows, cols, ld, ctx->ws, dst, ldo, u8_out, (cudaStream_t)stream), "morph", 4 + (u8_out ? 1 : 0));
   return SPECGPU_OK;
 }
 

@@ -42,11 +42,13 @@ struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) int2 { int x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 typedef int cudaError_t;
@@ -293,6 +295,40 @@ static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) {
 static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 
 // ---- intrinsics ----------------------------------------------------------------------------------
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+  const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+  return (unsigned)(v >> (shift & 31));
+}
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+  for (int s = 0; s < 4; ++s) c += ((a >> (8 * s)) & 255u) * ((b >> (8 * s)) & 255u);
+  return c;
+}
+static inline unsigned __vmaxu4(unsigned a, unsigned b) {
+  unsigned r = 0;
+  for (int s = 0; s < 4; ++s) {
+    const unsigned x = (a >> (8 * s)) & 255u, y = (b >> (8 * s)) & 255u;
+    r |= (x > y ? x : y) << (8 * s);
+  }
+  return r;
+}
+static inline unsigned __vmaxs2(unsigned a, unsigned b) {
+  const int16_t a0 = (int16_t)a, a1 = (int16_t)(a >> 16), b0 = (int16_t)b, b1 = (int16_t)(b >> 16);
+  return (unsigned)(uint16_t)(a0 > b0 ? a0 : b0) | ((unsigned)(uint16_t)(a1 > b1 ? a1 : b1) << 16);
+}
+static inline unsigned __vmins2(unsigned a, unsigned b) {
+  const int16_t a0 = (int16_t)a, a1 = (int16_t)(a >> 16), b0 = (int16_t)b, b1 = (int16_t)(b >> 16);
+  return (unsigned)(uint16_t)(a0 < b0 ? a0 : b0) | ((unsigned)(uint16_t)(a1 < b1 ? a1 : b1) << 16);
+}
+static inline unsigned __vimax3_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vmaxs2(a, b), c); }
+static inline unsigned __vimin3_s16x2(unsigned a, unsigned b, unsigned c) { return __vmins2(__vmins2(a, b), c); }
+static inline unsigned __vminu4(unsigned a, unsigned b) {
+  unsigned r = 0;
+  for (int s = 0; s < 4; ++s) {
+    const unsigned x = (a >> (8 * s)) & 255u, y = (b >> (8 * s)) & 255u;
+    r |= (x < y ? x : y) << (8 * s);
+  }
+  return r;
+}
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }

@@ -202,6 +202,35 @@ def case_csd_row_block(rt, C, n, nperseg, i0, ni, nblocks=2, fs=1.6e6):
     assert_spec_close(got, Pr[i0:i0 + ni])
 
 
+def case_cv2_tiles(rt, shapes, ksizes, seed=11):
+    """gaussblr / morph on noise images that span several shared-memory tiles (and on degenerate ones), uint8 results
+    bit-exact against the oracle; meansub to float64 round-off."""
+    rng = np.random.default_rng(seed)
+    for shape in shapes:
+        img = rng.random(shape)
+        img[rng.random(shape) < 0.02] *= 4.0          # a few outliers so the quantised image keeps low values
+        for ks in ksizes:
+            g, g8 = api.gaussblr(img, ks, return_uint8=True, runtime=rt)
+            q = (oc.rescale(img) * 255).astype("uint8")
+            assert np.array_equal(g8, oc.gaussian_blur_u8(q, ks)), (shape, ks)
+            with np.errstate(invalid="ignore"):          # a constant blurred image rescales to 0 / 0 = NaN on both sides
+                assert np.array_equal(g, oc.gaussblr(img, ks), equal_nan=True), (shape, ks)
+        mo, mo8 = api.morph(img, return_uint8=True, runtime=rt)
+        assert np.array_equal(mo8, oc.morph_close_open_u8((oc.rescale(img) * 255).astype("uint8"))), shape
+        with np.errstate(invalid="ignore"):
+            assert np.array_equal(mo, oc.morph(img), equal_nan=True), shape
+        np.testing.assert_allclose(api.meansub(img, runtime=rt), oc.meansub(img), rtol=1e-12, atol=1e-13)
+        f32 = img.astype(np.float32)
+        with np.errstate(invalid="ignore"):
+            assert np.array_equal(api.morph(f32, runtime=rt), oc.morph(f32), equal_nan=True), shape
+
+
+def case_meansub_wide(rt):
+    """Rows wider than the 4096 columns the row-statistics kernel keeps in registers."""
+    img = np.random.default_rng(3).random((3, 5000))
+    np.testing.assert_allclose(api.meansub(img, runtime=rt), oc.meansub(img), rtol=1e-12, atol=1e-13)
+
+
 # ---- whole path ------------------------------------------------------------------------------------
 def case_pipeline(rt, sp, n, B=2, tile=None):
     x = signals(B, n)

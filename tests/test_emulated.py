@@ -168,6 +168,15 @@ def test_cv2_chain_batched_small(emu_rt):
     out = api.gaussblr(S, (9, 3), runtime=emu_rt)
     for i in range(2):
         assert np.array_equal(out[i], oc.gaussblr(S[i], (9, 3)))
+    pc.case_meansub_wide(emu_rt)
+
+
+def test_cv2_chain_tiles(emu_rt):
+    # several blur tiles (16 x 512) and morphology tiles (32 x 256) with ragged edges, plus degenerate images
+    # (every emulated launch costs a fixed ~0.2 s, so the case list is short; tests/test_gpu_parity.py runs the long one)
+    pc.case_cv2_tiles(emu_rt, [(37, 1100)], [(31, 3)])
+    pc.case_cv2_tiles(emu_rt, [(70, 300)], [(5, 7)])
+    pc.case_cv2_tiles(emu_rt, [(3, 9), (40, 1), (2, 2)], [(1, 1), (9, 3)])
 
 
 # ---- host logic / error behaviour ---------------------------------------------------------------

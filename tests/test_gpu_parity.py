@@ -219,6 +219,15 @@ def test_svd_batched_and_tall(cuda_rt):
     pc.assert_denoise_close(api.denoiseSignal(m, runtime=cuda_rt), oc.denoiseSignal(m.astype(np.float64)))
 
 
+def test_cv2_chain_tiles_and_degenerate(cuda_rt):
+    """Fused blur (16 x 512 tiles, IDP.4A) and morphology (32 x 256 tiles) across tile seams, ragged edges, the
+    unpacked kw = 1 path, wide kernels and images smaller than the kernel; uint8 bit-exact."""
+    pc.case_cv2_tiles(cuda_rt, [(256, 3905), (70, 1100), (33, 257)], [(31, 3), (5, 7), (1, 1)])
+    pc.case_cv2_tiles(cuda_rt, [(300, 700)], [(63, 31), (3, 101)])
+    pc.case_cv2_tiles(cuda_rt, [(3, 9), (1, 40), (40, 1), (2, 2)], [(1, 1), (3, 1), (9, 3), (31, 3)])
+    pc.case_meansub_wide(cuda_rt)
+
+
 # ---- K2b: cross-power spectrum -------------------------------------------------------------------------
 def test_config3_co2_csd(cuda_rt):
     """BASELINE config 3: 4 chords, 2 s @ 1.6 MHz, nperseg 4096, all pairs."""
