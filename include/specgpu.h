@@ -130,6 +130,11 @@ int specgpu_meansub(specgpu_ctx* ctx, const double* src, int64_t B, int64_t rows
  * receives the uint8 mask before the final rescale (bit-exact). */
 int specgpu_morph(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld,
                   double* dst, int64_t ldo, uint8_t* u8_out, void* stream);
+/* The whole denoising body of the reference's main loop (pipeline_data.py:101-110) on a [B][rows][cols] float32 stack:
+ * quantfilt(thr) -> gaussblr((kw, kh)) -> meansub -> morph -> meansub, float64 out.  Identical, bit for bit, to chaining
+ * the five calls above; between the stages only uint8 planes (and their min / max) exist on the device. */
+int specgpu_filter_chain(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float thr,
+                         int32_t kw, int32_t kh, double* dst, int64_t ldo, void* stream);
 
 /* ---- SVD denoise (denoising_by_svd.ipynb:155-229, 280-281) --------------------------------- */
 /* out = U[:,a:b] diag(s[a:b]) Vh[a:b,:] of each S[b] (rows x cols, rows <= cols, rows <= 512), where

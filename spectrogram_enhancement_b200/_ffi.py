@@ -55,6 +55,7 @@ PROTOTYPES = {
     "specgpu_quantfilt": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp]),
     "specgpu_gaussblr": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _i64, _vp, _vp]),
     "specgpu_meansub": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "specgpu_filter_chain": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.c_float, _i32, _i32, _vp, _i64, _vp]),
     "specgpu_morph": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "specgpu_svd_denoise": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp,
                                       _vp, _vp]),

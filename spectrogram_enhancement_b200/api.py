@@ -481,19 +481,30 @@ def morph(src, return_uint8=False, runtime=None):
     return (rt.ret(out, as_torch), rt.ret(u8, as_torch)) if return_uint8 else rt.ret(out, as_torch)
 
 
-def filter_chain(Sxx, thr=0.9, filt=(31, 3), runtime=None):
+def filter_chain(Sxx, thr=0.9, filt=(31, 3), runtime=None, fused=True):
     """The denoising pipeline of pipeline_data.py:101-110 on a spectrogram (or a [B, F, T] stack), kept on the device
-    between stages: quantfilt -> gaussblr -> meansub -> morph -> meansub.  Returns `pipeline_out` (float64)."""
+    between stages: quantfilt -> gaussblr -> meansub -> morph -> meansub.  Returns `pipeline_out` (float64).
+    `fused=True` is one library call (specgpu_filter_chain: uint8 planes between the stages); `fused=False` chains the
+    five public functions - the results are identical bit for bit."""
     rt = _rt(runtime)
     as_torch = _is_torch(Sxx)
     d, _ = rt.to_device(Sxx)
-    if d.dim() == 2:
-        q = quantfilt(d, thr, runtime=rt)
-    else:                                   # [B, F, T] stack: one batched launch
-        B, rows, cols = d.shape
+    squeeze = d.dim() == 2
+    if squeeze:
+        d = d.unsqueeze(0)
+    if not 0.0 <= float(thr) <= 1.0:
+        raise ValueError("Quantiles must be in the range [0, 1]")
+    B, rows, cols = d.shape
+    if fused:
+        out = torch.empty((B, rows, cols), dtype=torch.float64, device=rt.device)
+        rt.check(rt.lib.filter_chain(rt._ctx, d.data_ptr(), B, rows, cols, _ld(d), float(thr), int(filt[0]), int(filt[1]),
+                                     out.data_ptr(), cols, rt.stream()))
+    else:
         q = torch.empty_like(d)
-        rt.check(rt.lib.quantfilt(rt._ctx, d.data_ptr(), B, rows, cols, cols, float(thr), q.data_ptr(), None, None, rt.stream()))
-    out = meansub(morph(meansub(gaussblr(q, filt, runtime=rt), runtime=rt), runtime=rt), runtime=rt)
+        rt.check(rt.lib.quantfilt(rt._ctx, d.data_ptr(), B, rows, cols, _ld(d), float(thr), q.data_ptr(), None, None, rt.stream()))
+        out = meansub(morph(meansub(gaussblr(q, filt, runtime=rt), runtime=rt), runtime=rt), runtime=rt)
+    if squeeze:
+        out = out[0]
     return rt.ret(out, as_torch)
 
 

@@ -15,12 +15,19 @@
 // shared memory, vertical pass out of it), the four morphology passes are ONE kernel per tile (separable min / max
 // on 16-bit lanes in shared-memory planes, halo 4 + 2 rows and 8 + 8 columns); both fold the image min / max of their uint8
 // result with integer atomics, and the final rescale is a 256-entry float64 table per CTA (uint8 has 256 quotients).
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace specgpu {
 
-constexpr int kImgThreads = 256;
-constexpr int kImgParts = 64;     // per-image partial min/max slots
+constexpr int kImgThreads = 256;   // the tile kernels (blur, morphology)
+#if defined(SPECGPU_EMULATE)
+constexpr int kRowThreads = 64;    // the CPU emulation pays per thread and barrier: narrower row CTAs, same code
+#else
+constexpr int kRowThreads = 256;   // the row-per-CTA kernels (min/max, quantise, rescale, meansub)
+#endif
+constexpr int kImgParts = 64;      // per-image partial min/max slots
 
 template <class T>
 struct MinMax {
@@ -43,11 +50,11 @@ __global__ void img_minmax_kernel(const T* src, int64_t rows, int64_t cols, int6
   (void)total;
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {          // a CTA walks whole rows: no division per element
     const T* row = src + (b * rows + r) * ld;
-    for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kImgThreads) {     // four loads in flight per thread
+    for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kRowThreads) {     // four loads in flight per thread
       T v[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const unsigned c = c0 + k * kImgThreads;
+        const unsigned c = c0 + k * kRowThreads;
         v[k] = row[c < (unsigned)cols ? c : c0];
       }
 #pragma unroll
@@ -57,11 +64,11 @@ __global__ void img_minmax_kernel(const T* src, int64_t rows, int64_t cols, int6
       }
     }
   }
-  __shared__ T s_min[kImgThreads], s_max[kImgThreads];
+  __shared__ T s_min[kRowThreads], s_max[kRowThreads];
   s_min[threadIdx.x] = vmin;
   s_max[threadIdx.x] = vmax;
   __syncthreads();
-  for (int o = kImgThreads / 2; o > 0; o >>= 1) {
+  for (int o = kRowThreads / 2; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) {
       const T a = s_min[threadIdx.x + o], c = s_max[threadIdx.x + o];
       if (a < s_min[threadIdx.x]) s_min[threadIdx.x] = a;
@@ -73,6 +80,12 @@ __global__ void img_minmax_kernel(const T* src, int64_t rows, int64_t cols, int6
     part[(b * kImgParts + blockIdx.x) * 2] = s_min[0];
     part[(b * kImgParts + blockIdx.x) * 2 + 1] = s_max[0];
   }
+  // images with fewer rows than slots launch fewer CTAs: the unused slots hold the identity
+  if (blockIdx.x == 0)
+    for (int q = gridDim.x + threadIdx.x; q < kImgParts; q += blockDim.x) {
+      part[(b * kImgParts + q) * 2] = sizeof(T) == 1 ? (T)255 : (T)INFINITY;
+      part[(b * kImgParts + q) * 2 + 1] = sizeof(T) == 1 ? (T)0 : (T)-INFINITY;
+    }
 }
 
 // Fold the kImgParts partial (min, max) pairs of image b: warp 0 reads two per lane and reduces with shuffles, the
@@ -112,6 +125,39 @@ __device__ __forceinline__ MinMax<T> fold_minmax(const T* part, int64_t b) {
   return m;
 }
 
+// t / den for many t and one den, correctly rounded: q = RN(t * y), r = t - q * den (exact in the FMA), q' = RN(q + r * y)
+// with y = RN(1 / den) is the IEEE quotient whenever den is normal and its significand is not all ones (Markstein);
+// `ok` is false otherwise and the caller divides.  Quotients so small that the residual underflows truncate to 0 in the
+// uint8 quantisation either way.
+struct FastDivF {
+  float den, y;
+  bool ok;
+  __device__ __forceinline__ FastDivF(float d) : den(d) {
+    y = __fdiv_rn(1.0f, d);
+    const uint32_t u = __float_as_uint(d), e = (u >> 23) & 255u;
+    ok = e > 1u && e < 254u && (u & 0x7fffffu) != 0x7fffffu;
+  }
+  __device__ __forceinline__ float div(float t) const {
+    if (!ok) return __fdiv_rn(t, den);
+    const float q = __fmul_rn(t, y);
+    return __fmaf_rn(__fmaf_rn(-q, den, t), y, q);
+  }
+};
+struct FastDivD {
+  double den, y;
+  bool ok;
+  __device__ __forceinline__ FastDivD(double d) : den(d) {
+    y = __ddiv_rn(1.0, d);
+    const uint64_t u = (uint64_t)__double_as_longlong(d), e = (u >> 52) & 2047u;
+    ok = e > 1u && e < 2046u && (u & 0xfffffffffffffull) != 0xfffffffffffffull;
+  }
+  __device__ __forceinline__ double div(double t) const {
+    if (!ok) return __ddiv_rn(t, den);
+    const double q = __dmul_rn(t, y);
+    return __fma_rn(__fma_rn(-q, den, t), y, q);
+  }
+};
+
 // pitch (bytes) of the workspace uint8 planes
 static inline int64_t img_pitch(int64_t cols) { return (cols + 15) & ~(int64_t)15; }
 
@@ -119,58 +165,63 @@ static inline int64_t img_pitch(int64_t cols) { return (cols + 15) & ~(int64_t)1
 // {min, max} slot the uint8 producers of image b fold into.
 template <class T>
 __global__ void img_quantise_kernel(const T* src, int64_t rows, int64_t cols, int64_t ld, const T* part, uint8_t* dst,
-                                    int64_t pitch, unsigned* mm8) {
+                                    int64_t pitch, unsigned* mm8, int rpc) {
   const int64_t b = blockIdx.y;
-  const int64_t r = blockIdx.x;
   const MinMax<T> m = fold_minmax(part, b);
-  if (r == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     mm8[2 * b] = 255u;
     mm8[2 * b + 1] = 0u;
   }
   const T den = m.mx - m.mn;
-  const T* row = src + (b * rows + r) * ld;
-  uint8_t* out = dst + (b * rows + r) * pitch;
-  for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kImgThreads) {
-    T v[4];
+  typename std::conditional<sizeof(T) == 4, FastDivF, FastDivD>::type fd(den);
+  const int64_t rend = min((int64_t)(blockIdx.x + 1) * rpc, rows);
+  for (int64_t r = (int64_t)blockIdx.x * rpc; r < rend; ++r) {      // rpc rows per CTA amortise the fold above
+    const T* row = src + (b * rows + r) * ld;
+    uint8_t* out = dst + (b * rows + r) * pitch;
+    for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kRowThreads) {
+      T v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned c = c0 + k * kImgThreads;
-      v[k] = row[c < (unsigned)cols ? c : c0];
-    }
+      for (int k = 0; k < 4; ++k) {
+        const unsigned c = c0 + k * kRowThreads;
+        v[k] = row[c < (unsigned)cols ? c : c0];
+      }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned c = c0 + k * kImgThreads;
-      T q;
-      if constexpr (sizeof(T) == 4) q = __fmul_rn(__fdiv_rn(__fsub_rn(v[k], m.mn), den), 255.0f);
-      else q = __dmul_rn(__ddiv_rn(__dsub_rn(v[k], m.mn), den), 255.0);
-      if (c < (unsigned)cols) out[c] = (uint8_t)(int)q;          // truncation toward zero; inputs are in [0, 255]
+      for (int k = 0; k < 4; ++k) {
+        const unsigned c = c0 + k * kRowThreads;
+        T q;
+        if constexpr (sizeof(T) == 4) q = __fmul_rn(fd.div(__fsub_rn(v[k], m.mn)), 255.0f);
+        else q = __dmul_rn(fd.div(__dsub_rn(v[k], m.mn)), 255.0);
+        if (c < (unsigned)cols) out[c] = (uint8_t)(int)q;          // truncation toward zero; inputs are in [0, 255]
+      }
     }
   }
 }
 
 // (u - min) / (max - min) with numpy's uint8 arithmetic and float64 true division: 256 possible quotients per image
 __global__ void img_rescale_u8_kernel(const uint8_t* src, int64_t rows, int64_t cols, int64_t pitch, const unsigned* mm8,
-                                      double* dst, int64_t ldo) {
+                                      double* dst, int64_t ldo, int rpc) {
   __shared__ double s_lut[256];
   const int64_t b = blockIdx.y;
-  const int64_t r = blockIdx.x;
   const uint8_t mn = (uint8_t)mm8[2 * b], mx = (uint8_t)mm8[2 * b + 1];
   const double den = (double)(uint8_t)(mx - mn);
   for (int v = threadIdx.x; v < 256; v += blockDim.x) s_lut[v] = __ddiv_rn((double)(uint8_t)((uint8_t)v - mn), den);
   __syncthreads();
-  const uint8_t* row = src + (b * rows + r) * pitch;
-  double* out = dst + (b * rows + r) * ldo;
-  for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kImgThreads) {
-    uint8_t v[4];
+  const int64_t rend = min((int64_t)(blockIdx.x + 1) * rpc, rows);
+  for (int64_t r = (int64_t)blockIdx.x * rpc; r < rend; ++r) {
+    const uint8_t* row = src + (b * rows + r) * pitch;
+    double* out = dst + (b * rows + r) * ldo;
+    for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kRowThreads) {
+      uint8_t v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned c = c0 + k * kImgThreads;
-      v[k] = row[c < (unsigned)cols ? c : c0];
-    }
+      for (int k = 0; k < 4; ++k) {
+        const unsigned c = c0 + k * kRowThreads;
+        v[k] = row[c < (unsigned)cols ? c : c0];
+      }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned c = c0 + k * kImgThreads;
-      if (c < (unsigned)cols) out[c] = s_lut[v[k]];
+      for (int k = 0; k < 4; ++k) {
+        const unsigned c = c0 + k * kRowThreads;
+        if (c < (unsigned)cols) out[c] = s_lut[v[k]];
+      }
     }
   }
 }
@@ -505,110 +556,184 @@ __global__ void __launch_bounds__(kImgThreads) morph_fused_kernel(const uint8_t*
 }
 
 // ---- meansub: |x - mean over the row| then the image rescale, two passes over the source -------------------------------
-// pass 1: one CTA per row: float64 mean (fixed-order tree => deterministic), then min / max of |x - mean| (from
+// The source is either a float64 image or - inside the fused chain - a uint8 plane standing for its own rescale
+// lut[v] = (v - min) / (max - min): the values, the summation order and therefore every bit are those of the float64
+// route, without the float64 image ever being written.
+struct MeanSrcF64 {
+  const double* row;
+  __device__ __forceinline__ double get(unsigned c) const { return row[c]; }
+};
+struct MeanSrcU8 {
+  const uint8_t* row;
+  const double* lut;
+  __device__ __forceinline__ double get(unsigned c) const { return lut[row[c]]; }
+};
+// rescale table of a uint8 image from its {min, max} slot (same expression as img_rescale_u8_kernel), once per image
+__global__ void u8_lut_kernel(const unsigned* mm8, double* lut) {
+  const int64_t b = blockIdx.x;
+  const uint8_t mn = (uint8_t)mm8[2 * b], mx = (uint8_t)mm8[2 * b + 1];
+  const double den = (double)(uint8_t)(mx - mn);
+  for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[b * 256 + v] = __ddiv_rn((double)(uint8_t)((uint8_t)v - mn), den);
+}
+__device__ __forceinline__ void load_u8_lut(double* s_lut, const double* lut, int64_t b) {
+  for (int v = threadIdx.x; v < 256; v += blockDim.x) s_lut[v] = lut[b * 256 + v];
+  __syncthreads();
+}
+template <bool U8>
+struct MeanSrcSel {
+  using type = MeanSrcF64;
+};
+template <>
+struct MeanSrcSel<true> {
+  using type = MeanSrcU8;
+};
+template <bool U8>
+__device__ __forceinline__ typename MeanSrcSel<U8>::type mean_src(const void* src, int64_t row, int64_t ld, const double* lut) {
+  if constexpr (U8) return MeanSrcU8{static_cast<const uint8_t*>(src) + row * ld, lut};
+  else return MeanSrcF64{static_cast<const double*>(src) + row * ld};
+}
+
+// CTA-wide reductions in a fixed order: xor-shuffle tree inside each warp, then the 8 warp results in warp order
+__device__ __forceinline__ double cta_sum(double v, double* s8) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s8[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = s8[0];
+#pragma unroll
+  for (int w = 1; w < kRowThreads / 32; ++w) t += s8[w];
+  __syncthreads();
+  return t;
+}
+__device__ __forceinline__ void cta_minmax(double& mn, double& mx, double* s8a, double* s8b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double a = __shfl_xor_sync(0xffffffffu, mn, o), c = __shfl_xor_sync(0xffffffffu, mx, o);
+    mn = a < mn ? a : mn;
+    mx = c > mx ? c : mx;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s8a[threadIdx.x >> 5] = mn;
+    s8b[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  mn = s8a[0];
+  mx = s8b[0];
+#pragma unroll
+  for (int w = 1; w < kRowThreads / 32; ++w) {
+    mn = s8a[w] < mn ? s8a[w] : mn;
+    mx = s8b[w] > mx ? s8b[w] : mx;
+  }
+  __syncthreads();
+}
+
+// pass 1: one CTA per row: float64 mean (fixed-order reduction => deterministic), then min / max of |x - mean| (from
 // registers for rows up to 4096 columns, else a second read that comes from cache) -> rowstat[row] = {mean, min, max}
 constexpr int kMeanRegs = 16;      // rows up to 16 * 256 = 4096 columns stay in registers between the two sweeps
 
-template <bool INREG>
-__global__ void meansub_stats_kernel(const double* src, int64_t cols, int64_t ld, double* rowstat) {
-  const int64_t row = blockIdx.x;       // over B * rows
-  const double* in = src + row * ld;
-  double v[INREG ? kMeanRegs : 1];
-  double s = 0.0;
-  if (INREG) {
+template <bool INREG, bool U8>
+__global__ void meansub_stats_kernel(const void* src, int64_t rows, int64_t cols, int64_t ld, const double* lut,
+                                     double* rowstat, int rpc) {
+  __shared__ double s_lut[U8 ? 256 : 1];
+  __shared__ double s8a[kRowThreads / 32], s8b[kRowThreads / 32];
+  const int64_t b = blockIdx.y;
+  if (U8) load_u8_lut(s_lut, lut, b);
+  const int64_t rend = min((int64_t)(blockIdx.x + 1) * rpc, rows);
+  for (int64_t r = (int64_t)blockIdx.x * rpc; r < rend; ++r) {      // rpc rows per CTA amortise the table load
+    const int64_t row = b * rows + r;
+    const auto in = mean_src<U8>(src, row, ld, s_lut);
+    double v[INREG ? kMeanRegs : 1];
+    double s = 0.0;
+    if (INREG) {
 #pragma unroll
-    for (int q = 0; q < kMeanRegs; ++q) {
-      const unsigned c = threadIdx.x + q * kImgThreads;
-      v[q] = c < (unsigned)cols ? in[c] : 0.0;
+      for (int q = 0; q < kMeanRegs; ++q) {
+        const unsigned c = threadIdx.x + q * kRowThreads;
+        v[q] = c < (unsigned)cols ? in.get(c) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < kMeanRegs; ++q)
+        if (threadIdx.x + q * kRowThreads < (unsigned)cols) s += v[q];          // same order as the strided loop below
+    } else {
+      for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) s += in.get(c);
     }
+    const double mean = __ddiv_rn(cta_sum(s, s8a), (double)cols);
+    double mn = INFINITY, mx = -INFINITY;
+    if (INREG) {
 #pragma unroll
-    for (int q = 0; q < kMeanRegs; ++q)
-      if (threadIdx.x + q * kImgThreads < (unsigned)cols) s += v[q];          // same order as the strided loop below
-  } else {
-    for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) s += in[c];
-  }
-  __shared__ double sh[kImgThreads], sh2[kImgThreads];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = kImgThreads / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  const double mean = __ddiv_rn(sh[0], (double)cols);
-  __syncthreads();
-  double mn = INFINITY, mx = -INFINITY;
-  if (INREG) {
-#pragma unroll
-    for (int q = 0; q < kMeanRegs; ++q)
-      if (threadIdx.x + q * kImgThreads < (unsigned)cols) {
-        const double d = fabs(v[q] - mean);
+      for (int q = 0; q < kMeanRegs; ++q)
+        if (threadIdx.x + q * kRowThreads < (unsigned)cols) {
+          const double d = fabs(v[q] - mean);
+          mn = d < mn ? d : mn;
+          mx = d > mx ? d : mx;
+        }
+    } else {
+      for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) {
+        const double d = fabs(in.get(c) - mean);
         mn = d < mn ? d : mn;
         mx = d > mx ? d : mx;
       }
-  } else {
-    for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) {
-      const double d = fabs(in[c] - mean);
-      mn = d < mn ? d : mn;
-      mx = d > mx ? d : mx;
     }
-  }
-  sh[threadIdx.x] = mn;
-  sh2[threadIdx.x] = mx;
-  __syncthreads();
-  for (int o = kImgThreads / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      const double a = sh[threadIdx.x + o], c = sh2[threadIdx.x + o];
-      if (a < sh[threadIdx.x]) sh[threadIdx.x] = a;
-      if (c > sh2[threadIdx.x]) sh2[threadIdx.x] = c;
+    cta_minmax(mn, mx, s8a, s8b);
+    if (threadIdx.x == 0) {
+      rowstat[row * 3] = mean;
+      rowstat[row * 3 + 1] = mn;
+      rowstat[row * 3 + 2] = mx;
     }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    rowstat[row * 3] = mean;
-    rowstat[row * 3 + 1] = sh[0];
-    rowstat[row * 3 + 2] = sh2[0];
   }
 }
 
-// pass 2: fold the image's row statistics, then (|x - mean| - min) / (max - min)
-__global__ void meansub_apply_kernel(const double* src, int64_t rows, int64_t cols, int64_t ld, const double* rowstat,
-                                     double* dst, int64_t ldo) {
-  const int64_t b = blockIdx.y;
-  const int64_t r = blockIdx.x;
-  __shared__ double sh[kImgThreads], sh2[kImgThreads];
+// fold the row statistics of image b -> imgstat[b] = {min, max - min}; optionally reset the {min, max} slot the next
+// uint8 producer folds into
+__global__ void meansub_fold_kernel(const double* rowstat, int64_t rows, double* imgstat, unsigned* mm8_next) {
+  __shared__ double s8a[kRowThreads / 32], s8b[kRowThreads / 32];
+  const int64_t b = blockIdx.x;
   double mn = INFINITY, mx = -INFINITY;
   for (int64_t q = threadIdx.x; q < rows; q += blockDim.x) {
     const double a = rowstat[(b * rows + q) * 3 + 1], c = rowstat[(b * rows + q) * 3 + 2];
     mn = a < mn ? a : mn;
     mx = c > mx ? c : mx;
   }
-  sh[threadIdx.x] = mn;
-  sh2[threadIdx.x] = mx;
-  __syncthreads();
-  for (int o = kImgThreads / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      const double a = sh[threadIdx.x + o], c = sh2[threadIdx.x + o];
-      if (a < sh[threadIdx.x]) sh[threadIdx.x] = a;
-      if (c > sh2[threadIdx.x]) sh2[threadIdx.x] = c;
+  cta_minmax(mn, mx, s8a, s8b);
+  if (threadIdx.x == 0) {
+    imgstat[2 * b] = mn;
+    imgstat[2 * b + 1] = mx - mn;
+    if (mm8_next) {
+      mm8_next[2 * b] = 255u;
+      mm8_next[2 * b + 1] = 0u;
     }
-    __syncthreads();
   }
-  mn = sh[0];
-  const double den = sh2[0] - mn;
-  const double mean = rowstat[(b * rows + r) * 3];
-  const double* in = src + (b * rows + r) * ld;
-  double* out = dst + (b * rows + r) * ldo;
-  for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kImgThreads) {
-    double v[4];
+}
+
+// pass 2: m = (|x - mean| - min) / (max - min).
+// QUANT = false: write m (float64).  QUANT = true: write morph's uint8 quantisation of m straight away - m is a
+// rescale, so its own min / max are exactly 0 and 1 and (rescale(m) * 255).astype(uint8) is trunc(m * 255).
+template <bool U8, bool QUANT>
+__global__ void meansub_apply_kernel(const void* src, int64_t rows, int64_t cols, int64_t ld, const double* lut,
+                                     const double* rowstat, const double* imgstat, void* dst, int64_t ldo, int rpc) {
+  __shared__ double s_lut[U8 ? 256 : 1];
+  const int64_t b = blockIdx.y;
+  if (U8) load_u8_lut(s_lut, lut, b);
+  const double mn = imgstat[2 * b], den = imgstat[2 * b + 1];
+  const FastDivD fd(den);
+  const int64_t rend = min((int64_t)(blockIdx.x + 1) * rpc, rows);
+  for (int64_t r = (int64_t)blockIdx.x * rpc; r < rend; ++r) {
+    const double mean = rowstat[(b * rows + r) * 3];
+    const auto in = mean_src<U8>(src, b * rows + r, ld, s_lut);
+    for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kRowThreads) {
+      double v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned c = c0 + k * kImgThreads;
-      v[k] = in[c < (unsigned)cols ? c : c0];
-    }
+      for (int k = 0; k < 4; ++k) {
+        const unsigned c = c0 + k * kRowThreads;
+        v[k] = in.get(c < (unsigned)cols ? c : c0);
+      }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned c = c0 + k * kImgThreads;
-      if (c < (unsigned)cols) out[c] = __ddiv_rn(fabs(v[k] - mean) - mn, den);
+      for (int k = 0; k < 4; ++k) {
+        const unsigned c = c0 + k * kRowThreads;
+        if (c < (unsigned)cols) {
+          const double m = fd.div(fabs(v[k] - mean) - mn);
+          if constexpr (QUANT) static_cast<uint8_t*>(dst)[(b * rows + r) * ldo + c] = (uint8_t)(int)__dmul_rn(m, 255.0);
+          else static_cast<double*>(dst)[(b * rows + r) * ldo + c] = m;
+        }
+      }
     }
   }
 }
@@ -617,15 +742,26 @@ __global__ void meansub_apply_kernel(const double* src, int64_t rows, int64_t co
 size_t imgchain_workspace_bytes(int64_t B, int64_t rows, int64_t cols) {
   const size_t plane = (size_t)B * rows * img_pitch(cols);
   // two pitched uint8 planes, float/double min-max partials, uint8 min-max slots, row statistics, kernel taps
-  return 2 * (plane + 256) + (size_t)B * kImgParts * 2 * 8 + 256 + (size_t)B * 2 * 4 + 256 + (size_t)B * rows * 3 * 8 + 256 + 4096;
+  return 2 * (plane + 256) + (size_t)B * kImgParts * 2 * 8 + 256 + 2 * ((size_t)B * 2 * 4 + 256) + (size_t)B * rows * 3 * 8 + 256 +
+         (size_t)B * 256 * 8 + 256 + (size_t)B * 2 * 8 + 256 + 4096;
 }
 
 namespace {
+// rows per CTA of the row kernels.  On the GPU one row per CTA measured best (40 x 256 rows: filter chain 0.81 ms
+// against 0.84 ms with 9 rows per CTA in a single wave - the short CTAs overlap their prologues better than a loop
+// amortises them); the CPU emulation runs CTAs one after another and pays per CTA, so it folds the rows into 16 CTAs.
+#if defined(SPECGPU_EMULATE)
+constexpr int64_t kRowSlots = 16;
+#else
+constexpr int64_t kRowSlots = (int64_t)1 << 40;
+#endif
+inline int rows_per_cta(int64_t B, int64_t rows) { return (int)std::max<int64_t>(1, ceil_div(B * rows, kRowSlots)); }
+inline dim3 row_grid(int64_t B, int64_t rows) { return dim3((unsigned)ceil_div(rows, rows_per_cta(B, rows)), (unsigned)B); }
 struct ImgWs {
   uint8_t *u8a, *u8b;
   void* part;
-  unsigned* mm8;
-  double* rowstat;
+  unsigned *mm8, *mm8b;
+  double *rowstat, *lut, *imgstat;
   uint16_t* taps;
 };
 ImgWs img_carve(void* ws, int64_t B, int64_t rows, int64_t cols) {
@@ -641,47 +777,62 @@ ImgWs img_carve(void* ws, int64_t B, int64_t rows, int64_t cols) {
   w.u8b = reinterpret_cast<uint8_t*>(take(plane));
   w.part = take((size_t)B * kImgParts * 2 * 8);
   w.mm8 = reinterpret_cast<unsigned*>(take((size_t)B * 2 * 4));
+  w.mm8b = reinterpret_cast<unsigned*>(take((size_t)B * 2 * 4));
   w.rowstat = reinterpret_cast<double*>(take((size_t)B * rows * 3 * 8));
+  w.lut = reinterpret_cast<double*>(take((size_t)B * 256 * 8));
+  w.imgstat = reinterpret_cast<double*>(take((size_t)B * 2 * 8));
   w.taps = reinterpret_cast<uint16_t*>(take(4096));
   return w;
 }
 template <class T>
 void run_minmax(const T* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, T* part, cudaStream_t st) {
-  SPECGPU_LAUNCH((img_minmax_kernel<T>), dim3(kImgParts, (unsigned)B), kImgThreads, 0, st, src, rows, cols, ld, part);
+  SPECGPU_LAUNCH((img_minmax_kernel<T>), dim3((unsigned)std::min<int64_t>(kImgParts, rows), (unsigned)B), kRowThreads, 0, st, src, rows, cols, ld, part);
 }
 // min / max of the source, then its uint8 quantisation into plane `dst`
 void run_quantise(const void* src, int in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld, const ImgWs& w, uint8_t* dst,
                   cudaStream_t st) {
-  const dim3 rowgrid((unsigned)rows, (unsigned)B);
+  const dim3 rowgrid = row_grid(B, rows);
+  const int rpc = rows_per_cta(B, rows);
   const int64_t pitch = img_pitch(cols);
   if (in_f64) {
     run_minmax<double>((const double*)src, B, rows, cols, ld, (double*)w.part, st);
-    SPECGPU_LAUNCH((img_quantise_kernel<double>), rowgrid, kImgThreads, 0, st, (const double*)src, rows, cols, ld,
-                   (const double*)w.part, dst, pitch, w.mm8);
+    SPECGPU_LAUNCH((img_quantise_kernel<double>), rowgrid, kRowThreads, 0, st, (const double*)src, rows, cols, ld,
+                   (const double*)w.part, dst, pitch, w.mm8, rpc);
   } else {
     run_minmax<float>((const float*)src, B, rows, cols, ld, (float*)w.part, st);
-    SPECGPU_LAUNCH((img_quantise_kernel<float>), rowgrid, kImgThreads, 0, st, (const float*)src, rows, cols, ld,
-                   (const float*)w.part, dst, pitch, w.mm8);
+    SPECGPU_LAUNCH((img_quantise_kernel<float>), rowgrid, kRowThreads, 0, st, (const float*)src, rows, cols, ld,
+                   (const float*)w.part, dst, pitch, w.mm8, rpc);
   }
 }
 // rescale of the uint8 result (+ the dense copy when the caller wants the uint8 image)
 void run_rescale_u8(const uint8_t* plane, int64_t B, int64_t rows, int64_t cols, const ImgWs& w, double* dst, int64_t ldo,
                     uint8_t* u8_out, cudaStream_t st) {
   const int64_t pitch = img_pitch(cols);
-  SPECGPU_LAUNCH(img_rescale_u8_kernel, dim3((unsigned)rows, (unsigned)B), kImgThreads, 0, st, plane, rows, cols, pitch,
-                 (const unsigned*)w.mm8, dst, ldo);
-  if (u8_out) SPECGPU_LAUNCH(img_unpitch_kernel, (unsigned)(B * rows), kImgThreads, 0, st, plane, cols, pitch, u8_out);
+  SPECGPU_LAUNCH(img_rescale_u8_kernel, row_grid(B, rows), kRowThreads, 0, st, plane, rows, cols, pitch,
+                 (const unsigned*)w.mm8, dst, ldo, rows_per_cta(B, rows));
+  if (u8_out) SPECGPU_LAUNCH(img_unpitch_kernel, (unsigned)(B * rows), kRowThreads, 0, st, plane, cols, pitch, u8_out);
 }
-}  // namespace
-
-// taps_host: kw + kh Q8.8 taps (kx then ky), built by the caller.
-int launch_gaussblr(const void* src, int in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld, const uint16_t* taps_host,
-                    int kw, int kh, void* ws, double* dst, int64_t ldo, uint8_t* u8_out, cudaStream_t st) {
-  if (B * rows * cols == 0) return 0;
-  ImgWs w = img_carve(ws, B, rows, cols);
+// both meansub passes from source `src` (float64 image or uint8 plane + its {min, max} slot)
+template <bool U8, bool QUANT>
+void run_meansub(const void* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* mm8, const ImgWs& w, void* dst,
+                 int64_t ldo, unsigned* mm8_next, cudaStream_t st) {
+  const dim3 rowgrid = row_grid(B, rows);
+  const int rpc = rows_per_cta(B, rows);
+  if (U8) SPECGPU_LAUNCH(u8_lut_kernel, (unsigned)B, kRowThreads, 0, st, mm8, w.lut);
+  if (cols <= kMeanRegs * kRowThreads)
+    SPECGPU_LAUNCH((meansub_stats_kernel<true, U8>), rowgrid, kRowThreads, 0, st, src, rows, cols, ld, (const double*)w.lut,
+                   w.rowstat, rpc);
+  else
+    SPECGPU_LAUNCH((meansub_stats_kernel<false, U8>), rowgrid, kRowThreads, 0, st, src, rows, cols, ld, (const double*)w.lut,
+                   w.rowstat, rpc);
+  SPECGPU_LAUNCH(meansub_fold_kernel, (unsigned)B, kRowThreads, 0, st, (const double*)w.rowstat, rows, w.imgstat, mm8_next);
+  SPECGPU_LAUNCH((meansub_apply_kernel<U8, QUANT>), rowgrid, kRowThreads, 0, st, src, rows, cols, ld, (const double*)w.lut,
+                 (const double*)w.rowstat, (const double*)w.imgstat, dst, ldo, rpc);
+}
+int run_blur(const ImgWs& w, int64_t B, int64_t rows, int64_t cols, const uint16_t* taps_host, int kw, int kh, const uint8_t* in,
+             uint8_t* out, cudaStream_t st) {
   cudaError_t e = cudaMemcpyAsync(w.taps, taps_host, (size_t)(kw + kh) * sizeof(uint16_t), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return (int)e;
-  run_quantise(src, in_f64, B, rows, cols, ld, w, w.u8a, st);
   int packed = 1;
   for (int d = 0; d < kw; ++d) packed &= taps_host[d] <= 255;
   const BlurGeom g = blur_geom(kw, kh);
@@ -692,27 +843,53 @@ int launch_gaussblr(const void* src, int in_f64, int64_t B, int64_t rows, int64_
     e = cudaFuncSetAttribute(blur_fused_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                           \
                              (int)std::max<size_t>(g.smem, 48 * 1024));                                                     \
     if (e != cudaSuccess) return (int)e;                                                                                    \
-    SPECGPU_LAUNCH(blur_fused_kernel<GT>, grid, kImgThreads, g.smem, st, (const uint8_t*)w.u8a, (int)rows, (int)cols,       \
-                   img_pitch(cols), (const uint16_t*)w.taps, kw, kh, g.tc, g.in_words, packed, w.u8b, w.mm8);               \
+    SPECGPU_LAUNCH(blur_fused_kernel<GT>, grid, kImgThreads, g.smem, st, in, (int)rows, (int)cols, img_pitch(cols),         \
+                   (const uint16_t*)w.taps, kw, kh, g.tc, g.in_words, packed, out, w.mm8);                                  \
   } while (0)
   if (packed && G == 8) SPECGPU_BLUR(8);          // ksize 29 / 31 (the reference's (31, 3))
   else if (packed && G == 2) SPECGPU_BLUR(2);     // ksize 5 / 7
   else SPECGPU_BLUR(0);
 #undef SPECGPU_BLUR
-  run_rescale_u8(w.u8b, B, rows, cols, w, dst, ldo, u8_out, st);
-  return (int)cudaGetLastError();
+  return 0;
 }
+}  // namespace
 
 int launch_meansub(const double* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* ws, double* dst, int64_t ldo,
                    cudaStream_t st) {
   if (B * rows * cols == 0) return 0;
   ImgWs w = img_carve(ws, B, rows, cols);
-  if (cols <= kMeanRegs * kImgThreads)
-    SPECGPU_LAUNCH(meansub_stats_kernel<true>, (unsigned)(B * rows), kImgThreads, 0, st, src, cols, ld, w.rowstat);
-  else
-    SPECGPU_LAUNCH(meansub_stats_kernel<false>, (unsigned)(B * rows), kImgThreads, 0, st, src, cols, ld, w.rowstat);
-  SPECGPU_LAUNCH(meansub_apply_kernel, dim3((unsigned)rows, (unsigned)B), kImgThreads, 0, st, src, rows, cols, ld,
-                 (const double*)w.rowstat, dst, ldo);
+  run_meansub<false, false>(src, B, rows, cols, ld, nullptr, w, dst, ldo, nullptr, st);
+  return (int)cudaGetLastError();
+}
+
+// gaussblr -> meansub -> morph -> meansub of pipeline_data.py:104-110 on an already thresholded float32 image, with
+// every intermediate kept as a uint8 plane + its {min, max}: 12 launches, the only float64 traffic is the result.
+int launch_filter_tail(const float* q, int64_t B, int64_t rows, int64_t cols, int64_t ld, const uint16_t* taps_host, int kw,
+                       int kh, void* ws, double* dst, int64_t ldo, cudaStream_t st) {
+  if (B * rows * cols == 0) return 0;
+  ImgWs w = img_carve(ws, B, rows, cols);
+  const int64_t pitch = img_pitch(cols);
+  run_quantise(q, 0, B, rows, cols, ld, w, w.u8a, st);                                    // gaussblr: quantise ...
+  int rc = run_blur(w, B, rows, cols, taps_host, kw, kh, w.u8a, w.u8b, st);              // ... blur -> plane b, slot mm8
+  if (rc) return rc;
+  // meansub of the blurred image + morph's quantisation -> plane a; resets slot mm8b
+  run_meansub<true, true>(w.u8b, B, rows, cols, pitch, w.mm8, w, w.u8a, pitch, w.mm8b, st);
+  const dim3 grid((unsigned)ceil_div(cols, kMorphCols), (unsigned)ceil_div(rows, kMorphRows), (unsigned)B);
+  SPECGPU_LAUNCH(morph_fused_kernel, grid, kImgThreads, 0, st, (const uint8_t*)w.u8a, (int)rows, (int)cols, pitch, w.u8b,
+                 w.mm8b);                                                                 // -> plane b, slot mm8b
+  run_meansub<true, false>(w.u8b, B, rows, cols, pitch, w.mm8b, w, dst, ldo, nullptr, st);  // final meansub -> float64
+  return (int)cudaGetLastError();
+}
+
+// taps_host: kw + kh Q8.8 taps (kx then ky), built by the caller.
+int launch_gaussblr(const void* src, int in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld, const uint16_t* taps_host,
+                    int kw, int kh, void* ws, double* dst, int64_t ldo, uint8_t* u8_out, cudaStream_t st) {
+  if (B * rows * cols == 0) return 0;
+  ImgWs w = img_carve(ws, B, rows, cols);
+  run_quantise(src, in_f64, B, rows, cols, ld, w, w.u8a, st);
+  const int rc = run_blur(w, B, rows, cols, taps_host, kw, kh, w.u8a, w.u8b, st);
+  if (rc) return rc;
+  run_rescale_u8(w.u8b, B, rows, cols, w, dst, ldo, u8_out, st);
   return (int)cudaGetLastError();
 }
 

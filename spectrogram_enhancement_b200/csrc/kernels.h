@@ -75,6 +75,8 @@ int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_
 size_t imgchain_workspace_bytes(int64_t B, int64_t rows, int64_t cols);
 int launch_gaussblr(const void* src, int in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld, const uint16_t* taps_host,
                     int kw, int kh, void* ws, double* dst, int64_t ldo, uint8_t* u8_out, cudaStream_t st);
+int launch_filter_tail(const float* q, int64_t B, int64_t rows, int64_t cols, int64_t ld, const uint16_t* taps_host, int kw,
+                       int kh, void* ws, double* dst, int64_t ldo, cudaStream_t st);
 int launch_meansub(const double* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* ws, double* dst, int64_t ldo,
                    cudaStream_t st);
 int launch_morph(const void* src, int in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* ws, double* dst,

@@ -720,7 +720,7 @@ int specgpu_meansub(specgpu_ctx* ctx, const double* src, int64_t B, int64_t rows
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
   cudaSetDevice(ctx->device);
   if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
-  CHECK_LAUNCH(ctx, launch_meansub(src, B, rows, cols, ld, ctx->ws, dst, ldo, (cudaStream_t)stream), "meansub", 2);
+  CHECK_LAUNCH(ctx, launch_meansub(src, B, rows, cols, ld, ctx->ws, dst, ldo, (cudaStream_t)stream), "meansub", 3);
   return SPECGPU_OK;
 }
 
@@ -734,6 +734,30 @@ int specgpu_morph(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, 
   cudaSetDevice(ctx->device);
   if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
   CHECK_LAUNCH(ctx, launch_morph(src, in_f64, B, rows, cols, ld, ctx->ws, dst, ldo, u8_out, (cudaStream_t)stream), "morph", 4 + (u8_out ? 1 : 0));
+  return SPECGPU_OK;
+}
+
+int specgpu_filter_chain(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float thr,
+                         int32_t kw, int32_t kh, double* dst, int64_t ldo, void* stream) {
+  int rc = check_matrix_args(ctx, src, B, rows, cols, ld);
+  if (rc) return rc;
+  if (kw < 1 || kh < 1 || !(kw & 1) || !(kh & 1) || kw > 255 || kh > 255)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "ksize (%d, %d): both must be odd and in [1, 255]", kw, kh);
+  if (!(thr >= 0.0f && thr <= 1.0f)) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "Quantiles must be in the range [0, 1]");
+  if (B * rows * cols == 0) return SPECGPU_OK;
+  if (cols > (1 << 30) || rows > 1024) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "filter_chain: rows=%lld > 1024 or image too large", (long long)rows);
+  if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
+  cudaSetDevice(ctx->device);
+  // workspace: the image-chain planes, then the thresholded float32 image
+  const size_t img_bytes = (imgchain_workspace_bytes(B, rows, cols) + 255) & ~(size_t)255;
+  if ((rc = ensure_ws(ctx, img_bytes + (size_t)B * rows * cols * sizeof(float) + 256))) return rc;
+  float* q = reinterpret_cast<float*>(static_cast<char*>(ctx->ws) + img_bytes);
+  if ((rc = specgpu_quantfilt(ctx, src, B, rows, cols, ld, thr, q, nullptr, nullptr, stream))) return rc;
+  uint16_t taps[512];
+  gaussian_taps_q8(kw, 0.0, taps);
+  gaussian_taps_q8(kh, 0.0, taps + kw);
+  CHECK_LAUNCH(ctx, launch_filter_tail(q, B, rows, cols, cols, taps, kw, kh, ctx->ws, dst, ldo, (cudaStream_t)stream),
+               "filter_tail", 12);
   return SPECGPU_OK;
 }
 

@@ -225,6 +225,18 @@ def case_cv2_tiles(rt, shapes, ksizes, seed=11):
             assert np.array_equal(api.morph(f32, runtime=rt), oc.morph(f32), equal_nan=True), shape
 
 
+def case_cv2_many_rows(rt, shape=(19, 63, 33)):
+    """Stacks with more than 148 * 8 rows: the row kernels take several rows per CTA (ragged last group)."""
+    S = np.random.default_rng(8).random(shape).astype(np.float32)
+    g = api.gaussblr(S, (5, 3), runtime=rt)
+    m = api.meansub(g, runtime=rt)
+    fin = api.filter_chain(S, runtime=rt)
+    for i in (0, shape[0] - 1):
+        assert np.array_equal(g[i], oc.gaussblr(S[i], (5, 3)))
+        np.testing.assert_allclose(m[i], oc.meansub(g[i]), rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(fin[i], oc.filter_chain(S[i]), rtol=1e-12, atol=1e-13)
+
+
 def case_meansub_wide(rt):
     """Rows wider than the 4096 columns the row-statistics kernel keeps in registers."""
     img = np.random.default_rng(3).random((3, 5000))
@@ -274,6 +286,8 @@ def case_filter_chain(rt, S):
     assert np.array_equal(mo, mo_ref)
     fin = api.filter_chain(S, runtime=rt)
     np.testing.assert_allclose(fin, oc.filter_chain(S), rtol=1e-12, atol=1e-13)
+    # the single fused call (uint8 planes between the stages) and the five chained public calls agree bit for bit
+    assert np.array_equal(fin, api.filter_chain(S, runtime=rt, fused=False))
     return g, fin
 
 

@@ -159,7 +159,7 @@ def test_pipeline_fused_normalise_route(emu_rt):
 def test_cv2_chain_small(emu_rt, golden):
     # a crop of the reference's spectrogram against the oracle (which test_oracle.py pins to cv2 and to the reference's
     # golden outputs); the full golden image runs in tests/test_gpu_parity.py -- the emulation is too slow for it
-    S = np.ascontiguousarray(golden("specgr_small.npz")["S_f32"][:48, :70])
+    S = np.ascontiguousarray(golden("specgr_small.npz")["S_f32"][:32, :70])
     pc.case_filter_chain(emu_rt, S)
 
 
@@ -169,14 +169,15 @@ def test_cv2_chain_batched_small(emu_rt):
     for i in range(2):
         assert np.array_equal(out[i], oc.gaussblr(S[i], (9, 3)))
     pc.case_meansub_wide(emu_rt)
+    pc.case_cv2_many_rows(emu_rt, (3, 21, 33))
 
 
 def test_cv2_chain_tiles(emu_rt):
     # several blur tiles (16 x 512) and morphology tiles (32 x 256) with ragged edges, plus degenerate images
     # (every emulated launch costs a fixed ~0.2 s, so the case list is short; tests/test_gpu_parity.py runs the long one)
-    pc.case_cv2_tiles(emu_rt, [(37, 1100)], [(31, 3)])
-    pc.case_cv2_tiles(emu_rt, [(70, 300)], [(5, 7)])
-    pc.case_cv2_tiles(emu_rt, [(3, 9), (40, 1), (2, 2)], [(1, 1), (9, 3)])
+    pc.case_cv2_tiles(emu_rt, [(30, 560)], [(31, 3)])
+    pc.case_cv2_tiles(emu_rt, [(17, 1030)], [(5, 7)])
+    pc.case_cv2_tiles(emu_rt, [(3, 9), (12, 1), (2, 2)], [(1, 1), (9, 3)])
 
 
 # ---- host logic / error behaviour ---------------------------------------------------------------

@@ -226,6 +226,21 @@ def test_cv2_chain_tiles_and_degenerate(cuda_rt):
     pc.case_cv2_tiles(cuda_rt, [(300, 700)], [(63, 31), (3, 101)])
     pc.case_cv2_tiles(cuda_rt, [(3, 9), (1, 40), (40, 1), (2, 2)], [(1, 1), (3, 1), (9, 3), (31, 3)])
     pc.case_meansub_wide(cuda_rt)
+    pc.case_cv2_many_rows(cuda_rt)
+    pc.case_cv2_many_rows(cuda_rt, (7, 333, 290))
+
+
+def test_filter_chain_fused_full_size(cuda_rt):
+    """specgpu_filter_chain on a [3, 256, 3905] stack (config 2's image size): bit-identical to chaining the five public
+    calls, and within float64 round-off of the oracle per image."""
+    rng = np.random.default_rng(21)
+    S = rng.random((3, 256, 3905)).astype(np.float32) ** 4
+    fused = api.filter_chain(S, runtime=cuda_rt)
+    assert fused.dtype == np.float64 and fused.shape == S.shape
+    assert np.array_equal(fused, api.filter_chain(S, runtime=cuda_rt, fused=False))
+    for i in (0, 2):
+        assert np.array_equal(fused[i], api.filter_chain(S[i], runtime=cuda_rt))          # batched == one by one
+    np.testing.assert_allclose(fused[1], oc.filter_chain(S[1]), rtol=1e-12, atol=1e-13)
 
 
 # ---- K2b: cross-power spectrum -------------------------------------------------------------------------

@@ -10,6 +10,9 @@ xs = [torch.rand((40, 256, 3905), device=rt.device, generator=g, dtype=dt) for _
 fns = dict(gaussblr=lambda x: api.gaussblr(x, (31, 3), runtime=rt), meansub=lambda x: api.meansub(x, runtime=rt),
            morph=lambda x: api.morph(x, runtime=rt))
 iters = int(os.environ.get("ITERS", "10"))
+if dt == torch.float32:
+    fns["filter_chain_fused"] = lambda x: api.filter_chain(x, runtime=rt)
+    fns["filter_chain_5_calls"] = lambda x: api.filter_chain(x, runtime=rt, fused=False)
 for name, fn in fns.items():
     if name == "meansub" and dt != torch.float64:
         continue
