@@ -71,6 +71,9 @@ report("meansub 40x[256x3905] f64", timeit(lambda i: rt.check(rt.lib.meansub(rt.
        40 * 256 * 3905 * 16)
 report("morph 40x[256x3905] f64", timeit(lambda i: rt.check(rt.lib.morph(rt._ctx, m64.data_ptr(), 1, 40, 256, 3905, 3905, o64.data_ptr(), 3905, None, rt.stream())), iters=5),
        40 * 256 * 3905 * 16)
+report("filter_chain fused (quantfilt -> gaussblr -> meansub -> morph -> meansub) 40x[256x3905] f32 -> f64",
+       timeit(lambda i: rt.check(rt.lib.filter_chain(rt._ctx, imgs[i % NB].data_ptr(), 40, 256, 3905, 3905, 0.9, 31, 3, o64.data_ptr(), 3905,
+                                                     rt.stream())), iters=5), 40 * 256 * 3905 * 12)
 # ---- specgr only (spectrogram + log + min-max), 40 channels ----
 xs = [torch.randn((40, 1_000_000), device=dev, generator=g) for _ in range(NB)]
 plan = rt.plan_from_params(api.DEFAULT_SPEC_PARAMS)
