@@ -15,11 +15,13 @@ import sys
 
 tag, launches, rep, benchlog = sys.argv[1:5]
 note = sys.argv[5] if len(sys.argv) > 5 else ""
+command = sys.argv[6] if len(sys.argv) > 6 else "python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 OURS = ("stft_kernel", "gram_tc_kernel", "gram_reduce", "gram_simt", "eig_power", "eig_jacobi", "eig_sort", "svd_", "lognorm",
-        "minmax", "quantfilt", "patch_kernel", "unpatch", "csd_", "rescale", "moments", "norm_apply")
+        "minmax", "quantfilt", "patch_kernel", "unpatch", "csd_", "rescale", "moments", "norm_apply", "img_", "blur_", "morph_",
+        "meansub_", "u8_lut")
 
 rows = list(csv.reader(open(launches)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -65,7 +67,7 @@ if benchlog != "-":
     bench = json.loads([l for l in open(benchlog).read().strip().split("\n") if l.startswith("{")][-1])
 with open(os.path.join(out, f"{tag}_summary.md"), "w") as f:
     f.write(f"# {tag}: ncu launch list + full capture summary\n\n{note}\n\n")
-    f.write("Command: `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e` on one B200 (gpurun); launch list from\n"
+    f.write(f"Command: `{command}` on one B200 (gpurun); launch list from\n"
             "`ncu --metrics gpu__time_duration.sum --clock-control none`, per-kernel metrics from `ncu --set full "
             "--clock-control none --import-source on`.\nncu launch times are cold-cache and serialised: compare SHARES.\n\n")
     f.write("## Launch list (our kernels; setup kernels of torch's synthetic-input generation excluded: "
