@@ -125,6 +125,9 @@ def test_csd_wide_stacks(emu_rt):
     pc.case_csd(emu_rt, 16, 2100, 32)
     pc.case_csd(emu_rt, 27, 2100, 32)
     pc.case_csd(emu_rt, 40, 2000, 64)
+    pc.case_csd(emu_rt, 40, 200, 64)          # fewer stages than the ring is deep
+    pc.case_csd(emu_rt, 40, 64, 64)           # a single segment
+    pc.case_csd(emu_rt, 33, 100, 8)           # five bins: most lanes of the frequency block idle
     pc.case_csd_row_block(emu_rt, 40, 2100, 32, 8, 24, nblocks=3)
     pc.case_csd_row_block(emu_rt, 40, 1500, 32, 20, 20, nblocks=1)
     pc.case_csd_row_block(emu_rt, 6, 1500, 32, 2, 3, nblocks=2)

@@ -262,6 +262,9 @@ def test_csd_wide_stacks_and_row_blocks(cuda_rt):
     pc.case_csd(cuda_rt, 20, 60_000, 128)
     pc.case_csd(cuda_rt, 27, 50_000, 256)
     pc.case_csd(cuda_rt, 64, 40_000, 512)
+    pc.case_csd(cuda_rt, 40, 200, 64)
+    pc.case_csd(cuda_rt, 40, 64, 64)
+    pc.case_csd(cuda_rt, 33, 100, 8)
     pc.case_csd_row_block(cuda_rt, 40, 120_000, 1024, 8, 24, nblocks=3)
     pc.case_csd_row_block(cuda_rt, 40, 120_000, 1024, 20, 20, nblocks=4)
     pc.case_csd_row_block(cuda_rt, 6, 30_000, 64, 2, 3, nblocks=2)
