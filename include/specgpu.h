@@ -113,7 +113,8 @@ int specgpu_clip(specgpu_ctx* ctx, const float* src, int64_t n, float* dst, void
 
 /* quantfilt (pipeline_data.py:46-49): per column, q = np.quantile(src[:,j], thr) over the `rows`
  * axis with numpy's float32 'linear' arithmetic (bit-exact), dst = src < q ? 0 : src.
- * thr_out[B][cols] and mask[B][rows][ld] (uint8, 1 = kept) are optional (NULL to skip). rows <= 1024. */
+ * dst (optional) has the row pitch ld of src; thr_out[B][cols] and mask[B][rows][ld] (uint8, 1 = kept) are optional
+ * (NULL to skip). rows <= 1024. */
 int specgpu_quantfilt(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld,
                       float thr, float* dst, float* thr_out, uint8_t* mask, void* stream);
 
@@ -132,7 +133,8 @@ int specgpu_morph(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, 
                   double* dst, int64_t ldo, uint8_t* u8_out, void* stream);
 /* The whole denoising body of the reference's main loop (pipeline_data.py:101-110) on a [B][rows][cols] float32 stack:
  * quantfilt(thr) -> gaussblr((kw, kh)) -> meansub -> morph -> meansub, float64 out.  Identical, bit for bit, to chaining
- * the five calls above; between the stages only uint8 planes (and their min / max) exist on the device. */
+ * the five calls above; between the stages only uint8 planes (and their min / max) exist on the device.  src rows have
+ * pitch ld, dst rows pitch ldo; rows <= 1024 (quantfilt's limit). */
 int specgpu_filter_chain(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float thr,
                          int32_t kw, int32_t kh, double* dst, int64_t ldo, void* stream);
 

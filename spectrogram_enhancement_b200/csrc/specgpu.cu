@@ -748,15 +748,15 @@ int specgpu_filter_chain(specgpu_ctx* ctx, const float* src, int64_t B, int64_t 
   if (cols > (1 << 30) || rows > 1024) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "filter_chain: rows=%lld > 1024 or image too large", (long long)rows);
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
   cudaSetDevice(ctx->device);
-  // workspace: the image-chain planes, then the thresholded float32 image
+  // workspace: the image-chain planes, then the thresholded float32 image (quantfilt writes it with the source's pitch)
   const size_t img_bytes = (imgchain_workspace_bytes(B, rows, cols) + 255) & ~(size_t)255;
-  if ((rc = ensure_ws(ctx, img_bytes + (size_t)B * rows * cols * sizeof(float) + 256))) return rc;
+  if ((rc = ensure_ws(ctx, img_bytes + (size_t)B * rows * ld * sizeof(float) + 256))) return rc;
   float* q = reinterpret_cast<float*>(static_cast<char*>(ctx->ws) + img_bytes);
   if ((rc = specgpu_quantfilt(ctx, src, B, rows, cols, ld, thr, q, nullptr, nullptr, stream))) return rc;
   uint16_t taps[512];
   gaussian_taps_q8(kw, 0.0, taps);
   gaussian_taps_q8(kh, 0.0, taps + kw);
-  CHECK_LAUNCH(ctx, launch_filter_tail(q, B, rows, cols, cols, taps, kw, kh, ctx->ws, dst, ldo, (cudaStream_t)stream),
+  CHECK_LAUNCH(ctx, launch_filter_tail(q, B, rows, cols, ld, taps, kw, kh, ctx->ws, dst, ldo, (cudaStream_t)stream),
                "filter_tail", 12);
   return SPECGPU_OK;
 }

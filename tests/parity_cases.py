@@ -237,6 +237,27 @@ def case_cv2_many_rows(rt, shape=(19, 63, 33)):
         np.testing.assert_allclose(fin[i], oc.filter_chain(S[i]), rtol=1e-12, atol=1e-13)
 
 
+def case_cv2_pitched(rt):
+    """The C ABI takes row pitches: source rows padded to ld > cols and a padded float64 output."""
+    import torch
+    rng = np.random.default_rng(1)
+    B, R, C, ld, ldo = 2, 20, 37, 45, 50
+    buf = torch.from_numpy(rng.random((B, R, ld)).astype(np.float32)).to(rt.device)
+    S = buf[:, :, :C].cpu().numpy().copy()
+    out = torch.empty((B, R, C), dtype=torch.float64, device=rt.device)
+    rt.check(rt.lib.filter_chain(rt._ctx, buf.data_ptr(), B, R, C, ld, 0.9, 31, 3, out.data_ptr(), C, rt.stream()))
+    g = torch.empty((B, R, C), dtype=torch.float64, device=rt.device)
+    rt.check(rt.lib.gaussblr(rt._ctx, buf.data_ptr(), 0, B, R, C, ld, 5, 3, g.data_ptr(), C, None, rt.stream()))
+    mo = torch.zeros((B, R, ldo), dtype=torch.float64, device=rt.device)
+    rt.check(rt.lib.morph(rt._ctx, buf.data_ptr(), 0, B, R, C, ld, mo.data_ptr(), ldo, None, rt.stream()))
+    out, g, mo = out.cpu().numpy(), g.cpu().numpy(), mo.cpu().numpy()
+    for i in range(B):
+        np.testing.assert_allclose(out[i], oc.filter_chain(S[i]), rtol=1e-12, atol=1e-13)
+        assert np.array_equal(g[i], oc.gaussblr(S[i], (5, 3)))
+        assert np.array_equal(mo[i, :, :C], oc.morph(S[i]))
+    assert not mo[:, :, C:].any()                    # the padding of the output rows is left alone
+
+
 def case_meansub_wide(rt):
     """Rows wider than the 4096 columns the row-statistics kernel keeps in registers."""
     img = np.random.default_rng(3).random((3, 5000))

@@ -173,6 +173,7 @@ def test_cv2_chain_batched_small(emu_rt):
         assert np.array_equal(out[i], oc.gaussblr(S[i], (9, 3)))
     pc.case_meansub_wide(emu_rt)
     pc.case_cv2_many_rows(emu_rt, (3, 21, 33))
+    pc.case_cv2_pitched(emu_rt)
 
 
 def test_cv2_chain_tiles(emu_rt):

@@ -227,6 +227,7 @@ def test_cv2_chain_tiles_and_degenerate(cuda_rt):
     pc.case_cv2_tiles(cuda_rt, [(3, 9), (1, 40), (40, 1), (2, 2)], [(1, 1), (3, 1), (9, 3), (31, 3)])
     pc.case_meansub_wide(cuda_rt)
     pc.case_cv2_many_rows(cuda_rt)
+    pc.case_cv2_pitched(cuda_rt)
     pc.case_cv2_many_rows(cuda_rt, (7, 333, 290))
 
 
