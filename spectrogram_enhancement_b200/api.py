@@ -20,6 +20,7 @@ no CPU implementation behind these functions: without libspecgpu.so and a B200 t
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pickle
 import threading
 
@@ -30,7 +31,7 @@ from . import _ffi
 
 __all__ = [
     "Runtime", "default_runtime", "DEFAULT_SPEC_PARAMS", "spectrogram", "stft", "csd", "csd_allpairs",
-    "spectrogram_batch", "specgr_array", "specgr", "norm", "rescale", "quantfilt", "quantfilt_mask", "gaussblr", "meansub", "morph",
+    "spectrogram_batch", "specgr_array", "specgr", "load_shot", "norm", "rescale", "quantfilt", "quantfilt_mask", "gaussblr", "meansub", "morph",
     "filter_chain", "omega",
     "computeSignal", "denoiseSignal", "clip", "patch", "unpatch", "reshape", "pipeline", "HostPipeline", "ae_co2",
 ]
@@ -343,10 +344,32 @@ def specgr_array(sig_in, spec_params=DEFAULT_SPEC_PARAMS, runtime=None):
     return spectrogram_batch(sig_in, spec_params, runtime)
 
 
+_SHOT_CACHE = {}
+
+
+def _load_shot_pickle(fname):
+    """The reference unpickles the whole shot once per channel (pipeline_data.py:29, 40 times per shot); keep the
+    last file, keyed by path, mtime and size."""
+    st = os.stat(fname)
+    key = (os.path.abspath(fname), st.st_mtime_ns, st.st_size)
+    if _SHOT_CACHE.get("key") != key:
+        with open(fname, "rb") as fh:
+            _SHOT_CACHE.update(key=key, data=pickle.load(fh))
+    return _SHOT_CACHE["data"]
+
+
+def load_shot(fname, channels=range(1, 41), cut_shot=2, fs=500000.0):
+    """One read of a shot pickle -> x[C, N] float32, the batched input of `pipeline` / `spectrogram_batch`
+    (channel keys and slice of pipeline_data.py:29-31)."""
+    data = _load_shot_pickle(fname)
+    n = int(np.int_(cut_shot * fs))
+    return np.stack([np.asarray(data["\\tecef%.2i" % c][:n], dtype=np.float32) for c in channels])
+
+
 def specgr(fname, ecen, spec_params, cut_shot=2, runtime=None):
-    """pipeline_data.py:28-36, same signature: load the shot pickle, take channel `ecen`, the first
-    cut_shot*fs samples, and return (Sxx[nperseg/2, T], f, t)."""
-    ece_data = pickle.load(open(fname, "rb"))
+    """pipeline_data.py:28-36, same signature: load the shot pickle (cached between calls), take channel `ecen`, the
+    first cut_shot*fs samples, and return (Sxx[nperseg/2, T], f, t)."""
+    ece_data = _load_shot_pickle(fname)
     ece_num = "\\tecef%.2i" % (ecen)
     sig_in = ece_data[ece_num][:np.int_(cut_shot * spec_params["fs"])]
     return spectrogram_batch(np.asarray(sig_in), spec_params, runtime)

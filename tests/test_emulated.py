@@ -4,6 +4,8 @@ ctypes/C-ABI/host-API stack as on the GPU, at sizes the emulation finishes in se
 tests proper are tests/test_gpu_parity.py (-m gpu); this suite exists so that indexing, tiling and
 host bookkeeping bugs are caught without a device.  tcgen05 PTX is not emulated (gram_tc.cu carries a
 numerically equivalent scalar stand-in under SPECGPU_EMULATE)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -182,6 +184,33 @@ def test_cv2_chain_tiles(emu_rt):
     pc.case_cv2_tiles(emu_rt, [(30, 560)], [(31, 3)])
     pc.case_cv2_tiles(emu_rt, [(17, 1030)], [(5, 7)])
     pc.case_cv2_tiles(emu_rt, [(3, 9), (12, 1), (2, 2)], [(1, 1), (9, 3)])
+
+
+def test_specgr_from_pickle_and_load_shot(emu_rt, tmp_path):
+    # the reference's file entry point (pipeline_data.py:28-36) and the load-once reader the batched calls use
+    import pickle
+    n = 3000
+    data = {"\\tecef%.2i" % c: oc.synth_ece(0, c, n=n + 50).astype(np.float64) for c in (1, 2, 8)}
+    fname = tmp_path / "shot.pkl"
+    with open(fname, "wb") as fh:
+        pickle.dump(data, fh)
+    sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=64, noverlap=32, fs=1500.0)      # cut_shot * fs = 3000 samples
+    S, f, t = api.specgr(str(fname), 8, sp, cut_shot=2, runtime=emu_rt)
+    Sr, fr, tr = oc.specgr_array(data["\\tecef08"][:n].astype(np.float32), sp)
+    assert S.shape == Sr.shape and np.array_equal(f, fr) and np.array_equal(t, tr)
+    pc.assert_spec_close(S, Sr)
+    x = api.load_shot(str(fname), channels=(1, 2, 8), cut_shot=2, fs=1500.0)
+    assert x.shape == (3, n) and x.dtype == np.float32
+    assert np.array_equal(x[2], data["\\tecef08"][:n].astype(np.float32))
+    Sb, _, _ = api.spectrogram_batch(x, sp, runtime=emu_rt)
+    assert np.array_equal(Sb[2], S)                              # batched == per channel
+    # a rewritten file is reloaded, not served from the cache
+    data["\\tecef08"] = data["\\tecef08"] * 2.0 + 1.0
+    with open(fname, "wb") as fh:
+        pickle.dump(data, fh)
+    os.utime(fname, ns=(1, 1))
+    x2 = api.load_shot(str(fname), channels=(8,), cut_shot=2, fs=1500.0)
+    assert np.array_equal(x2[0], data["\\tecef08"][:n].astype(np.float32))
 
 
 # ---- host logic / error behaviour ---------------------------------------------------------------
