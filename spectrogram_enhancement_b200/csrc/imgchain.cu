@@ -710,6 +710,8 @@ template <bool U8, bool QUANT>
 __global__ void meansub_apply_kernel(const void* src, int64_t rows, int64_t cols, int64_t ld, const double* lut,
                                      const double* rowstat, const double* imgstat, void* dst, int64_t ldo, int rpc) {
   __shared__ double s_lut[U8 ? 256 : 1];
+  __shared__ double s_rowd[(U8 && !QUANT) ? 256 : 1];       // a uint8 source has 256 possible results per row:
+  __shared__ uint8_t s_rowq[(U8 && QUANT) ? 256 : 1];       // evaluate the expression once per value, then look up
   const int64_t b = blockIdx.y;
   if (U8) load_u8_lut(s_lut, lut, b);
   const double mn = imgstat[2 * b], den = imgstat[2 * b + 1];
@@ -717,21 +719,64 @@ __global__ void meansub_apply_kernel(const void* src, int64_t rows, int64_t cols
   const int64_t rend = min((int64_t)(blockIdx.x + 1) * rpc, rows);
   for (int64_t r = (int64_t)blockIdx.x * rpc; r < rend; ++r) {
     const double mean = rowstat[(b * rows + r) * 3];
-    const auto in = mean_src<U8>(src, b * rows + r, ld, s_lut);
-    for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kRowThreads) {
-      double v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const unsigned c = c0 + k * kRowThreads;
-        v[k] = in.get(c < (unsigned)cols ? c : c0);
+    if constexpr (U8) {
+      for (int u = threadIdx.x; u < 256; u += blockDim.x) {
+        const double m = fd.div(fabs(s_lut[u] - mean) - mn);
+        if constexpr (QUANT) s_rowq[u] = (uint8_t)(int)__dmul_rn(m, 255.0);
+        else s_rowd[u] = m;
       }
+      __syncthreads();
+      const uint8_t* row = static_cast<const uint8_t*>(src) + (b * rows + r) * ld;
+      if constexpr (QUANT) {
+        // uint8 plane -> uint8 plane, both pitched to 16 bytes: four pixels per word (pad columns receive table values
+        // of pad bytes - nobody reads them)
+        if (((ld | ldo) & 3) == 0) {
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(row);
+          uint32_t* ow = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(dst) + (b * rows + r) * ldo);
+          const unsigned nw = ((unsigned)cols + 3) >> 2;
+          for (unsigned i = threadIdx.x; i < nw; i += kRowThreads) {
+            const uint32_t w = rw[i];
+            ow[i] = (uint32_t)s_rowq[w & 255u] | ((uint32_t)s_rowq[(w >> 8) & 255u] << 8) |
+                    ((uint32_t)s_rowq[(w >> 16) & 255u] << 16) | ((uint32_t)s_rowq[w >> 24] << 24);
+          }
+          __syncthreads();
+          continue;
+        }
+      }
+      for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kRowThreads) {
+        uint8_t v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const unsigned c = c0 + k * kRowThreads;
-        if (c < (unsigned)cols) {
-          const double m = fd.div(fabs(v[k] - mean) - mn);
-          if constexpr (QUANT) static_cast<uint8_t*>(dst)[(b * rows + r) * ldo + c] = (uint8_t)(int)__dmul_rn(m, 255.0);
-          else static_cast<double*>(dst)[(b * rows + r) * ldo + c] = m;
+        for (int k = 0; k < 4; ++k) {
+          const unsigned c = c0 + k * kRowThreads;
+          v[k] = row[c < (unsigned)cols ? c : c0];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned c = c0 + k * kRowThreads;
+          if (c < (unsigned)cols) {
+            if constexpr (QUANT) static_cast<uint8_t*>(dst)[(b * rows + r) * ldo + c] = s_rowq[v[k]];
+            else static_cast<double*>(dst)[(b * rows + r) * ldo + c] = s_rowd[v[k]];
+          }
+        }
+      }
+      __syncthreads();                       // the next row rebuilds the table
+    } else {
+      const double* row = static_cast<const double*>(src) + (b * rows + r) * ld;
+      for (unsigned c0 = threadIdx.x; c0 < (unsigned)cols; c0 += 4 * kRowThreads) {
+        double v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned c = c0 + k * kRowThreads;
+          v[k] = row[c < (unsigned)cols ? c : c0];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned c = c0 + k * kRowThreads;
+          if (c < (unsigned)cols) {
+            const double m = fd.div(fabs(v[k] - mean) - mn);
+            if constexpr (QUANT) static_cast<uint8_t*>(dst)[(b * rows + r) * ldo + c] = (uint8_t)(int)__dmul_rn(m, 255.0);
+            else static_cast<double*>(dst)[(b * rows + r) * ldo + c] = m;
+          }
         }
       }
     }
