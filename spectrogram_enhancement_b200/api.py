@@ -32,7 +32,7 @@ from . import _ffi
 __all__ = [
     "Runtime", "default_runtime", "DEFAULT_SPEC_PARAMS", "spectrogram", "stft", "csd", "csd_allpairs",
     "spectrogram_batch", "specgr_array", "specgr", "load_shot", "norm", "rescale", "quantfilt", "quantfilt_mask", "gaussblr", "meansub", "morph",
-    "filter_chain", "omega",
+    "filter_chain", "process_shot", "omega",
     "computeSignal", "denoiseSignal", "clip", "patch", "unpatch", "reshape", "pipeline", "HostPipeline", "ae_co2",
 ]
 
@@ -686,6 +686,23 @@ def pipeline(x, spec_params=DEFAULT_SPEC_PARAMS, clip=True, tiles=False, tile=12
     if return_info:
         res.append(info.cpu().numpy())
     return tuple(res)
+
+
+def process_shot(x, spec_params=DEFAULT_SPEC_PARAMS, thr=0.9, filt=(31, 3), channels=range(1, 41), cut_shot=2, runtime=None):
+    """One shot of the reference's main loop (pipeline_data.py:92-116) in two library calls: `x` is the shot pickle's
+    path (read once with `load_shot`) or the signals x[C, N].  Returns the datasets the loop writes per channel, stacked
+    over channels: {'spec': Sxx[C, F, T], 'f': f, 't': t, 'pipeline_out': [C, F, T] float64}."""
+    rt = _rt(runtime)
+    if isinstance(x, (str, os.PathLike)):
+        x = load_shot(x, channels=channels, cut_shot=cut_shot, fs=spec_params["fs"])
+    plan = rt.plan_from_params(spec_params)
+    xd, as_torch = rt.to_device(x)
+    if xd.dim() != 2:
+        raise ValueError("process_shot expects x[C, N] or a pickle path")
+    f, t = rt.axes(plan, xd.shape[-1])
+    S = rt.specgr_dev(plan, xd)                                  # stays on the device between the two calls
+    out = filter_chain(S, thr, filt, runtime=rt)
+    return {"spec": rt.ret(S, as_torch), "f": f[:-1], "t": t, "pipeline_out": rt.ret(out, as_torch)}
 
 
 class HostPipeline:

@@ -16,6 +16,8 @@
 // on 16-bit lanes in shared-memory planes, halo 4 + 2 rows and 8 + 8 columns); both fold the image min / max of their uint8
 // result with integer atomics, and the final rescale is a 256-entry float64 table per CTA (uint8 has 256 quotients).
 #include <type_traits>
+#include <utility>
+#include <vector>
 
 #include "kernels.h"
 
@@ -560,13 +562,19 @@ __global__ void __launch_bounds__(kImgThreads) morph_fused_kernel(const uint8_t*
 // lut[v] = (v - min) / (max - min): the values, the summation order and therefore every bit are those of the float64
 // route, without the float64 image ever being written.
 struct MeanSrcF64 {
+  typedef double raw_t;                    // what a thread keeps between the two sweeps
   const double* row;
   __device__ __forceinline__ double get(unsigned c) const { return row[c]; }
+  __device__ __forceinline__ raw_t raw(unsigned c) const { return row[c]; }
+  __device__ __forceinline__ double val(raw_t v) const { return v; }
 };
 struct MeanSrcU8 {
+  typedef uint8_t raw_t;                   // the byte: a quarter of a register instead of two
   const uint8_t* row;
   const double* lut;
   __device__ __forceinline__ double get(unsigned c) const { return lut[row[c]]; }
+  __device__ __forceinline__ raw_t raw(unsigned c) const { return row[c]; }
+  __device__ __forceinline__ double val(raw_t v) const { return lut[v]; }
 };
 // rescale table of a uint8 image from its {min, max} slot (same expression as img_rescale_u8_kernel), once per image
 __global__ void u8_lut_kernel(const unsigned* mm8, double* lut) {
@@ -593,17 +601,7 @@ __device__ __forceinline__ typename MeanSrcSel<U8>::type mean_src(const void* sr
   else return MeanSrcF64{static_cast<const double*>(src) + row * ld};
 }
 
-// CTA-wide reductions in a fixed order: xor-shuffle tree inside each warp, then the 8 warp results in warp order
-__device__ __forceinline__ double cta_sum(double v, double* s8) {
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) s8[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = s8[0];
-#pragma unroll
-  for (int w = 1; w < kRowThreads / 32; ++w) t += s8[w];
-  __syncthreads();
-  return t;
-}
+// CTA-wide min / max: xor-shuffle tree inside each warp, then the warp results
 __device__ __forceinline__ void cta_minmax(double& mn, double& mx, double* s8a, double* s8b) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -630,38 +628,90 @@ __device__ __forceinline__ void cta_minmax(double& mn, double& mx, double* s8a, 
 // registers for rows up to 4096 columns, else a second read that comes from cache) -> rowstat[row] = {mean, min, max}
 constexpr int kMeanRegs = 16;      // rows up to 16 * 256 = 4096 columns stay in registers between the two sweeps
 
+// np.mean(src, axis=1) sums a contiguous float64 row with numpy's pairwise summation (umath loops, `pairwise_sum`):
+//   n < 8: sequential from 0;  n <= 128: eight accumulators r[j] += a[i + j] over blocks of eight,
+//   ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)), then the n % 8 tail sequentially;  n > 128: split at
+//   n2 = n / 2 - (n / 2) % 8 and add the two halves.
+// The row mean feeds a truncating uint8 quantisation two stages later, so the sum is reproduced operation for
+// operation: the host lists the leaves (start, length <= 128) and the post-order combine steps of the recursion for
+// this row length; an 8-lane group owns a leaf (lane j = accumulator j, xor-shuffles 1, 2, 4 are exactly the bracketed
+// tree), then one thread runs the combine steps.
+constexpr int kMeanMaxLevels = 40;
+struct MeanPlan {
+  const int2* leaves;   // (start, length) in row order
+  const int2* steps;    // L[x] = L[x] + L[y]; sorted by the height of the node in the recursion tree
+  int nleaf, nlevels;
+  int level_end[kMeanMaxLevels];   // steps [level_end[h - 1], level_end[h]) are independent of each other
+};
+constexpr int kMeanMaxLeaves = 2048;     // leaf sums live in shared memory: rows up to ~131 000 columns
+
 template <bool INREG, bool U8>
-__global__ void meansub_stats_kernel(const void* src, int64_t rows, int64_t cols, int64_t ld, const double* lut,
-                                     double* rowstat, int rpc) {
+__global__ void __launch_bounds__(kRowThreads, U8 ? 6 : 4) meansub_stats_kernel(const void* src, int64_t rows, int64_t cols, int64_t ld, const double* lut,
+                                     MeanPlan plan, double* rowstat, int rpc) {
   __shared__ double s_lut[U8 ? 256 : 1];
   __shared__ double s8a[kRowThreads / 32], s8b[kRowThreads / 32];
+  SPECGPU_DYN_SMEM(smem);
+  double* s_leaf = reinterpret_cast<double*>(smem);          // [nleaf]
   const int64_t b = blockIdx.y;
   if (U8) load_u8_lut(s_lut, lut, b);
+  const int lane8 = threadIdx.x & 7, group = threadIdx.x >> 3;
   const int64_t rend = min((int64_t)(blockIdx.x + 1) * rpc, rows);
   for (int64_t r = (int64_t)blockIdx.x * rpc; r < rend; ++r) {      // rpc rows per CTA amortise the table load
     const int64_t row = b * rows + r;
     const auto in = mean_src<U8>(src, row, ld, s_lut);
-    double v[INREG ? kMeanRegs : 1];
-    double s = 0.0;
+    // the strided copy of the row for the second sweep; it also pulls the row into L1 for the leaf sums
+    typename MeanSrcSel<U8>::type::raw_t v[INREG ? kMeanRegs : 1];
     if (INREG) {
 #pragma unroll
       for (int q = 0; q < kMeanRegs; ++q) {
         const unsigned c = threadIdx.x + q * kRowThreads;
-        v[q] = c < (unsigned)cols ? in.get(c) : 0.0;
+        v[q] = in.raw(c < (unsigned)cols ? c : 0u);
       }
-#pragma unroll
-      for (int q = 0; q < kMeanRegs; ++q)
-        if (threadIdx.x + q * kRowThreads < (unsigned)cols) s += v[q];          // same order as the strided loop below
-    } else {
-      for (unsigned c = threadIdx.x; c < (unsigned)cols; c += blockDim.x) s += in.get(c);
     }
-    const double mean = __ddiv_rn(cta_sum(s, s8a), (double)cols);
+    // ---- numpy's pairwise row sum ----
+    for (int l0 = 0; l0 < plan.nleaf; l0 += kRowThreads / 8) {      // uniform trip count: the shuffles stay converged
+      const int leaf = l0 + group;
+      const int2 lf = leaf < plan.nleaf ? plan.leaves[leaf] : make_int2(0, 0);
+      const int start = lf.x, len = lf.y;
+      double acc = 0.0;
+      if (len >= 8) {
+        acc = in.get(start + lane8);
+        const int body = len - (len & 7);
+#pragma unroll 4
+        for (int i = 8; i < body; i += 8) acc = __dadd_rn(acc, in.get(start + i + lane8));
+      }
+      acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+      acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+      acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+      if (lane8 == 0 && leaf < plan.nleaf) {
+        if (len < 8) acc = 0.0;                                     // short rows: sequential from zero
+        for (int i = len >= 8 ? len - (len & 7) : 0; i < len; ++i) acc = __dadd_rn(acc, in.get(start + i));
+        s_leaf[leaf] = acc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                         // warp 0 climbs the tree level by level
+      int begin = 0;
+      for (int h = 0; h < plan.nlevels; ++h) {
+        const int end = plan.level_end[h];
+        for (int t = begin + (int)threadIdx.x; t < end; t += 32) {
+          const int2 st = plan.steps[t];
+          s_leaf[st.x] = __dadd_rn(s_leaf[st.x], s_leaf[st.y]);
+        }
+        begin = end;
+        __syncwarp();
+      }
+      if (threadIdx.x == 0) s8a[0] = __ddiv_rn(s_leaf[0], (double)cols);
+    }
+    __syncthreads();
+    const double mean = s8a[0];
+    __syncthreads();
     double mn = INFINITY, mx = -INFINITY;
     if (INREG) {
 #pragma unroll
       for (int q = 0; q < kMeanRegs; ++q)
         if (threadIdx.x + q * kRowThreads < (unsigned)cols) {
-          const double d = fabs(v[q] - mean);
+          const double d = fabs(in.val(v[q]) - mean);
           mn = d < mn ? d : mn;
           mx = d > mx ? d : mx;
         }
@@ -788,7 +838,7 @@ size_t imgchain_workspace_bytes(int64_t B, int64_t rows, int64_t cols) {
   const size_t plane = (size_t)B * rows * img_pitch(cols);
   // two pitched uint8 planes, float/double min-max partials, uint8 min-max slots, row statistics, kernel taps
   return 2 * (plane + 256) + (size_t)B * kImgParts * 2 * 8 + 256 + 2 * ((size_t)B * 2 * 4 + 256) + (size_t)B * rows * 3 * 8 + 256 +
-         (size_t)B * 256 * 8 + 256 + (size_t)B * 2 * 8 + 256 + 4096;
+         (size_t)B * 256 * 8 + 256 + (size_t)B * 2 * 8 + 256 + 2 * ((size_t)kMeanMaxLeaves * 8 + 256) + 4096;
 }
 
 namespace {
@@ -807,6 +857,7 @@ struct ImgWs {
   void* part;
   unsigned *mm8, *mm8b;
   double *rowstat, *lut, *imgstat;
+  int2 *leaves, *steps;
   uint16_t* taps;
 };
 ImgWs img_carve(void* ws, int64_t B, int64_t rows, int64_t cols) {
@@ -826,6 +877,8 @@ ImgWs img_carve(void* ws, int64_t B, int64_t rows, int64_t cols) {
   w.rowstat = reinterpret_cast<double*>(take((size_t)B * rows * 3 * 8));
   w.lut = reinterpret_cast<double*>(take((size_t)B * 256 * 8));
   w.imgstat = reinterpret_cast<double*>(take((size_t)B * 2 * 8));
+  w.leaves = reinterpret_cast<int2*>(take((size_t)kMeanMaxLeaves * 8));
+  w.steps = reinterpret_cast<int2*>(take((size_t)kMeanMaxLeaves * 8));
   w.taps = reinterpret_cast<uint16_t*>(take(4096));
   return w;
 }
@@ -858,21 +911,60 @@ void run_rescale_u8(const uint8_t* plane, int64_t B, int64_t rows, int64_t cols,
   if (u8_out) SPECGPU_LAUNCH(img_unpitch_kernel, (unsigned)(B * rows), kRowThreads, 0, st, plane, cols, pitch, u8_out);
 }
 // both meansub passes from source `src` (float64 image or uint8 plane + its {min, max} slot)
+// leaves and combine steps of numpy's pairwise_sum recursion for a row of n elements; a step carries the height of its
+// node so that the steps of one height (independent of each other) can run in parallel.  Returns (first leaf, height).
+struct MeanStep {
+  int x, y, h;
+};
+std::pair<int, int> mean_plan_build(int start, int n, std::vector<int2>& leaves, std::vector<MeanStep>& steps) {
+  if (n <= 128) {
+    leaves.push_back(make_int2(start, n));
+    return {(int)leaves.size() - 1, 0};
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  const auto l = mean_plan_build(start, n2, leaves, steps);
+  const auto r = mean_plan_build(start + n2, n - n2, leaves, steps);
+  const int h = std::max(l.second, r.second) + 1;
+  steps.push_back(MeanStep{l.first, r.first, h});
+  return {l.first, h};
+}
+
 template <bool U8, bool QUANT>
-void run_meansub(const void* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* mm8, const ImgWs& w, void* dst,
-                 int64_t ldo, unsigned* mm8_next, cudaStream_t st) {
+int run_meansub(const void* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* mm8, const ImgWs& w, void* dst,
+                int64_t ldo, unsigned* mm8_next, cudaStream_t st) {
   const dim3 rowgrid = row_grid(B, rows);
   const int rpc = rows_per_cta(B, rows);
+  std::vector<int2> leaves, steps;
+  std::vector<MeanStep> tree;
+  const int height = mean_plan_build(0, (int)cols, leaves, tree).second;
+  if ((int)leaves.size() > kMeanMaxLeaves || height > kMeanMaxLevels) return -1;
+  MeanPlan plan{};
+  plan.leaves = w.leaves;
+  plan.steps = w.steps;
+  plan.nleaf = (int)leaves.size();
+  plan.nlevels = height;
+  for (int h = 1; h <= height; ++h) {                 // stable by height: children always sit in lower levels
+    for (const MeanStep& t : tree)
+      if (t.h == h) steps.push_back(make_int2(t.x, t.y));
+    plan.level_end[h - 1] = (int)steps.size();
+  }
+  cudaError_t e = cudaMemcpyAsync(w.leaves, leaves.data(), leaves.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && !steps.empty())
+    e = cudaMemcpyAsync(w.steps, steps.data(), steps.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return (int)e;
+  const size_t smem = leaves.size() * sizeof(double);
   if (U8) SPECGPU_LAUNCH(u8_lut_kernel, (unsigned)B, kRowThreads, 0, st, mm8, w.lut);
   if (cols <= kMeanRegs * kRowThreads)
-    SPECGPU_LAUNCH((meansub_stats_kernel<true, U8>), rowgrid, kRowThreads, 0, st, src, rows, cols, ld, (const double*)w.lut,
-                   w.rowstat, rpc);
+    SPECGPU_LAUNCH((meansub_stats_kernel<true, U8>), rowgrid, kRowThreads, smem, st, src, rows, cols, ld, (const double*)w.lut,
+                   plan, w.rowstat, rpc);
   else
-    SPECGPU_LAUNCH((meansub_stats_kernel<false, U8>), rowgrid, kRowThreads, 0, st, src, rows, cols, ld, (const double*)w.lut,
-                   w.rowstat, rpc);
+    SPECGPU_LAUNCH((meansub_stats_kernel<false, U8>), rowgrid, kRowThreads, smem, st, src, rows, cols, ld, (const double*)w.lut,
+                   plan, w.rowstat, rpc);
   SPECGPU_LAUNCH(meansub_fold_kernel, (unsigned)B, kRowThreads, 0, st, (const double*)w.rowstat, rows, w.imgstat, mm8_next);
   SPECGPU_LAUNCH((meansub_apply_kernel<U8, QUANT>), rowgrid, kRowThreads, 0, st, src, rows, cols, ld, (const double*)w.lut,
                  (const double*)w.rowstat, (const double*)w.imgstat, dst, ldo, rpc);
+  return (int)cudaGetLastError();
 }
 int run_blur(const ImgWs& w, int64_t B, int64_t rows, int64_t cols, const uint16_t* taps_host, int kw, int kh, const uint8_t* in,
              uint8_t* out, cudaStream_t st) {
@@ -903,8 +995,7 @@ int launch_meansub(const double* src, int64_t B, int64_t rows, int64_t cols, int
                    cudaStream_t st) {
   if (B * rows * cols == 0) return 0;
   ImgWs w = img_carve(ws, B, rows, cols);
-  run_meansub<false, false>(src, B, rows, cols, ld, nullptr, w, dst, ldo, nullptr, st);
-  return (int)cudaGetLastError();
+  return run_meansub<false, false>(src, B, rows, cols, ld, nullptr, w, dst, ldo, nullptr, st);
 }
 
 // gaussblr -> meansub -> morph -> meansub of pipeline_data.py:104-110 on an already thresholded float32 image, with
@@ -918,12 +1009,11 @@ int launch_filter_tail(const float* q, int64_t B, int64_t rows, int64_t cols, in
   int rc = run_blur(w, B, rows, cols, taps_host, kw, kh, w.u8a, w.u8b, st);              // ... blur -> plane b, slot mm8
   if (rc) return rc;
   // meansub of the blurred image + morph's quantisation -> plane a; resets slot mm8b
-  run_meansub<true, true>(w.u8b, B, rows, cols, pitch, w.mm8, w, w.u8a, pitch, w.mm8b, st);
+  if ((rc = run_meansub<true, true>(w.u8b, B, rows, cols, pitch, w.mm8, w, w.u8a, pitch, w.mm8b, st))) return rc;
   const dim3 grid((unsigned)ceil_div(cols, kMorphCols), (unsigned)ceil_div(rows, kMorphRows), (unsigned)B);
   SPECGPU_LAUNCH(morph_fused_kernel, grid, kImgThreads, 0, st, (const uint8_t*)w.u8a, (int)rows, (int)cols, pitch, w.u8b,
                  w.mm8b);                                                                 // -> plane b, slot mm8b
-  run_meansub<true, false>(w.u8b, B, rows, cols, pitch, w.mm8b, w, dst, ldo, nullptr, st);  // final meansub -> float64
-  return (int)cudaGetLastError();
+  return run_meansub<true, false>(w.u8b, B, rows, cols, pitch, w.mm8b, w, dst, ldo, nullptr, st);  // final meansub -> float64
 }
 
 // taps_host: kw + kh Q8.8 taps (kx then ky), built by the caller.

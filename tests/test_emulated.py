@@ -204,6 +204,13 @@ def test_specgr_from_pickle_and_load_shot(emu_rt, tmp_path):
     assert np.array_equal(x[2], data["\\tecef08"][:n].astype(np.float32))
     Sb, _, _ = api.spectrogram_batch(x, sp, runtime=emu_rt)
     assert np.array_equal(Sb[2], S)                              # batched == per channel
+    # the whole loop body for the shot: spec + f + t + pipeline_out, from the path or from the array
+    res = api.process_shot(str(fname), sp, channels=(1, 2, 8), cut_shot=2, runtime=emu_rt)
+    assert sorted(res) == ["f", "pipeline_out", "spec", "t"] and np.array_equal(res["spec"][2], S)
+    assert res["pipeline_out"].dtype == np.float64 and res["pipeline_out"].shape == res["spec"].shape
+    pc.assert_same_f64(res["pipeline_out"][2], oc.filter_chain(S))
+    res2 = api.process_shot(x, sp, runtime=emu_rt)
+    assert np.array_equal(res2["pipeline_out"], res["pipeline_out"])
     # a rewritten file is reloaded, not served from the cache
     data["\\tecef08"] = data["\\tecef08"] * 2.0 + 1.0
     with open(fname, "wb") as fh:

@@ -145,9 +145,9 @@ def test_cv2_chain_golden(cuda_rt, golden):
     g = golden("specgr_small.npz")
     pc.case_filter_chain(cuda_rt, g["S_f32"])
     assert np.array_equal(api.gaussblr(g["quant_f32"], (31, 3), runtime=cuda_rt), g["gauss"])
-    np.testing.assert_allclose(api.meansub(g["gauss"], runtime=cuda_rt), g["mean"], rtol=1e-12, atol=1e-13)
+    pc.assert_same_f64(api.meansub(g["gauss"], runtime=cuda_rt), g["mean"])
     assert np.array_equal(api.morph(g["mean"], runtime=cuda_rt), g["morph"])
-    np.testing.assert_allclose(api.filter_chain(g["S_f32"], runtime=cuda_rt), g["final"], rtol=1e-12, atol=1e-13)
+    pc.assert_same_f64(api.filter_chain(g["S_f32"], runtime=cuda_rt), g["final"])
 
 
 def test_cv2_chain_full_size(cuda_rt):
@@ -241,7 +241,7 @@ def test_filter_chain_fused_full_size(cuda_rt):
     assert np.array_equal(fused, api.filter_chain(S, runtime=cuda_rt, fused=False))
     for i in (0, 2):
         assert np.array_equal(fused[i], api.filter_chain(S[i], runtime=cuda_rt))          # batched == one by one
-    np.testing.assert_allclose(fused[1], oc.filter_chain(S[1]), rtol=1e-12, atol=1e-13)
+    pc.assert_same_f64(fused[1], oc.filter_chain(S[1]))
 
 
 # ---- K2b: cross-power spectrum -------------------------------------------------------------------------
