@@ -124,7 +124,8 @@ int specgpu_quantfilt(specgpu_ctx* ctx, const float* src, int64_t B, int64_t row
  * src is float32 (in_f64 = 0) or float64; u8_out (optional) receives the blurred uint8 image [B][rows][cols] (bit-exact). */
 int specgpu_gaussblr(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, int64_t rows, int64_t cols, int64_t ld,
                      int32_t kw, int32_t kh, double* dst, int64_t ldo, uint8_t* u8_out, void* stream);
-/* meansub (:58-61): rescale(|src - mean over the contiguous axis of each row|), float64 in and out. */
+/* meansub (:58-61): rescale(|src - mean over the contiguous axis of each row|), float64 in and out; the row means are
+ * np.mean's (pairwise summation reproduced), so the result is bit-identical to numpy's.  cols <= 120000. */
 int specgpu_meansub(specgpu_ctx* ctx, const double* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, double* dst,
                     int64_t ldo, void* stream);
 /* morph (:64-72): uint8-quantise -> MORPH_CLOSE rect(4,4) -> MORPH_OPEN rect(3,1) -> rescale -> float64; u8_out (optional)
@@ -134,7 +135,7 @@ int specgpu_morph(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, 
 /* The whole denoising body of the reference's main loop (pipeline_data.py:101-110) on a [B][rows][cols] float32 stack:
  * quantfilt(thr) -> gaussblr((kw, kh)) -> meansub -> morph -> meansub, float64 out.  Identical, bit for bit, to chaining
  * the five calls above; between the stages only uint8 planes (and their min / max) exist on the device.  src rows have
- * pitch ld, dst rows pitch ldo; rows <= 1024 (quantfilt's limit). */
+ * pitch ld, dst rows pitch ldo; rows <= 1024 (quantfilt's limit), cols <= 120000 (meansub's). */
 int specgpu_filter_chain(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float thr,
                          int32_t kw, int32_t kh, double* dst, int64_t ldo, void* stream);
 

@@ -716,7 +716,8 @@ int specgpu_meansub(specgpu_ctx* ctx, const double* src, int64_t B, int64_t rows
   int rc = check_matrix_args(ctx, src, B, rows, cols, ld);
   if (rc) return rc;
   if (B * rows * cols == 0) return SPECGPU_OK;
-  if (rows > 65535) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "image too large");
+  if (rows > 65535 || cols > 120000)      // the pairwise-sum leaves of a row live in shared memory
+    return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "meansub: rows=%lld > 65535 or cols=%lld > 120000", (long long)rows, (long long)cols);
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
   cudaSetDevice(ctx->device);
   if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
@@ -745,7 +746,8 @@ int specgpu_filter_chain(specgpu_ctx* ctx, const float* src, int64_t B, int64_t 
     return fail(ctx, SPECGPU_ERR_INVALID_ARG, "ksize (%d, %d): both must be odd and in [1, 255]", kw, kh);
   if (!(thr >= 0.0f && thr <= 1.0f)) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "Quantiles must be in the range [0, 1]");
   if (B * rows * cols == 0) return SPECGPU_OK;
-  if (cols > (1 << 30) || rows > 1024) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "filter_chain: rows=%lld > 1024 or image too large", (long long)rows);
+  if (cols > 120000 || rows > 1024)
+    return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "filter_chain: rows=%lld > 1024 or cols=%lld > 120000", (long long)rows, (long long)cols);
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
   cudaSetDevice(ctx->device);
   // workspace: the image-chain planes, then the thresholded float32 image (quantfilt writes it with the source's pitch)

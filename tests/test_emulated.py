@@ -233,6 +233,10 @@ def test_errors_mirror_scipy(emu_rt):
         api.quantfilt(np.zeros((4, 4), np.float32), 1.5, runtime=emu_rt)
     with pytest.raises(ValueError):
         api.stft(x, nperseg=8, boundary="even", runtime=emu_rt)
+    with pytest.raises(ValueError, match="cols=120001"):
+        api.meansub(np.zeros((1, 120001)), runtime=emu_rt)
+    with pytest.raises(ValueError, match="Quantiles must be in the range"):
+        api.filter_chain(np.zeros((4, 8), np.float32), thr=-0.1, runtime=emu_rt)
 
 
 def test_empty_and_short_inputs(emu_rt):
