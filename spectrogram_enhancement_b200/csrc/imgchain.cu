@@ -641,6 +641,7 @@ struct MeanPlan {
   const int2* leaves;   // (start, length) in row order
   const int2* steps;    // L[x] = L[x] + L[y]; sorted by the height of the node in the recursion tree
   int nleaf, nlevels;
+  int stage_words;      // uint8 source: 32-bit words of a row to stage in shared memory (0: read the bytes from global)
   int level_end[kMeanMaxLevels];   // steps [level_end[h - 1], level_end[h]) are independent of each other
 };
 constexpr int kMeanMaxLeaves = 2048;     // leaf sums live in shared memory: rows up to ~131 000 columns
@@ -649,6 +650,7 @@ template <bool INREG, bool U8>
 __global__ void __launch_bounds__(kRowThreads, U8 ? 6 : 4) meansub_stats_kernel(const void* src, int64_t rows, int64_t cols, int64_t ld, const double* lut,
                                      MeanPlan plan, double* rowstat, int rpc) {
   __shared__ double s_lut[U8 ? 256 : 1];
+  __shared__ uint8_t s_present[U8 ? 256 : 1];                // which byte values occur in the row
   __shared__ double s8a[kRowThreads / 32], s8b[kRowThreads / 32];
   SPECGPU_DYN_SMEM(smem);
   double* s_leaf = reinterpret_cast<double*>(smem);          // [nleaf]
@@ -659,15 +661,38 @@ __global__ void __launch_bounds__(kRowThreads, U8 ? 6 : 4) meansub_stats_kernel(
   for (int64_t r = (int64_t)blockIdx.x * rpc; r < rend; ++r) {      // rpc rows per CTA amortise the table load
     const int64_t row = b * rows + r;
     const auto in = mean_src<U8>(src, row, ld, s_lut);
-    // the strided copy of the row for the second sweep; it also pulls the row into L1 for the leaf sums
-    typename MeanSrcSel<U8>::type::raw_t v[INREG ? kMeanRegs : 1];
-    if (INREG) {
+    // float64 source: a strided copy of the row for the second sweep (it also pulls the row into L1 for the leaf sums).
+    // uint8 source: the deviations take at most 256 values, so the second sweep runs over the byte values that
+    // occur - the leaf sums flag them on the way.
+    double v[(INREG && !U8) ? kMeanRegs : 1];
+    const uint8_t* rowb = nullptr;                                  // uint8 source: the row, staged in shared memory
+    if constexpr (U8) {
+      for (int u = threadIdx.x; u < 256; u += blockDim.x) s_present[u] = 0;
+      if (plan.stage_words > 0) {                                   // coalesced words in, strided bytes out
+        uint32_t* s_row = reinterpret_cast<uint32_t*>(s_leaf + ((plan.nleaf + 1) & ~1));
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(in.row);
+        for (int i = threadIdx.x; i < plan.stage_words; i += blockDim.x) s_row[i] = gw[i];
+        rowb = reinterpret_cast<const uint8_t*>(s_row);
+      } else {
+        rowb = in.row;
+      }
+      __syncthreads();
+    } else if (INREG) {
 #pragma unroll
       for (int q = 0; q < kMeanRegs; ++q) {
         const unsigned c = threadIdx.x + q * kRowThreads;
-        v[q] = in.raw(c < (unsigned)cols ? c : 0u);
+        v[q] = in.get(c < (unsigned)cols ? c : 0u);
       }
     }
+    auto fetch = [&](unsigned c) -> double {
+      if constexpr (U8) {
+        const uint8_t u = rowb[c];
+        s_present[u] = 1;                                           // every writer stores the same value
+        return in.lut[u];
+      } else {
+        return in.get(c);
+      }
+    };
     // ---- numpy's pairwise row sum ----
     for (int l0 = 0; l0 < plan.nleaf; l0 += kRowThreads / 8) {      // uniform trip count: the shuffles stay converged
       const int leaf = l0 + group;
@@ -675,17 +700,17 @@ __global__ void __launch_bounds__(kRowThreads, U8 ? 6 : 4) meansub_stats_kernel(
       const int start = lf.x, len = lf.y;
       double acc = 0.0;
       if (len >= 8) {
-        acc = in.get(start + lane8);
+        acc = fetch(start + lane8);
         const int body = len - (len & 7);
 #pragma unroll 4
-        for (int i = 8; i < body; i += 8) acc = __dadd_rn(acc, in.get(start + i + lane8));
+        for (int i = 8; i < body; i += 8) acc = __dadd_rn(acc, fetch(start + i + lane8));
       }
       acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
       acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
       acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
       if (lane8 == 0 && leaf < plan.nleaf) {
         if (len < 8) acc = 0.0;                                     // short rows: sequential from zero
-        for (int i = len >= 8 ? len - (len & 7) : 0; i < len; ++i) acc = __dadd_rn(acc, in.get(start + i));
+        for (int i = len >= 8 ? len - (len & 7) : 0; i < len; ++i) acc = __dadd_rn(acc, fetch(start + i));
         s_leaf[leaf] = acc;
       }
     }
@@ -707,11 +732,18 @@ __global__ void __launch_bounds__(kRowThreads, U8 ? 6 : 4) meansub_stats_kernel(
     const double mean = s8a[0];
     __syncthreads();
     double mn = INFINITY, mx = -INFINITY;
-    if (INREG) {
+    if constexpr (U8) {
+      for (int u = threadIdx.x; u < 256; u += blockDim.x)
+        if (s_present[u]) {
+          const double d = fabs(s_lut[u] - mean);
+          mn = d < mn ? d : mn;
+          mx = d > mx ? d : mx;
+        }
+    } else if (INREG) {
 #pragma unroll
       for (int q = 0; q < kMeanRegs; ++q)
         if (threadIdx.x + q * kRowThreads < (unsigned)cols) {
-          const double d = fabs(in.val(v[q]) - mean);
+          const double d = fabs(v[q] - mean);
           mn = d < mn ? d : mn;
           mx = d > mx ? d : mx;
         }
@@ -953,7 +985,11 @@ int run_meansub(const void* src, int64_t B, int64_t rows, int64_t cols, int64_t 
   if (e == cudaSuccess && !steps.empty())
     e = cudaMemcpyAsync(w.steps, steps.data(), steps.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return (int)e;
-  const size_t smem = leaves.size() * sizeof(double);
+  size_t smem = leaves.size() * sizeof(double);
+  if (U8 && (ld & 3) == 0 && cols <= 16384) {         // pitched plane rows: whole words, up to 16 KB per row
+    plan.stage_words = (int)((cols + 3) / 4);
+    smem = ((leaves.size() + 1) & ~(size_t)1) * sizeof(double) + (size_t)plan.stage_words * 4;
+  }
   if (U8) SPECGPU_LAUNCH(u8_lut_kernel, (unsigned)B, kRowThreads, 0, st, mm8, w.lut);
   if (cols <= kMeanRegs * kRowThreads)
     SPECGPU_LAUNCH((meansub_stats_kernel<true, U8>), rowgrid, kRowThreads, smem, st, src, rows, cols, ld, (const double*)w.lut,
