@@ -653,30 +653,41 @@ __global__ void __launch_bounds__(kRowThreads, U8 ? 6 : 4) meansub_stats_kernel(
   __shared__ uint8_t s_present[U8 ? 256 : 1];                // which byte values occur in the row
   __shared__ double s8a[kRowThreads / 32], s8b[kRowThreads / 32];
   SPECGPU_DYN_SMEM(smem);
-  double* s_leaf = reinterpret_cast<double*>(smem);          // [nleaf]
+  // dynamic shared memory: leaf sums | the plan's leaves and steps | (uint8 source) the staged row
+  const int nlp = (plan.nleaf + 1) & ~1;
+  double* s_leaf = reinterpret_cast<double*>(smem);          // [nlp]
+  int2* s_leaves = reinterpret_cast<int2*>(s_leaf + nlp);    // [nlp]
+  int2* s_steps = s_leaves + nlp;                            // [nlp]
+  uint32_t* s_row = reinterpret_cast<uint32_t*>(s_steps + nlp);
   const int64_t b = blockIdx.y;
-  if (U8) load_u8_lut(s_lut, lut, b);
   const int lane8 = threadIdx.x & 7, group = threadIdx.x >> 3;
   const int64_t rend = min((int64_t)(blockIdx.x + 1) * rpc, rows);
-  for (int64_t r = (int64_t)blockIdx.x * rpc; r < rend; ++r) {      // rpc rows per CTA amortise the table load
+  for (int64_t r = (int64_t)blockIdx.x * rpc; r < rend; ++r) {      // rpc rows per CTA (1 on the GPU)
     const int64_t row = b * rows + r;
     const auto in = mean_src<U8>(src, row, ld, s_lut);
     // float64 source: a strided copy of the row for the second sweep (it also pulls the row into L1 for the leaf sums).
     // uint8 source: the deviations take at most 256 values, so the second sweep runs over the byte values that
     // occur - the leaf sums flag them on the way.
+    // All the global loads of the prologue (rescale table, plan, row) are issued together, then one barrier.
     double v[(INREG && !U8) ? kMeanRegs : 1];
     const uint8_t* rowb = nullptr;                                  // uint8 source: the row, staged in shared memory
+    if (r == (int64_t)blockIdx.x * rpc) {
+      for (int i = threadIdx.x; i < plan.nleaf; i += blockDim.x) {
+        s_leaves[i] = plan.leaves[i];
+        if (i + 1 < plan.nleaf) s_steps[i] = plan.steps[i];
+      }
+      if constexpr (U8)
+        for (int u = threadIdx.x; u < 256; u += blockDim.x) s_lut[u] = lut[b * 256 + u];
+    }
     if constexpr (U8) {
       for (int u = threadIdx.x; u < 256; u += blockDim.x) s_present[u] = 0;
       if (plan.stage_words > 0) {                                   // coalesced words in, strided bytes out
-        uint32_t* s_row = reinterpret_cast<uint32_t*>(s_leaf + ((plan.nleaf + 1) & ~1));
         const uint32_t* gw = reinterpret_cast<const uint32_t*>(in.row);
         for (int i = threadIdx.x; i < plan.stage_words; i += blockDim.x) s_row[i] = gw[i];
         rowb = reinterpret_cast<const uint8_t*>(s_row);
       } else {
         rowb = in.row;
       }
-      __syncthreads();
     } else if (INREG) {
 #pragma unroll
       for (int q = 0; q < kMeanRegs; ++q) {
@@ -684,6 +695,7 @@ __global__ void __launch_bounds__(kRowThreads, U8 ? 6 : 4) meansub_stats_kernel(
         v[q] = in.get(c < (unsigned)cols ? c : 0u);
       }
     }
+    __syncthreads();
     auto fetch = [&](unsigned c) -> double {
       if constexpr (U8) {
         const uint8_t u = rowb[c];
@@ -696,7 +708,7 @@ __global__ void __launch_bounds__(kRowThreads, U8 ? 6 : 4) meansub_stats_kernel(
     // ---- numpy's pairwise row sum ----
     for (int l0 = 0; l0 < plan.nleaf; l0 += kRowThreads / 8) {      // uniform trip count: the shuffles stay converged
       const int leaf = l0 + group;
-      const int2 lf = leaf < plan.nleaf ? plan.leaves[leaf] : make_int2(0, 0);
+      const int2 lf = leaf < plan.nleaf ? s_leaves[leaf] : make_int2(0, 0);
       const int start = lf.x, len = lf.y;
       double acc = 0.0;
       if (len >= 8) {
@@ -720,7 +732,7 @@ __global__ void __launch_bounds__(kRowThreads, U8 ? 6 : 4) meansub_stats_kernel(
       for (int h = 0; h < plan.nlevels; ++h) {
         const int end = plan.level_end[h];
         for (int t = begin + (int)threadIdx.x; t < end; t += 32) {
-          const int2 st = plan.steps[t];
+          const int2 st = s_steps[t];
           s_leaf[st.x] = __dadd_rn(s_leaf[st.x], s_leaf[st.y]);
         }
         begin = end;
@@ -985,10 +997,14 @@ int run_meansub(const void* src, int64_t B, int64_t rows, int64_t cols, int64_t 
   if (e == cudaSuccess && !steps.empty())
     e = cudaMemcpyAsync(w.steps, steps.data(), steps.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return (int)e;
-  size_t smem = leaves.size() * sizeof(double);
+  size_t smem = ((leaves.size() + 1) & ~(size_t)1) * (sizeof(double) + 2 * sizeof(int2));      // leaf sums + plan copy
   if (U8 && (ld & 3) == 0 && cols <= 16384) {         // pitched plane rows: whole words, up to 16 KB per row
     plan.stage_words = (int)((cols + 3) / 4);
-    smem = ((leaves.size() + 1) & ~(size_t)1) * sizeof(double) + (size_t)plan.stage_words * 4;
+    smem += (size_t)plan.stage_words * 4;
+  }
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(meansub_stats_kernel<true, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(meansub_stats_kernel<false, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   if (U8) SPECGPU_LAUNCH(u8_lut_kernel, (unsigned)B, kRowThreads, 0, st, mm8, w.lut);
   if (cols <= kMeanRegs * kRowThreads)
