@@ -268,6 +268,24 @@ def case_cv2_pitched(rt):
     assert not mo[:, :, C:].any()                    # the padding of the output rows is left alone
 
 
+def case_cv2_division_corners(rt):
+    """Denominators the reciprocal-based quotient hands to the divider: an all-ones significand and a subnormal range."""
+    rng = np.random.default_rng(12)
+    base = rng.random((9, 40))
+    base[0, 0], base[-1, -1] = 0.0, 1.0
+    for dt, top in ((np.float32, np.float32(1.9999999)), (np.float64, np.nextafter(2.0, 0.0)),
+                    (np.float32, np.float32(3e-41)), (np.float64, 5e-310)):
+        img = (base * float(top)).astype(dt)
+        img[-1, -1] = top
+        assert float(img.max() - img.min()) == float(top)
+        g, g8 = api.gaussblr(img, (5, 3), return_uint8=True, runtime=rt)
+        assert np.array_equal(g8, oc.gaussian_blur_u8((oc.rescale(img) * 255).astype("uint8"), (5, 3))), (dt, top)
+        mo, mo8 = api.morph(img, return_uint8=True, runtime=rt)
+        assert np.array_equal(mo8, oc.morph_close_open_u8((oc.rescale(img) * 255).astype("uint8"))), (dt, top)
+    m = rng.random((6, 50)) * float(np.nextafter(2.0, 0.0))
+    assert_same_f64(api.meansub(m, runtime=rt), oc.meansub(m))
+
+
 def case_meansub_wide(rt):
     """Rows wider than the 4096 columns the row-statistics kernel keeps in registers."""
     img = np.random.default_rng(3).random((3, 5000))

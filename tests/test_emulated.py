@@ -176,6 +176,7 @@ def test_cv2_chain_batched_small(emu_rt):
     pc.case_meansub_wide(emu_rt)
     pc.case_cv2_many_rows(emu_rt, (3, 21, 33))
     pc.case_cv2_pitched(emu_rt)
+    pc.case_cv2_division_corners(emu_rt)
 
 
 def test_cv2_chain_tiles(emu_rt):

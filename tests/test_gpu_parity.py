@@ -228,6 +228,7 @@ def test_cv2_chain_tiles_and_degenerate(cuda_rt):
     pc.case_meansub_wide(cuda_rt)
     pc.case_cv2_many_rows(cuda_rt)
     pc.case_cv2_pitched(cuda_rt)
+    pc.case_cv2_division_corners(cuda_rt)
     pc.case_cv2_many_rows(cuda_rt, (7, 333, 290))
 
 
