@@ -226,9 +226,11 @@ def run_ours(args):
     D = [rt.empty((N_CH, ROWS, ldt))[:, :, :NSEG] for _ in range(nbuf)]
     info = torch.zeros((N_CH, 4), dtype=torch.int32, device=device)
 
+    fallback = os.environ.get("SPECGPU_BENCH_FALLBACK", "1") != "0"     # A/B knob; the API default is on
+
     def step(i):
         b = i % nbuf
-        rt.pipeline_dev(plan, xs[b], S[b], D[b], clip=True, info=info)
+        rt.pipeline_dev(plan, xs[b], S[b], D[b], clip=True, info=info, fallback=fallback)
 
     # ---- correctness on these exact bytes (rank 0, untimed): one channel against the oracle ----
     step(0)

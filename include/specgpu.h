@@ -13,7 +13,10 @@
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls only enqueue
  *     work; they do not synchronise unless documented.
  *   - Return value: SPECGPU_OK (0) or a negative specgpu_status; text via specgpu_last_error().
- *   - A ctx belongs to one device and is not thread-safe; distinct ctxs are independent.
+ *   - A ctx belongs to one device and owns ONE scratch workspace: use it from one host thread and one
+ *     stream at a time (calls on different streams through the same ctx are not ordered against each
+ *     other and would share the scratch).  Distinct ctxs are independent; create one per (thread, stream).
+ *   - Entry points run on the ctx's device and restore the caller's current device before returning.
  *   - Matrices are row-major; `ld*` arguments are leading dimensions in ELEMENTS.
  *   - There is no CPU fallback anywhere behind this header.
  */
@@ -190,14 +193,34 @@ int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float
                          int64_t ldx, float* P, void* stream);
 
 /* ---- the whole path for one batch of channels (bench / production entry) -------------------- */
-/* specgr -> denoiseSignal(default: drop the leading component) -> clip, for x[B][ldx]:
- * S[B][nfreq-1][ldt] (normalised spectrogram) and D[B][nfreq-1][ldt] (denoised, clipped if clip != 0).
+/* specgr -> denoiseSignal(default: drop the leading component) -> clip, for x[B][ldx]
+ * (the loop body of pipeline_data.py:92-97 + denoising_by_svd.ipynb:263, 280-281):
+ * S[B][nfreq-1][ldt] (normalised spectrogram) and D[B][nfreq-1][ldt] (denoised).
+ * flags: SPECGPU_PIPE_CLIP      clip D at 0 (hacked[hacked<0] = 0);
+ *        SPECGPU_PIPE_FALLBACK  channels whose leading singular pair did not converge in the power iteration
+ *                               (a (nearly) degenerate pair, an iterate in the null space) are redone IN THE STREAM by
+ *                               the full float64 eigensolver -- three launches that return at once when every channel
+ *                               converged.  Always on when `info` is NULL (the caller could not see the status).
  * Optional tiles (NULL to skip): float32 [B*ntiles][nfreq-1][tile_w] cut from D.
- * info[B][4] (optional) = {1, nfreq-1, -1, status}; status 1 = the leading pair of that channel is (nearly) degenerate
- * and its power iteration hit the cap -- re-run that channel through specgpu_svd_denoise(mode = 1). */
+ * info[B][4] (optional, device) = {1, nfreq-1, -1, status}; status 1 (only possible without SPECGPU_PIPE_FALLBACK) =
+ * the leading pair of that channel did not converge: D of that channel must be recomputed with
+ * specgpu_svd_denoise(S, mode = 1). */
+enum { SPECGPU_PIPE_CLIP = 1, SPECGPU_PIPE_FALLBACK = 2 };
 int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t B, int64_t n, int64_t ldx,
-                     float* S, float* D, int64_t ldt, int32_t clip, float* tiles, int32_t tile_w, int32_t ntiles,
+                     float* S, float* D, int64_t ldt, int32_t flags, float* tiles, int32_t tile_w, int32_t ntiles,
                      int32_t* info, void* stream);
+
+/* specgpu_pipeline processes the batch in groups of `channels` channels, alternating between two library-owned
+ * streams that are forked from and joined to the caller's stream, so that the log image a group's STFT writes is read
+ * back by its Gram and projection kernels while it is still in the L2 cache.  0 = automatic (about 24 MB of image
+ * per group); a value >= B runs the batch as one group on the caller's stream.  Results do not depend on it. */
+int specgpu_set_pipeline_group(specgpu_ctx* ctx, int32_t channels);
+
+/* Cap of the power iteration that finds the leading singular pair on the default denoise route (0 restores the
+ * default, 200).  A channel that does not converge within the cap is flagged (info[b][3] = 1) and, where the fallback is
+ * on, redone by the full float64 eigensolver; a cap of 1 therefore sends every channel down the fallback route, which
+ * is how the tests exercise it on spectrogram images (their leading pair is never degenerate by itself). */
+int specgpu_set_power_iterations(specgpu_ctx* ctx, int32_t max_iter);
 
 /* Number of kernel launches the library has enqueued on this ctx since creation (for bench.py's
  * gpu_launches claim). */

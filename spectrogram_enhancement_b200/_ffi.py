@@ -19,6 +19,8 @@ ERR_CUDA = -3
 ERR_NCCL = -4
 ERR_WORKSPACE = -5
 ERR_UNSUPPORTED_SHAPE = -6
+PIPE_CLIP = 1          # specgpu_pipeline flags
+PIPE_FALLBACK = 2
 
 DETREND = {False: 0, None: 0, "constant": 1, "linear": 2}
 SCALING = {"density": 0, "spectrum": 1}
@@ -68,6 +70,8 @@ PROTOTYPES = {
     "specgpu_csd_frames": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i64, _vp, _vp]),
     "specgpu_csd_allpairs": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "specgpu_pipeline": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "specgpu_set_pipeline_group": (C.c_int, [_vp, _i32]),
+    "specgpu_set_power_iterations": (C.c_int, [_vp, _i32]),
     "specgpu_launch_count": (_i64, [_vp]),
     "specgpu_profile_enable": (C.c_int, [_vp, C.c_int]),
     "specgpu_profile_count": (C.c_int, [_vp]),

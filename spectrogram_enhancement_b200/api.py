@@ -102,6 +102,15 @@ class Runtime:
     def launch_count(self) -> int:
         return int(self.lib.launch_count(self._ctx))
 
+    def set_pipeline_group(self, channels: int):
+        """Channels per group of `pipeline` (0 = automatic; >= batch = one group on the caller's stream)."""
+        self.check(self.lib.set_pipeline_group(self._ctx, int(channels)))
+
+    def set_power_iterations(self, max_iter: int):
+        """Cap of the leading-pair power iteration (0 = default).  Channels that do not converge within it take the
+        float64 fallback route; a cap of 1 forces that route (tests)."""
+        self.check(self.lib.set_power_iterations(self._ctx, int(max_iter)))
+
     def profile(self, enable: bool):
         """Bracket every kernel launch group with CUDA events (bench.py's roofline leg)."""
         self.check(self.lib.profile_enable(self._ctx, 1 if enable else 0))
@@ -119,6 +128,13 @@ class Runtime:
     def empty(self, shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    def empty_image(self, B, rows, cols, dtype=torch.float32):
+        """[B, rows, cols] view of a buffer whose rows are pitched to a multiple of 32 elements (128 bytes for float32):
+        every row then starts on a cache line, 16-byte vector / bulk (TMA) accesses are legal, and the library takes
+        its fast paths.  The view indexes like a dense array; .contiguous() / .cpu() give the dense copy."""
+        pitch = (int(cols) + 31) // 32 * 32
+        return torch.empty((B, rows, pitch), dtype=dtype, device=self.device)[:, :, :cols]
+
     def to_device(self, x, dtype=torch.float32):
         """-> (contiguous device tensor, came_from_torch)."""
         if _is_torch(x):
@@ -128,6 +144,17 @@ class Runtime:
             raise TypeError("object arrays are not supported")
         t = torch.from_numpy(a)
         return t.to(device=self.device, dtype=dtype).contiguous(), False
+
+    def to_device_image(self, x, dtype=torch.float32):
+        """Like to_device for [..., rows, cols] images, but a device tensor whose rows are pitched (unit column stride,
+        uniform row and plane pitch -- what empty_image hands out) is used in place instead of being densified."""
+        if _is_torch(x) and x.device == self.device and x.dtype == dtype and x.dim() >= 2 and x.stride(-1) == 1:
+            ok = x.stride(-2) >= x.shape[-1]
+            for d in range(x.dim() - 2):
+                ok = ok and x.stride(d) == x.stride(d + 1) * x.shape[d + 1]
+            if ok:
+                return x, True
+        return self.to_device(x, dtype)
 
     @staticmethod
     def ret(t, as_torch):
@@ -188,7 +215,7 @@ class Runtime:
         T = self.lib.plan_num_segments(plan, n)
         F = self.lib.plan_num_freqs(plan)
         if S is None:
-            S = self.empty((B, F - 1, T))
+            S = self.empty_image(B, F - 1, T)
         mmp = minmax.data_ptr() if minmax is not None else None
         self.check(self.lib.specgr(self._ctx, plan, x2d.data_ptr(), B, n, _ld(x2d), S.data_ptr(), _ld(S), mmp,
                                    self.stream()))
@@ -199,35 +226,47 @@ class Runtime:
         T = self.lib.plan_num_segments(plan, n)
         F = self.lib.plan_num_freqs(plan)
         if Sxx is None:
-            Sxx = self.empty((B, F, T))
+            Sxx = self.empty_image(B, F, T)
         self.check(self.lib.spectrogram(self._ctx, plan, x2d.data_ptr(), B, n, _ld(x2d), Sxx.data_ptr(),
                                         _ld(Sxx), self.stream()))
         return Sxx
 
-    def pipeline_dev(self, plan, x2d, S=None, D=None, clip=True, tiles=None, tile_w=128, ntiles=0, info=None):
+    def pipeline_dev(self, plan, x2d, S=None, D=None, clip=True, tiles=None, tile_w=128, ntiles=0, info=None,
+                     fallback=True):
+        """specgpu_pipeline on device tensors.  `fallback` (default on): channels whose leading singular pair did not
+        converge in the power iteration are redone in the stream by the float64 eigensolver; with fallback=False the
+        caller must look at info[:, 3] itself."""
         B, n = x2d.shape
         T = self.lib.plan_num_segments(plan, n)
         F = self.lib.plan_num_freqs(plan)
         if S is None:
-            S = self.empty((B, F - 1, T))
+            S = self.empty_image(B, F - 1, T)
         if D is None:
-            D = self.empty((B, F - 1, T))
+            D = self.empty_image(B, F - 1, T)
+        flags = (_ffi.PIPE_CLIP if clip else 0) | (_ffi.PIPE_FALLBACK if fallback else 0)
         self.check(self.lib.pipeline(self._ctx, plan, x2d.data_ptr(), B, n, _ld(x2d), S.data_ptr(), D.data_ptr(),
-                                     _ld(S), 1 if clip else 0, tiles.data_ptr() if tiles is not None else None,
+                                     _ld(S), flags, tiles.data_ptr() if tiles is not None else None,
                                      tile_w, ntiles, info.data_ptr() if info is not None else None, self.stream()))
         return S, D
 
 
-_default = None
+_defaults = {}
 _default_lock = threading.Lock()
 
 
 def default_runtime() -> Runtime:
-    global _default
+    """The Runtime behind the module-level functions.  A libspecgpu context owns one scratch workspace and its calls are
+    only ordered by the stream they are enqueued on, so there is one default Runtime per (host thread, device,
+    current CUDA stream): work issued under different torch streams or from different threads never shares scratch."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("libspecgpu needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.cuda.current_device()
+    key = (threading.get_ident(), dev, int(torch.cuda.current_stream(dev).cuda_stream))
     with _default_lock:
-        if _default is None:
-            _default = Runtime()
-        return _default
+        rt = _defaults.get(key)
+        if rt is None:
+            rt = _defaults[key] = Runtime(device=torch.device("cuda", dev))
+        return rt
 
 
 def _rt(rt):
@@ -511,7 +550,7 @@ def filter_chain(Sxx, thr=0.9, filt=(31, 3), runtime=None, fused=True):
     five public functions - the results are identical bit for bit."""
     rt = _rt(runtime)
     as_torch = _is_torch(Sxx)
-    d, _ = rt.to_device(Sxx)
+    d, _ = rt.to_device_image(Sxx)
     squeeze = d.dim() == 2
     if squeeze:
         d = d.unsqueeze(0)

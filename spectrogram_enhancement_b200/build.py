@@ -46,7 +46,7 @@ def _deps_digest(extra=()) -> str:
     for f in files:
         p = f if os.path.isabs(f) else os.path.join(CSRC, f)
         if os.path.isfile(p):
-            h.update(p.encode())
+            h.update(os.path.relpath(p, ROOT).encode())      # relative: the stamp survives a move of the checkout
             h.update(open(p, "rb").read())
     return h.hexdigest()
 

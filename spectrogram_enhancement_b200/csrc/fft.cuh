@@ -75,13 +75,16 @@ __device__ __forceinline__ void dft_reg(float2 (&v)[R]) {
 
 // One Stockham pass (radix R, p = product of the radices of earlier passes) on the R0 register values of
 // thread `tg` of a G-thread group.  Registers v[q*R + r] hold element r of butterfly i_q = tg + q*G.
-//   load : v <- line[i_q + r*M/R] * W_M^(k*r*M/(p*R)),  k = i_q mod p
+//   load : v <- line[i_q + r*M/R] * W_(pR)^(k*r),  k = i_q mod p
 //   store: line[(i_q-k)*R + k + r*p] <- DFT_R(v)
+// The twiddles of a pass come from their own table tw[r*p + k] = exp(-2 pi i k r / (p R)): for one r the threads of a
+// group read consecutive entries (no bank conflicts; indexing one table exp(-2 pi i j / M) with j = k r (M/(pR)) made
+// the even-r loads 2- to 8-way conflicted and cost 20 % of the kernel's shared-memory wavefronts).
 template <int M, int R0, int R, int P>
 struct FftPass {
   static constexpr int G = M / R0;
   static constexpr int NB = R0 / R;
-  static __device__ __forceinline__ void load(float2 (&v)[R0], const float2* line, const float2* twM, int tg) {
+  static __device__ __forceinline__ void load(float2 (&v)[R0], const float2* line, const float2* tw, int tg) {
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
       const int i = tg + q * G;
@@ -89,7 +92,7 @@ struct FftPass {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         float2 a = line[fft_pad(i + r * (M / R))];
-        if (r > 0 && P > 1) a = cmul(a, twM[k * r * (M / (P * R))]);
+        if (r > 0 && P > 1) a = cmul(a, tw[r * P + k]);
         v[q * R + r] = a;
       }
     }
@@ -126,11 +129,28 @@ __device__ __forceinline__ void fft_group_sync() {
   else __syncthreads();
 }
 
-// Full transform.  On entry v holds the first-pass inputs of thread tg (element r = z[tg + r*G]);
-// on exit line[fft_pad(k)] = Z[k], k < M, and every thread of the group has passed a group barrier.
+// Number of float2 entries of the per-pass twiddle tables of a length-M transform: pass 1 (R1 x R0) then pass 2 (R2 x R0 R1).
+__host__ __device__ constexpr int fft_twiddle_count(int log2m) {
+  const int r0 = fft_radix_at(log2m, 0), r1 = fft_radix_at(log2m, 1), r2 = fft_radix_at(log2m, 2);
+  return (r1 > 1 ? r0 * r1 : 0) + (r2 > 1 ? r0 * r1 * r2 : 0);
+}
+// Radix of the last pass, and the register that holds output element m of thread tg after it:
+// thread tg ends up with Z[tg + G m], m < R0, in v[(m % NB) * RL + m / NB] with NB = R0 / RL.
+__host__ __device__ constexpr int fft_last_radix(int log2m) {
+  return fft_radix_at(log2m, 2) > 1 ? fft_radix_at(log2m, 2) : (fft_radix_at(log2m, 1) > 1 ? fft_radix_at(log2m, 1) : fft_radix_at(log2m, 0));
+}
+__host__ __device__ constexpr int fft_out_reg(int log2m, int m) {
+  const int rl = fft_last_radix(log2m), nb = fft_radix_at(log2m, 0) / rl;
+  return (m % nb) * rl + m / nb;
+}
+
+// Full transform.  On entry v holds the first-pass inputs of thread tg (element r = z[tg + r*G]).
+// KEEP_REGS = false: on exit line[fft_pad(k)] = Z[k], k < M, and every thread of the group has passed a group barrier.
+// KEEP_REGS = true : the outputs of the last pass stay in registers -- thread tg holds Z[tg + G m] in
+//                    v[fft_out_reg(LOG2M, m)] -- and the line is only used between passes.
 // All threads of the CTA must call this together (groups of more than 32 threads use __syncthreads()).
-template <int LOG2M>
-__device__ __forceinline__ void fft_group(float2 (&v)[fft_radix_at(LOG2M, 0)], float2* line, const float2* twM, int tg) {
+template <int LOG2M, bool KEEP_REGS = false>
+__device__ __forceinline__ void fft_group(float2 (&v)[fft_radix_at(LOG2M, 0)], float2* line, const float2* tw, int tg) {
   constexpr int M = 1 << LOG2M;
   constexpr int R0 = fft_radix_at(LOG2M, 0);
   constexpr int R1 = fft_radix_at(LOG2M, 1);
@@ -138,18 +158,21 @@ __device__ __forceinline__ void fft_group(float2 (&v)[fft_radix_at(LOG2M, 0)], f
   constexpr int G = M / R0;
   // pass 0: a single radix-R0 butterfly straight from registers
   FftPass<M, R0, R0, 1>::butterflies(v);
+  if constexpr (R1 == 1 && KEEP_REGS) return;
   FftPass<M, R0, R0, 1>::store(v, line, tg);
   fft_group_sync<G>();
   if constexpr (R1 > 1) {
-    FftPass<M, R0, R1, R0>::load(v, line, twM, tg);
+    FftPass<M, R0, R1, R0>::load(v, line, tw, tg);
     FftPass<M, R0, R1, R0>::butterflies(v);
+    if constexpr (R2 == 1 && KEEP_REGS) return;
     fft_group_sync<G>();
     FftPass<M, R0, R1, R0>::store(v, line, tg);
     fft_group_sync<G>();
   }
   if constexpr (R2 > 1) {
-    FftPass<M, R0, R2, R0 * R1>::load(v, line, twM, tg);
+    FftPass<M, R0, R2, R0 * R1>::load(v, line, tw + R0 * R1, tg);
     FftPass<M, R0, R2, R0 * R1>::butterflies(v);
+    if constexpr (KEEP_REGS) return;
     fft_group_sync<G>();
     FftPass<M, R0, R2, R0 * R1>::store(v, line, tg);
     fft_group_sync<G>();

@@ -1,6 +1,7 @@
 // Internal launcher interface between the C ABI (specgpu.cu) and the kernel translation units.
 #pragma once
 #include "common.cuh"
+#include "tensor_map.h"
 
 namespace specgpu {
 
@@ -18,12 +19,18 @@ struct StftArgs {
   float scale;           // psd scale (sqrt(scale) for STFT_MODE_COMPLEX)
   float eps;
   const float* window;   // [nperseg]
-  const float2* twM;     // exp(-2 pi i j / M), j < M
+  const float2* twM;     // per-pass twiddle tables of the M-point transform (fft.cuh: fft_twiddle_count entries)
   const float2* twN;     // exp(-2 pi i k / N), k <= M/2
   void* out;
   int64_t ld_out;
   unsigned* minmax;      // [B][2] ordered-uint min / max (STFT_MODE_LOGPSD)
   int64_t tiles_per_signal, ntiles;   // filled by the launcher (persistent tile loop)
+  // filled by the launcher:
+  int stage_in;          // the tile's sample span goes through shared memory (bulk copy for interior tiles)
+  int bulk_ok;           // base pointer / hop / first_start allow 16-byte aligned bulk copies
+  int span;              // samples in a tile's span: (TT-1)*hop + nperseg
+  int tma_out;           // whole boxes of the output tile leave through a TMA tensor store
+  int tma_rows, tma_nbox;   // rows per box, boxes per tile (rows beyond tma_rows*tma_nbox use plain stores)
 };
 
 // stft.cu
@@ -49,14 +56,15 @@ int launch_quantfilt(const float* src, int64_t B, int64_t rows, int64_t cols, in
                      float* thr_out, uint8_t* mask, cudaStream_t stream);
 
 // svd.cu
-int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* G, int g_f64, cudaStream_t stream);
-int launch_eig_power(const float* G, int64_t B, int n, float* U, float* lam, int32_t* plan, cudaStream_t stream);
+int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* G, int g_f64, cudaStream_t stream,
+                     const unsigned* minmax = nullptr, const int32_t* only_flagged = nullptr);
+int launch_eig_power(const float* G, int64_t B, int n, int max_iter /* <= 0: default */, float* U, float* lam, int32_t* plan, cudaStream_t stream);
 size_t jacobi_workspace_bytes(int64_t B, int n);
 bool eig_jacobi_f64_supported(int n);
 int launch_eig_jacobi(const void* G, int g_f64, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan, void* ws,
                       cudaStream_t stream);
 // kind 0: explicit (start, stop); 1: use_optimal; 2: computeSignal.  plan[b] = {a, e, num_sing, status}
-int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int stop, float omega_f, int32_t* plan,
+int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int stop, double omega, int32_t* plan,
                     float* s_out, cudaStream_t stream);
 // Leading-component removal fused with the min-max normalisation: L (log image) -> S = (L-min)/(max-min) and
 // D = S - u0 (u0^T S) [clipped]; S may alias L.  minmax == nullptr: L is already normalised (S not written if null).

@@ -1,10 +1,12 @@
 // libspecgpu C ABI: context / plan plumbing and the entry points declared in include/specgpu.h.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
 
+#include "fft.cuh"
 #include "kernels.h"
 
 using namespace specgpu;
@@ -17,6 +19,12 @@ struct specgpu_ctx {
   int64_t launches = 0;
   int num_sms = 148;
   size_t ws_csd_off = 0;   // offset of the pair partials inside ws (set by specgpu_csd_allpairs)
+  int power_max_iter = 0;  // cap of the leading-pair power iteration (0: the kernel default; specgpu_set_power_iterations)
+  // specgpu_pipeline: channel groups alternate between two library-owned side streams (forked from / joined to the
+  // caller's stream with events) so that a group's log image is consumed while it is still in L2
+  int pipe_group = 0;      // channels per group (0: automatic, see specgpu_set_pipeline_group)
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   // optional per-kernel timing (specgpu_profile_*): CUDA events recorded around every launch group
   bool prof_on = false;
   std::vector<std::string> prof_names;
@@ -41,6 +49,22 @@ struct specgpu_plan {
 };
 
 namespace {
+
+// Entry points run on the context's device and leave the caller's current device as they found it (a process that
+// drives several GPUs, e.g. through torch, must not have its device changed behind its back).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 int fail(specgpu_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {
@@ -210,8 +234,9 @@ int specgpu_version(void) { return SPECGPU_VERSION_MAJOR * 1000 + SPECGPU_VERSIO
 int specgpu_init(int device, specgpu_ctx** out) {
   if (!out) return SPECGPU_ERR_INVALID_ARG;
   *out = nullptr;
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) return SPECGPU_ERR_CUDA;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SPECGPU_ERR_CUDA;
+  DeviceGuard dev_guard(device);
   specgpu_ctx* ctx = new (std::nothrow) specgpu_ctx();
   if (!ctx) return SPECGPU_ERR_WORKSPACE;
   ctx->device = device;
@@ -231,9 +256,14 @@ int specgpu_init(int device, specgpu_ctx** out) {
 
 int specgpu_destroy(specgpu_ctx* ctx) {
   if (!ctx) return SPECGPU_OK;
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   if (ctx->ws) cudaFree(ctx->ws);
 #ifndef SPECGPU_EMULATE
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   prof_collect(ctx);
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
 #endif
@@ -245,16 +275,28 @@ const char* specgpu_last_error(const specgpu_ctx* ctx) { return ctx ? ctx->err.c
 
 int specgpu_workspace_reserve(specgpu_ctx* ctx, int64_t bytes) {
   if (!ctx || bytes < 0) return SPECGPU_ERR_INVALID_ARG;
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   return ensure_ws(ctx, (size_t)bytes);
 }
 
 int64_t specgpu_launch_count(const specgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int specgpu_set_pipeline_group(specgpu_ctx* ctx, int32_t channels) {
+  if (!ctx || channels < 0) return SPECGPU_ERR_INVALID_ARG;
+  ctx->pipe_group = channels;
+  return SPECGPU_OK;
+}
+
+int specgpu_set_power_iterations(specgpu_ctx* ctx, int32_t max_iter) {
+  if (!ctx || max_iter < 0) return SPECGPU_ERR_INVALID_ARG;
+  ctx->power_max_iter = max_iter;
+  return SPECGPU_OK;
+}
+
 int specgpu_profile_enable(specgpu_ctx* ctx, int enable) {
   if (!ctx) return SPECGPU_ERR_INVALID_ARG;
 #ifndef SPECGPU_EMULATE
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   prof_collect(ctx);
 #endif
   ctx->prof_on = enable != 0;
@@ -269,7 +311,7 @@ int specgpu_profile_enable(specgpu_ctx* ctx, int enable) {
 int specgpu_profile_count(specgpu_ctx* ctx) {
   if (!ctx) return 0;
 #ifndef SPECGPU_EMULATE
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   prof_collect(ctx);
 #endif
   return (int)ctx->prof_names.size();
@@ -327,25 +369,40 @@ int specgpu_plan_create(specgpu_ctx* ctx, const specgpu_stft_params* p, const do
   const int M = N / 2;
   std::vector<float> wf(N);
   for (int i = 0; i < N; ++i) wf[i] = (float)w[i];
-  std::vector<float2> twM(M), twN(M / 2 + 1);
-  for (int j = 0; j < M; ++j) {
-    twM[j].x = (float)std::cos(two_pi * j / M);
-    twM[j].y = (float)(-std::sin(two_pi * j / M));
+  // per-pass twiddle tables of the M-point complex transform (fft.cuh): pass p holds exp(-2 pi i k r / (P R)) at
+  // [r * P + k], P = product of the earlier radices
+  const int log2m = log2n - 1;
+  const int ntw = std::max(fft_twiddle_count(log2m), 1);
+  std::vector<float2> twM(ntw), twN(M / 2 + 1);
+  {
+    int off = 0, P = fft_radix_at(log2m, 0);
+    for (int pass = 1; pass <= 2; ++pass) {
+      const int R = fft_radix_at(log2m, pass);
+      if (R <= 1) break;
+      for (int r = 0; r < R; ++r)
+        for (int k = 0; k < P; ++k) {
+          const int j = (int)(((int64_t)k * r) % ((int64_t)P * R));
+          twM[off + r * P + k].x = (float)std::cos(two_pi * j / ((double)P * R));
+          twM[off + r * P + k].y = (float)(-std::sin(two_pi * j / ((double)P * R)));
+        }
+      off += R * P;
+      P *= R;
+    }
   }
   for (int k = 0; k <= M / 2; ++k) {
     twN[k].x = (float)std::cos(two_pi * k / N);
     twN[k].y = (float)(-std::sin(two_pi * k / N));
   }
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   cudaError_t e;
   if ((e = cudaMalloc(&plan->d_window, N * sizeof(float))) != cudaSuccess ||
-      (e = cudaMalloc(&plan->d_twM, M * sizeof(float2))) != cudaSuccess ||
+      (e = cudaMalloc(&plan->d_twM, ntw * sizeof(float2))) != cudaSuccess ||
       (e = cudaMalloc(&plan->d_twN, (M / 2 + 1) * sizeof(float2))) != cudaSuccess) {
     specgpu_plan_destroy(plan);
     return cuda_fail(ctx, (int)e, "plan tables");
   }
   cudaMemcpy(plan->d_window, wf.data(), N * sizeof(float), cudaMemcpyHostToDevice);
-  cudaMemcpy(plan->d_twM, twM.data(), M * sizeof(float2), cudaMemcpyHostToDevice);
+  cudaMemcpy(plan->d_twM, twM.data(), ntw * sizeof(float2), cudaMemcpyHostToDevice);
   cudaMemcpy(plan->d_twN, twN.data(), (M / 2 + 1) * sizeof(float2), cudaMemcpyHostToDevice);
   *out = plan;
   return SPECGPU_OK;
@@ -353,7 +410,7 @@ int specgpu_plan_create(specgpu_ctx* ctx, const specgpu_stft_params* p, const do
 
 int specgpu_plan_destroy(specgpu_plan* plan) {
   if (!plan) return SPECGPU_OK;
-  if (plan->ctx) cudaSetDevice(plan->ctx->device);
+  DeviceGuard dev_guard(plan->ctx ? plan->ctx->device : 0);
   if (plan->d_window) cudaFree(plan->d_window);
   if (plan->d_twM) cudaFree(plan->d_twM);
   if (plan->d_twN) cudaFree(plan->d_twN);
@@ -402,7 +459,7 @@ int specgpu_specgr(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, i
   const int64_t nseg = num_segments(n, plan->p.nperseg, plan->p.noverlap);
   if (nseg == 0 || B == 0) return SPECGPU_OK;
   if (!S || ldt < nseg) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output (ldt=%lld < nseg=%lld)", (long long)ldt, (long long)nseg);
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   if ((rc = ensure_ws(ctx, carve_size({(size_t)B * 2 * sizeof(unsigned)})))) return rc;
   Carver cv(ctx->ws);
   unsigned* mm = cv.take<unsigned>(B * 2);
@@ -460,7 +517,7 @@ int specgpu_rescale(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows,
   if (rc) return rc;
   if (B * rows * cols == 0) return SPECGPU_OK;
   if (!dst) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null output pointer");
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   if ((rc = ensure_ws(ctx, carve_size({(size_t)B * 2 * sizeof(unsigned)})))) return rc;
   Carver cv(ctx->ws);
   unsigned* mm = cv.take<unsigned>(B * 2);
@@ -474,7 +531,7 @@ int specgpu_norm(specgpu_ctx* ctx, const float* src, int64_t B, int64_t rows, in
   if (rc) return rc;
   if (B * rows * cols == 0) return SPECGPU_OK;
   if (!dst) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null output pointer");
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   const int parts = norm_num_parts(rows, cols);
   if ((rc = ensure_ws(ctx, carve_size({(size_t)B * parts * 2 * sizeof(double)})))) return rc;
   Carver cv(ctx->ws);
@@ -513,10 +570,10 @@ int specgpu_quantfilt(specgpu_ctx* ctx, const float* src, int64_t B, int64_t row
 // ---- SVD denoise ---------------------------------------------------------------------------------
 namespace {
 
-// omega(beta) of the notebook (denoising_by_svd.ipynb:155-159), evaluated in double as Python does.  With a
-// float32 matrix np.median(s) is a float32 scalar and NumPy >= 2 keeps `omega * median` in float32 (the
-// Python float is a weak scalar), so the device multiplies float32(omega) by the float32 median.
-double omega_of(double beta) { return 0.56 * beta * beta * beta - 0.95 * beta * beta + 1.82 * beta + 1.43; }
+// omega(beta) of the notebook (denoising_by_svd.ipynb:155-159).  beta = np.min(shape) / np.max(shape) is an np.float64
+// (a strong scalar), so omega(beta) is float64 and t* = omega * np.median(s) is evaluated and compared in float64 even
+// when s is float32: the device multiplies the double omega by the float32 median in double.
+double omega_of(double beta) { return 0.56 * std::pow(beta, 3.0) - 0.95 * std::pow(beta, 2.0) + 1.82 * beta + 1.43; }   // as Python: beta ** 3
 
 struct SvdWs {
   float* G;
@@ -550,18 +607,15 @@ SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
 // `raw_mm` != nullptr (pipeline only): S holds the un-normalised log image and raw_mm its per-matrix
 // (min, max); the normalisation is then fused into the Gram producer and the rank-1 projection, which
 // also writes the normalised image back over S.
-// `fallback`: after the power iteration also enqueue the full solver for matrices whose iteration hit its cap
-// (a degenerate leading pair).  The pipeline leaves it out (two launches on the critical path for a case in which the
-// reference's own answer is ill-conditioned) and reports info[3] = 1 instead.
-int svd_run(specgpu_ctx* ctx, void* ws_base, float* S, const unsigned* raw_mm, int64_t B, int64_t rows, int64_t cols,
+// `fallback`: after the power iteration also enqueue the full float64 solver for the matrices whose iteration did not
+// converge (info[3] would be 1); three launches that exit at once when every matrix converged.
+int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const unsigned* raw_mm, int64_t B, int64_t rows, int64_t cols,
             int64_t ld, int kind, int start, int stop, int clip, bool power_ok, bool fallback, void* out, int out_f64,
             int64_t ldo, float* s_out, int32_t* info, cudaStream_t st) {
   void* stream = (void*)st;
   const bool tc = power_ok && gram_tc_supported(rows);   // TF32 Gram only feeds the leading-pair route
   // full decomposition: Gram and Jacobi in double (float would square the condition number into the noise floor)
   const int g_f64 = (!power_ok && eig_jacobi_f64_supported((int)rows)) ? 1 : 0;
-  const bool full = true;                                // Jacobi scratch is always carved (fallback for power)
-  SvdWs w = svd_carve(ws_base, B, rows, tc, full);
   if (tc) {
     CHECK_LAUNCH(ctx, launch_gram_tc(S, B, rows, cols, ld, raw_mm, w.gram_partial, w.G, ctx->num_sms, st), "gram_tc", 2);
   } else {
@@ -572,16 +626,21 @@ int svd_run(specgpu_ctx* ctx, void* ws_base, float* S, const unsigned* raw_mm, i
     CHECK_LAUNCH(ctx, launch_gram_simt(S, B, rows, cols, ld, w.G, g_f64, st), "gram_simt", 1);
   }
   if (power_ok) {
-    CHECK_LAUNCH(ctx, launch_eig_power(w.G, B, (int)rows, w.U, w.lam, w.plan, st), "eig_power", 1);
-    // matrices whose iteration hit its cap are redone by the full solver (it skips the others)
-    if (fallback)
-      CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 0, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+    CHECK_LAUNCH(ctx, launch_eig_power(w.G, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st), "eig_power", 1);
+    // Matrices whose iteration did not converge (degenerate leading pair, iterate fallen into the null space) are
+    // redone by the full solver in float64: Gram matrix of the flagged matrices only, straight from the image (the
+    // TF32 Gram is dead after the power iteration and is overwritten), then the cluster Jacobi, which skips the
+    // converged ones.  All three launches return at once when nothing is flagged.
+    if (fallback) {
+      CHECK_LAUNCH(ctx, launch_gram_simt(S, B, rows, cols, ld, w.G, 1, st, raw_mm, w.plan), "gram_simt_flagged", 1);
+      CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 1, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+    }
   } else {
     CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, g_f64, B, (int)rows, 0, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
   }
   const double beta = (double)std::min(rows, cols) / (double)std::max(rows, cols);
   if (!power_ok)   // the power kernel writes the (fixed) default plan itself
-    CHECK_LAUNCH(ctx, launch_svd_plan(w.lam, B, (int)rows, kind, start, stop, (float)omega_of(beta), w.plan, s_out, st),
+    CHECK_LAUNCH(ctx, launch_svd_plan(w.lam, B, (int)rows, kind, start, stop, omega_of(beta), w.plan, s_out, st),
                  "svd_plan", 1);
   if (power_ok && !out_f64) {
     // power_ok implies the range [1, rows): only the leading component is removed
@@ -615,10 +674,10 @@ int specgpu_svd_denoise(specgpu_ctx* ctx, const float* S, int64_t B, int64_t row
   int rc = check_svd_args(ctx, S, B, rows, cols, ld, out, ldo);
   if (rc) return rc;
   if (B * rows * cols == 0) return SPECGPU_OK;
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   const bool power_ok = (mode == 0) && !use_optimal && start == 1 && stop >= rows && s_out == nullptr && rows <= 256;
   if ((rc = ensure_ws(ctx, svd_ws_bytes(B, rows, power_ok && gram_tc_supported(rows), true)))) return rc;
-  return svd_run(ctx, ctx->ws, const_cast<float*>(S), nullptr, B, rows, cols, ld, use_optimal ? 1 : 0, start, stop, clip,
+  return svd_run(ctx, svd_carve(ctx->ws, B, rows, power_ok && gram_tc_supported(rows), true), const_cast<float*>(S), nullptr, B, rows, cols, ld, use_optimal ? 1 : 0, start, stop, clip,
                  power_ok, true, out, 0, ldo, s_out, info, (cudaStream_t)stream);
 }
 
@@ -627,9 +686,9 @@ int specgpu_compute_signal(specgpu_ctx* ctx, const float* S, int64_t B, int64_t 
   int rc = check_svd_args(ctx, S, B, rows, cols, ld, out, ldo);
   if (rc) return rc;
   if (B * rows * cols == 0) return SPECGPU_OK;
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   if ((rc = ensure_ws(ctx, svd_ws_bytes(B, rows, false, true)))) return rc;
-  return svd_run(ctx, ctx->ws, const_cast<float*>(S), nullptr, B, rows, cols, ld, 2, 0, 0, 0, false, false, out, 1, ldo,
+  return svd_run(ctx, svd_carve(ctx->ws, B, rows, false, true), const_cast<float*>(S), nullptr, B, rows, cols, ld, 2, 0, 0, 0, false, false, out, 1, ldo,
                  s_out, info, (cudaStream_t)stream);
 }
 
@@ -701,7 +760,7 @@ int specgpu_gaussblr(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t 
   if (B * rows * cols == 0) return SPECGPU_OK;
   if (cols > (1 << 30) || rows > 65535) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "image too large");
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
   uint16_t taps[512];
   gaussian_taps_q8(kw, 0.0, taps);
@@ -719,7 +778,7 @@ int specgpu_meansub(specgpu_ctx* ctx, const double* src, int64_t B, int64_t rows
   if (rows > 65535 || cols > 120000)      // the pairwise-sum leaves of a row live in shared memory
     return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "meansub: rows=%lld > 65535 or cols=%lld > 120000", (long long)rows, (long long)cols);
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
   CHECK_LAUNCH(ctx, launch_meansub(src, B, rows, cols, ld, ctx->ws, dst, ldo, (cudaStream_t)stream), "meansub", 3);
   return SPECGPU_OK;
@@ -732,7 +791,7 @@ int specgpu_morph(specgpu_ctx* ctx, const void* src, int32_t in_f64, int64_t B, 
   if (B * rows * cols == 0) return SPECGPU_OK;
   if (cols > (1 << 30) || rows > 65535) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "image too large");
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   if ((rc = ensure_ws(ctx, imgchain_workspace_bytes(B, rows, cols)))) return rc;
   CHECK_LAUNCH(ctx, launch_morph(src, in_f64, B, rows, cols, ld, ctx->ws, dst, ldo, u8_out, (cudaStream_t)stream), "morph", 4 + (u8_out ? 1 : 0));
   return SPECGPU_OK;
@@ -749,7 +808,7 @@ int specgpu_filter_chain(specgpu_ctx* ctx, const float* src, int64_t B, int64_t 
   if (cols > 120000 || rows > 1024)
     return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "filter_chain: rows=%lld > 1024 or cols=%lld > 120000", (long long)rows, (long long)cols);
   if (!dst || ldo < cols) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output");
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   // workspace: the image-chain planes, then the thresholded float32 image (quantfilt writes it with the source's pitch)
   const size_t img_bytes = (imgchain_workspace_bytes(B, rows, cols) + 255) & ~(size_t)255;
   if ((rc = ensure_ws(ctx, img_bytes + (size_t)B * rows * ld * sizeof(float) + 256))) return rc;
@@ -789,7 +848,7 @@ int specgpu_csd_pairs_block(specgpu_ctx* ctx, const specgpu_plan* plan, const fl
   if (C == 0 || ni == 0) return SPECGPU_OK;
   if (nseg == 0) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_pairs: no segments to average");
   if (!X || !P) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null pointer");
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   // the pair partials live behind whatever specgpu_csd_allpairs put in front (its spectra)
   const size_t need = ctx->ws_csd_off + csd_pairs_workspace_bytes(C, ni, nfreq, nseg) + 256;
   int rc = ensure_ws(ctx, need);
@@ -833,7 +892,7 @@ int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float
   if (!P) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null output pointer");
   const int nfreq = plan->p.nperseg / 2 + 1;
   const int64_t ldf = (nfreq + 15) & ~(int64_t)15;  // 128-byte aligned rows of float2
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   const size_t xbytes = (((size_t)C * nseg * ldf * 8) + 255) & ~(size_t)255;
   if ((rc = ensure_ws(ctx, xbytes + csd_pairs_workspace_bytes(C, C, nfreq, nseg) + 512))) return rc;
   float* X = static_cast<float*>(ctx->ws);
@@ -845,9 +904,29 @@ int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float
 }
 
 // ---- whole path --------------------------------------------------------------------------------------
+namespace {
+// Channels per group of specgpu_pipeline: the log image of a group (and the two groups in flight) should sit in the
+// 126 MB L2 between the STFT that writes it and the Gram / projection kernels that read it back.
+int64_t pipeline_group_size(const specgpu_ctx* ctx, int64_t B, int64_t rows, int64_t ldt) {
+  int64_t g = ctx->pipe_group;
+  if (const char* env = std::getenv("SPECGPU_PIPELINE_GROUP")) g = std::atoll(env);
+  if (g <= 0) {
+    const int64_t img = rows * ldt * 4;
+    g = std::max<int64_t>(1, ((int64_t)24 << 20) / std::max<int64_t>(img, 1));
+    // groups of equal size (40 channels, 6 per group by bytes -> 5 groups of 8 would overshoot: use ceil(B / ngroups))
+    const int64_t ng = ceil_div(B, g);
+    g = ceil_div(B, ng);
+  }
+  return std::min(g, B);
+}
+}  // namespace
+
 int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t B, int64_t n, int64_t ldx, float* S,
-                     float* D, int64_t ldt, int32_t clip, float* tiles, int32_t tile_w, int32_t ntiles, int32_t* info,
+                     float* D, int64_t ldt, int32_t flags, float* tiles, int32_t tile_w, int32_t ntiles, int32_t* info,
                      void* stream) {
+  const int clip = (flags & SPECGPU_PIPE_CLIP) ? 1 : 0;
+  // without `info` the caller cannot see a non-converged leading pair: the repair runs in the stream regardless
+  const bool fallback = (flags & SPECGPU_PIPE_FALLBACK) != 0 || info == nullptr;
   int rc = check_signal_args(ctx, plan, x, B, n, ldx);
   if (rc) return rc;
   const int64_t nseg = num_segments(n, plan->p.nperseg, plan->p.noverlap);
@@ -858,21 +937,86 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
   if (rows > 512) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "pipeline: nperseg/2=%lld > 512 rows for the SVD stage", (long long)rows);
   if (tiles && (tile_w <= 0 || ntiles < 0 || (int64_t)tile_w * ntiles > nseg))
     return fail(ctx, SPECGPU_ERR_INVALID_ARG, "pipeline: tile_w*ntiles exceeds the %lld columns", (long long)nseg);
-  cudaSetDevice(ctx->device);
+  DeviceGuard dev_guard(ctx->device);
   const bool power_ok = rows <= 256;
-  const size_t mm_bytes = carve_size({(size_t)B * 2 * sizeof(unsigned)});
-  if ((rc = ensure_ws(ctx, mm_bytes + svd_ws_bytes(B, rows, power_ok && gram_tc_supported(rows), true)))) return rc;
-  unsigned* mm = static_cast<unsigned*>(ctx->ws);
-  void* svd_ws = static_cast<char*>(ctx->ws) + mm_bytes;
-  cudaStream_t st = (cudaStream_t)stream;
-  CHECK_LAUNCH(ctx, launch_minmax_init(mm, B, st), "minmax_init", 1);
-  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, (float)plan->scale, S, ldt, mm);
-  CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, B, st), "stft_kernel", 1);
-  // S holds the raw log image until the rank-1 projection normalises it in place (see svd_run)
-  if ((rc = svd_run(ctx, svd_ws, S, mm, B, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, false, D, 0, ldt, nullptr, info,
-                    st)))
+  const bool tc = power_ok && gram_tc_supported(rows);
+  const int64_t gsz = pipeline_group_size(ctx, B, rows, ldt);
+  const int64_t ngroups = ceil_div(B, gsz);
+  const int nlanes = ngroups > 1 ? 2 : 1;        // streams in use
+  // ---- workspace: min/max pairs and per-channel SVD arrays for the whole batch; Gram partials and Jacobi scratch per lane ----
+  const size_t part_bytes = tc ? gram_tc_workspace_bytes(gsz, rows) : 0;
+  const size_t jac_bytes = jacobi_workspace_bytes(gsz, (int)rows);
+  if ((rc = ensure_ws(ctx, carve_size({(size_t)B * 2 * sizeof(unsigned), (size_t)B * rows * rows * 8, (size_t)B * rows * rows * 4,
+                                       (size_t)B * rows * 4, (size_t)B * 16, part_bytes, part_bytes, jac_bytes, jac_bytes}))))
     return rc;
-  if (tiles && ntiles > 0) CHECK_LAUNCH(ctx, launch_patch(D, B, rows, ldt, tile_w, ntiles, tiles, 0, st), "patch", 1);
+  Carver cv(ctx->ws);
+  unsigned* mm = cv.take<unsigned>(B * 2);
+  double* Gall = cv.take<double>(B * rows * rows);
+  float* Uall = cv.take<float>(B * rows * rows);
+  float* lam_all = cv.take<float>(B * rows);
+  int32_t* plan_all = cv.take<int32_t>(B * 4);
+  float* part[2];
+  void* jac[2];
+  for (int i = 0; i < 2; ++i) part[i] = tc ? cv.take<float>(part_bytes / 4) : nullptr;
+  for (int i = 0; i < 2; ++i) jac[i] = cv.take<char>(jac_bytes);
+
+  cudaStream_t user = (cudaStream_t)stream;
+  cudaStream_t lane[2] = {user, user};
+#ifndef SPECGPU_EMULATE
+  if (nlanes > 1) {
+    for (int i = 0; i < 2; ++i) {
+      if (!ctx->side[i] && cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) != cudaSuccess)
+        return cuda_fail(ctx, (int)cudaGetLastError(), "side stream");
+      if (!ctx->ev_join[i] && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess)
+        return cuda_fail(ctx, (int)cudaGetLastError(), "join event");
+      lane[i] = ctx->side[i];
+    }
+    if (!ctx->ev_fork && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess)
+      return cuda_fail(ctx, (int)cudaGetLastError(), "fork event");
+  }
+#endif
+  {
+    CHECK_LAUNCH(ctx, launch_minmax_init(mm, B, user), "minmax_init", 1);
+  }
+#ifndef SPECGPU_EMULATE
+  if (nlanes > 1) {
+    cudaEventRecord(ctx->ev_fork, user);
+    cudaStreamWaitEvent(lane[0], ctx->ev_fork, 0);
+    cudaStreamWaitEvent(lane[1], ctx->ev_fork, 0);
+  }
+#endif
+  for (int64_t g = 0; g < ngroups; ++g) {
+    const int64_t b0 = g * gsz, nb = std::min(gsz, B - b0);
+    const int li = (int)(g % nlanes);
+    void* stream = (void*)lane[li];            // CHECK_LAUNCH / ProfScope take the stream from this name
+    cudaStream_t st = lane[li];
+    float* Sg = S + b0 * rows * ldt;
+    float* Dg = D + b0 * rows * ldt;
+    unsigned* mmg = mm + 2 * b0;
+    StftArgs a = make_args(plan, x + b0 * ldx, n, ldx, 0, nseg, (float)plan->scale, Sg, ldt, mmg);
+    CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, nb, st), "stft_kernel", 1);
+    SvdWs w{};
+    w.G = reinterpret_cast<float*>(Gall + b0 * rows * rows);
+    w.U = Uall + b0 * rows * rows;
+    w.lam = lam_all + b0 * rows;
+    w.plan = plan_all + b0 * 4;
+    w.gram_partial = part[li];
+    w.jacobi = jac[li];
+    // Sg holds the raw log image until the rank-1 projection normalises it in place (see svd_run)
+    if ((rc = svd_run(ctx, w, Sg, mmg, nb, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, fallback, Dg, 0, ldt, nullptr,
+                      info ? info + b0 * 4 : nullptr, st)))
+      return rc;
+    if (tiles && ntiles > 0)
+      CHECK_LAUNCH(ctx, launch_patch(Dg, nb, rows, ldt, tile_w, ntiles, tiles + (size_t)b0 * ntiles * rows * tile_w, 0, st), "patch", 1);
+  }
+#ifndef SPECGPU_EMULATE
+  if (nlanes > 1) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEventRecord(ctx->ev_join[i], lane[i]);
+      cudaStreamWaitEvent(user, ctx->ev_join[i], 0);
+    }
+  }
+#endif
   return SPECGPU_OK;
 }
 

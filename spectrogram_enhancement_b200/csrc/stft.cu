@@ -10,10 +10,14 @@
 
 #include "fft.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace specgpu {
 
 constexpr int kStftThreads = 256;
+// internal variant of STFT_MODE_LOGPSD: eps >= FLT_MIN, so log2's argument is never subnormal and the
+// flush-to-zero MUFU form (no range-scaling instructions) is exact enough
+constexpr int STFT_MODE_LOGPSD_FAST = 4;
 
 template <int LOG2N>
 struct StftCfg {
@@ -25,37 +29,51 @@ struct StftCfg {
   static constexpr int G = M / R0;                      // threads per segment
   static constexpr int NG = kStftThreads / G;           // segments in flight per CTA
   static constexpr int LINE = M + (M >> 4) + 1;          // padded float2 per FFT line
-  // Extra columns of the transposed output tile.  A warp holds 32/G segment groups (consecutive tile columns) whose
-  // threads store 16 consecutive frequencies each: with a pitch of TT + 32/G (float tiles) the 32 lanes of such a
-  // store fall into 32 different banks (pitch TT + 1 left the groups one bank apart: 2-way conflicts).
-  static constexpr int PAD4 = (G >= 2 && G <= 16) ? 32 / G : 1;
-  // tile width (segments per CTA): >= NG, grown towards 32 while the float tile stays <= 72 KB
+  // tile width (segments per CTA tile): >= NG, grown towards 16 while the tile stays <= 36 KB.  (nperseg 512: 16
+  // segments = 64-byte rows of the float tile, one round of the 16 segment groups per tile.)
   __host__ __device__ static constexpr int tile_w(int bytes_per_elem) {
     int tt = NG;
-    while (tt < 32 && (long)F * (2 * tt + 1) * bytes_per_elem <= 72 * 1024) tt *= 2;
+    while (tt < 16 && (long)F * (2 * tt) * bytes_per_elem <= 36 * 1024) tt *= 2;
     return tt;
   }
 };
 
+__host__ __device__ constexpr bool stft_mode_is_log(int mode) { return mode == STFT_MODE_LOGPSD || mode == STFT_MODE_LOGPSD_FAST; }
+__host__ __device__ constexpr int stft_elem_bytes(int mode) { return mode == STFT_MODE_COMPLEX ? 8 : 4; }
+
+// The output tile [F rows][TT segments] lives in shared memory as dense rows of ROWB = TT * elem bytes with the
+// 16-byte chunks of a row XOR-swizzled by the row index -- exactly the CU_TENSOR_MAP_SWIZZLE_{32,64,128}B patterns
+// (address bits 4..6 ^= bits 7..9, masked to the span), so that a TMA tensor store can read it in place while the
+// column-wise writes of the segment groups spread over the banks.  The tile base is 1024-byte aligned.
+__host__ __device__ constexpr int stft_swizzle_mask(int rowb) { return rowb >= 128 ? 0x70 : (rowb == 64 ? 0x30 : (rowb == 32 ? 0x10 : 0)); }
+
 struct StftSmem {
-  int window_off, twm_off, twn_off, line_off, red_off, tile_off, total;
+  int window_off, twm_off, twn_off, line_off, red_off, bar_off, in_off, tile_off, total;
 };
 
+// span_floats: samples of the staged input span of one tile, (TT-1)*hop + N (0: segments are loaded straight from
+// global memory).
 template <int LOG2N>
-__host__ __device__ inline StftSmem stft_smem_layout(int mode) {
+__host__ __device__ inline StftSmem stft_smem_layout(int mode, int span_floats) {
   using C = StftCfg<LOG2N>;
   StftSmem s;
   int off = 0;
   s.window_off = off; off += C::N * 4;
-  s.twm_off = off;    off += C::M * 8;
+  s.twm_off = off;    off += (fft_twiddle_count(C::LOG2M) > 0 ? fft_twiddle_count(C::LOG2M) : 1) * 8;
   s.twn_off = off;    off += (C::M / 2 + 1) * 8;
   off = (off + 15) & ~15;
   s.line_off = off;   off += C::NG * C::LINE * 8;
   s.red_off = off;    off += (kStftThreads / 32) * 2 * 4 + 64;
   off = (off + 15) & ~15;
+  s.bar_off = off;    off += 16;
+  off = (off + 127) & ~127;
+  s.in_off = off;     off += (span_floats * 4 + 127) & ~127;
   s.tile_off = off;
-  if (mode == STFT_MODE_PSD || mode == STFT_MODE_LOGPSD) off += C::F * (C::tile_w(4) + C::PAD4) * 4;
-  else if (mode == STFT_MODE_COMPLEX) off += C::F * (C::tile_w(8) + 1) * 8;
+  if (mode != STFT_MODE_SPECTRA) {
+    off = (off + 1023) & ~1023;
+    s.tile_off = off;
+    off += C::F * C::tile_w(stft_elem_bytes(mode)) * stft_elem_bytes(mode);
+  }
   s.total = off;
   return s;
 }
@@ -94,76 +112,176 @@ __device__ __forceinline__ void group_sum2(float& a, float& b, float* red, int t
   }
 }
 
+// log2 for arguments known to be normal (>= FLT_MIN): one MUFU, no subnormal range scaling.
+__device__ __forceinline__ float log2_normal(float x) {
+#if defined(SPECGPU_EMULATE)
+  return __log2f(x);
+#else
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#endif
+}
+
 // Resident CTAs per SM the register allocator should aim for: what the shared-memory footprint of the mode allows
 // (the spectra mode has no output tile).  Without it the 3-pass sizes compile to ~195 registers = one CTA per SM.
 __host__ __device__ constexpr int stft_min_blocks(int log2n, int mode) {
-  if (mode == STFT_MODE_COMPLEX) return 1;
+  if (mode == STFT_MODE_COMPLEX) return log2n <= 9 ? 2 : 1;
   if (log2n <= 9) return 3;
   if (mode == STFT_MODE_SPECTRA) return log2n <= 12 ? 3 : 1;
   return log2n == 10 ? 2 : 1;
 }
 
+#if defined(SPECGPU_EMULATE)
+#define SPECGPU_GRID_CONSTANT
+#else
+#define SPECGPU_GRID_CONSTANT __grid_constant__
+#endif
+
 template <int LOG2N, int MODE>
-__global__ void __launch_bounds__(kStftThreads, stft_min_blocks(LOG2N, MODE)) stft_kernel(StftArgs a) {
+__global__ void __launch_bounds__(kStftThreads, stft_min_blocks(LOG2N, MODE))
+stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   using C = StftCfg<LOG2N>;
   constexpr int N = C::N, M = C::M, F = C::F, R0 = C::R0, G = C::G, NG = C::NG;
-  constexpr int TT = (MODE == STFT_MODE_COMPLEX) ? C::tile_w(8) : C::tile_w(4);
-  constexpr int PITCH = (MODE == STFT_MODE_COMPLEX) ? TT + 1 : TT + C::PAD4;
+  constexpr bool LOGM = stft_mode_is_log(MODE);
+  constexpr int E = stft_elem_bytes(MODE);
+  constexpr int TT = C::tile_w(E);
+  constexpr int ROUNDS = TT / NG;
+  constexpr int ROWB = TT * E;                       // bytes per tile row
+  constexpr int SWMASK = stft_swizzle_mask(ROWB);
+  constexpr int JSTEP = G * ROWB;                     // tile byte offset between rows k and k + G
+  static_assert(JSTEP % 1024 == 0, "row stride between a thread's bins must not touch the swizzle bits");
   SPECGPU_DYN_SMEM(smem);
-  const StftSmem L = stft_smem_layout<LOG2N>(MODE);
+  const StftSmem L = stft_smem_layout<LOG2N>(MODE, a.stage_in ? a.span : 0);
   float* s_win = reinterpret_cast<float*>(smem + L.window_off);
   float2* s_twm = reinterpret_cast<float2*>(smem + L.twm_off);
   float2* s_twn = reinterpret_cast<float2*>(smem + L.twn_off);
   float2* s_line = reinterpret_cast<float2*>(smem + L.line_off);
   float* s_red = reinterpret_cast<float*>(smem + L.red_off);
-  float* s_tile = reinterpret_cast<float*>(smem + L.tile_off);
-  float2* s_tile2 = reinterpret_cast<float2*>(smem + L.tile_off);
+  float* s_in = reinterpret_cast<float*>(smem + L.in_off);
+  unsigned char* s_tile = smem + L.tile_off;
 
   const int tid = threadIdx.x;
   const int grp = tid / G;  // which in-flight segment
   const int tg = tid % G;   // thread within the segment group
+  const bool stage = a.stage_in != 0;
+  const bool tma_out = (MODE != STFT_MODE_SPECTRA) && a.tma_out != 0;
 
   for (int i = tid; i < N; i += kStftThreads) s_win[i] = a.window[i];
-  for (int i = tid; i < M; i += kStftThreads) s_twm[i] = a.twM[i];
+  for (int i = tid; i < fft_twiddle_count(C::LOG2M); i += kStftThreads) s_twm[i] = a.twM[i];
   for (int i = tid; i <= M / 2; i += kStftThreads) s_twn[i] = a.twN[i];
+#if !defined(SPECGPU_EMULATE)
+  const uint32_t bar = smem_u32(smem + L.bar_off);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    if (tma_out) tma_prefetch_desc(&tmap);
+  }
+  // the input is read once (both overlapping segments come out of the staged span): do not let it displace the log
+  // image, which the Gram and projection kernels read back while it is still in L2
+  const uint64_t pol_in = l2_policy_evict_first();
+  const uint64_t pol_out = l2_policy_evict_last();
+#endif
   __syncthreads();
 
-  float2* line = s_line + grp * C::LINE;
-  // persistent CTAs: the tables above are loaded once, then the CTA walks tiles (signal b, TT segments)
   const unsigned tps = (unsigned)a.tiles_per_signal;      // ntiles < 2^31 is checked by the launcher
-  for (unsigned tile = blockIdx.x; tile < (unsigned)a.ntiles; tile += gridDim.x) {
+  const unsigned ntiles = (unsigned)a.ntiles;
+  // Can the span of this tile come in as ONE aligned, in-range bulk copy?  (Otherwise -- first/last tiles of a
+  // signal, odd alignments -- all threads fill the span with guarded loads, zero outside [0, n).)
+  auto tile_bulk = [&](int64_t b, int64_t s0) -> bool {
+#if defined(SPECGPU_EMULATE)
+    (void)b; (void)s0;
+    return false;
+#else
+    return a.bulk_ok && s0 >= 0 && s0 + a.span <= a.n && (((b * a.ldx + s0) & 3) == 0);
+#endif
+  };
+  // Stage the span of `tile` (all threads call this; only after every thread is done reading the previous span).
+  auto prefetch = [&](unsigned tile) {
+    const unsigned b32 = tile / tps;
+    const int64_t b = b32;
+    const int64_t s0 = a.first_start + (int64_t)(tile - b32 * tps) * TT * (int64_t)a.hop;
+    const float* xb = a.x + b * a.ldx;
+    if (tile_bulk(b, s0)) {
+#if !defined(SPECGPU_EMULATE)
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar, (uint32_t)a.span * 4u);
+        bulk_g2s(smem_u32(s_in), xb + s0, (uint32_t)a.span * 4u, bar, pol_in);
+      }
+#endif
+    } else {
+      for (int i = tid; i < a.span; i += kStftThreads) {
+        const int64_t idx = s0 + i;
+        s_in[i] = (idx >= 0 && idx < a.n) ? __ldg(xb + idx) : 0.f;
+      }
+    }
+  };
+
+  float2* line = s_line + grp * C::LINE;
+  unsigned bulk_parity = 0;
+  if (stage && blockIdx.x < ntiles) prefetch(blockIdx.x);
+  // persistent CTAs: the tables above are loaded once, then the CTA walks tiles (signal b, TT segments)
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
   const unsigned b32 = tile / tps;
   const int64_t b = b32;
   const int64_t seg0 = (int64_t)(tile - b32 * tps) * TT;
   const float* xb = a.x + b * a.ldx;
   float vmin = INFINITY, vmax = -INFINITY;
+  const bool bulk = stage && tile_bulk(b, a.first_start + seg0 * (int64_t)a.hop);
 
-  for (int round = 0; round < TT / NG; ++round) {
+#if !defined(SPECGPU_EMULATE)
+  // the previous tile's tensor store must have finished reading the shared tile before anybody rewrites it; with one
+  // round per tile the barrier inside the round orders this wait before the first tile write
+  if (tma_out && tid == 0) bulk_wait_read<0>();
+  if (bulk) {
+    mbar_wait(bar, bulk_parity);
+    bulk_parity ^= 1u;
+  }
+#endif
+  if (!bulk || (tma_out && ROUNDS > 1)) __syncthreads();   // guarded fill visible / tile free
+
+  for (int round = 0; round < ROUNDS; ++round) {
     const int tl = round * NG + grp;  // column inside the tile
     const int64_t seg = seg0 + tl;
     const bool live = seg < a.nseg;
-    const int64_t s0 = a.first_start + seg * (int64_t)a.hop;
 
-    // ---- load the group's segment: element r of this thread is complex sample m = tg + r*G ----
+    // ---- the group's segment: element r of this thread is complex sample m = tg + r*G ----
     float2 v[R0];
-    if (live && a.vec_ok && s0 >= 0 && s0 + N <= a.n) {
-      const float2* p = reinterpret_cast<const float2*>(xb + s0);
+    if (stage) {
+      const float* p = s_in + (int64_t)tl * a.hop + 2 * tg;
+      if ((a.hop & 1) == 0) {
 #pragma unroll
-      for (int r = 0; r < R0; ++r) v[r] = __ldg(p + tg + r * G);
+        for (int r = 0; r < R0; ++r) v[r] = *reinterpret_cast<const float2*>(p + 2 * r * G);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R0; ++r) v[r] = make_float2(p[2 * r * G], p[2 * r * G + 1]);
+      }
+      if (round == ROUNDS - 1) {
+        __syncthreads();     // every thread holds its samples: the span may be overwritten
+        if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);
+      }
     } else {
+      const int64_t s0 = a.first_start + seg * (int64_t)a.hop;
+      if (live && a.vec_ok && s0 >= 0 && s0 + N <= a.n) {
+        const float2* p = reinterpret_cast<const float2*>(xb + s0);
 #pragma unroll
-      for (int r = 0; r < R0; ++r) {
-        const int64_t i0 = s0 + 2 * (tg + r * G);
-        v[r].x = (live && i0 >= 0 && i0 < a.n) ? __ldg(xb + i0) : 0.f;
-        v[r].y = (live && i0 + 1 >= 0 && i0 + 1 < a.n) ? __ldg(xb + i0 + 1) : 0.f;
+        for (int r = 0; r < R0; ++r) v[r] = __ldg(p + tg + r * G);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R0; ++r) {
+          const int64_t i0 = s0 + 2 * (tg + r * G);
+          v[r].x = (live && i0 >= 0 && i0 < a.n) ? __ldg(xb + i0) : 0.f;
+          v[r].y = (live && i0 + 1 >= 0 && i0 + 1 < a.n) ? __ldg(xb + i0 + 1) : 0.f;
+        }
       }
     }
     // ---- detrend (scipy.signal.detrend per segment) ----
     if (a.detrend != SPECGPU_DETREND_NONE) {
       float sx = 0.f, sc = 0.f;
+      const float cb = (float)(2 * tg) - 0.5f * (float)(N - 1);    // c_n = n - (N-1)/2 of this thread's first sample
 #pragma unroll
       for (int r = 0; r < R0; ++r) {
-        const float c0 = (float)(2 * (tg + r * G)) - 0.5f * (float)(N - 1);
+        const float c0 = cb + (float)(2 * r * G);
         sx += v[r].x + v[r].y;
         sc += c0 * v[r].x + (c0 + 1.0f) * v[r].y;
       }
@@ -175,7 +293,7 @@ __global__ void __launch_bounds__(kStftThreads, stft_min_blocks(LOG2N, MODE)) st
                               : 0.f;
 #pragma unroll
       for (int r = 0; r < R0; ++r) {
-        const float c0 = (float)(2 * (tg + r * G)) - 0.5f * (float)(N - 1);
+        const float c0 = cb + (float)(2 * r * G);
         v[r].x -= mean + slope * c0;
         v[r].y -= mean + slope * (c0 + 1.0f);
       }
@@ -188,19 +306,23 @@ __global__ void __launch_bounds__(kStftThreads, stft_min_blocks(LOG2N, MODE)) st
       v[r].y *= w.y;
     }
     // ---- M-point complex FFT of the packed segment ----
-    fft_group<C::LOG2M>(v, line, s_twm, tg);
+    // Groups that live inside one warp keep the outputs of the last pass in registers and fetch the mirrored bins
+    // from their partner thread with shuffles (no second trip through the line); wider groups go through the line.
+    constexpr bool REGS = (G <= 32);
+    fft_group<C::LOG2M, REGS>(v, line, s_twm, tg);
 
     // ---- untangle: 2 X[k] = E + W_N^k O, 2 X[M-k] = conj(E - W_N^k O) with E = Z[k] + conj(Z[M-k]),
-    //      O = -i (Z[k] - conj(Z[M-k])); the factor 2 is folded into the output scales.  (Splitting the special bins
-    //      k = 0 and k = M/2 out of the loop was measured 4 % slower: they belong to one thread per group, so the
-    //      warp issues two more, nearly empty iterations.) ----
+    //      O = -i (Z[k] - conj(Z[M-k])); the factor 2 is folded into the output scales.  Thread tg owns the bin pairs
+    //      k = tg + j G, j < R0/2 (thread 0 also k = M/2); the loop is unrolled with the shared-memory offsets of the
+    //      twiddles and the tile rows as compile-time strides from per-round bases. ----
     const float cscale = 0.5f * a.scale;             // complex / spectra outputs
     const float pscale1 = 0.25f * a.scale;           // |2X|^2 -> PSD, bins 0 and Nyquist
     const float pscale2 = 0.5f * a.scale;            // one-sided doubling for every other bin
-    auto bin_pair = [&](int k, auto generic_c) {
+    float2* o2 = nullptr;
+    if (MODE == STFT_MODE_SPECTRA) o2 = reinterpret_cast<float2*>(a.out) + (b * a.nseg + seg) * a.ld_out;
+    float rmin = INFINITY, rmax = -INFINITY;         // this segment's extremes (merged below if the segment is live)
+    auto bin_pair = [&](int k, float2 zk, float2 zm, int offk, int offm, auto generic_c) {
       constexpr bool GENERIC = decltype(generic_c)::value;     // 0 < k < M/2: two distinct, doubled bins
-      const float2 zk = line[fft_pad(k)];
-      const float2 zm = line[fft_pad((M - k) & (M - 1))];
       const float2 e = make_float2(zk.x + zm.x, zk.y - zm.y);
       const float2 o = make_float2(zk.y + zm.y, zm.x - zk.x);
       const float2 wo = cmul(s_twn[k], o);
@@ -211,76 +333,145 @@ __global__ void __launch_bounds__(kStftThreads, stft_min_blocks(LOG2N, MODE)) st
       const bool two = GENERIC || km != k;
       if (MODE == STFT_MODE_SPECTRA) {
         if (live) {
-          float2* o2 = reinterpret_cast<float2*>(a.out) + (b * a.nseg + seg) * a.ld_out;
           o2[k] = make_float2(0.5f * xk.x, 0.5f * xk.y);
           if (two) o2[km] = make_float2(0.5f * xm.x, 0.5f * xm.y);
         }
       } else if (MODE == STFT_MODE_COMPLEX) {
-        s_tile2[k * PITCH + tl] = make_float2(xk.x * cscale, xk.y * cscale);
-        if (two) s_tile2[km * PITCH + tl] = make_float2(xm.x * cscale, xm.y * cscale);
+        *reinterpret_cast<float2*>(s_tile + offk) = make_float2(xk.x * cscale, xk.y * cscale);
+        if (two) *reinterpret_cast<float2*>(s_tile + offm) = make_float2(xm.x * cscale, xm.y * cscale);
       } else {
         // conj(X) X scale, doubled on 1..M-1 (one-sided, even nfft): only k == 0 (bins 0 and M) is not doubled
         const float ps = (GENERIC || k != 0) ? pscale2 : pscale1;
         float pk = xk.x * xk.x + xk.y * xk.y;
         float pm = xm.x * xm.x + xm.y * xm.y;
-        if (MODE == STFT_MODE_LOGPSD) {
+        if (LOGM) {
           // log2 (one MUFU): the min-max normalisation that follows is invariant to the base of the logarithm, only the
           // exported (min, max) are converted to natural logs.  lg2.approx: absolute error ~1e-6 on values in [-37, 14].
-          pk = __log2f(fmaf(pk, ps, a.eps));
-          pm = __log2f(fmaf(pm, ps, a.eps));
-          if (live) {
-            vmin = fminf(vmin, fminf(pk, pm));       // k == km (k = M/2) gives pk == pm: harmless
-            vmax = fmaxf(vmax, fmaxf(pk, pm));
+          if (MODE == STFT_MODE_LOGPSD_FAST) {
+            pk = log2_normal(fmaf(pk, ps, a.eps));
+            pm = log2_normal(fmaf(pm, ps, a.eps));
+          } else {
+            pk = __log2f(fmaf(pk, ps, a.eps));
+            pm = __log2f(fmaf(pm, ps, a.eps));
           }
+          rmin = fminf(rmin, fminf(pk, pm));       // k == km (k = M/2) gives pk == pm: harmless
+          rmax = fmaxf(rmax, fmaxf(pk, pm));
         } else {
           pk *= ps;
           pm *= ps;
         }
-        s_tile[k * PITCH + tl] = pk;
-        if (two) s_tile[km * PITCH + tl] = pm;
+        *reinterpret_cast<float*>(s_tile + offk) = pk;
+        if (two) *reinterpret_cast<float*>(s_tile + offm) = pm;
       }
     };
-    for (int k = tg; k <= M / 2; k += G) bin_pair(k, std::false_type{});
-    fft_group_sync<G>();  // line is reused by the next round
-  }
-
-  if (MODE == STFT_MODE_SPECTRA) continue;
-  __syncthreads();   // the tile is complete
-
-  // ---- write the tile: rows = frequency, runs of up to TT consecutive segments ----
-  const int64_t ncol = (a.nseg - seg0 < TT) ? (a.nseg - seg0) : TT;
-  const int rows_out = (MODE == STFT_MODE_LOGPSD) ? (F - 1) : F;  // Nyquist row dropped after min/max
-  constexpr int LANES_T = TT < 32 ? TT : 32;   // lanes along time
-  constexpr int ROWS_W = 32 / LANES_T;         // rows per warp step
-  const int lane = tid & 31, warp = tid >> 5;
-  const int lt = lane % LANES_T, lr = lane / LANES_T;
-  for (int k = warp * ROWS_W + lr; k < rows_out; k += (kStftThreads / 32) * ROWS_W) {
-    for (int t = lt; t < ncol; t += LANES_T) {
-      const int64_t o = (b * rows_out + k) * a.ld_out + seg0 + t;
-      if (MODE == STFT_MODE_COMPLEX) reinterpret_cast<float2*>(a.out)[o] = s_tile2[k * PITCH + t];
-      else reinterpret_cast<float*>(a.out)[o] = s_tile[k * PITCH + t];
+    {
+      auto tile_off = [&](int row) {
+        const int o = row * ROWB + tl * E;
+        return o ^ ((o >> 3) & SWMASK);
+      };
+      const int offk0 = tile_off(tg);            // rows tg + j G: + j * JSTEP (JSTEP is a multiple of 1024: the
+      const int offm0 = tile_off(M - tg);        // swizzle bits do not change); rows M - tg - j G: - j * JSTEP
+      constexpr int J = R0 / 2;
+      if constexpr (REGS) {
+        // Thread tg holds Z[tg + G m] in v[fft_out_reg(m)].  Z[M - (tg + G j)] = Z[(G - tg) + G (R0-1-j)] sits in thread
+        // G - tg, register R0-1-j; thread 0 is its own partner with Z[M - G j] = Z[G (R0 - j)] in register (R0 - j) % R0.
+        const int partner = ((tid & 31) & ~(G - 1)) | ((G - tg) & (G - 1));
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const float2 zk = v[fft_out_reg(C::LOG2M, j)];
+          float2 zm = v[fft_out_reg(C::LOG2M, (R0 - j) % R0)];
+          if constexpr (G > 1) {
+            const float2 snd = v[fft_out_reg(C::LOG2M, R0 - 1 - j)];
+            const float rx = __shfl_sync(0xffffffffu, snd.x, partner);
+            const float ry = __shfl_sync(0xffffffffu, snd.y, partner);
+            if (tg != 0) zm = make_float2(rx, ry);
+          }
+          if (j == 0) bin_pair(tg, zk, zm, offk0, offm0, std::false_type{});
+          else bin_pair(tg + j * G, zk, zm, offk0 + j * JSTEP, offm0 - j * JSTEP, std::true_type{});
+        }
+        if (tg == 0) {
+          const float2 zh = v[fft_out_reg(C::LOG2M, R0 / 2)];
+          bin_pair(M / 2, zh, zh, tile_off(M / 2), tile_off(M / 2), std::false_type{});
+        }
+        if constexpr (G > 1) __syncwarp();   // the line (pass exchanges) is reused by the next round
+      } else {
+        // j = 0: k = tg; for thread 0 that is the DC / Nyquist pair, whose partner index wraps to 0
+        bin_pair(tg, line[fft_pad(tg)], line[fft_pad((M - tg) & (M - 1))], offk0, offm0, std::false_type{});
+#pragma unroll
+        for (int j = 1; j < J; ++j) {
+          const int k = tg + j * G;
+          // fft_pad is linear along a thread's bins (G is a multiple of 16 here)
+          const int ik = fft_pad(tg) + j * (G + G / 16);
+          const int im = fft_pad(M - tg) - j * (G + G / 16);
+          bin_pair(k, line[ik], line[im], offk0 + j * JSTEP, offm0 - j * JSTEP, std::true_type{});
+        }
+        if (tg == 0) bin_pair(M / 2, line[fft_pad(M / 2)], line[fft_pad(M / 2)], tile_off(M / 2), tile_off(M / 2), std::false_type{});
+        fft_group_sync<G>();  // line is reused by the next round
+      }
+    }
+    if (LOGM && live) {
+      vmin = fminf(vmin, rmin);
+      vmax = fmaxf(vmax, rmax);
     }
   }
 
-  if (MODE == STFT_MODE_LOGPSD) {
+  if (MODE == STFT_MODE_SPECTRA) continue;
+  constexpr int LANES_T = TT < 32 ? TT : 32;   // lanes along time
+  constexpr int ROWS_W = 32 / LANES_T;         // rows per warp step
+  const int lane = tid & 31, warp = tid >> 5;
+  if (LOGM) {
     vmin = warp_min(vmin);
     vmax = warp_max(vmax);
     if (lane == 0) {
       s_red[2 * warp] = vmin;
       s_red[2 * warp + 1] = vmax;
     }
-    __syncthreads();
+  }
+#if !defined(SPECGPU_EMULATE)
+  if (tma_out) fence_proxy_async();   // this thread's tile writes -> visible to the TMA engine (async proxy)
+#endif
+  __syncthreads();   // the tile is complete
+
+  // ---- write the tile: rows = frequency, runs of up to TT consecutive segments ----
+  const int64_t ncol = (a.nseg - seg0 < TT) ? (a.nseg - seg0) : TT;
+  const int rows_out = LOGM ? (F - 1) : F;  // Nyquist row dropped after min/max
+  int row_first = 0;                        // rows below this leave through the tensor store
+#if !defined(SPECGPU_EMULATE)
+  if (tma_out) {
     if (tid == 0) {
-      for (int w = 1; w < kStftThreads / 32; ++w) {
-        vmin = fminf(vmin, s_red[2 * w]);
-        vmax = fmaxf(vmax, s_red[2 * w + 1]);
-      }
-      atomicMin(a.minmax + 2 * b, float_to_ordered(vmin));
-      atomicMax(a.minmax + 2 * b + 1, float_to_ordered(vmax));
+      for (int rb = 0; rb < a.tma_nbox; ++rb)
+        tma_store_3d(&tmap, smem_u32(s_tile + (size_t)rb * a.tma_rows * ROWB), (int)(seg0 * (E / 4)), rb * a.tma_rows, (int)b, pol_out);
+      bulk_commit();
+    }
+    row_first = a.tma_nbox * a.tma_rows;
+  }
+#endif
+  const int lt = lane % LANES_T, lr = lane / LANES_T;
+  for (int k = row_first + warp * ROWS_W + lr; k < rows_out; k += (kStftThreads / 32) * ROWS_W) {
+    for (int t = lt; t < ncol; t += LANES_T) {
+      const int64_t o = (b * rows_out + k) * a.ld_out + seg0 + t;
+      const int so = k * ROWB + t * E;
+      const unsigned char* sp = s_tile + (so ^ ((so >> 3) & SWMASK));
+      if (MODE == STFT_MODE_COMPLEX) reinterpret_cast<float2*>(a.out)[o] = *reinterpret_cast<const float2*>(sp);
+      else reinterpret_cast<float*>(a.out)[o] = *reinterpret_cast<const float*>(sp);
     }
   }
-  __syncthreads();   // tile and reduction scratch are reused by the next tile
+
+  if (LOGM && tid == 0) {
+    for (int w = 1; w < kStftThreads / 32; ++w) {
+      vmin = fminf(vmin, s_red[2 * w]);
+      vmax = fmaxf(vmax, s_red[2 * w + 1]);
+    }
+    atomicMin(a.minmax + 2 * b, float_to_ordered(vmin));
+    atomicMax(a.minmax + 2 * b + 1, float_to_ordered(vmax));
+  }
+  // tile and reduction scratch are reused by the next tile.  With a staged span and a tensor store the barrier inside the
+  // next tile's round (and thread 0's wait on the store) already orders both.
+  if (!(stage && tma_out && ROUNDS == 1 && G <= 32)) __syncthreads();
   }  // tile loop
+#if !defined(SPECGPU_EMULATE)
+  if (tma_out && tid == 0) bulk_wait<0>();   // the last store must be complete before the CTA's shared memory goes away
+#endif
 }
 
 // minmax[b] = {0xffffffff, 0}
@@ -319,27 +510,63 @@ static int stft_num_sms() {
   return n;
 }
 
+// Largest dynamic shared memory a CTA may ask for (227 KB on sm_100).
+static int stft_max_smem() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    n = (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0) ? v : 227 * 1024;
+  }
+  return n;
+}
+
 template <int LOG2N, int MODE>
 static int launch_stft_t(const StftArgs& a, int64_t B, cudaStream_t stream) {
   using C = StftCfg<LOG2N>;
-  constexpr int TT = (MODE == STFT_MODE_COMPLEX) ? C::tile_w(8) : C::tile_w(4);
-  const StftSmem L = stft_smem_layout<LOG2N>(MODE);
+  constexpr int E = stft_elem_bytes(MODE);
+  constexpr int TT = C::tile_w(E);
+  constexpr int ROWB = TT * E;
   auto kern = stft_kernel<LOG2N, MODE>;
-  if (L.total > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
-    if (e != cudaSuccess) return (int)e;
-  }
   const int64_t tiles = ceil_div(a.nseg, TT);
   if (tiles == 0 || B == 0) return 0;
   StftArgs args = a;
   args.tiles_per_signal = tiles;
   args.ntiles = tiles * B;
   if (args.ntiles >= ((int64_t)1 << 31)) return (int)cudaErrorInvalidValue;
+  // ---- input staging: the span of a tile ((TT-1) hops + one segment) goes through shared memory when it fits ----
+  const int64_t span = (int64_t)(TT - 1) * a.hop + C::N;
+  args.span = (int)span;
+  args.stage_in = stft_smem_layout<LOG2N>(MODE, (int)span).total <= stft_max_smem() ? 1 : 0;
+  args.bulk_ok = (args.stage_in && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && a.hop % 4 == 0 && a.first_start % 4 == 0 &&
+                  (span * 4) % 16 == 0) ? 1 : 0;
+  const StftSmem L = stft_smem_layout<LOG2N>(MODE, args.stage_in ? (int)span : 0);
+  // ---- output: TMA tensor store of the swizzled shared tile when the layout allows it ----
+  TensorMap tmap{};
+  args.tma_out = 0;
+  args.tma_rows = args.tma_nbox = 0;
+#if !defined(SPECGPU_EMULATE)
+  if (MODE != STFT_MODE_SPECTRA && (ROWB == 16 || ROWB == 32 || ROWB == 64 || ROWB == 128)) {
+    const int rows_out = stft_mode_is_log(MODE) ? C::F - 1 : C::F;
+    const int box_rows = rows_out < 256 ? rows_out : 256;
+    const uint64_t w = E / 4;    // floats per element
+    if (make_tensor_map_f32_3d(&tmap, a.out, (uint64_t)a.nseg * w, (uint64_t)rows_out, (uint64_t)B, (uint64_t)a.ld_out * w,
+                               (uint64_t)rows_out * a.ld_out * w, (uint32_t)(TT * w), (uint32_t)box_rows, ROWB >= 32 ? ROWB : 0)) {
+      args.tma_out = 1;
+      args.tma_rows = box_rows;
+      args.tma_nbox = rows_out / box_rows;
+    }
+  }
+#endif
+  if (L.total > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (e != cudaSuccess) return (int)e;
+  }
   // persistent grid: as many CTAs as can be resident (the kernel is smem/register limited to 1-3 per SM)
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStftThreads, L.total) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t grid = std::min<int64_t>(args.ntiles, (int64_t)per_sm * stft_num_sms());
-  SPECGPU_LAUNCH(kern, (unsigned)grid, kStftThreads, L.total, stream, args);
+  SPECGPU_LAUNCH(kern, (unsigned)grid, kStftThreads, L.total, stream, args, tmap);
   return (int)cudaGetLastError();
 }
 
@@ -364,7 +591,10 @@ static int launch_stft_m(int log2n, const StftArgs& a, int64_t B, cudaStream_t s
 int launch_stft(int log2n, int mode, const StftArgs& a, int64_t B, cudaStream_t stream) {
   switch (mode) {
     case STFT_MODE_PSD: return launch_stft_m<STFT_MODE_PSD>(log2n, a, B, stream);
-    case STFT_MODE_LOGPSD: return launch_stft_m<STFT_MODE_LOGPSD>(log2n, a, B, stream);
+    case STFT_MODE_LOGPSD:
+      // eps >= FLT_MIN: log2's argument is never subnormal
+      if (a.eps >= 1.17549435e-38f) return launch_stft_m<STFT_MODE_LOGPSD_FAST>(log2n, a, B, stream);
+      return launch_stft_m<STFT_MODE_LOGPSD>(log2n, a, B, stream);
     case STFT_MODE_COMPLEX: return launch_stft_m<STFT_MODE_COMPLEX>(log2n, a, B, stream);
     case STFT_MODE_SPECTRA: return launch_stft_m<STFT_MODE_SPECTRA>(log2n, a, B, stream);
     default: return -1;

@@ -29,12 +29,23 @@ namespace specgpu {
 // ======================================================================================================
 constexpr int kGramTile = 64, kGramKB = 32, kGramThreads = 256;
 
+// minmax != nullptr: S holds an un-normalised log image, operands are (x - min) / (max - min) exactly as the
+// rank-1 projection writes them.  only_flagged != nullptr: only matrices whose plan[b][3] != 0 (leading pair not
+// converged) are computed; that launch uses ksplit == 1 and stores its tiles directly (no atomics, no zeroed G).
 template <class T>
 __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S, int rows, int64_t cols, int64_t ld,
-                                                                 int ksplit, T* G) {
+                                                                 int ksplit, T* G, const unsigned* minmax,
+                                                                 const int32_t* only_flagged) {
   __shared__ float sa[kGramTile][kGramKB + 1];
   __shared__ float sb[kGramTile][kGramKB + 1];
   const int64_t b = blockIdx.z;
+  if (only_flagged != nullptr && only_flagged[b * 4 + 3] == 0) return;   // uniform over the CTA
+  float mn = 0.f, den = 1.f;
+  if (minmax != nullptr) {
+    mn = ordered_to_float(minmax[2 * b]);
+    den = ordered_to_float(minmax[2 * b + 1]) - mn;
+  }
+  const float inv = 1.0f / den;
   const int nt = (rows + kGramTile - 1) / kGramTile;
   // blockIdx.x enumerates tile pairs (ti <= tj)
   int ti = 0, rem = blockIdx.x;
@@ -54,8 +65,14 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
     for (int i = tid; i < kGramTile * kGramKB; i += kGramThreads) {
       const int r = i / kGramKB, c = i % kGramKB;
       const int ra = ti * kGramTile + r, rb = tj * kGramTile + r;
-      sa[r][c] = (ra < rows && k + c < k1) ? Sb[(int64_t)ra * ld + k + c] : 0.f;
-      sb[r][c] = (rb < rows && k + c < k1) ? Sb[(int64_t)rb * ld + k + c] : 0.f;
+      float xa = (ra < rows && k + c < k1) ? Sb[(int64_t)ra * ld + k + c] : 0.f;
+      float xb = (rb < rows && k + c < k1) ? Sb[(int64_t)rb * ld + k + c] : 0.f;
+      if (minmax != nullptr) {
+        xa = (ra < rows && k + c < k1) ? div_by(xa - mn, den, inv) : 0.f;
+        xb = (rb < rows && k + c < k1) ? div_by(xb - mn, den, inv) : 0.f;
+      }
+      sa[r][c] = xa;
+      sb[r][c] = xb;
     }
     __syncthreads();
 #pragma unroll 8
@@ -81,8 +98,13 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
       const int r = ti * kGramTile + ty + 16 * i, c = tj * kGramTile + tx + 16 * j;
       if (r < rows && c < rows) {
         if (ti != tj || c >= r) {
-          atomicAdd(Gb + (int64_t)r * rows + c, acc[i][j]);
-          if (r != c) atomicAdd(Gb + (int64_t)c * rows + r, acc[i][j]);
+          if (ksplit == 1) {        // this CTA owns the whole sum
+            Gb[(int64_t)r * rows + c] = acc[i][j];
+            if (r != c) Gb[(int64_t)c * rows + r] = acc[i][j];
+          } else {
+            atomicAdd(Gb + (int64_t)r * rows + c, acc[i][j]);
+            if (r != c) atomicAdd(Gb + (int64_t)c * rows + r, acc[i][j]);
+          }
         }
       }
     }
@@ -90,16 +112,23 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
 
 // g_f64: accumulate and store G in double (the full-decomposition route; squaring the condition number in fp32 would
 // blur cuts between close singular values), else float.
-int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* G, int g_f64, cudaStream_t stream) {
+int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* G, int g_f64, cudaStream_t stream,
+                     const unsigned* minmax, const int32_t* only_flagged) {
   if (B == 0 || rows == 0) return 0;
-  cudaError_t e = cudaMemsetAsync(G, 0, (size_t)B * rows * rows * (g_f64 ? sizeof(double) : sizeof(float)), stream);
-  if (e != cudaSuccess) return (int)e;
   const int nt = (int)ceil_div(rows, kGramTile);
   const int npairs = nt * (nt + 1) / 2;
   int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(cols, 512), 16));
+  if (only_flagged != nullptr) {
+    ksplit = 1;     // rare repair path: direct stores, nothing to zero
+  } else {
+    cudaError_t e = cudaMemsetAsync(G, 0, (size_t)B * rows * rows * (g_f64 ? sizeof(double) : sizeof(float)), stream);
+    if (e != cudaSuccess) return (int)e;
+  }
   const dim3 grid((unsigned)npairs, (unsigned)ksplit, (unsigned)B);
-  if (g_f64) SPECGPU_LAUNCH(gram_simt_kernel<double>, grid, kGramThreads, 0, stream, S, (int)rows, cols, ld, ksplit, (double*)G);
-  else SPECGPU_LAUNCH(gram_simt_kernel<float>, grid, kGramThreads, 0, stream, S, (int)rows, cols, ld, ksplit, (float*)G);
+  if (g_f64)
+    SPECGPU_LAUNCH(gram_simt_kernel<double>, grid, kGramThreads, 0, stream, S, (int)rows, cols, ld, ksplit, (double*)G, minmax, only_flagged);
+  else
+    SPECGPU_LAUNCH(gram_simt_kernel<float>, grid, kGramThreads, 0, stream, S, (int)rows, cols, ld, ksplit, (float*)G, minmax, only_flagged);
   return (int)cudaGetLastError();
 }
 
@@ -110,7 +139,7 @@ int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int6
 constexpr int kPowThreads = 1024;
 constexpr int kPowMaxIter = 200;
 
-__global__ void __launch_bounds__(kPowThreads) eig_power_kernel(const float* G, int n, float* U, float* lam, int32_t* plan) {
+__global__ void __launch_bounds__(kPowThreads) eig_power_kernel(const float* G, int n, int max_iter, float* U, float* lam, int32_t* plan) {
   __shared__ __align__(16) float sx[256];
   __shared__ __align__(16) float sy[256];
   const int64_t b = blockIdx.x;
@@ -140,11 +169,46 @@ __global__ void __launch_bounds__(kPowThreads) eig_power_kernel(const float* G, 
       g[i] = v;
     }
   }
-  if (tid < 256) sx[tid] = (tid < n) ? rsqrtf((float)n) : 0.f;
+  // Start vector: the column of G with the largest diagonal entry (a first power step from the unit vector of the
+  // most energetic row).  A fixed vector such as (1, ..., 1) can be exactly orthogonal to the leading eigenvector
+  // (every column of the matrix summing to zero) and the iteration would then sit in the wrong subspace.
+  if (tid < 256) sy[tid] = (tid < n) ? Gb[(int64_t)tid * n + tid] : -INFINITY;
+  __syncthreads();
+  {
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = sy[lane + 32 * i];
+      if (d > best) {
+        best = d;
+        arg = lane + 32 * i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    __syncthreads();
+    if (tid < 256) sx[tid] = (tid < n) ? Gb[(int64_t)arg * n + tid] : 0.f;
+    __syncthreads();
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += sx[lane + 32 * i] * sx[lane + 32 * i];
+    ss = warp_sum(ss);
+    const float sinv = (ss > 0.f && ss < INFINITY) ? rsqrtf(ss) : 0.f;
+    __syncthreads();
+    if (tid < 256) sx[tid] *= sinv;
+  }
   __syncthreads();
   float lambda = 0.f, prev_delta = INFINITY;
   int status = 1;
-  for (int it = 0; it < kPowMaxIter; ++it) {
+  for (int it = 0; it < max_iter; ++it) {
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -165,7 +229,10 @@ __global__ void __launch_bounds__(kPowThreads) eig_power_kernel(const float* G, 
     }
     yy = warp_sum(yy);
     xy = warp_sum(xy);
-    const float inv = (yy > 0.f) ? rsqrtf(yy) : 0.f;
+    // a zero or non-finite iterate (G x == 0: x has fallen into the null space; NaN input) is NOT convergence: leave
+    // status = 1 so that the full solver redoes this matrix (yy is identical in every warp: uniform exit)
+    if (!(yy > 0.f) || !(yy < INFINITY)) break;
+    const float inv = rsqrtf(yy);
     float dd = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -194,10 +261,11 @@ __global__ void __launch_bounds__(kPowThreads) eig_power_kernel(const float* G, 
   }
 }
 
-int launch_eig_power(const float* G, int64_t B, int n, float* U, float* lam, int32_t* plan, cudaStream_t stream) {
+int launch_eig_power(const float* G, int64_t B, int n, int max_iter, float* U, float* lam, int32_t* plan, cudaStream_t stream) {
   if (B == 0) return 0;
   if (n > 256) return -1;
-  SPECGPU_LAUNCH(eig_power_kernel, (unsigned)B, kPowThreads, 0, stream, G, n, U, lam, plan);
+  if (max_iter <= 0) max_iter = kPowMaxIter;
+  SPECGPU_LAUNCH(eig_power_kernel, (unsigned)B, kPowThreads, 0, stream, G, n, max_iter, U, lam, plan);
   return (int)cudaGetLastError();
 }
 
@@ -505,7 +573,7 @@ int launch_eig_jacobi(const void* G, int g_f64, int64_t B, int n, int skip_conve
 // Plan: singular values, median, optimal hard threshold count, start/stop with the reference's clamps and
 // Python slice semantics.  kind 0: explicit (start, stop); 1: use_optimal; 2: computeSignal (1, 2*num_sing).
 // ======================================================================================================
-__global__ void svd_plan_kernel(const float* lam, int n, int kind, int start, int stop, float omega_f, int32_t* plan,
+__global__ void svd_plan_kernel(const float* lam, int n, int kind, int start, int stop, double omega, int32_t* plan,
                                 float* s_out) {
   const int64_t b = blockIdx.x;
   __shared__ float s_s[512];
@@ -523,9 +591,11 @@ __global__ void svd_plan_kernel(const float* lam, int n, int kind, int start, in
   if (kind != 0) {
     // np.median of the descending s: mean of the two middle values for even n
     const float med = (n & 1) ? s_s[n / 2] : __fdiv_rn(__fadd_rn(s_s[n / 2 - 1], s_s[n / 2]), 2.0f);
-    const float t_star = __fmul_rn(omega_f, med);
+    // beta = np.min(shape) / np.max(shape) is an np.float64, so omega(beta) and t* = omega * median are float64 and
+    // `s > t*` compares in float64 (denoising_by_svd.ipynb:210-215)
+    const double t_star = __dmul_rn(omega, (double)med);
     int cnt = 0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) cnt += (s_s[k] > t_star) ? 1 : 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) cnt += ((double)s_s[k] > t_star) ? 1 : 0;
     atomicAdd(&s_cnt, cnt);
     __syncthreads();
     num_sing = s_cnt;
@@ -549,11 +619,11 @@ __global__ void svd_plan_kernel(const float* lam, int n, int kind, int start, in
   }
 }
 
-int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int stop, float omega_f, int32_t* plan,
+int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int stop, double omega, int32_t* plan,
                     float* s_out, cudaStream_t stream) {
   if (B == 0) return 0;
   if (n > 512) return -1;
-  SPECGPU_LAUNCH(svd_plan_kernel, (unsigned)B, 256, 0, stream, lam, n, kind, start, stop, omega_f, plan, s_out);
+  SPECGPU_LAUNCH(svd_plan_kernel, (unsigned)B, 256, 0, stream, lam, n, kind, start, stop, omega, plan, s_out);
   return (int)cudaGetLastError();
 }
 

@@ -161,6 +161,15 @@ def test_pipeline_fused_normalise_route(emu_rt):
     pc.case_pipeline(emu_rt, sp, 20000, B=3, tile=64)
 
 
+def test_pipeline_fallback_route(emu_rt):
+    # power iteration capped at one step: every channel goes through the float64 repair route inside specgpu_pipeline
+    pc.case_pipeline_fallback(emu_rt, dict(oc.DEFAULT_SPEC_PARAMS, nperseg=64, noverlap=32), 6000, B=2)
+
+
+def test_svd_degenerate_leading_pair_and_null_start(emu_rt):
+    pc.case_svd_degenerate(emu_rt, rows=32, cols=120)
+
+
 def test_cv2_chain_small(emu_rt, golden):
     # a crop of the reference's spectrogram against the oracle (which test_oracle.py pins to cv2 and to the reference's
     # golden outputs); the full golden image runs in tests/test_gpu_parity.py -- the emulation is too slow for it

@@ -313,6 +313,40 @@ def test_config2_pipeline_40ch(cuda_rt):
     np.testing.assert_allclose(D5[0], D[5], rtol=0, atol=2e-5)
 
 
+def test_config2_denoise_vs_pure_oracle_chain(cuda_rt):
+    """Config 2 at full size, end to end: D of the GPU pipeline against the oracle's own chain
+    clip(denoiseSignal(specgr(x))) in float64 (NOT the oracle applied to the GPU's S), at the north star's tolerance
+    for the denoised reconstruction (rtol 1e-3, atol 1e-3 max|D|), on 3 of the 40 channels."""
+    x = pc.signals(40, 1_000_000, shot=11)
+    S, D = api.pipeline(x, SP, clip=True, runtime=cuda_rt)
+    for c in (2, 19, 37):
+        Sr, _, _ = oc.specgr_array(x[c].astype(np.float64), SP)
+        pc.assert_denoise_close(D[c], oc.clip(oc.denoiseSignal(Sr)))
+
+
+def test_pipeline_fallback_route(cuda_rt):
+    pc.case_pipeline_fallback(cuda_rt, dict(SP, nperseg=256, noverlap=128), 60_000, B=3)
+    pc.case_pipeline_fallback(cuda_rt, SP, 300_000, B=4)       # 256 rows: the 4-CTA cluster float64 Jacobi
+
+
+def test_svd_degenerate_leading_pair_and_null_start(cuda_rt):
+    pc.case_svd_degenerate(cuda_rt, rows=64, cols=300)
+    pc.case_svd_degenerate(cuda_rt, rows=256, cols=1500)
+    pc.case_svd_degenerate(cuda_rt, rows=128, cols=777)
+
+
+def test_clip(cuda_rt):
+    """denoising_by_svd.ipynb:280-281 as a standalone call: negatives (and -0.0) -> 0, NaN stays NaN, any shape."""
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal((3, 257, 131)).astype(np.float32)
+    a[0, 0, :4] = [np.nan, -0.0, 0.0, -np.inf]
+    got = api.clip(a, runtime=cuda_rt)
+    assert np.array_equal(got, oc.clip(a), equal_nan=True)
+    assert api.clip(np.zeros((0,), np.float32), runtime=cuda_rt).shape == (0,)
+    one = api.clip(np.float32([-1.5]), runtime=cuda_rt)
+    assert one.tolist() == [0.0]
+
+
 def test_host_pipeline_streams(cuda_rt):
     """HostPipeline (pinned host in/out, channel groups on several streams, shots in flight) == api.pipeline."""
     import torch
