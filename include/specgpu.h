@@ -210,10 +210,10 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
                      float* S, float* D, int64_t ldt, int32_t flags, float* tiles, int32_t tile_w, int32_t ntiles,
                      int32_t* info, void* stream);
 
-/* specgpu_pipeline processes the batch in groups of `channels` channels, alternating between two library-owned
- * streams that are forked from and joined to the caller's stream, so that the log image a group's STFT writes is read
- * back by its Gram and projection kernels while it is still in the L2 cache.  0 = automatic (about 24 MB of image
- * per group); a value >= B runs the batch as one group on the caller's stream.  Results do not depend on it. */
+/* specgpu_pipeline can process the batch in groups of `channels` channels, alternating between two library-owned
+ * streams that are forked from and joined to the caller's stream.  0 (default) or a value >= B runs the batch as one
+ * group on the caller's stream, which is what measures fastest on B200; the knob exists for batches far
+ * larger than the L2 cache and for experiments.  Results do not depend on it. */
 int specgpu_set_pipeline_group(specgpu_ctx* ctx, int32_t channels);
 
 /* Cap of the power iteration that finds the leading singular pair on the default denoise route (0 restores the

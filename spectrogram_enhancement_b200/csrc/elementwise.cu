@@ -143,11 +143,19 @@ static unsigned stream_blocks(int64_t total) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, kEwThreads * 4), 148 * 8));
 }
 
+// mm[b] = {0xffffffff, 0}: identity of the ordered-uint (min, max) pair of rescale()
+__global__ void rescale_minmax_init_kernel(unsigned* mm, int64_t B) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    mm[2 * i] = 0xffffffffu;
+    mm[2 * i + 1] = 0u;
+  }
+}
+
 int launch_rescale(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst, unsigned* mm_ws,
                    cudaStream_t stream) {
   if (B == 0 || rows * cols == 0) return 0;
-  int e = launch_minmax_init(mm_ws, B, stream);
-  if (e) return e;
+  SPECGPU_LAUNCH(rescale_minmax_init_kernel, (unsigned)ceil_div(B, 128), 128, 0, stream, mm_ws, B);
   const unsigned gx = stream_blocks(rows * cols);
   SPECGPU_LAUNCH(minmax_reduce_kernel, dim3(gx, (unsigned)B), kEwThreads, 0, stream, src, rows, cols, ld, mm_ws);
   SPECGPU_LAUNCH(rescale_apply_kernel, dim3(gx, (unsigned)B), kEwThreads, 0, stream, src, rows, cols, ld,

@@ -24,6 +24,7 @@
 // The emulation build (tests only, no tensor cores on a CPU) replaces the kernel body by a scalar
 // loop with the same TF32 operand rounding and the same partial layout.
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace specgpu {
 
@@ -38,8 +39,9 @@ struct GramTcArgs {
   int64_t B, cols, ld;
   int64_t nchunk;           // chunks per matrix
   int64_t per;              // chunks per CTA
-  const unsigned* minmax;   // optional [B][2] ordered-uint (min, max): operands are (x - min) / (max - min)
+  const MinMaxWord* minmax; // optional [B][2] (min, max) words (common.cuh): operands are (x - min) / (max - min)
   int vec16;                // base and pitch allow 16-byte copies
+  float l2_pin;             // fraction of S the producer asked L2 to keep (same address-hash policy on these loads); 0: none
   float* partial;           // [grid][2][128][PW] with PW = rows + (rows == 256 ? 128 : 0)
 };
 
@@ -55,23 +57,6 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 #if !defined(SPECGPU_EMULATE)
 // ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"     // suspend-time hint: do not spin on issue slots
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity), "r"(1000000u)
-      : "memory");
-}
 // Hardware named barriers for the producer -> MMA-issuer hand-off.  An mbarrier.arrive has release semantics and
 // compiles to MEMBAR.ALL.CTA, which drains the producers' global loads that are still in flight for the NEXT slabs
 // (measured: it serialised every slab on the memory latency); bar.arrive / bar.sync order shared memory like
@@ -82,7 +67,6 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -145,8 +129,8 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
     const float* Sb = a.S + b * ROWS * a.ld;
     float e_mn = 0.f, e_den = 1.f;
     if (a.minmax != nullptr) {
-      e_mn = ordered_to_float(a.minmax[2 * b]);
-      e_den = ordered_to_float(a.minmax[2 * b + 1]) - e_mn;
+      e_mn = minmax_get_min(a.minmax, b);
+      e_den = minmax_get_max(a.minmax, b) - e_mn;
     }
     for (int i = tid; i < 128 * PW; i += kGtcThreads) {
       const int r = i / PW, c = i % PW;
@@ -214,6 +198,8 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
         const int r0 = 4 * warp + sub;                        // rows r0 + 16 i; (r0 + 16 i) & 7 == r0 & 7
         const uint32_t voff = (uint32_t)(r0 * 128 + ((c16 ^ (r0 & 7)) << 4));
         const int64_t vstride = 16 * a.ld;
+        // same address-hash policy as the producer of S: the pinned fraction stays pinned, the rest keeps streaming
+        const uint64_t pol = a.l2_pin > 0.f ? l2_policy_pin_fraction(a.l2_pin) : l2_policy_evict_normal();
         for (int64_t gg = g; gg < gend; ++gg) {
           const int64_t ci = gg - g0;
           const int stage = (int)(ci % kGtcStages);
@@ -225,7 +211,7 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
           const uint32_t dst = smem_u32(slabs + stage * SLAB) + voff;
 #pragma unroll 8
           for (int i = 0; i < ROWS / 16; ++i, q += vstride)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * (16 * 128)), "l"(q), "r"(nbytes) : "memory");
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst + i * (16 * 128)), "l"(q), "r"(nbytes), "l"(pol) : "memory");
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_loaded[stage])) : "memory");
         }
       } else {
@@ -254,8 +240,8 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
       const int t = tid - kLoadThreads;
       float mn = 0.f, den = 1.f;
       if (do_norm) {
-        mn = ordered_to_float(a.minmax[2 * b]);
-        den = ordered_to_float(a.minmax[2 * b + 1]) - mn;
+        mn = minmax_get_min(a.minmax, b);
+        den = minmax_get_max(a.minmax, b) - mn;
       }
       const float nscale = do_norm ? 1.0f / den : 1.0f;        // x -> (x - mn) / den as x * nscale + noff
       const float noff = do_norm ? -mn / den : 0.0f;
@@ -416,8 +402,14 @@ size_t gram_tc_workspace_bytes(int64_t B, int64_t rows) {
 
 bool gram_tc_supported(int64_t rows) { return rows == 128 || rows == 256; }
 
-int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* minmax,
-                   float* partial_ws, float* G, int num_sms, cudaStream_t stream) {
+void gram_tc_geometry(int64_t B, int64_t cols, int num_sms, int64_t* nchunk, int64_t* per) {
+  const GramTcGeom g = gram_tc_geom(B, cols, std::min(num_sms, 160));
+  *nchunk = g.nchunk;
+  *per = g.per;
+}
+
+int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const MinMaxWord* minmax,
+                   float* partial_ws, float* G, int num_sms, cudaStream_t stream, float l2_pin) {
   if (B == 0) return 0;
   const GramTcGeom g = gram_tc_geom(B, cols, std::min(num_sms, 160));
   GramTcArgs a{};
@@ -430,6 +422,7 @@ int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_
   a.minmax = minmax;
   a.vec16 = (((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (ld % 4 == 0) && (ld >= ((cols + 3) & ~(int64_t)3))) ? 1 : 0;
   a.partial = partial_ws;
+  a.l2_pin = l2_pin;
   const size_t smem = std::max((size_t)kGtcStages * rows * 128, (size_t)kGtcWarps * 32 * 33 * sizeof(float)) + 1024;
   if (rows == 256) {
     cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -442,6 +435,7 @@ int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_
   }
   int e = (int)cudaGetLastError();
   if (e) return e;
+  if (G == nullptr) return 0;      // the partials are consumed by launch_gram_eig
   SPECGPU_LAUNCH(gram_reduce_kernel, dim3((unsigned)ceil_div(32 * gram_tc_partial_width((int)rows), 256), (unsigned)B), 256,
                  0, stream, (const float*)partial_ws, (int)rows, g.nchunk, g.per, G);
   return (int)cudaGetLastError();

@@ -23,7 +23,8 @@ struct StftArgs {
   const float2* twN;     // exp(-2 pi i k / N), k <= M/2
   void* out;
   int64_t ld_out;
-  unsigned* minmax;      // [B][2] ordered-uint min / max (STFT_MODE_LOGPSD)
+  MinMaxWord* minmax;    // [B][2] generation-tagged min / max words (STFT_MODE_LOGPSD), see common.cuh
+  unsigned minmax_gen;   // generation of this call
   int64_t tiles_per_signal, ntiles;   // filled by the launcher (persistent tile loop)
   // filled by the launcher:
   int stage_in;          // the tile's sample span goes through shared memory (bulk copy for interior tiles)
@@ -31,12 +32,14 @@ struct StftArgs {
   int span;              // samples in a tile's span: (TT-1)*hop + nperseg
   int tma_out;           // whole boxes of the output tile leave through a TMA tensor store
   int tma_rows, tma_nbox;   // rows per box, boxes per tile (rows beyond tma_rows*tma_nbox use plain stores)
+  // set by the caller (0 by default): fraction of the output's cache lines to keep in L2 (evict_last) because a later
+  // kernel of the same call reads the output back; the rest streams out (evict_first).  0: no preference.
+  float l2_pin;
 };
 
 // stft.cu
 int launch_stft(int log2n, int mode, const StftArgs& a, int64_t B, cudaStream_t stream);
-int launch_minmax_init(unsigned* mm, int64_t B, cudaStream_t stream);
-int launch_lognorm(float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* mm, float* mm_out,
+int launch_lognorm(float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const MinMaxWord* mm, float* mm_out,
                    cudaStream_t stream);
 
 // elementwise.cu
@@ -57,8 +60,12 @@ int launch_quantfilt(const float* src, int64_t B, int64_t rows, int64_t cols, in
 
 // svd.cu
 int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* G, int g_f64, cudaStream_t stream,
-                     const unsigned* minmax = nullptr, const int32_t* only_flagged = nullptr);
+                     const MinMaxWord* minmax = nullptr, const int32_t* only_flagged = nullptr);
 int launch_eig_power(const float* G, int64_t B, int n, int max_iter /* <= 0: default */, float* U, float* lam, int32_t* plan, cudaStream_t stream);
+// split-K reduce of launch_gram_tc's partials fused with the leading-pair power iteration (n in {128, 256}); G itself is
+// never written.  (nchunk, per) = gram_tc_geometry of the launch that produced the partials.
+int launch_gram_eig(const float* partial, int64_t nchunk, int64_t per, int64_t B, int n, int max_iter, float* U, float* lam,
+                    int32_t* plan, cudaStream_t stream);
 size_t jacobi_workspace_bytes(int64_t B, int n);
 bool eig_jacobi_f64_supported(int n);
 int launch_eig_jacobi(const void* G, int g_f64, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan, void* ws,
@@ -68,16 +75,18 @@ int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int
                     float* s_out, cudaStream_t stream);
 // Leading-component removal fused with the min-max normalisation: L (log image) -> S = (L-min)/(max-min) and
 // D = S - u0 (u0^T S) [clipped]; S may alias L.  minmax == nullptr: L is already normalised (S not written if null).
-int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const unsigned* minmax, const float* U,
-                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream);
+int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const MinMaxWord* minmax, const float* U,
+                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out = 0);
 int launch_svd_project(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U, const int32_t* plan,
                        int clip, void* out, int out_f64, int64_t ldo, cudaStream_t stream);
 
 // gram_tc.cu
 bool gram_tc_supported(int64_t rows);
 size_t gram_tc_workspace_bytes(int64_t B, int64_t rows);
-int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* minmax,
-                   float* partial_ws, float* G, int num_sms, cudaStream_t stream);
+// G == nullptr: leave the split-K partials in partial_ws (launch_gram_eig consumes them) and skip the reduce launch.
+int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const MinMaxWord* minmax,
+                   float* partial_ws, float* G, int num_sms, cudaStream_t stream, float l2_pin = 0.f);
+void gram_tc_geometry(int64_t B, int64_t cols, int num_sms, int64_t* nchunk, int64_t* per);
 
 // imgchain.cu (the cv2 chain: gaussblr / meansub / morph)
 size_t imgchain_workspace_bytes(int64_t B, int64_t rows, int64_t cols);

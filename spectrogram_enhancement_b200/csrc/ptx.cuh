@@ -46,6 +46,28 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   return p;
 }
 
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+// `frac` of the lines (chosen by an address hash, so the same lines for every kernel that uses the same fraction)
+// evict_last, the rest evict_first: pins a uniform sample of a buffer that is larger than the L2.
+__device__ __forceinline__ uint64_t l2_policy_pin_fraction(float frac) {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(p) : "f"(frac));
+  return p;
+}
+__device__ __forceinline__ float ld_global_hint(const float* p, uint64_t policy) {
+  float v;
+  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void st_global_hint(float* p, float v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+}
+
 // 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP): 16-byte aligned addresses, size a multiple of 16;
 // completes `bytes` of transaction on the mbarrier.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {

@@ -22,6 +22,9 @@ struct specgpu_ctx {
   int power_max_iter = 0;  // cap of the leading-pair power iteration (0: the kernel default; specgpu_set_power_iterations)
   // specgpu_pipeline: channel groups alternate between two library-owned side streams (forked from / joined to the
   // caller's stream with events) so that a group's log image is consumed while it is still in L2
+  // per-signal (min, max) words of the log image (common.cuh): persistent, generation-tagged, never reset between calls
+  MinMaxWord* mm64 = nullptr;
+  unsigned mm_gen = 0;
   int pipe_group = 0;      // channels per group (0: automatic, see specgpu_set_pipeline_group)
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -189,13 +192,31 @@ inline size_t carve_size(std::initializer_list<size_t> parts) {
   return ((off + 255) & ~(size_t)255) + 256;
 }
 
+// The persistent (min, max) buffer for up to 65535 signals and a fresh generation for this call.
+constexpr int64_t kMaxBatch = 65535;
+int minmax_begin(specgpu_ctx* ctx, MinMaxWord** mm, unsigned* gen) {
+  if (!ctx->mm64 || ctx->mm_gen == 0xffffffffu) {
+    if (!ctx->mm64) {
+      cudaError_t e = cudaMalloc(&ctx->mm64, (size_t)kMaxBatch * 2 * sizeof(MinMaxWord));
+      if (e != cudaSuccess) return fail(ctx, SPECGPU_ERR_WORKSPACE, "min/max buffer: %s", cudaGetErrorString(e));
+    } else {
+      cudaDeviceSynchronize();     // generation counter wrapped (once per 4 billion calls)
+    }
+    cudaMemset(ctx->mm64, 0, (size_t)kMaxBatch * 2 * sizeof(MinMaxWord));
+    ctx->mm_gen = 0;
+  }
+  *mm = ctx->mm64;
+  *gen = ++ctx->mm_gen;
+  return SPECGPU_OK;
+}
+
 int64_t num_segments(int64_t n, int nperseg, int noverlap) {
   if (n < nperseg) return 0;
   return (n - noverlap) / (nperseg - noverlap);
 }
 
 StftArgs make_args(const specgpu_plan* plan, const float* x, int64_t n, int64_t ldx, int64_t first_start, int64_t nseg,
-                   float scale, void* out, int64_t ld_out, unsigned* mm) {
+                   float scale, void* out, int64_t ld_out, MinMaxWord* mm, unsigned mm_gen = 0) {
   StftArgs a{};
   a.x = x;
   a.n = n;
@@ -214,6 +235,7 @@ StftArgs make_args(const specgpu_plan* plan, const float* x, int64_t n, int64_t 
   a.out = out;
   a.ld_out = ld_out;
   a.minmax = mm;
+  a.minmax_gen = mm_gen;
   return a;
 }
 
@@ -258,6 +280,7 @@ int specgpu_destroy(specgpu_ctx* ctx) {
   if (!ctx) return SPECGPU_OK;
   DeviceGuard dev_guard(ctx->device);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->mm64) cudaFree(ctx->mm64);
 #ifndef SPECGPU_EMULATE
   for (int i = 0; i < 2; ++i) {
     if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
@@ -460,12 +483,11 @@ int specgpu_specgr(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, i
   if (nseg == 0 || B == 0) return SPECGPU_OK;
   if (!S || ldt < nseg) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad output (ldt=%lld < nseg=%lld)", (long long)ldt, (long long)nseg);
   DeviceGuard dev_guard(ctx->device);
-  if ((rc = ensure_ws(ctx, carve_size({(size_t)B * 2 * sizeof(unsigned)})))) return rc;
-  Carver cv(ctx->ws);
-  unsigned* mm = cv.take<unsigned>(B * 2);
+  MinMaxWord* mm = nullptr;
+  unsigned gen = 0;
+  if ((rc = minmax_begin(ctx, &mm, &gen))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  CHECK_LAUNCH(ctx, launch_minmax_init(mm, B, st), "minmax_init", 1);
-  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, (float)plan->scale, S, ldt, mm);
+  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, (float)plan->scale, S, ldt, mm, gen);
   CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, B, st), "stft_kernel", 1);
   CHECK_LAUNCH(ctx, launch_lognorm(S, B, plan->p.nperseg / 2, nseg, ldt, mm, minmax, st), "lognorm", 1);
   return SPECGPU_OK;
@@ -609,15 +631,16 @@ SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
 // also writes the normalised image back over S.
 // `fallback`: after the power iteration also enqueue the full float64 solver for the matrices whose iteration did not
 // converge (info[3] would be 1); three launches that exit at once when every matrix converged.
-int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const unsigned* raw_mm, int64_t B, int64_t rows, int64_t cols,
+int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm, int64_t B, int64_t rows, int64_t cols,
             int64_t ld, int kind, int start, int stop, int clip, bool power_ok, bool fallback, void* out, int out_f64,
-            int64_t ldo, float* s_out, int32_t* info, cudaStream_t st) {
+            int64_t ldo, float* s_out, int32_t* info, cudaStream_t st, float l2_pin = 0.f) {
   void* stream = (void*)st;
   const bool tc = power_ok && gram_tc_supported(rows);   // TF32 Gram only feeds the leading-pair route
   // full decomposition: Gram and Jacobi in double (float would square the condition number into the noise floor)
   const int g_f64 = (!power_ok && eig_jacobi_f64_supported((int)rows)) ? 1 : 0;
   if (tc) {
-    CHECK_LAUNCH(ctx, launch_gram_tc(S, B, rows, cols, ld, raw_mm, w.gram_partial, w.G, ctx->num_sms, st), "gram_tc", 2);
+    // tensor-core Gram partials, then ONE cluster kernel per matrix that sums them and runs the power iteration
+    CHECK_LAUNCH(ctx, launch_gram_tc(S, B, rows, cols, ld, raw_mm, w.gram_partial, nullptr, ctx->num_sms, st, l2_pin), "gram_tc", 1);
   } else {
     if (raw_mm) {   // no fused route for this shape: normalise in place first
       CHECK_LAUNCH(ctx, launch_lognorm(S, B, rows, cols, ld, raw_mm, nullptr, st), "lognorm", 1);
@@ -626,7 +649,14 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const unsigned* raw_mm, 
     CHECK_LAUNCH(ctx, launch_gram_simt(S, B, rows, cols, ld, w.G, g_f64, st), "gram_simt", 1);
   }
   if (power_ok) {
-    CHECK_LAUNCH(ctx, launch_eig_power(w.G, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st), "eig_power", 1);
+    if (tc) {
+      int64_t nchunk = 0, per = 0;
+      gram_tc_geometry(B, cols, ctx->num_sms, &nchunk, &per);
+      CHECK_LAUNCH(ctx, launch_gram_eig(w.gram_partial, nchunk, per, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st),
+                   "gram_eig", 1);
+    } else {
+      CHECK_LAUNCH(ctx, launch_eig_power(w.G, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st), "eig_power", 1);
+    }
     // Matrices whose iteration did not converge (degenerate leading pair, iterate fallen into the null space) are
     // redone by the full solver in float64: Gram matrix of the flagged matrices only, straight from the image (the
     // TF32 Gram is dead after the power iteration and is overwritten), then the cluster Jacobi, which skips the
@@ -644,7 +674,7 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const unsigned* raw_mm, 
                  "svd_plan", 1);
   if (power_ok && !out_f64) {
     // power_ok implies the range [1, rows): only the leading component is removed
-    CHECK_LAUNCH(ctx, launch_svd_rank1(S, B, (int)rows, cols, ld, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st),
+    CHECK_LAUNCH(ctx, launch_svd_rank1(S, B, (int)rows, cols, ld, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, l2_pin > 0.f ? 1 : 0),
                  "svd_rank1", 1);
   } else {
     CHECK_LAUNCH(ctx, launch_svd_project(S, B, (int)rows, cols, ld, w.U, w.plan, clip, out, out_f64, ldo, st), "svd_project", 1);
@@ -910,13 +940,13 @@ namespace {
 int64_t pipeline_group_size(const specgpu_ctx* ctx, int64_t B, int64_t rows, int64_t ldt) {
   int64_t g = ctx->pipe_group;
   if (const char* env = std::getenv("SPECGPU_PIPELINE_GROUP")) g = std::atoll(env);
-  if (g <= 0) {
-    const int64_t img = rows * ldt * 4;
-    g = std::max<int64_t>(1, ((int64_t)24 << 20) / std::max<int64_t>(img, 1));
-    // groups of equal size (40 channels, 6 per group by bytes -> 5 groups of 8 would overshoot: use ceil(B / ngroups))
-    const int64_t ng = ceil_div(B, g);
-    g = ceil_div(B, ng);
-  }
+  (void)rows;
+  (void)ldt;
+  // Measured on B200 (profiles/r02_summary.md): groups on two streams are SLOWER than one batch-wide pass (40 channels:
+  // 287 us as one group, 290 / 337 / 384 / 429 us in groups of 20 / 10 / 8 / 5) -- every kernel already fills the GPU,
+  // the persistent kernels do not co-reside, and each group pays the ramp / tail and the latency-bound eigen step again.
+  // So the default is ONE group; L2 reuse is obtained with eviction-priority hints instead (see l2_pin below).
+  if (g <= 0) g = B;
   return std::min(g, B);
 }
 }  // namespace
@@ -946,11 +976,13 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
   // ---- workspace: min/max pairs and per-channel SVD arrays for the whole batch; Gram partials and Jacobi scratch per lane ----
   const size_t part_bytes = tc ? gram_tc_workspace_bytes(gsz, rows) : 0;
   const size_t jac_bytes = jacobi_workspace_bytes(gsz, (int)rows);
-  if ((rc = ensure_ws(ctx, carve_size({(size_t)B * 2 * sizeof(unsigned), (size_t)B * rows * rows * 8, (size_t)B * rows * rows * 4,
+  if ((rc = ensure_ws(ctx, carve_size({(size_t)B * rows * rows * 8, (size_t)B * rows * rows * 4,
                                        (size_t)B * rows * 4, (size_t)B * 16, part_bytes, part_bytes, jac_bytes, jac_bytes}))))
     return rc;
+  MinMaxWord* mm = nullptr;
+  unsigned gen = 0;
+  if ((rc = minmax_begin(ctx, &mm, &gen))) return rc;
   Carver cv(ctx->ws);
-  unsigned* mm = cv.take<unsigned>(B * 2);
   double* Gall = cv.take<double>(B * rows * rows);
   float* Uall = cv.take<float>(B * rows * rows);
   float* lam_all = cv.take<float>(B * rows);
@@ -975,9 +1007,6 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
       return cuda_fail(ctx, (int)cudaGetLastError(), "fork event");
   }
 #endif
-  {
-    CHECK_LAUNCH(ctx, launch_minmax_init(mm, B, user), "minmax_init", 1);
-  }
 #ifndef SPECGPU_EMULATE
   if (nlanes > 1) {
     cudaEventRecord(ctx->ev_fork, user);
@@ -985,6 +1014,16 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     cudaStreamWaitEvent(lane[1], ctx->ev_fork, 0);
   }
 #endif
+  // The log image of a group is written by the STFT and read back twice (Gram, projection).  When it is larger than what
+  // the L2 can hold next to the streams passing through, keep an address-hashed fraction of its lines (evict_last) and
+  // let the rest stream, instead of letting an LRU sweep evict every line just before it is reused.
+  float l2_pin = 1.0f;
+  {
+    double pin_mb = 64.0;
+    if (const char* env = std::getenv("SPECGPU_L2_PIN_MB")) pin_mb = std::atof(env);
+    const double img_mb = (double)gsz * rows * ldt * 4.0 / (1024.0 * 1024.0) * nlanes;
+    l2_pin = pin_mb <= 0.0 ? 0.f : (float)std::min(1.0, pin_mb / std::max(img_mb, 1e-9));
+  }
   for (int64_t g = 0; g < ngroups; ++g) {
     const int64_t b0 = g * gsz, nb = std::min(gsz, B - b0);
     const int li = (int)(g % nlanes);
@@ -992,8 +1031,9 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     cudaStream_t st = lane[li];
     float* Sg = S + b0 * rows * ldt;
     float* Dg = D + b0 * rows * ldt;
-    unsigned* mmg = mm + 2 * b0;
-    StftArgs a = make_args(plan, x + b0 * ldx, n, ldx, 0, nseg, (float)plan->scale, Sg, ldt, mmg);
+    MinMaxWord* mmg = mm + 2 * b0;
+    StftArgs a = make_args(plan, x + b0 * ldx, n, ldx, 0, nseg, (float)plan->scale, Sg, ldt, mmg, gen);
+    a.l2_pin = l2_pin;
     CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, nb, st), "stft_kernel", 1);
     SvdWs w{};
     w.G = reinterpret_cast<float*>(Gall + b0 * rows * rows);
@@ -1004,7 +1044,7 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     w.jacobi = jac[li];
     // Sg holds the raw log image until the rank-1 projection normalises it in place (see svd_run)
     if ((rc = svd_run(ctx, w, Sg, mmg, nb, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, fallback, Dg, 0, ldt, nullptr,
-                      info ? info + b0 * 4 : nullptr, st)))
+                      info ? info + b0 * 4 : nullptr, st, l2_pin)))
       return rc;
     if (tiles && ntiles > 0)
       CHECK_LAUNCH(ctx, launch_patch(Dg, nb, rows, ldt, tile_w, ntiles, tiles + (size_t)b0 * ntiles * rows * tile_w, 0, st), "patch", 1);

@@ -180,7 +180,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   // the input is read once (both overlapping segments come out of the staged span): do not let it displace the log
   // image, which the Gram and projection kernels read back while it is still in L2
   const uint64_t pol_in = l2_policy_evict_first();
-  const uint64_t pol_out = l2_policy_evict_last();
+  const uint64_t pol_out = a.l2_pin > 0.f ? l2_policy_pin_fraction(a.l2_pin) : l2_policy_evict_normal();
 #endif
   __syncthreads();
 
@@ -462,8 +462,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       vmin = fminf(vmin, s_red[2 * w]);
       vmax = fmaxf(vmax, s_red[2 * w + 1]);
     }
-    atomicMin(a.minmax + 2 * b, float_to_ordered(vmin));
-    atomicMax(a.minmax + 2 * b + 1, float_to_ordered(vmax));
+    atomicMax(a.minmax + 2 * b, minmax_word_min(a.minmax_gen, vmin));
+    atomicMax(a.minmax + 2 * b + 1, minmax_word_max(a.minmax_gen, vmax));
   }
   // tile and reduction scratch are reused by the next tile.  With a staged span and a tensor store the barrier inside the
   // next tile's round (and thread 0's wait on the store) already orders both.
@@ -474,21 +474,12 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
 #endif
 }
 
-// minmax[b] = {0xffffffff, 0}
-__global__ void minmax_init_kernel(unsigned* mm, int64_t B) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) {
-    mm[2 * i] = 0xffffffffu;
-    mm[2 * i + 1] = 0u;
-  }
-}
-
 // S = (L - min) / (max - min) in place; optionally export (min, max) as floats.  One CTA per (signal, row).
-__global__ void lognorm_kernel(float* S, int64_t rows, int64_t cols, int64_t ld, const unsigned* mm, float* mm_out) {
+__global__ void lognorm_kernel(float* S, int64_t rows, int64_t cols, int64_t ld, const MinMaxWord* mm, float* mm_out) {
   const int64_t b = blockIdx.y;
   const int64_t r = blockIdx.x;
-  const float mn = ordered_to_float(mm[2 * b]);
-  const float mx = ordered_to_float(mm[2 * b + 1]);
+  const float mn = minmax_get_min(mm, b);
+  const float mx = minmax_get_max(mm, b);
   const float den = mx - mn;
   const float inv = 1.0f / den;
   if (mm_out != nullptr && r == 0 && threadIdx.x == 0) {   // the log image is kept in base 2 (see stft_kernel)
@@ -601,12 +592,7 @@ int launch_stft(int log2n, int mode, const StftArgs& a, int64_t B, cudaStream_t 
   }
 }
 
-int launch_minmax_init(unsigned* mm, int64_t B, cudaStream_t stream) {
-  SPECGPU_LAUNCH(minmax_init_kernel, (unsigned)ceil_div(B, 128), 128, 0, stream, mm, B);
-  return (int)cudaGetLastError();
-}
-
-int launch_lognorm(float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const unsigned* mm, float* mm_out,
+int launch_lognorm(float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const MinMaxWord* mm, float* mm_out,
                    cudaStream_t stream) {
   if (B == 0 || rows == 0 || cols == 0) return 0;
   SPECGPU_LAUNCH(lognorm_kernel, dim3((unsigned)rows, (unsigned)B), 256, 0, stream, S, rows, cols, ld, mm, mm_out);

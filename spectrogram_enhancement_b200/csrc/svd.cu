@@ -8,6 +8,7 @@
 //   plan      singular values, median, Gavish-Donoho count, the reference's start/stop bookkeeping
 //   project   out = U_r U_r^T S  (or S - U_c U_c^T S when the complement is smaller), optional clip
 #include "kernels.h"
+#include "ptx.cuh"
 
 #ifndef SPECGPU_EMULATE
 #include <cooperative_groups.h>
@@ -34,7 +35,7 @@ constexpr int kGramTile = 64, kGramKB = 32, kGramThreads = 256;
 // converged) are computed; that launch uses ksplit == 1 and stores its tiles directly (no atomics, no zeroed G).
 template <class T>
 __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S, int rows, int64_t cols, int64_t ld,
-                                                                 int ksplit, T* G, const unsigned* minmax,
+                                                                 int ksplit, T* G, const MinMaxWord* minmax,
                                                                  const int32_t* only_flagged) {
   __shared__ float sa[kGramTile][kGramKB + 1];
   __shared__ float sb[kGramTile][kGramKB + 1];
@@ -42,8 +43,8 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
   if (only_flagged != nullptr && only_flagged[b * 4 + 3] == 0) return;   // uniform over the CTA
   float mn = 0.f, den = 1.f;
   if (minmax != nullptr) {
-    mn = ordered_to_float(minmax[2 * b]);
-    den = ordered_to_float(minmax[2 * b + 1]) - mn;
+    mn = minmax_get_min(minmax, b);
+    den = minmax_get_max(minmax, b) - mn;
   }
   const float inv = 1.0f / den;
   const int nt = (rows + kGramTile - 1) / kGramTile;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
 // g_f64: accumulate and store G in double (the full-decomposition route; squaring the condition number in fp32 would
 // blur cuts between close singular values), else float.
 int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* G, int g_f64, cudaStream_t stream,
-                     const unsigned* minmax, const int32_t* only_flagged) {
+                     const MinMaxWord* minmax, const int32_t* only_flagged) {
   if (B == 0 || rows == 0) return 0;
   const int nt = (int)ceil_div(rows, kGramTile);
   const int npairs = nt * (nt + 1) / 2;
@@ -267,6 +268,244 @@ int launch_eig_power(const float* G, int64_t B, int n, int max_iter, float* U, f
   if (max_iter <= 0) max_iter = kPowMaxIter;
   SPECGPU_LAUNCH(eig_power_kernel, (unsigned)B, kPowThreads, 0, stream, G, n, max_iter, U, lam, plan);
   return (int)cudaGetLastError();
+}
+
+// ======================================================================================================
+// Split-K reduce of the tensor-core Gram partials fused with the leading-pair power iteration: one thread-block
+// cluster per matrix, CTA r owns rows [32 r, 32 r + 32) of G.  Each CTA sums its rows over the (CTA, segment)
+// partials of gram_tc.cu in a fixed order (deterministic) straight into registers -- G never exists in global
+// memory -- and the iteration exchanges the 32 new entries of y per CTA through distributed shared memory, one
+// cluster barrier per step.  Replaces gram_reduce + eig_power (two launches, a 36 MB round trip and a 1-CTA-per-
+// matrix kernel that spent most of its 17 us loading G) on the default route.
+//   partial layout (gram_tc.cu): [cta][2][128][PW], PW = 384: D1 = [G00 | G01] in columns 0..255 of rows 0..127,
+//   D2 = G11 in columns 256..383; PW = 128 for 128 rows (D1 = G only).  G10 = G01^T is transposed through shared memory.
+// ======================================================================================================
+constexpr int kGeThreads = 512, kGeRows = 32;
+
+struct GramEigArgs {
+  const float* partial;
+  int64_t nchunk, per;     // geometry of the gram_tc launch that wrote the partials
+  int max_iter;
+  float* U;                // [B][n][n]: column 0 receives u0
+  float* lam;              // [B][n]
+  int32_t* plan;           // [B][4] = {1, n, -1, status}
+};
+
+template <int N>
+__global__ void __launch_bounds__(kGeThreads) gram_eig_kernel(GramEigArgs a) {
+  constexpr int CL = N / kGeRows;                 // CTAs per cluster
+  constexpr int PW = (N == 256) ? 384 : N;
+  constexpr int NJ = N / 64;                      // float4 per thread: columns q*4 + 64 j + {0..3}
+  SPECGPU_DYN_SMEM(smem);
+  float* sx = reinterpret_cast<float*>(smem);     // [N] current iterate (every CTA holds all of it)
+  float* sy = sx + N;                             // [2][N] G x, double buffered across iterations
+  float* sdiag = sy + 2 * N;                      // [CL][2] (largest diagonal, its row) per CTA
+  float* sT = sdiag + 2 * CL + 8;                 // [32][132] transposed G10 rows (N == 256, ranks >= CL/2)
+  const int rank = SPECGPU_CLUSTER_RANK();
+  const int64_t b = blockIdx.x / CL;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int rl = tid >> 4, q = tid & 15;
+  const int row0 = rank * kGeRows;
+  const int i0 = (int)((b * a.nchunk) / a.per), i1 = (int)(((b + 1) * a.nchunk - 1) / a.per);
+  const int64_t bstart = b * a.nchunk;
+  const bool lower = (N == 256) && row0 >= 128;   // rows of [G10 | G11]
+  float4 g[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lower) {
+    for (int i = tid; i < kGeRows * 132; i += kGeThreads) sT[i] = 0.f;
+    __syncthreads();
+  }
+  for (int cta = i0; cta <= i1; ++cta) {
+    // a CTA whose range starts before this matrix began in matrix b-1: matrix b is its second segment
+    const int sg = ((int64_t)cta * a.per < bstart) ? 1 : 0;
+    const float* base = a.partial + (size_t)(cta * 2 + sg) * 128 * PW;
+    if (!lower) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)(row0 + rl) * PW + q * 4 + 64 * j));
+        g[j].x += v.x; g[j].y += v.y; g[j].z += v.z; g[j].w += v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 2; j < NJ; ++j) {   // G11 from D2
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)(row0 - 128 + rl) * PW + 256 + q * 4 + 64 * (j - 2)));
+        g[j].x += v.x; g[j].y += v.y; g[j].z += v.z; g[j].w += v.w;
+      }
+      // G10[row][c] = D1[c][row]: 128-byte runs D1[c][row0 .. row0 + 31], accumulated transposed in shared memory (every
+      // cell is owned by one thread for all partials: no atomics)
+      for (int i = tid; i < 128 * 8; i += kGeThreads) {
+        const int c = i >> 3, e4 = i & 7;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)c * PW + row0 + e4 * 4));
+        sT[(e4 * 4 + 0) * 132 + c] += v.x;
+        sT[(e4 * 4 + 1) * 132 + c] += v.y;
+        sT[(e4 * 4 + 2) * 132 + c] += v.z;
+        sT[(e4 * 4 + 3) * 132 + c] += v.w;
+      }
+    }
+  }
+  if (lower) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) g[j] = *reinterpret_cast<const float4*>(sT + rl * 132 + q * 4 + 64 * j);
+  }
+  // ---- start vector: the row of G with the largest diagonal entry, cluster-wide (see eig_power_kernel) ----
+  {
+    // the diagonal entry of row row0 + rl sits in the thread whose columns contain it
+    const int dc = row0 + rl;
+    float dval = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c0 = q * 4 + 64 * j;
+      if (dc >= c0 && dc < c0 + 4) {
+        const int e = dc - c0;
+        dval = e == 0 ? g[j].x : (e == 1 ? g[j].y : (e == 2 ? g[j].z : g[j].w));
+      }
+    }
+    // reduce over the 16 threads of the row, then over the 32 rows (2 rows per warp)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) dval = fmaxf(dval, __shfl_xor_sync(0xffffffffu, dval, o));
+    if (q == 0) sy[rl] = dval;
+    __syncthreads();
+    if (tid < 32) {
+      float best = sy[tid];
+      int arg = row0 + tid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) {
+          best = ob;
+          arg = oa;
+        }
+      }
+      if (tid < CL) {   // tell every CTA of the cluster
+        float* remote = SPECGPU_MAP_SHARED(sdiag, tid);
+        remote[2 * rank] = best;
+        remote[2 * rank + 1] = __int_as_float(arg);
+      }
+    }
+    SPECGPU_CLUSTER_SYNC();
+    float best = sdiag[0];
+    int arg = __float_as_int(sdiag[1]);
+#pragma unroll
+    for (int r = 1; r < CL; ++r) {
+      const float ob = sdiag[2 * r];
+      const int oa = __float_as_int(sdiag[2 * r + 1]);
+      if (ob > best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    // the owner of that row broadcasts it (row == column by symmetry) as the unnormalised start vector
+    if (arg >= row0 && arg < row0 + kGeRows && rl == arg - row0) {
+#pragma unroll
+      for (int r = 0; r < CL; ++r) {
+        float* remote = SPECGPU_MAP_SHARED(sx, r);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) *reinterpret_cast<float4*>(remote + q * 4 + 64 * j) = g[j];
+      }
+    }
+    SPECGPU_CLUSTER_SYNC();
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < N / 32; ++i) ss += sx[lane + 32 * i] * sx[lane + 32 * i];
+    ss = warp_sum(ss);
+    const float sinv = (ss > 0.f && ss < INFINITY) ? rsqrtf(ss) : 0.f;
+    __syncthreads();
+    if (tid < N) sx[tid] *= sinv;
+    __syncthreads();
+  }
+  float lambda = 0.f, prev_delta = INFINITY;
+  int status = 1;
+  for (int it = 0; it < a.max_iter; ++it) {
+    float* syc = sy + (it & 1) * N;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float4 xv = *reinterpret_cast<const float4*>(sx + q * 4 + 64 * j);
+      acc += g[j].x * xv.x + g[j].y * xv.y + g[j].z * xv.z + g[j].w * xv.w;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (q < CL) {   // thread q of the row sends y[row] to CTA q
+      float* remote = SPECGPU_MAP_SHARED(syc, q);
+      remote[row0 + rl] = acc;
+    }
+    SPECGPU_CLUSTER_SYNC();
+    // every warp of every CTA redundantly reduces |y|^2, x.y and |y/|y| - x|^2 (identical values: uniform control flow)
+    float yy = 0.f, xy = 0.f;
+#pragma unroll
+    for (int i = 0; i < N / 32; ++i) {
+      const float y = syc[lane + 32 * i], x = sx[lane + 32 * i];
+      yy += y * y;
+      xy += x * y;
+    }
+    yy = warp_sum(yy);
+    xy = warp_sum(xy);
+    if (!(yy > 0.f) || !(yy < INFINITY)) break;   // zero / non-finite iterate: not convergence (status stays 1)
+    const float inv = rsqrtf(yy);
+    float dd = 0.f;
+#pragma unroll
+    for (int i = 0; i < N / 32; ++i) {
+      const float d = syc[lane + 32 * i] * inv - sx[lane + 32 * i];
+      dd += d * d;
+    }
+    dd = warp_sum(dd);
+    lambda = xy;  // Rayleigh quotient x^T G x with |x| = 1
+    __syncthreads();
+    if (tid < N) sx[tid] = syc[tid] * inv;
+    __syncthreads();
+    if (dd < 1e-13f || (dd < 1e-10f && dd >= prev_delta)) {
+      status = 0;
+      break;
+    }
+    prev_delta = dd;
+  }
+  // nobody may leave while a peer can still write into its shared memory
+  SPECGPU_CLUSTER_SYNC();
+  if (tid < kGeRows) a.U[b * (int64_t)N * N + (int64_t)(row0 + tid) * N] = sx[row0 + tid];
+  if (rank == 0 && tid == 0) {
+    a.lam[b * N] = lambda;
+    a.plan[b * 4 + 0] = 1;
+    a.plan[b * 4 + 1] = N;
+    a.plan[b * 4 + 2] = -1;
+    a.plan[b * 4 + 3] = status;
+  }
+}
+
+template <int N>
+static int launch_gram_eig_t(const GramEigArgs& a, int64_t B, cudaStream_t stream) {
+  constexpr int CL = N / kGeRows;
+  const size_t smem = (size_t)(3 * N + 2 * CL + 8 + kGeRows * 132) * sizeof(float);
+#ifdef SPECGPU_EMULATE
+  SPECGPU_LAUNCH_CLUSTER(gram_eig_kernel<N>, (unsigned)(B * CL), kGeThreads, smem, stream, CL, a);
+#else
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(B * CL));
+  cfg.blockDim = dim3(kGeThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gram_eig_kernel<N>, a);
+  if (e != cudaSuccess) return (int)e;
+#endif
+  return (int)cudaGetLastError();
+}
+
+int launch_gram_eig(const float* partial, int64_t nchunk, int64_t per, int64_t B, int n, int max_iter, float* U, float* lam,
+                    int32_t* plan, cudaStream_t stream) {
+  if (B == 0) return 0;
+  GramEigArgs a{partial, nchunk, per, max_iter > 0 ? max_iter : kPowMaxIter, U, lam, plan};
+  if (n == 256) return launch_gram_eig_t<256>(a, B, stream);
+  if (n == 128) return launch_gram_eig_t<128>(a, B, stream);
+  return -1;
 }
 
 // ======================================================================================================
@@ -715,10 +954,36 @@ __global__ void __launch_bounds__(kRecThreads) svd_project_kernel(const float* S
 // ------------------------------------------------------------------------------------------------------
 constexpr int kR1Warps = 16, kR1Threads = kR1Warps * 32;
 
-template <int RPW, bool NORM, bool CLIP>   // RPW = rows per thread = ceil(rows / 16)
+// STREAM (pipeline): L was left in L2 by the producer for this, its last, reader -- the loads mark their lines evict_first
+// and the S / D stores stream out (evict_first) so that they do not push out lines of L that are still to be read.
+template <bool STREAM>
+__device__ __forceinline__ float r1_load(const float* p, uint64_t pol) {
+#if !defined(SPECGPU_EMULATE)
+  if (STREAM) return ld_global_hint(p, pol);
+#endif
+  (void)pol;
+  return __ldg(p);
+}
+template <bool STREAM>
+__device__ __forceinline__ void r1_store(float* p, float v, uint64_t pol) {
+#if !defined(SPECGPU_EMULATE)
+  if (STREAM) {
+    st_global_hint(p, v, pol);
+    return;
+  }
+#endif
+  (void)pol;
+  *p = v;
+}
+
+template <int RPW, bool NORM, bool CLIP, bool STREAM>   // RPW = rows per thread = ceil(rows / 16)
 __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L, int rows, int64_t cols, int64_t ld,
-                                                                  const unsigned* minmax, const float* U, float* S,
+                                                                  const MinMaxWord* minmax, const float* U, float* S,
                                                                   float* D, int64_t ldo) {
+  uint64_t pol = 0;
+#if !defined(SPECGPU_EMULATE)
+  if (STREAM) pol = l2_policy_evict_first();
+#endif
   SPECGPU_DYN_SMEM(smem);
   float* s_u = reinterpret_cast<float*>(smem);          // [rows]
   float* s_w = s_u + rows;                              // [16][32] partial coefficients
@@ -727,8 +992,8 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float mn = 0.f, den = 1.f;
   if (NORM) {
-    mn = ordered_to_float(minmax[2 * b]);
-    den = ordered_to_float(minmax[2 * b + 1]) - mn;
+    mn = minmax_get_min(minmax, b);
+    den = minmax_get_max(minmax, b) - mn;
   }
   const float inv = 1.0f / den;
   for (int r = tid; r < rows; r += kR1Threads) s_u[r] = U[b * (int64_t)rows * rows + (int64_t)r * rows];
@@ -741,7 +1006,7 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
   if (c0 + kRecCols <= cols && rows == kR1Warps * RPW) {
     // ---- full tile: no per-element predicates ----
 #pragma unroll
-    for (int i = 0; i < RPW; ++i) x[i] = __ldg(pl + i * stepl);
+    for (int i = 0; i < RPW; ++i) x[i] = r1_load<STREAM>(pl + i * stepl, pol);
     __syncthreads();
     float u[RPW];
     float w = 0.f;
@@ -754,7 +1019,7 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
     s_w[warp * 32 + lane] = w;
     if (write_s) {
 #pragma unroll
-      for (int i = 0; i < RPW; ++i) ps[i * stepo] = x[i];
+      for (int i = 0; i < RPW; ++i) r1_store<STREAM>(ps + i * stepo, x[i], pol);
     }
     __syncthreads();
     w = 0.f;
@@ -764,7 +1029,7 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
     for (int i = 0; i < RPW; ++i) {
       float v = fmaf(-u[i], w, x[i]);
       if (CLIP) v = (v < 0.f) ? 0.f : v;   // NaN stays NaN, like hacked[hacked < 0] = 0
-      pd[i * stepo] = v;
+      r1_store<STREAM>(pd + i * stepo, v, pol);
     }
     return;
   }
@@ -801,24 +1066,30 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
   }
 }
 
+template <int RPW, bool STREAM>
+static void launch_rank1_ts(dim3 grid, size_t smem, cudaStream_t stream, const float* L, int rows, int64_t cols, int64_t ld,
+                            const MinMaxWord* minmax, const float* U, int clip, float* S, float* D, int64_t ldo) {
+  const bool nrm = minmax != nullptr;
+  if (nrm && clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, true, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
+  else if (nrm) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, false, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
+  else if (clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, true, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
+  else SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, false, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
+}
 template <int RPW>
 static void launch_rank1_t(dim3 grid, size_t smem, cudaStream_t stream, const float* L, int rows, int64_t cols, int64_t ld,
-                           const unsigned* minmax, const float* U, int clip, float* S, float* D, int64_t ldo) {
-  const bool nrm = minmax != nullptr;
-  if (nrm && clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, true>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
-  else if (nrm) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, false>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
-  else if (clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, true>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
-  else SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, false>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
+                           const MinMaxWord* minmax, const float* U, int clip, float* S, float* D, int64_t ldo, int stream_out) {
+  if (stream_out) launch_rank1_ts<RPW, true>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  else launch_rank1_ts<RPW, false>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
 }
 
-int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const unsigned* minmax, const float* U,
-                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream) {
+int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const MinMaxWord* minmax, const float* U,
+                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out) {
   if (B == 0 || rows == 0 || cols == 0) return 0;
   const size_t smem = ((size_t)rows + kR1Warps * 32) * sizeof(float);
   const dim3 grid((unsigned)ceil_div(cols, kRecCols), (unsigned)B);
-  if (rows <= 64) launch_rank1_t<4>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
-  else if (rows <= 128) launch_rank1_t<8>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
-  else if (rows <= 256) launch_rank1_t<16>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+  if (rows <= 64) launch_rank1_t<4>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out);
+  else if (rows <= 128) launch_rank1_t<8>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out);
+  else if (rows <= 256) launch_rank1_t<16>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out);
   else return -1;
   return (int)cudaGetLastError();
 }
