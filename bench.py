@@ -168,9 +168,6 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-NCU_TRAFFIC = {   # dram__bytes_read.sum + dram__bytes_write.sum per 40-channel launch, profiles/r01e_ncu_raw.csv
-    "stft_kernel": 278.1e6, "gram_tc": 169.5e6 + 36.1e6, "svd_rank1": 425.2e6,      # gram_tc group = kernel + reduce
-}
 ALGO_BYTES = {   # algorithmic HBM bytes of one launch over B channels (DESIGN.md "kernels")
     "stft_kernel": lambda B: B * (4 * N_SAMP + 4 * ROWS * NSEG),          # read x, write log-PSD (Nyquist dropped)
     "lognorm": lambda B: B * 8 * ROWS * NSEG,                              # read + write the image
@@ -180,6 +177,35 @@ ALGO_BYTES = {   # algorithmic HBM bytes of one launch over B channels (DESIGN.m
     "svd_rank1": lambda B: B * 12 * ROWS * NSEG,                           # read log image, write S and D
     "patch": lambda B: B * 8 * ROWS * (NSEG // 128) * 128,
 }
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed ncu summary
+    (profiles/rNN*_ncu_raw.csv, written by tools/summarize_profiles.py from an `ncu --set full` capture)."""
+    import csv
+    import glob
+    import re
+    best = None
+    for path in glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_raw.csv")):
+        m = re.match(r"r(\d+)([a-z]*)_", os.path.basename(path))
+        if not m:
+            continue
+        try:
+            rows = list(csv.DictReader(open(path)))
+        except Exception:
+            continue
+        for r in rows:
+            name = r.get("Kernel Name", "")
+            if kernel in name and "dram__bytes_read.sum [Mbyte]" in r:
+                try:
+                    val = (float(r["dram__bytes_read.sum [Mbyte]"]) + float(r["dram__bytes_write.sum [Mbyte]"])) * 1e6
+                except ValueError:
+                    continue
+                key = (int(m.group(1)), m.group(2))
+                if best is None or key > best[0]:
+                    best = (key, val, os.path.basename(path))
+                break
+    return (best[1], best[2]) if best else (None, None)
 
 
 def synth_on_device(torch, device, shot, gen):
@@ -197,7 +223,7 @@ def synth_on_device(torch, device, shot, gen):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from spectrogram_enhancement_b200 import api
+    from spectrogram_enhancement_b200 import api, parallel
 
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
@@ -214,18 +240,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     rt = api.Runtime(device=device)
     plan = rt.plan_from_params(SP)
     gen = torch.Generator(device=device)
     gen.manual_seed(1234 + rank)
     nbuf = 3   # rotate over 3 resident shots (3 x 160 MB in, 2 x 160 MB out each) so no step finds its data in L2
     xs = [synth_on_device(torch, device, rank * 1000 + i, gen) for i in range(nbuf)]
-    # image rows are pitched to a multiple of 32 floats so every row starts on a 128-byte line (the C ABI takes any ld)
-    ldt = int(os.environ.get("SPECGPU_BENCH_LDT", (NSEG + 31) // 32 * 32))
-    S = [rt.empty((N_CH, ROWS, ldt))[:, :, :NSEG] for _ in range(nbuf)]
-    D = [rt.empty((N_CH, ROWS, ldt))[:, :, :NSEG] for _ in range(nbuf)]
+    # the buffers the public API itself allocates (Runtime.empty_image: rows pitched to 32 floats; the C ABI takes any ld)
+    S = [rt.empty_image(N_CH, ROWS, NSEG) for _ in range(nbuf)]
+    D = [rt.empty_image(N_CH, ROWS, NSEG) for _ in range(nbuf)]
+    ldt = int(S[0].stride(1))
     info = torch.zeros((N_CH, 4), dtype=torch.int32, device=device)
-
     fallback = os.environ.get("SPECGPU_BENCH_FALLBACK", "1") != "0"     # A/B knob; the API default is on
 
     def step(i):
@@ -242,12 +273,25 @@ def run_ours(args):
         Sr, _, _ = oc.specgr_array(xc.astype(np.float64), SP)
         Sg = S[0][3].contiguous().cpu().numpy()
         Dg = D[0][3].contiguous().cpu().numpy()
-        Dr = oc.clip(oc.denoiseSignal(Sg.astype(np.float64)))
+        Dr = oc.clip(oc.denoiseSignal(Sr))                 # the pure oracle chain, not the oracle on our S
         parity = {"spec_max_abs_err": float(np.abs(Sg - Sr).max()),
                   "denoise_max_err_rel_to_max": float(np.abs(Dg - Dr).max() / np.abs(Dr).max())}
         assert parity["spec_max_abs_err"] < 1e-4 and parity["denoise_max_err_rel_to_max"] < 1e-3, parity
+        assert int(info[:, 3].max().item()) == 0
 
-    # ---- device-resident timing ----
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    # ---- device-resident timing (config 2) ----
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
@@ -270,50 +314,141 @@ def run_ours(args):
         step(i)
     prof = rt.profile_read()
     rt.profile(False)
-    t = torch.tensor([ms], device=device, dtype=torch.float64)
     lt = torch.tensor([launches], device=device, dtype=torch.int64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(ms)
     value = world * args.steps * N_CH * N_SAMP / (ms_max * 1e-3)
+
+    # ---- the same with DENSE image rows (3905 floats: no 16-byte alignment -> plain-store / 4-byte-copy paths) ----
+    Sd = [torch.empty((N_CH, ROWS, NSEG), device=device) for _ in range(nbuf)]
+    Dd = [torch.empty((N_CH, ROWS, NSEG), device=device) for _ in range(nbuf)]
+    ms_dense = max_over_ranks(timed(lambda i: rt.pipeline_dev(plan, xs[i % nbuf], Sd[i % nbuf], Dd[i % nbuf], clip=True, info=info,
+                                                              fallback=fallback), args.steps, 3))
+    value_dense = world * args.steps * N_CH * N_SAMP / (ms_dense * 1e-3)
+    del Sd, Dd
+
+    # ---- config 4: 1000 shots x 40 channels streamed through resident buffers, sharded by shot, tiles written ----
+    cfg4 = None
+    if not args.no_config4:
+        shots_total = int(os.environ.get("SPECGPU_BENCH_SHOTS", 1000))
+        lo, hi = parallel.shot_range(rank, world, shots_total)
+        ntile = NSEG // 128
+        tl = [rt.empty((N_CH * ntile, ROWS, 128)) for _ in range(2)]
+
+        def shot(i):
+            b = i % nbuf
+            rt.pipeline_dev(plan, xs[b], S[b], D[b], clip=True, tiles=tl[i % 2], tile_w=128, ntiles=ntile, info=info,
+                            fallback=fallback)
+
+        l4 = rt.launch_count()
+        clk4 = ClockSampler(local)
+        with clk4:
+            ms4 = max_over_ranks(timed(shot, hi - lo, 3))
+        launches4 = rt.launch_count() - l4
+        ok4 = None
+        if rank == 0:
+            from oracle import spec_oracle as oc
+            last = (hi - lo - 1)
+            c = 17
+            Sr, _, _ = oc.specgr_array(xs[last % nbuf][c].cpu().numpy().astype(np.float64), SP)
+            Tr = oc.patch([oc.clip(oc.denoiseSignal(Sr))], 128, ntile)
+            Tg = tl[last % 2][c * ntile:(c + 1) * ntile].cpu().numpy()
+            err = float(np.abs(Tg - Tr).max() / np.abs(Tr).max())
+            ok4 = {"shot": int(lo + last), "channel": c, "tiles_max_err_rel_to_max": err}
+            assert err < 1e-3, ok4
+        cfg4 = {"workload": "config4: 1000 synthetic shots x 40 channels x 1M samples, contiguous shot ranges per GPU "
+                            "(parallel.shot_range), pipeline + clip + 30 tiles of 256x128 per channel written; "
+                            f"{nbuf} resident input shots rotated, every shot's S, D and tiles written to HBM",
+                "shots_total": shots_total, "shots_this_rank": hi - lo, "value": shots_total * N_CH * N_SAMP / (ms4 * 1e-3),
+                "unit": UNIT, "ms_per_shot_per_gpu": ms4 / max(hi - lo, 1), "seconds": ms4 * 1e-3, "scaling": "strong",
+                "gpu_launches_this_rank": int(launches4), "bytes_per_sample": 16, "clocks": clk4.summary(),
+                "parity_sampled": ok4}
+        del tl
+
+    # ---- config 5: all-pairs Welch CSD of 40 channels x 1M samples, nperseg 1024 ----
+    cfg5 = None
+    if not args.no_csd5:
+        g5 = torch.Generator(device=device)
+        g5.manual_seed(77)                                  # the same record on every rank
+        x5 = synth_on_device(torch, device, 5, g5)
+        nps = 1024
+        kw = dict(fs=float(SP["fs"]), nperseg=nps, runtime=rt)
+        res5 = {}
+        P1 = None
+        if rank == 0 or world == 1:
+            _, P1 = api.csd_allpairs(x5, **kw)
+        res5["single_gpu_ms"] = timed(lambda i: api.csd_allpairs(x5, **kw), 10, 3) / 10
+        if world > 1:
+            clo, chi = parallel.channel_block(rank, world, N_CH)
+            xl = x5[clo:chi].contiguous()
+            legs = {"channel_block_allgather": lambda i: parallel.csd_allpairs_sharded(xl, **kw),
+                    "frequency_block_alltoall": lambda i: parallel.csd_allpairs_freq_sharded(xl, **kw),
+                    "segment_allreduce": lambda i: parallel.csd_allpairs_segment_sharded(x5, **kw)}
+            for name, fn in legs.items():
+                res5[name + "_ms"] = max_over_ranks(timed(fn, 10, 3) / 10)
+            # parity of every sharding against the single-GPU matrix (itself checked against the oracle in tests/)
+            _, Pa = parallel.csd_allpairs_sharded(xl, **kw)
+            _, Pf = parallel.csd_allpairs_freq_sharded(xl, **kw)
+            _, Ps = parallel.csd_allpairs_segment_sharded(x5, **kw)
+            ga = [torch.empty_like(Pa) for _ in range(world)]
+            dist.all_gather(ga, Pa.contiguous())
+            F = nps // 2 + 1
+            wf = -(-F // world)
+            Pfp = torch.zeros((N_CH, N_CH, wf), dtype=Pf.dtype, device=device)
+            Pfp[:, :, :Pf.shape[-1]] = Pf
+            gf = [torch.empty_like(Pfp) for _ in range(world)]
+            dist.all_gather(gf, Pfp)
+            if rank == 0:
+                scale = float(P1.abs().max().item())
+                res5["parity_rel_to_max"] = {
+                    "channel_block_allgather": float((torch.cat(ga) - P1).abs().max().item()) / scale,
+                    "frequency_block_alltoall": float((torch.cat(gf, dim=-1)[:, :, :F] - P1).abs().max().item()) / scale,
+                    "segment_allreduce": float((Ps - P1).abs().max().item()) / scale}
+                assert max(res5["parity_rel_to_max"].values()) < 1e-5, res5
+        cfg5 = {"workload": f"config5: all-pairs CSD, 40 channels x 1M samples, hann, nperseg {nps}, noverlap {nps // 2}; "
+                            "times include the collective (CUDA events, max over ranks)", **res5}
+        del x5
 
     # ---- end to end through the public API with host buffers ----
     # api.HostPipeline: the shot sits in pinned host memory; per step H2D of the 40 channels, the whole path, D2H of
     # the denoised spectrogram (channel groups on 3 streams so uploads, kernels and downloads overlap).
-    xh = [torch.empty((N_CH, N_SAMP), dtype=torch.float32).pin_memory() for _ in range(2)]
-    for i in range(2):
-        xh[i].copy_(xs[i])
-    dh = [torch.empty((N_CH, ROWS, NSEG), dtype=torch.float32).pin_memory() for _ in range(2)]
     e2e_steps = max(2, min(args.steps, 10))
     if args.no_e2e:
         e2e_steps = 0
-    hp = api.HostPipeline(SP, channels=N_CH, samples=N_SAMP, groups=8, streams=3, clip=True, device=device) if e2e_steps else None
-    e2e_ok, e2e_launches, e2e_value = None, 0, None
-    if hp is not None:
+    e2e_ok, e2e_launches, e2e_value, e2e_ceiling = None, 0, None, None
+    if e2e_steps:
+        xh = [torch.empty((N_CH, N_SAMP), dtype=torch.float32).pin_memory() for _ in range(2)]
+        for i in range(2):
+            xh[i].copy_(xs[i])
+        dh = [torch.empty((N_CH, ROWS, NSEG), dtype=torch.float32).pin_memory() for _ in range(2)]
+        hp = api.HostPipeline(SP, channels=N_CH, samples=N_SAMP, groups=8, streams=3, clip=True, device=device)
         for i in range(2):
             hp.run(xh[i % 2], dh[i % 2])
         e2e_ok = bool(torch.allclose(dh[1][3], D[1][3].cpu(), rtol=0, atol=2e-5))   # dh[1] holds shot xs[1], as D[1] does
-        barrier()
+
+        def e2e_loop(copy_only):
+            barrier()
+            t0 = time.perf_counter()
+            # shots are submitted back to back (double-buffered host results): every step uploads its shot from pinned
+            # memory and downloads its denoised spectrogram; the download of step i overlaps the upload of step i+1, and
+            # step i is waited for right after step i+1 has been enqueued
+            prev = None
+            for i in range(e2e_steps):
+                ev = hp.submit(xh[i % 2], dh[i % 2], copy_only=copy_only)
+                if prev is not None:
+                    prev.synchronize()
+                prev = ev
+            prev.synchronize()
+            barrier()
+            return max_over_ranks(time.perf_counter() - t0)
+
         l0e = hp.launch_count()
-        t0 = time.perf_counter()
-        # shots are submitted back to back (double-buffered host results): every step uploads its shot from pinned memory
-        # and downloads its denoised spectrogram; the download of step i overlaps the upload of step i+1, and step i is
-        # waited for right after step i+1 has been enqueued
-        prev = None
-        for i in range(e2e_steps):
-            ev = hp.submit(xh[i % 2], dh[i % 2])
-            if prev is not None:
-                prev.synchronize()
-            prev = ev
-        prev.synchronize()
-        barrier()
-        e2e_s = time.perf_counter() - t0
+        e2e_s = e2e_loop(False)
         e2e_launches = hp.launch_count() - l0e
-        te = torch.tensor([e2e_s], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_value = world * e2e_steps * N_CH * N_SAMP / float(te.item())
+        e2e_value = world * e2e_steps * N_CH * N_SAMP / e2e_s
+        # the same buffers, streams and copies with the kernels skipped: what the host link alone allows
+        e2e_ceiling = world * e2e_steps * N_CH * N_SAMP / e2e_loop(True)
     clk.__exit__()
 
     if rank != 0:
@@ -334,8 +469,9 @@ def run_ours(args):
     if dom is not None:
         dur_s = prof[dom][0] / max(prof[dom][1], 1) * 1e-3
         ach = ALGO_BYTES[dom](N_CH) / dur_s / 1e9
+        traffic, traffic_src = ncu_traffic(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": NCU_TRAFFIC.get(dom), "traffic_source": "ncu --set full capture in profiles/r01e_ncu_raw.csv",
+                "traffic": traffic, "traffic_source": f"ncu --set full capture, profiles/{traffic_src}" if traffic_src else None,
                 "peak_source": peak_src, "timing": "CUDA events around each launch, second pass of the same K steps",
                 "algorithmic_bytes_per_launch": ALGO_BYTES[dom](N_CH), "ms_per_launch": dur_s * 1e3}
     pipeline_gbs = 12.0 * N_CH * N_SAMP * args.steps / (ms * 1e-3) / 1e9      # 12 B/sample
@@ -356,15 +492,21 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "channels": N_CH, "samples_per_channel": N_SAMP, "shots_per_step_per_gpu": 1,
                    "sharding": "by shot, no data-path collective" if world > 1 else "single GPU",
                    "l2": f"inputs larger than L2: {nbuf} resident shots rotated (160 MB in + 320 MB out per step)",
-                   "image_row_pitch_floats": ldt},
+                   "image_row_pitch_floats": ldt, "buffers": "allocated by the public API (Runtime.empty_image)",
+                   "in_stream_fallback": fallback},
+        "value_dense_layout": value_dense, "ms_per_step_dense_layout": ms_dense / args.steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_CH * N_SAMP * 4,
                 "d2h_bytes_per_step": N_CH * ROWS * NSEG * 4, "steps": e2e_steps, "api": "HostPipeline(groups=8, streams=3).submit, two shots in flight",
-                "gpu_launches": int(e2e_launches), "matches_device_path": e2e_ok},
+                "gpu_launches": int(e2e_launches), "matches_device_path": e2e_ok,
+                "copy_only_ceiling": e2e_ceiling,
+                "frac_of_copy_ceiling": (e2e_value / e2e_ceiling) if e2e_value and e2e_ceiling else None},
         "gpu_launches": int(lt.item()),
         "clocks": clk.summary(),
         "roofline": roof,
         "pipeline_hbm": {"algorithmic_gbs": pipeline_gbs, "frac_of_peak": pipeline_gbs / peak, "bytes_per_sample": 12},
         "kernels": kernels,
+        "config4": cfg4,
+        "csd5": cfg5,
         "cpu_baseline": cpu,
         "parity_on_bench_bytes": parity,
     }
@@ -381,6 +523,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-to-host leg (e2e is then null)")
+    ap.add_argument("--no-config4", action="store_true", help="profiling aid: skip the 1000-shot streamed leg")
+    ap.add_argument("--no-csd5", action="store_true", help="profiling aid: skip the all-pairs CSD leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -184,6 +184,18 @@ int specgpu_csd_pairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X
 int specgpu_csd_pairs_block(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg,
                             int64_t nseg_total, int64_t ldf, int64_t i0, int64_t ni, int32_t accumulate, float* P,
                             void* stream);
+/* specgpu_csd_spectra with the bins of a row grouped into blocks of block_w bins, block h starting at column
+ * h * block_ld (block_ld >= block_w, ldf >= ceil(nfreq / block_w) * block_ld): X viewed as [C][nseg][nblocks][block_ld] is
+ * what a frequency-block all-to-all sends (block h goes to rank h). */
+int specgpu_csd_spectra_blocked(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n,
+                                int64_t ldx, float* X, int64_t ldf, int32_t block_w, int32_t block_ld, void* stream);
+/* All pairs over a BLOCK OF FREQUENCY BINS: X[C][nseg][ldf] holds bins f0 .. f0 + nf - 1 of every channel's one-sided
+ * spectra in columns 0 .. nf - 1 (the layout a frequency-block all-to-all of specgpu_csd_spectra outputs produces on
+ * each rank; pair products are independent per bin); P[C][C][nf] (+)= sum_t conj(X_i) X_j * scale / nseg_total with the
+ * one-sided doubling decided by the global bin index f0 + f. */
+int specgpu_csd_pairs_bins(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg,
+                           int64_t nseg_total, int64_t ldf, int64_t f0, int64_t nf, int32_t accumulate, float* P,
+                           void* stream);
 /* Time-resolved cross-power amplitude for the `ampsp[n_time, n_freq]` image of interferometer/crosspowerspec.py:39-50:
  * amp[k][f] = | mean over segments [k*seg_stride, k*seg_stride + navg) of conj(X_i) X_j | * scale (one-sided doubled),
  * from the spectra of specgpu_csd_spectra.  amp is [nframes][nfreq] float32. */
@@ -209,6 +221,12 @@ enum { SPECGPU_PIPE_CLIP = 1, SPECGPU_PIPE_FALLBACK = 2 };
 int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t B, int64_t n, int64_t ldx,
                      float* S, float* D, int64_t ldt, int32_t flags, float* tiles, int32_t tile_w, int32_t ntiles,
                      int32_t* info, void* stream);
+
+/* Strided copy of `nrows` rows of `row_bytes` bytes between any two of {pinned host, device} buffers with independent row
+ * pitches (cudaMemcpy2DAsync, enqueued on `stream`): moves the row-pitched images the pipeline works on to and from the
+ * dense host arrays of the reference's interface without a staging pass. */
+int specgpu_copy_rows(specgpu_ctx* ctx, void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes,
+                      int64_t nrows, void* stream);
 
 /* specgpu_pipeline can process the batch in groups of `channels` channels, alternating between two library-owned
  * streams that are forked from and joined to the caller's stream.  0 (default) or a value >= B runs the batch as one

@@ -67,9 +67,12 @@ PROTOTYPES = {
     "specgpu_csd_spectra": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "specgpu_csd_pairs": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "specgpu_csd_pairs_block": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _vp]),
+    "specgpu_csd_spectra_blocked": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "specgpu_csd_pairs_bins": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _vp]),
     "specgpu_csd_frames": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i64, _vp, _vp]),
     "specgpu_csd_allpairs": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "specgpu_pipeline": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "specgpu_copy_rows": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "specgpu_set_pipeline_group": (C.c_int, [_vp, _i32]),
     "specgpu_set_power_iterations": (C.c_int, [_vp, _i32]),
     "specgpu_launch_count": (_i64, [_vp]),

@@ -772,8 +772,8 @@ class HostPipeline:
         self.T = int(rt0.lib.plan_num_segments(self.plans[0], samples))
         self.rows = int(rt0.lib.plan_num_freqs(self.plans[0])) - 1
         self.xd = [rt0.empty((gmax, samples)) for _ in range(streams)]
-        self.Sd = [rt0.empty((gmax, self.rows, self.T)) for _ in range(streams)]
-        self.Dd = [rt0.empty((gmax, self.rows, self.T)) for _ in range(streams)]
+        self.Sd = [rt0.empty_image(gmax, self.rows, self.T) for _ in range(streams)]     # row-pitched: the fast paths
+        self.Dd = [rt0.empty_image(gmax, self.rows, self.T) for _ in range(streams)]
         self.channels, self.samples = channels, samples
         for i, rt in enumerate(self.rts):      # grow the workspaces now (growing synchronises the device)
             with torch.cuda.stream(self.streams[i]):
@@ -793,7 +793,16 @@ class HostPipeline:
             for e in self.events:
                 e.synchronize()
 
-    def submit(self, x_host, D_host, S_host=None):
+    def _download(self, i, dst_host, src_dev):
+        """Pitched device image [n, rows, T] -> dense host array, one strided DMA copy on stream i."""
+        rt = self.rts[i]
+        n = src_dev.shape[0]
+        if not dst_host.is_contiguous():
+            raise ValueError("host result buffers must be contiguous")
+        rt.check(rt.lib.copy_rows(rt._ctx, dst_host.data_ptr(), self.T * 4, src_dev.data_ptr(), int(src_dev.stride(1)) * 4,
+                                  self.T * 4, n * self.rows, C.c_void_p(self.streams[i].cuda_stream)))
+
+    def submit(self, x_host, D_host, S_host=None, copy_only=False):
         """Enqueue one shot (uploads, kernels, downloads) on the worker streams and return a handle whose
         synchronize() returns when its last download has completed.  The shot is ordered only after earlier work on
         the same worker streams, so shots submitted back to back overlap (the downloads of one run under the uploads
@@ -805,10 +814,11 @@ class HostPipeline:
             n = b - a
             with torch.cuda.stream(self.streams[i]):
                 self.xd[i][:n].copy_(x_host[a:b], non_blocking=True)
-                self.rts[i].pipeline_dev(self.plans[i], self.xd[i][:n], self.Sd[i][:n], self.Dd[i][:n], clip=self.clip)
-                D_host[a:b].copy_(self.Dd[i][:n], non_blocking=True)
+                if not copy_only:       # copy_only: the same transfers without the kernels (bench.py's copy ceiling)
+                    self.rts[i].pipeline_dev(self.plans[i], self.xd[i][:n], self.Sd[i][:n], self.Dd[i][:n], clip=self.clip)
+                self._download(i, D_host[a:b], self.Dd[i][:n])
                 if S_host is not None:
-                    S_host[a:b].copy_(self.Sd[i][:n], non_blocking=True)
+                    self._download(i, S_host[a:b], self.Sd[i][:n])
         events = []
         for st in self.streams:
             e = torch.cuda.Event()

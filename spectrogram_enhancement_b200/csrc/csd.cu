@@ -290,8 +290,10 @@ __global__ void __launch_bounds__(kCsdThreads, 1) csd_pairs_staged_kernel(CsdArg
   }
 }
 
+// f0 / nfreq_total: the nfreq columns are bins f0 .. f0 + nfreq - 1 of a one-sided spectrum of nfreq_total bins (a
+// frequency block of a sharded run); only global bins 0 and nfreq_total - 1 are not doubled.
 __global__ void csd_reduce_kernel(const float2* partial, int nchunk, int ni, int C, int nfreq, int sym, int ti, float scale,
-                                  int accumulate, float2* P) {
+                                  int accumulate, int f0, int nfreq_total, float2* P) {
   const int64_t count = (int64_t)ni * C * nfreq;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * blockDim.x) {
     const int f = (int)(idx % nfreq);
@@ -307,7 +309,7 @@ __global__ void csd_reduce_kernel(const float2* partial, int nchunk, int ni, int
       s.y += v.y;
     }
     if (mirror) s.y = -s.y;
-    const float sc = (f == 0 || f == nfreq - 1) ? scale : 2.0f * scale;
+    const float sc = (f0 + f == 0 || f0 + f == nfreq_total - 1) ? scale : 2.0f * scale;
     float2 r = make_float2(s.x * sc, s.y * sc);
     if (accumulate) {            // a later block of segments of the same average (channel-sharded, chunked exchange)
       const float2 p = P[idx];
@@ -398,10 +400,10 @@ static CsdGeom csd_geom(int64_t C, int64_t i0, int64_t ni, int nfreq, int64_t ns
 }
 
 static int launch_csd_reduce(const CsdArgs& a, const CsdGeom& g, int64_t ni, int64_t C, int nfreq, float scale, int accumulate,
-                             float* P, cudaStream_t stream) {
+                             int f0, int nfreq_total, float* P, cudaStream_t stream) {
   const int64_t count = ni * C * nfreq;
   SPECGPU_LAUNCH(csd_reduce_kernel, (unsigned)std::min<int64_t>(ceil_div(count, 256), 148 * 8), 256, 0, stream,
-                 (const float2*)a.partial, g.nchunk, (int)ni, (int)C, nfreq, g.sym, g.ti, scale, accumulate,
+                 (const float2*)a.partial, g.nchunk, (int)ni, (int)C, nfreq, g.sym, g.ti, scale, accumulate, f0, nfreq_total,
                  reinterpret_cast<float2*>(P));
   return (int)cudaGetLastError();
 }
@@ -415,8 +417,10 @@ size_t csd_pairs_workspace_bytes(int64_t C, int64_t ni, int nfreq, int64_t nseg)
 }
 
 int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t nseg_total, int64_t ldf, int nfreq, int64_t i0,
-                     int64_t ni, float scale, int accumulate, float* partial_ws, float* P, cudaStream_t stream) {
+                     int64_t ni, float scale, int accumulate, float* partial_ws, float* P, cudaStream_t stream, int f0,
+                     int nfreq_total) {
   if (C == 0 || ni == 0 || nfreq == 0) return 0;
+  if (nfreq_total <= 0) nfreq_total = nfreq;
   if (C > 64) return -1;
   const CsdGeom g = csd_geom(C, i0, ni, nfreq, nseg, ldf);
   CsdArgs a{};
@@ -451,7 +455,7 @@ int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t nseg_total
     else SPECGPU_CSD_STAGED(4, 1);
 #undef SPECGPU_CSD_STAGED
     if ((err = (int)cudaGetLastError())) return err;
-    return launch_csd_reduce(a, g, ni, C, nfreq, scale / (float)nseg_total, accumulate, P, stream);
+    return launch_csd_reduce(a, g, ni, C, nfreq, scale / (float)nseg_total, accumulate, f0, nfreq_total, P, stream);
   }
   const size_t smem = (size_t)kCsdWarps * (2 * g.ti * kCsdTileJ) * 32 * sizeof(float);
   const dim3 grid((unsigned)ceil_div(nfreq, 32), (unsigned)g.nchunk, (unsigned)g.ngroups);
@@ -466,7 +470,7 @@ int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t nseg_total
   }
   int err = (int)cudaGetLastError();
   if (err) return err;
-  return launch_csd_reduce(a, g, ni, C, nfreq, scale / (float)nseg_total, accumulate, P, stream);
+  return launch_csd_reduce(a, g, ni, C, nfreq, scale / (float)nseg_total, accumulate, f0, nfreq_total, P, stream);
 }
 
 }  // namespace specgpu

@@ -35,6 +35,9 @@ struct StftArgs {
   // set by the caller (0 by default): fraction of the output's cache lines to keep in L2 (evict_last) because a later
   // kernel of the same call reads the output back; the rest streams out (evict_first).  0: no preference.
   float l2_pin;
+  // STFT_MODE_SPECTRA only: write bin k to column (k / fblock_w) * fblock_ld + k % fblock_w (frequency blocks for the
+  // all-to-all of a frequency-sharded CSD); fblock_w == 0: bin k to column k.
+  int fblock_w, fblock_ld;
 };
 
 // stft.cu
@@ -100,8 +103,10 @@ int launch_morph(const void* src, int in_f64, int64_t B, int64_t rows, int64_t c
                  int64_t ldo, uint8_t* u8_out, cudaStream_t st);
 
 // csd.cu
+// X holds bins f0 .. f0 + nfreq - 1 of a one-sided spectrum of nfreq_total bins (0: nfreq itself) in columns 0 .. nfreq - 1.
 int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t nseg_total, int64_t ldf, int nfreq, int64_t i0,
-                     int64_t ni, float scale, int accumulate, float* partial_ws, float* P, cudaStream_t stream);
+                     int64_t ni, float scale, int accumulate, float* partial_ws, float* P, cudaStream_t stream, int f0 = 0,
+                     int nfreq_total = 0);
 int launch_csd_frames(const float* X, int64_t nseg, int64_t ldf, int nfreq, int ci, int cj, int64_t seg_stride, int navg,
                       int64_t nframes, float scale, float* amp, cudaStream_t stream);
 size_t csd_pairs_workspace_bytes(int64_t C, int64_t ni, int nfreq, int64_t nseg);

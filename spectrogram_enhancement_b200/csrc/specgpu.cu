@@ -304,6 +304,24 @@ int specgpu_workspace_reserve(specgpu_ctx* ctx, int64_t bytes) {
 
 int64_t specgpu_launch_count(const specgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int specgpu_copy_rows(specgpu_ctx* ctx, void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes,
+                      int64_t nrows, void* stream) {
+  if (!ctx || row_bytes < 0 || nrows < 0 || dst_pitch < row_bytes || src_pitch < row_bytes) return SPECGPU_ERR_INVALID_ARG;
+  if (row_bytes == 0 || nrows == 0) return SPECGPU_OK;
+  if (!dst || !src) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null pointer");
+#ifdef SPECGPU_EMULATE
+  for (int64_t r = 0; r < nrows; ++r)
+    std::memcpy(static_cast<char*>(dst) + r * dst_pitch, static_cast<const char*>(src) + r * src_pitch, (size_t)row_bytes);
+  (void)stream;
+#else
+  DeviceGuard dev_guard(ctx->device);
+  cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)row_bytes, (size_t)nrows, cudaMemcpyDefault,
+                                    (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, (int)e, "copy_rows");
+#endif
+  return SPECGPU_OK;
+}
+
 int specgpu_set_pipeline_group(specgpu_ctx* ctx, int32_t channels) {
   if (!ctx || channels < 0) return SPECGPU_ERR_INVALID_ARG;
   ctx->pipe_group = channels;
@@ -886,6 +904,44 @@ int specgpu_csd_pairs_block(specgpu_ctx* ctx, const specgpu_plan* plan, const fl
   float* partial = reinterpret_cast<float*>(static_cast<char*>(ctx->ws) + ctx->ws_csd_off);
   CHECK_LAUNCH(ctx, launch_csd_pairs(X, C, nseg, nseg_total, ldf, nfreq, i0, ni, (float)plan->scale, accumulate ? 1 : 0, partial,
                                      P, (cudaStream_t)stream),
+               "csd_pairs", 2);
+  return SPECGPU_OK;
+}
+
+int specgpu_csd_spectra_blocked(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n, int64_t ldx,
+                                float* X, int64_t ldf, int32_t block_w, int32_t block_ld, void* stream) {
+  int rc = check_signal_args(ctx, plan, x, C, n, ldx);
+  if (rc) return rc;
+  const int64_t nseg = num_segments(n, plan->p.nperseg, plan->p.noverlap);
+  if (nseg == 0 || C == 0) return SPECGPU_OK;
+  const int nfreq = plan->p.nperseg / 2 + 1;
+  if (block_w < 1 || block_ld < block_w) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad frequency block (%d bins, pitch %d)", block_w, block_ld);
+  const int64_t nblocks = (nfreq + block_w - 1) / block_w;
+  if (!X || ldf < nblocks * block_ld)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad spectra buffer (ldf=%lld < %lld blocks x %d)", (long long)ldf, (long long)nblocks, block_ld);
+  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, 1.0f, X, ldf, nullptr);
+  a.fblock_w = block_w;
+  a.fblock_ld = block_ld;
+  CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_SPECTRA, a, C, (cudaStream_t)stream), "stft_kernel", 1);
+  return SPECGPU_OK;
+}
+
+int specgpu_csd_pairs_bins(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg,
+                           int64_t nseg_total, int64_t ldf, int64_t f0, int64_t nf, int32_t accumulate, float* P, void* stream) {
+  if (!ctx || !plan) return SPECGPU_ERR_INVALID_ARG;
+  const int nfreq = plan->p.nperseg / 2 + 1;
+  if (C < 0 || nseg < 0 || nseg_total < nseg || f0 < 0 || nf < 0 || f0 + nf > nfreq || ldf < nf)
+    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_pairs_bins: bad shape C=%lld nseg=%lld/%lld ldf=%lld bins [%lld, %lld) of %d", (long long)C,
+                (long long)nseg, (long long)nseg_total, (long long)ldf, (long long)f0, (long long)(f0 + nf), nfreq);
+  if (C > 64) return fail(ctx, SPECGPU_ERR_UNSUPPORTED_SHAPE, "csd_pairs_bins: C=%lld > 64 channels", (long long)C);
+  if (C == 0 || nf == 0) return SPECGPU_OK;
+  if (nseg == 0) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "csd_pairs_bins: no segments to average");
+  if (!X || !P) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null pointer");
+  DeviceGuard dev_guard(ctx->device);
+  int rc = ensure_ws(ctx, csd_pairs_workspace_bytes(C, C, (int)nf, nseg) + 256);
+  if (rc) return rc;
+  CHECK_LAUNCH(ctx, launch_csd_pairs(X, C, nseg, nseg_total, ldf, (int)nf, 0, C, (float)plan->scale, accumulate ? 1 : 0,
+                                     static_cast<float*>(ctx->ws), P, (cudaStream_t)stream, (int)f0, nfreq),
                "csd_pairs", 2);
   return SPECGPU_OK;
 }

@@ -320,6 +320,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
     const float pscale2 = 0.5f * a.scale;            // one-sided doubling for every other bin
     float2* o2 = nullptr;
     if (MODE == STFT_MODE_SPECTRA) o2 = reinterpret_cast<float2*>(a.out) + (b * a.nseg + seg) * a.ld_out;
+    const float fblock_inv = (MODE == STFT_MODE_SPECTRA && a.fblock_w > 0) ? 1.0f / (float)a.fblock_w : 0.f;
     float rmin = INFINITY, rmax = -INFINITY;         // this segment's extremes (merged below if the segment is live)
     auto bin_pair = [&](int k, float2 zk, float2 zm, int offk, int offm, auto generic_c) {
       constexpr bool GENERIC = decltype(generic_c)::value;     // 0 < k < M/2: two distinct, doubled bins
@@ -333,8 +334,14 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       const bool two = GENERIC || km != k;
       if (MODE == STFT_MODE_SPECTRA) {
         if (live) {
-          o2[k] = make_float2(0.5f * xk.x, 0.5f * xk.y);
-          if (two) o2[km] = make_float2(0.5f * xm.x, 0.5f * xm.y);
+          int ck = k, cm = km;
+          if (a.fblock_w > 0) {     // blocked columns; (k + 0.5) / w in float is exact for these small integers
+            const int hk = (int)(((float)k + 0.5f) * fblock_inv), hm = (int)(((float)km + 0.5f) * fblock_inv);
+            ck = hk * a.fblock_ld + (k - hk * a.fblock_w);
+            cm = hm * a.fblock_ld + (km - hm * a.fblock_w);
+          }
+          o2[ck] = make_float2(0.5f * xk.x, 0.5f * xk.y);
+          if (two) o2[cm] = make_float2(0.5f * xm.x, 0.5f * xm.y);
         }
       } else if (MODE == STFT_MODE_COMPLEX) {
         *reinterpret_cast<float2*>(s_tile + offk) = make_float2(xk.x * cscale, xk.y * cscale);

@@ -18,8 +18,8 @@ import torch.distributed as dist
 
 from . import api
 
-__all__ = ["shot_range", "channel_block", "segment_range", "csd_allpairs_sharded", "csd_allpairs_segment_sharded",
-           "pipeline_sharded"]
+__all__ = ["shot_range", "channel_block", "segment_range", "frequency_block", "csd_allpairs_sharded",
+           "csd_allpairs_freq_sharded", "csd_allpairs_segment_sharded", "pipeline_sharded"]
 
 
 def shot_range(rank: int, world: int, n_shots: int):
@@ -83,7 +83,8 @@ def csd_allpairs_sharded(x_local, fs=1.0, window="hann", nperseg=256, noverlap=N
             rt.check(rt.lib.csd_spectra(rt._ctx, plan, xs.data_ptr(), Cl, xs.shape[1], api._ld(xd), X_loc.data_ptr(), ldf,
                                         rt.stream()))
             if world > 1:
-                dist.all_gather_into_tensor(X_all, X_loc.clone(), group=group)
+                # in place: rank r's block of the gather buffer is X_loc itself (no staging copy)
+                dist.all_gather_into_tensor(X_all.view(-1), X_loc.reshape(-1), group=group)
             if cuda:
                 ev = torch.cuda.Event()
                 ev.record(side)
@@ -97,6 +98,61 @@ def csd_allpairs_sharded(x_local, fs=1.0, window="hann", nperseg=256, noverlap=N
         if cuda:
             X_all.record_stream(main)
     f = np.fft.rfftfreq(int(nperseg), 1.0 / fs)
+    return f, rt.ret(torch.view_as_complex(P), as_torch)
+
+
+def frequency_block(rank: int, world: int, n_freqs: int):
+    """Bins [f0, f1) of `rank` when the one-sided spectrum is cut into `world` blocks of ceil(n_freqs / world) bins (the
+    last blocks may be short or empty)."""
+    w = -(-n_freqs // world)
+    f0 = min(rank * w, n_freqs)
+    return f0, min(f0 + w, n_freqs)
+
+
+def csd_allpairs_freq_sharded(x_local, fs=1.0, window="hann", nperseg=256, noverlap=None, detrend="constant",
+                              scaling="density", group=None, runtime=None):
+    """All-pairs Welch CSD of a channel stack sharded by channel block, with the OUTPUT sharded by frequency: this rank
+    holds `x_local[Cl, N]` and returns (f[f0:f1], P[C, C, f1 - f0]) for its block of bins `frequency_block(rank, ...)`,
+    C = world * Cl.
+
+    Pair products are independent per frequency bin, so instead of gathering every rank's full spectra everywhere
+    (`csd_allpairs_sharded`: C T F values received per rank) each rank transforms its channels and sends rank h only
+    bins `frequency_block(h)` of them -- one all-to-all in which a rank receives C T F / world values -- and then forms
+    ALL pairs for its bins (specgpu_csd_pairs_bins)."""
+    rt = runtime if runtime is not None else api.default_runtime()
+    if noverlap is None:
+        noverlap = int(nperseg) // 2
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    plan = rt.plan(nperseg, noverlap, fs, window, scaling, detrend)
+    xd, as_torch = rt.to_device(x_local)
+    if xd.dim() != 2:
+        raise ValueError("csd_allpairs_freq_sharded expects x_local[Cl, N]")
+    Cl, n = xd.shape
+    C = world * Cl
+    F = rt.lib.plan_num_freqs(plan)
+    T = rt.lib.plan_num_segments(plan, n)
+    if T == 0:
+        raise ValueError("record shorter than nperseg")
+    wf = -(-F // world)                         # bins per block
+    ldb = (wf + 15) & ~15                       # 128-byte rows of a block
+    ldf = world * ldb                           # spectra rows: block h starts at column h * ldb
+    # spectra of this rank's channels, laid out [Cl, T, world, ldb] with bin k at block k // wf, column k % wf
+    X = rt.empty((Cl, T, ldf, 2))
+    rt.check(rt.lib.csd_spectra_blocked(rt._ctx, plan, xd.data_ptr(), Cl, n, api._ld(xd), X.data_ptr(), ldf, wf, ldb,
+                                        rt.stream()))
+    if world > 1:
+        send = X.view(Cl, T, world, ldb, 2).permute(2, 0, 1, 3, 4).contiguous()      # [world][Cl, T, ldb]
+        recv = torch.empty_like(send)                                                 # [world (source)][Cl, T, ldb]
+        dist.all_to_all_single(recv, send, group=group)
+        Xf = recv                                # == X_f[C, T, ldb]: channels in rank order
+    else:
+        Xf = X
+    f0, f1 = frequency_block(rank, world, F)
+    P = rt.empty((C, C, max(f1 - f0, 0), 2))
+    if f1 > f0:
+        rt.check(rt.lib.csd_pairs_bins(rt._ctx, plan, Xf.data_ptr(), C, T, T, ldb, f0, f1 - f0, 0, P.data_ptr(), rt.stream()))
+    f = np.fft.rfftfreq(int(nperseg), 1.0 / fs)[f0:f1]
     return f, rt.ret(torch.view_as_complex(P), as_torch)
 
 
