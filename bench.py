@@ -276,8 +276,9 @@ def run_ours(args):
         Dr = oc.clip(oc.denoiseSignal(Sr))                 # the pure oracle chain, not the oracle on our S
         parity = {"spec_max_abs_err": float(np.abs(Sg - Sr).max()),
                   "denoise_max_err_rel_to_max": float(np.abs(Dg - Dr).max() / np.abs(Dr).max())}
-        assert parity["spec_max_abs_err"] < 1e-4 and parity["denoise_max_err_rel_to_max"] < 1e-3, parity
-        assert int(info[:, 3].max().item()) == 0
+        if not os.environ.get("SPECGPU_BENCH_NOASSERT"):       # (timing ablations produce wrong results on purpose)
+            assert parity["spec_max_abs_err"] < 1e-4 and parity["denoise_max_err_rel_to_max"] < 1e-3, parity
+            assert int(info[:, 3].max().item()) == 0
 
     def timed(fn, steps, warm):
         for i in range(warm):

@@ -184,11 +184,11 @@ int specgpu_csd_pairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X
 int specgpu_csd_pairs_block(specgpu_ctx* ctx, const specgpu_plan* plan, const float* X, int64_t C, int64_t nseg,
                             int64_t nseg_total, int64_t ldf, int64_t i0, int64_t ni, int32_t accumulate, float* P,
                             void* stream);
-/* specgpu_csd_spectra with the bins of a row grouped into blocks of block_w bins, block h starting at column
- * h * block_ld (block_ld >= block_w, ldf >= ceil(nfreq / block_w) * block_ld): X viewed as [C][nseg][nblocks][block_ld] is
- * what a frequency-block all-to-all sends (block h goes to rank h). */
+/* specgpu_csd_spectra with the output cut into frequency blocks of block_w bins, BLOCK-MAJOR:
+ * X[nblocks][C][nseg][block_ld] (nblocks = ceil(nfreq / block_w), block_ld >= block_w), bin k of a segment at block
+ * k / block_w, column k % block_w.  Plane h is exactly what a frequency-block all-to-all sends to rank h. */
 int specgpu_csd_spectra_blocked(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n,
-                                int64_t ldx, float* X, int64_t ldf, int32_t block_w, int32_t block_ld, void* stream);
+                                int64_t ldx, float* X, int32_t block_w, int32_t block_ld, void* stream);
 /* All pairs over a BLOCK OF FREQUENCY BINS: X[C][nseg][ldf] holds bins f0 .. f0 + nf - 1 of every channel's one-sided
  * spectra in columns 0 .. nf - 1 (the layout a frequency-block all-to-all of specgpu_csd_spectra outputs produces on
  * each rank; pair products are independent per bin); P[C][C][nf] (+)= sum_t conj(X_i) X_j * scale / nseg_total with the

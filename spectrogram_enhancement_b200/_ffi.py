@@ -67,7 +67,7 @@ PROTOTYPES = {
     "specgpu_csd_spectra": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "specgpu_csd_pairs": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "specgpu_csd_pairs_block": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _vp]),
-    "specgpu_csd_spectra_blocked": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "specgpu_csd_spectra_blocked": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _vp]),
     "specgpu_csd_pairs_bins": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _vp]),
     "specgpu_csd_frames": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i64, _vp, _vp]),
     "specgpu_csd_allpairs": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),

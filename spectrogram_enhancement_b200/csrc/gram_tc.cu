@@ -23,10 +23,18 @@
 //
 // The emulation build (tests only, no tensor cores on a CPU) replaces the kernel body by a scalar
 // loop with the same TF32 operand rounding and the same partial layout.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
 namespace specgpu {
+
+#if defined(SPECGPU_EMULATE)
+#define SPECGPU_GRID_CONSTANT
+#else
+#define SPECGPU_GRID_CONSTANT __grid_constant__
+#endif
 
 constexpr int kGtcStages = 6;             // 32 KB slabs in the ring (rows = 256): 192 KB of loads in flight per SM
 constexpr int kGtcChunk = 32;            // K elements per slab (128 bytes of tf32 per row)
@@ -45,7 +53,10 @@ struct GramTcArgs {
   float* partial;           // [grid][2][128][PW] with PW = rows + (rows == 256 ? 128 : 0)
 };
 
+// A partial is [128][pitch]: the accumulators (logical width 384 = [G00 | G01 | G11] for 256 rows, `rows` for 128) and, in
+// the next two columns, the row sums of rows r and 128 + r (the TMA-fed kernel's raw-operand route; unused otherwise).
 __host__ __device__ inline int gram_tc_partial_width(int rows) { return rows == 256 ? 384 : rows; }
+__host__ __device__ inline int gram_tc_partial_pitch(int rows) { return gram_tc_partial_width(rows) + 4; }
 
 // Round to TF32 (10 mantissa bits), nearest with ties away from zero -- what cvt.rna.tf32.f32 does -- as two integer
 // instructions on the sign-magnitude bit pattern (the cvt expands to about four).
@@ -110,7 +121,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 template <int ROWS>
 __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
-  constexpr int PW = (ROWS == 256) ? 384 : ROWS;
+  constexpr int PW = (ROWS == 256) ? 384 : ROWS;   // accumulator columns
+  constexpr int PP = PW + 4;                        // row pitch of a partial
   const int tid = threadIdx.x;
   const int64_t total = a.B * a.nchunk;
   const int64_t g0 = (int64_t)blockIdx.x * a.per;
@@ -118,7 +130,7 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
   if (g0 >= g1) return;                          // uniform over the CTA
   const int64_t b_first = g0 / a.nchunk;
   const int nsegs = (int)((g1 - 1) / a.nchunk - b_first) + 1;     // 1 or 2 (per <= nchunk)
-  float* part0 = a.partial + (size_t)blockIdx.x * 2 * 128 * PW;
+  float* part0 = a.partial + (size_t)blockIdx.x * 2 * 128 * PP;
 
 #if defined(SPECGPU_EMULATE)
   // scalar stand-in with identical operand rounding, work split and partial layout
@@ -145,7 +157,7 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
         }
         acc += round_tf32(xa) * round_tf32(xb);
       }
-      part0[(size_t)sg * 128 * PW + i] = acc;
+      part0[(size_t)sg * 128 * PP + (size_t)r * PP + c] = acc;
     }
   }
 #else
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
       // ================= epilogue (all worker warps): TMEM -> registers -> partial[sg][128][PW] =================
       mbar_wait(smem_u32(&s_accum), (uint32_t)sg & 1);
       tc_fence_after();
-      float* part = part0 + (size_t)sg * 128 * PW;
+      float* part = part0 + (size_t)sg * 128 * PP;
       const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
       constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the warps of a quarter
       // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns); a per-warp [32][33] tile transposes it so
@@ -326,9 +338,9 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
         __syncwarp();
-        float* dst = part + (size_t)(q * 32) * PW + c + lane;
+        float* dst = part + (size_t)(q * 32) * PP + c + lane;
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) dst[(size_t)r * PW] = tr[r * 33 + lane];
+        for (int r = 0; r < 32; ++r) dst[(size_t)r * PP] = tr[r * 33 + lane];
         __syncwarp();
       }
       tc_fence_before();
@@ -346,11 +358,254 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tc_kernel(GramTcArgs a) {
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------------
+// TMA-fed variant (row-pitched images: 16-byte aligned rows).  Nobody touches the operands in registers or rewrites
+// them in shared memory: one thread issues cp.async.bulk.tensor loads of [rows x 32] boxes straight into the ring
+// in the SWIZZLE_128B K-major layout (columns past the end are zero-filled by the TMA unit), one thread issues the
+// MMAs on the RAW fp32 bits (kind::tf32 reads the upper 19 bits), and the min-max normalisation is applied
+// algebraically afterwards: with r = rowsums and T columns,
+//     (L - m 1 1^T)(L - m 1 1^T)^T = L L^T - m (r 1^T + 1 r^T) + m^2 T 1 1^T,
+// where the row sums come out of the same pipeline as two 16-column MMAs against a slab of ones (so the identity
+// holds exactly for the truncated operands).  gram_eig_kernel applies the correction while it sums the partials.
+// ------------------------------------------------------------------------------------------------------
+// A stage of the TMA-fed ring holds kGtmChunk = 64 columns as two [rows x 32] boxes: a row then contributes 256
+// contiguous bytes per visit instead of 128 (the images' rows are 15.7 KB apart, and DRAM pages like longer bursts).
+constexpr int kGtmChunk = 64;
+constexpr int kGtmStages = 3;
+
+struct GramTmaArgs {
+  int64_t B, cols, nchunk, per;
+  int tiled;               // S is the tiled scratch image (common.cuh): tile t of matrix b is the box at row t * rows
+  int debug;               // timing ablations (SPECGPU_GRAM_DEBUG): 1 = no MMAs, 2 = no epilogue stores (results invalid)
+  float l2_pin;
+  float* partial;
+};
+
+#if !defined(SPECGPU_EMULATE)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+#endif
+
+template <int ROWS>
+__global__ void __launch_bounds__(kGtcThreads, 1) gram_tma_kernel(const GramTmaArgs a, const float* S, int64_t ld,
+                                                                  const SPECGPU_GRID_CONSTANT TensorMap tmap) {
+  constexpr int PW = (ROWS == 256) ? 384 : ROWS;
+  constexpr int PP = PW + 4;
+  const int tid = threadIdx.x;
+  // CTA i = part (i % k) of matrix i / k, k = CTAs per matrix: chunks [part * per, min((part + 1) * per, nchunk)) of that
+  // matrix.  Expressed in the global chunk numbering g = b * nchunk + c the loops below share with the cp.async kernel.
+  const int64_t kparts = (a.nchunk + a.per - 1) / a.per;
+  const int64_t b_first = blockIdx.x / kparts;
+  const int64_t g0 = b_first * a.nchunk + (blockIdx.x % kparts) * a.per;
+  const int64_t g1 = (g0 + a.per < (b_first + 1) * a.nchunk) ? g0 + a.per : (b_first + 1) * a.nchunk;
+  if (g0 >= g1) return;                          // uniform over the CTA
+  constexpr int nsegs = 1;
+  float* part0 = a.partial + (size_t)blockIdx.x * 128 * PP;
+#if defined(SPECGPU_EMULATE)
+  // scalar stand-in: truncated-to-TF32 raw operands, same work split and partial layout (row sums in columns PW, PW+1)
+  auto trunc = [](float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); };
+  for (int sg = 0; sg < nsegs; ++sg) {
+    const int64_t b = b_first + sg;
+    const int64_t lo = (g0 > b * a.nchunk ? g0 : b * a.nchunk) - b * a.nchunk;
+    const int64_t hi = (g1 < (b + 1) * a.nchunk ? g1 : (b + 1) * a.nchunk) - b * a.nchunk;
+    auto at = [&](int r, int64_t k) { return S[img_off(b, r, k, ROWS, ld)]; };
+    for (int i = tid; i < 128 * (PW + 2); i += kGtcThreads) {
+      const int r = i / (PW + 2), c = i % (PW + 2);
+      float acc = 0.f;
+      if (c < PW) {
+        const int ra = (c < ROWS) ? r : 128 + r;
+        const int rb = (c < ROWS) ? c : c - ROWS + 128;
+        for (int64_t k = lo * kGtmChunk; k < hi * kGtmChunk && k < a.cols; ++k)
+          acc += trunc(at(ra, k)) * trunc(at(rb, k));
+      } else if (c == PW || ROWS == 256) {
+        const int ra = (c == PW) ? r : 128 + r;
+        for (int64_t k = lo * kGtmChunk; k < hi * kGtmChunk && k < a.cols; ++k) acc += trunc(at(ra, k));
+      }
+      part0[(size_t)sg * 128 * PP + (size_t)r * PP + c] = acc;
+    }
+  }
+#else
+  (void)S;
+  (void)ld;
+  SPECGPU_DYN_SMEM(smem);   // SWIZZLE_128B atoms need 1024-byte alignment (re-aligned below)
+  constexpr int BOX = ROWS * 128;   // bytes of one [rows x 32] box
+  constexpr int SLAB = 2 * BOX;     // bytes per stage (two boxes)
+  constexpr int kGtcStages = kGtmStages;   // (shadows the cp.async kernel's ring depth)
+  __shared__ __align__(8) uint64_t s_full[kGtcStages];     // the TMA boxes of this stage have landed
+  __shared__ __align__(8) uint64_t s_empty[kGtcStages];    // the tensor core has consumed the slab
+  __shared__ __align__(8) uint64_t s_accum;
+  __shared__ uint32_t s_tmem;
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t TMEM_COLS = (ROWS == 256) ? 512 : 128;
+  constexpr int kSegBarrier = 1;                    // named barrier: every worker warp is done with a segment
+  // Row sums of the (truncated) operands for the algebraic normalisation: the worker warps have nothing to do during the
+  // main loop, so warps 1 .. ROWS/32 read every landed stage back from shared memory, one thread per image row
+  // (MMAs against a slab of ones did the same on the tensor pipe but cost as much as a third of the Gram MMAs).
+  constexpr int kRsWarps = ROWS / 32;
+  __shared__ float s_rowsum[ROWS];
+
+  if (tid == 0) {
+    for (int i = 0; i < kGtcStages; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_empty[i]), 1 + kRsWarps);      // the MMA commit + one arrival per row-sum warp
+    }
+    mbar_init(smem_u32(&s_accum), 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap);
+  }
+  if (warp == kGtcWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  unsigned char* slabs = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  int64_t g = g0;                                   // first chunk of the current segment
+  for (int sg = 0; sg < nsegs; ++sg) {
+    const int64_t b = b_first + sg;
+    const int64_t gend = (g1 < (b + 1) * a.nchunk) ? g1 : (b + 1) * a.nchunk;
+    if (warp == 0 && lane == 0) {
+      // ================= producer: one TMA box per chunk =================
+      const uint64_t pol = a.l2_pin > 0.f ? l2_policy_pin_fraction(a.l2_pin) : l2_policy_evict_normal();
+      for (int64_t gg = g; gg < gend; ++gg) {
+        const int64_t ci = gg - g0;
+        const int stage = (int)(ci % kGtcStages);
+        const uint32_t use = (uint32_t)(ci / kGtcStages);
+        if (use > 0) mbar_wait(smem_u32(&s_empty[stage]), (use - 1) & 1);
+        if (a.debug & 4) {     // ablation: no loads (the MMAs run on whatever the ring holds)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[stage])) : "memory");
+          continue;
+        }
+        mbar_arrive_expect_tx(smem_u32(&s_full[stage]), SLAB);
+        const int kcol = (int)(gg - b * a.nchunk) * kGtmChunk;
+        if (a.tiled) {    // two contiguous [rows x 32] tiles (a tile past the last one is out of bounds: zero-filled)
+          const int t0 = kcol >> 5;
+          tma_load_3d(smem_u32(slabs + stage * SLAB), &tmap, 0, t0 * ROWS, (int)b, smem_u32(&s_full[stage]), pol);
+          tma_load_3d(smem_u32(slabs + stage * SLAB + BOX), &tmap, 0, (t0 + 1) * ROWS, (int)b, smem_u32(&s_full[stage]), pol);
+        } else {
+          tma_load_3d(smem_u32(slabs + stage * SLAB), &tmap, kcol, 0, (int)b, smem_u32(&s_full[stage]), pol);
+          tma_load_3d(smem_u32(slabs + stage * SLAB + BOX), &tmap, kcol + 32, 0, (int)b, smem_u32(&s_full[stage]), pol);
+        }
+      }
+    } else if (warp == kGtcWarps) {
+      // ================= MMA issuer warp: lane 0 issues =================
+      const uint32_t idesc1 = umma_idesc_tf32(128, ROWS);
+      const uint32_t idesc2 = umma_idesc_tf32(128, 128);
+      if (lane == 0) {
+        for (int64_t gg = g; gg < gend; ++gg) {
+          const int64_t ci = gg - g0;
+          const int stage = (int)(ci % kGtcStages);
+          const uint32_t use = (uint32_t)(ci / kGtcStages);
+          mbar_wait(smem_u32(&s_full[stage]), use & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < kGtmChunk / 8; ++ks) {   // K = 8 tf32 (32 bytes) per instruction; 4 steps per box
+            const uint32_t base = smem_u32(slabs + stage * SLAB + (ks >> 2) * BOX);
+            const uint32_t accumulate = (gg > g || ks > 0) ? 1u : 0u;
+            if (a.debug & 1) continue;
+            const uint64_t d_lo = umma_desc_k_sw128(base + (ks & 3) * 32);
+            umma_tf32(tmem_base, d_lo, d_lo, idesc1, accumulate);
+            if (ROWS == 256) {
+              const uint64_t d_hi = umma_desc_k_sw128(base + 128 * 128 + (ks & 3) * 32);
+              umma_tf32(tmem_base + 256, d_hi, d_hi, idesc2, accumulate);
+            }
+          }
+          umma_commit(smem_u32(&s_empty[stage]));   // slab may be refilled once these MMAs retire
+        }
+        umma_commit(smem_u32(&s_accum));            // accumulators of this segment complete
+      }
+      __syncwarp();
+    } else if (warp >= 1 && warp <= kRsWarps) {
+      // ================= row sums over every stage as it lands =================
+      // warp w covers rows 32 (w-1) .. +31; 8 lanes share a row (one 16-byte chunk each), so a warp load reads 4 whole
+      // rows = 512 contiguous bytes (conflict-free); lane (row sub-index s = lane / 8) accumulates rows 4 i + s, i < 8.
+      const int rbase = (warp - 1) * 32, sub = lane >> 3, ch = lane & 7;
+      float rs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rs[i] = 0.f;
+      for (int64_t gg = g; gg < gend; ++gg) {
+        const int64_t ci = gg - g0;
+        const int stage = (int)(ci % kGtcStages);
+        const uint32_t use = (uint32_t)(ci / kGtcStages);
+        mbar_wait(smem_u32(&s_full[stage]), use & 1);
+        // the 16-byte chunks of a row are swizzled within the row: the order does not matter for a sum.  Truncate like
+        // the tensor core (kind::tf32 drops the low 13 mantissa bits) so that the identity in the header holds exactly
+        // for what the MMAs accumulate.
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const unsigned char* bx = slabs + stage * SLAB + h * BOX + (rbase + sub) * 128 + ch * 16;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(bx + i * 4 * 128);
+            rs[i] += (__uint_as_float(__float_as_uint(v.x) & 0xffffe000u) + __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)) +
+                     (__uint_as_float(__float_as_uint(v.z) & 0xffffe000u) + __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[stage])) : "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = rs[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (ch == 0) s_rowsum[rbase + 4 * i + sub] = v;
+      }
+    }
+    if (warp < kGtcWarps) {
+      __syncwarp();
+      // ================= epilogue (all worker warps): TMEM -> registers -> partial[sg][128][PP] =================
+      mbar_wait(smem_u32(&s_accum), (uint32_t)sg & 1);
+      tc_fence_after();
+      float* part = part0 + (size_t)sg * 128 * PP;
+      const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+      constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the warps of a quarter
+      // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns = 128 contiguous bytes of its partial
+      // row): eight 16-byte stores per lane, no trip through shared memory
+      for (int cg = warp >> 2; cg < NCG && !(a.debug & 2); cg += kGtcWarps / 4) {
+        const int c = cg * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        float4* dst = reinterpret_cast<float4*>(part + (size_t)(q * 32 + lane) * PP + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+      }
+      named_bar_sync(kSegBarrier + 1, kGtcWarps * 32);      // the row-sum warps have published s_rowsum
+      if (warp < 4) {
+        part[(size_t)(warp * 32 + lane) * PP + PW] = s_rowsum[warp * 32 + lane];
+        part[(size_t)(warp * 32 + lane) * PP + PW + 1] = (ROWS == 256) ? s_rowsum[128 + warp * 32 + lane] : 0.f;
+      }
+      tc_fence_before();
+      // every worker warp has read its part of TMEM and is done with its transpose tile before the next segment's
+      // boxes land in the ring and its first MMA overwrites the accumulators
+      if (sg + 1 < nsegs) named_bar_sync(kSegBarrier, kGtcWarps * 32);
+    }
+    g = gend;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kGtcWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+#endif
+}
+
 // G[b] = sum of the (CTA, segment) partials that cover matrix b, in CTA order; G10 mirrored from G01.
 // One thread per four consecutive partial elements (pr, pc..pc+3): float4 reads along pc, float4 writes of the
 // direct blocks; the mirrored block is the only scattered write (1/4 of a 256 KB matrix).
 __global__ void gram_reduce_kernel(const float* partial, int rows, int64_t nchunk, int64_t per, float* G) {
-  const int PW = gram_tc_partial_width(rows);
+  const int PW = gram_tc_partial_width(rows), PP = gram_tc_partial_pitch(rows);
   const int PW4 = PW / 4;
   const int64_t b = blockIdx.y;
   const int i0 = (int)((b * nchunk) / per), i1 = (int)(((b + 1) * nchunk - 1) / per);
@@ -363,7 +618,7 @@ __global__ void gram_reduce_kernel(const float* partial, int rows, int64_t nchun
   for (int cta = i0; cta <= i1; ++cta) {
     // a CTA whose range starts before this matrix began in matrix b-1: matrix b is its second segment
     const int sg = ((int64_t)cta * per < bstart) ? 1 : 0;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)(cta * 2 + sg) * 128 + pr) * PW + pc));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)(cta * 2 + sg) * 128 + pr) * PP + pc));
     s.x += v.x;
     s.y += v.y;
     s.z += v.z;
@@ -386,9 +641,17 @@ struct GramTcGeom {
   int64_t nchunk, per, grid;
 };
 
-static GramTcGeom gram_tc_geom(int64_t B, int64_t cols, int num_sms) {
+static GramTcGeom gram_tc_geom(int64_t B, int64_t cols, int num_sms, int chunk = kGtcChunk) {
   GramTcGeom g;
-  g.nchunk = ceil_div(cols, kGtcChunk);
+  g.nchunk = ceil_div(cols, chunk);
+  if (chunk == kGtmChunk) {
+    // TMA-fed kernel: a whole number of CTAs per matrix (3 for 40 matrices on 148 SMs), so that no CTA straddles two
+    // matrices (one epilogue per CTA) and every matrix has the same, small number of partials to sum
+    const int64_t k = std::max<int64_t>(1, std::min<int64_t>(num_sms / std::max<int64_t>(B, 1), g.nchunk));
+    g.per = ceil_div(g.nchunk, k);
+    g.grid = B * ceil_div(g.nchunk, g.per);
+    return g;
+  }
   const int64_t total = B * g.nchunk;
   g.per = std::min<int64_t>(std::max<int64_t>(ceil_div(total, num_sms), 1), g.nchunk);   // <= nchunk: at most 2 segments per CTA
   g.grid = ceil_div(total, g.per);
@@ -397,20 +660,61 @@ static GramTcGeom gram_tc_geom(int64_t B, int64_t cols, int num_sms) {
 
 size_t gram_tc_workspace_bytes(int64_t B, int64_t rows) {
   // grid <= max(B, num_sms) + 1 CTAs, two partial slots each
-  return (size_t)(std::max<int64_t>(B, 160) + 1) * 2 * 128 * gram_tc_partial_width((int)rows) * sizeof(float) + 256;
+  return (size_t)(std::max<int64_t>(B, 160) + 8) * 2 * 128 * gram_tc_partial_pitch((int)rows) * sizeof(float) + 256;
 }
 
 bool gram_tc_supported(int64_t rows) { return rows == 128 || rows == 256; }
 
-void gram_tc_geometry(int64_t B, int64_t cols, int num_sms, int64_t* nchunk, int64_t* per) {
-  const GramTcGeom g = gram_tc_geom(B, cols, std::min(num_sms, 160));
+void gram_tc_geometry(int64_t B, int64_t cols, int num_sms, int tma, int64_t* nchunk, int64_t* per) {
+  const GramTcGeom g = gram_tc_geom(B, cols, std::min(num_sms, 160), tma ? kGtmChunk : kGtcChunk);
   *nchunk = g.nchunk;
   *per = g.per;
+}
+
+// Raw-operand Gram partials through the TMA-fed kernel (see gram_tma_kernel); returns 1 when the layout does not allow a
+// tensor map (rows not 16-byte aligned), 0 on success, otherwise a CUDA error.  *raw_out tells the consumer
+// (launch_gram_eig) that the partials are of the un-normalised operands and carry row sums.
+int launch_gram_tma(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* partial_ws, int num_sms,
+                    cudaStream_t stream, float l2_pin) {
+  if (B == 0) return 0;
+  const GramTcGeom g = gram_tc_geom(B, cols, std::min(num_sms, 160), kGtmChunk);
+  TensorMap tmap{};
+#if !defined(SPECGPU_EMULATE)
+  if (ld < 0) {
+    const uint64_t nt = (uint64_t)(-ld);
+    if (!make_tensor_map_f32_3d(&tmap, S, kTileCols, nt * rows, (uint64_t)B, kTileCols, nt * rows * kTileCols, 32, (uint32_t)rows, 128))
+      return 1;
+  } else if (!make_tensor_map_f32_3d(&tmap, S, (uint64_t)cols, (uint64_t)rows, (uint64_t)B, (uint64_t)ld, (uint64_t)rows * ld, 32,
+                                     (uint32_t)rows, 128)) {
+    return 1;
+  }
+#endif
+  GramTmaArgs a{};
+  a.tiled = ld < 0 ? 1 : 0;
+  a.B = B;
+  a.cols = cols;
+  a.nchunk = g.nchunk;
+  a.per = g.per;
+  a.l2_pin = l2_pin;
+  a.partial = partial_ws;
+  if (const char* env = std::getenv("SPECGPU_GRAM_DEBUG")) a.debug = std::atoi(env);
+  const size_t smem = (size_t)kGtmStages * 2 * rows * 128 + 1024;
+  if (rows == 256) {
+    cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    SPECGPU_LAUNCH(gram_tma_kernel<256>, (unsigned)g.grid, kGtcThreads, smem, stream, a, S, ld, tmap);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    SPECGPU_LAUNCH(gram_tma_kernel<128>, (unsigned)g.grid, kGtcThreads, smem, stream, a, S, ld, tmap);
+  }
+  return (int)cudaGetLastError();
 }
 
 int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const MinMaxWord* minmax,
                    float* partial_ws, float* G, int num_sms, cudaStream_t stream, float l2_pin) {
   if (B == 0) return 0;
+  if (ld < 0) return (int)cudaErrorInvalidValue;     // the cp.async-fed kernel reads row-major images only
   const GramTcGeom g = gram_tc_geom(B, cols, std::min(num_sms, 160));
   GramTcArgs a{};
   a.S = S;

@@ -35,9 +35,11 @@ struct StftArgs {
   // set by the caller (0 by default): fraction of the output's cache lines to keep in L2 (evict_last) because a later
   // kernel of the same call reads the output back; the rest streams out (evict_first).  0: no preference.
   float l2_pin;
-  // STFT_MODE_SPECTRA only: write bin k to column (k / fblock_w) * fblock_ld + k % fblock_w (frequency blocks for the
-  // all-to-all of a frequency-sharded CSD); fblock_w == 0: bin k to column k.
-  int fblock_w, fblock_ld;
+  // STFT_MODE_SPECTRA only: write bin k to element (k / fblock_w) * fblock_stride + k % fblock_w of the segment's row
+  // (frequency blocks for the all-to-all of a frequency-sharded CSD; fblock_stride = the block pitch inside a row, or
+  // the size of a whole [C][nseg][ld_out] plane for block-major output); fblock_w == 0: bin k to column k.
+  int fblock_w;
+  int64_t fblock_stride;
 };
 
 // stft.cu
@@ -67,8 +69,12 @@ int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int6
 int launch_eig_power(const float* G, int64_t B, int n, int max_iter /* <= 0: default */, float* U, float* lam, int32_t* plan, cudaStream_t stream);
 // split-K reduce of launch_gram_tc's partials fused with the leading-pair power iteration (n in {128, 256}); G itself is
 // never written.  (nchunk, per) = gram_tc_geometry of the launch that produced the partials.
+// raw_minmax != nullptr: the partials are of the raw log image (launch_gram_tma) and G of the normalised image is formed as
+// G_raw - m (r 1^T + 1 r^T) + m^2 cols 1 1^T with m = min of the matrix and r its row sums (scale 1 / (max - min)^2 dropped:
+// eigenvectors do not care); raw_minmax == nullptr: the partials already are of the operands to decompose.
 int launch_gram_eig(const float* partial, int64_t nchunk, int64_t per, int64_t B, int n, int max_iter, float* U, float* lam,
-                    int32_t* plan, cudaStream_t stream);
+                    int32_t* plan, cudaStream_t stream, const MinMaxWord* raw_minmax = nullptr, int64_t cols = 0,
+                    int per_matrix = 0 /* partials written by launch_gram_tma */);
 size_t jacobi_workspace_bytes(int64_t B, int n);
 bool eig_jacobi_f64_supported(int n);
 int launch_eig_jacobi(const void* G, int g_f64, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan, void* ws,
@@ -89,7 +95,11 @@ size_t gram_tc_workspace_bytes(int64_t B, int64_t rows);
 // G == nullptr: leave the split-K partials in partial_ws (launch_gram_eig consumes them) and skip the reduce launch.
 int launch_gram_tc(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const MinMaxWord* minmax,
                    float* partial_ws, float* G, int num_sms, cudaStream_t stream, float l2_pin = 0.f);
-void gram_tc_geometry(int64_t B, int64_t cols, int num_sms, int64_t* nchunk, int64_t* per);
+void gram_tc_geometry(int64_t B, int64_t cols, int num_sms, int tma /* launch_gram_tma wrote the partials */, int64_t* nchunk, int64_t* per);
+// TMA-fed Gram partials of the RAW (un-normalised) operands plus their row sums (row-pitched S only): 0 = launched,
+// 1 = layout not describable by a tensor map (use launch_gram_tc), else a CUDA error.
+int launch_gram_tma(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* partial_ws, int num_sms,
+                    cudaStream_t stream, float l2_pin = 0.f);
 
 // imgchain.cu (the cv2 chain: gaussblr / meansub / morph)
 size_t imgchain_workspace_bytes(int64_t B, int64_t rows, int64_t cols);

@@ -649,16 +649,36 @@ SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
 // also writes the normalised image back over S.
 // `fallback`: after the power iteration also enqueue the full float64 solver for the matrices whose iteration did not
 // converge (info[3] would be 1); three launches that exit at once when every matrix converged.
+// `Limg` / `ldL` (pipeline only, with raw_mm): the raw log image lives in a separate scratch buffer (tiled when ldL < 0,
+// see img_off) and S is only written -- by the rank-1 projection, normalised, with pitch ldo.
 int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm, int64_t B, int64_t rows, int64_t cols,
             int64_t ld, int kind, int start, int stop, int clip, bool power_ok, bool fallback, void* out, int out_f64,
-            int64_t ldo, float* s_out, int32_t* info, cudaStream_t st, float l2_pin = 0.f) {
+            int64_t ldo, float* s_out, int32_t* info, cudaStream_t st, float l2_pin = 0.f, const float* Limg = nullptr,
+            int64_t ldL = 0) {
   void* stream = (void*)st;
+  const float* Lsrc = Limg ? Limg : S;       // what the Gram and projection kernels read
+  const int64_t ldsrc = Limg ? ldL : ld;
   const bool tc = power_ok && gram_tc_supported(rows);   // TF32 Gram only feeds the leading-pair route
   // full decomposition: Gram and Jacobi in double (float would square the condition number into the noise floor)
   const int g_f64 = (!power_ok && eig_jacobi_f64_supported((int)rows)) ? 1 : 0;
+  bool gram_raw = false;     // the Gram partials are of the un-normalised image (TMA-fed kernel) and carry row sums
+  bool gram_tma = false;
   if (tc) {
     // tensor-core Gram partials, then ONE cluster kernel per matrix that sums them and runs the power iteration
-    CHECK_LAUNCH(ctx, launch_gram_tc(S, B, rows, cols, ld, raw_mm, w.gram_partial, nullptr, ctx->num_sms, st, l2_pin), "gram_tc", 1);
+    int e__ = 1;
+    if (!std::getenv("SPECGPU_NO_GRAM_TMA")) {
+      ProfScope prof__(ctx, st, "gram_tc");
+      e__ = launch_gram_tma(Lsrc, B, rows, cols, ldsrc, w.gram_partial, ctx->num_sms, st, l2_pin);
+    }
+    if (e__ == 0) {
+      gram_tma = true;
+      gram_raw = raw_mm != nullptr;
+      ctx->launches += 1;
+    } else if (e__ == 1) {   // rows not 16-byte aligned: the cp.async-fed kernel normalises the operands itself
+      CHECK_LAUNCH(ctx, launch_gram_tc(Lsrc, B, rows, cols, ldsrc, raw_mm, w.gram_partial, nullptr, ctx->num_sms, st, l2_pin), "gram_tc", 1);
+    } else {
+      return cuda_fail(ctx, e__, "gram_tc");
+    }
   } else {
     if (raw_mm) {   // no fused route for this shape: normalise in place first
       CHECK_LAUNCH(ctx, launch_lognorm(S, B, rows, cols, ld, raw_mm, nullptr, st), "lognorm", 1);
@@ -669,8 +689,9 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
   if (power_ok) {
     if (tc) {
       int64_t nchunk = 0, per = 0;
-      gram_tc_geometry(B, cols, ctx->num_sms, &nchunk, &per);
-      CHECK_LAUNCH(ctx, launch_gram_eig(w.gram_partial, nchunk, per, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st),
+      gram_tc_geometry(B, cols, ctx->num_sms, gram_tma ? 1 : 0, &nchunk, &per);
+      CHECK_LAUNCH(ctx, launch_gram_eig(w.gram_partial, nchunk, per, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st,
+                                        gram_raw ? raw_mm : nullptr, cols, gram_tma ? 1 : 0),
                    "gram_eig", 1);
     } else {
       CHECK_LAUNCH(ctx, launch_eig_power(w.G, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st), "eig_power", 1);
@@ -680,7 +701,7 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
     // TF32 Gram is dead after the power iteration and is overwritten), then the cluster Jacobi, which skips the
     // converged ones.  All three launches return at once when nothing is flagged.
     if (fallback) {
-      CHECK_LAUNCH(ctx, launch_gram_simt(S, B, rows, cols, ld, w.G, 1, st, raw_mm, w.plan), "gram_simt_flagged", 1);
+      CHECK_LAUNCH(ctx, launch_gram_simt(Lsrc, B, rows, cols, ldsrc, w.G, 1, st, raw_mm, w.plan), "gram_simt_flagged", 1);
       CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 1, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
     }
   } else {
@@ -692,7 +713,7 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
                  "svd_plan", 1);
   if (power_ok && !out_f64) {
     // power_ok implies the range [1, rows): only the leading component is removed
-    CHECK_LAUNCH(ctx, launch_svd_rank1(S, B, (int)rows, cols, ld, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, l2_pin > 0.f ? 1 : 0),
+    CHECK_LAUNCH(ctx, launch_svd_rank1(Lsrc, B, (int)rows, cols, ldsrc, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, l2_pin > 0.f ? 1 : 0),
                  "svd_rank1", 1);
   } else {
     CHECK_LAUNCH(ctx, launch_svd_project(S, B, (int)rows, cols, ld, w.U, w.plan, clip, out, out_f64, ldo, st), "svd_project", 1);
@@ -909,19 +930,17 @@ int specgpu_csd_pairs_block(specgpu_ctx* ctx, const specgpu_plan* plan, const fl
 }
 
 int specgpu_csd_spectra_blocked(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t C, int64_t n, int64_t ldx,
-                                float* X, int64_t ldf, int32_t block_w, int32_t block_ld, void* stream) {
+                                float* X, int32_t block_w, int32_t block_ld, void* stream) {
   int rc = check_signal_args(ctx, plan, x, C, n, ldx);
   if (rc) return rc;
   const int64_t nseg = num_segments(n, plan->p.nperseg, plan->p.noverlap);
   if (nseg == 0 || C == 0) return SPECGPU_OK;
-  const int nfreq = plan->p.nperseg / 2 + 1;
   if (block_w < 1 || block_ld < block_w) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad frequency block (%d bins, pitch %d)", block_w, block_ld);
-  const int64_t nblocks = (nfreq + block_w - 1) / block_w;
-  if (!X || ldf < nblocks * block_ld)
-    return fail(ctx, SPECGPU_ERR_INVALID_ARG, "bad spectra buffer (ldf=%lld < %lld blocks x %d)", (long long)ldf, (long long)nblocks, block_ld);
-  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, 1.0f, X, ldf, nullptr);
+  if (!X) return fail(ctx, SPECGPU_ERR_INVALID_ARG, "null spectra buffer");
+  // block-major: X[nblocks][C][nseg][block_ld]; a row of one block is block_ld wide, blocks are whole planes apart
+  StftArgs a = make_args(plan, x, n, ldx, 0, nseg, 1.0f, X, block_ld, nullptr);
   a.fblock_w = block_w;
-  a.fblock_ld = block_ld;
+  a.fblock_stride = C * nseg * (int64_t)block_ld;
   CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_SPECTRA, a, C, (cudaStream_t)stream), "stft_kernel", 1);
   return SPECGPU_OK;
 }
@@ -1032,8 +1051,15 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
   // ---- workspace: min/max pairs and per-channel SVD arrays for the whole batch; Gram partials and Jacobi scratch per lane ----
   const size_t part_bytes = tc ? gram_tc_workspace_bytes(gsz, rows) : 0;
   const size_t jac_bytes = jacobi_workspace_bytes(gsz, (int)rows);
+  // On the tensor-core route the raw log image goes to a TILED scratch buffer ([rows x 32] column tiles stored
+  // contiguously, see img_off): the STFT's tile stores, the Gram kernel's box loads and the projection's tile reads are
+  // then contiguous 16-32 KB blocks instead of 64-128 byte pieces 15.7 KB apart.  S is written once, by the projection.
+  const int64_t ntile = ceil_div(nseg, kTileCols);
+  const bool tiled = tc && plan->log2n <= 9 && !std::getenv("SPECGPU_NO_TILED");
+  const size_t scratch_bytes = tiled ? (size_t)B * ntile * rows * kTileCols * sizeof(float) : 0;
   if ((rc = ensure_ws(ctx, carve_size({(size_t)B * rows * rows * 8, (size_t)B * rows * rows * 4,
-                                       (size_t)B * rows * 4, (size_t)B * 16, part_bytes, part_bytes, jac_bytes, jac_bytes}))))
+                                       (size_t)B * rows * 4, (size_t)B * 16, part_bytes, part_bytes, jac_bytes, jac_bytes,
+                                       scratch_bytes}))))
     return rc;
   MinMaxWord* mm = nullptr;
   unsigned gen = 0;
@@ -1047,6 +1073,7 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
   void* jac[2];
   for (int i = 0; i < 2; ++i) part[i] = tc ? cv.take<float>(part_bytes / 4) : nullptr;
   for (int i = 0; i < 2; ++i) jac[i] = cv.take<char>(jac_bytes);
+  float* Lt = tiled ? cv.take<float>(scratch_bytes / sizeof(float)) : nullptr;
 
   cudaStream_t user = (cudaStream_t)stream;
   cudaStream_t lane[2] = {user, user};
@@ -1088,7 +1115,8 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     float* Sg = S + b0 * rows * ldt;
     float* Dg = D + b0 * rows * ldt;
     MinMaxWord* mmg = mm + 2 * b0;
-    StftArgs a = make_args(plan, x + b0 * ldx, n, ldx, 0, nseg, (float)plan->scale, Sg, ldt, mmg, gen);
+    float* Lg = tiled ? Lt + (size_t)b0 * ntile * rows * kTileCols : nullptr;
+    StftArgs a = make_args(plan, x + b0 * ldx, n, ldx, 0, nseg, (float)plan->scale, tiled ? Lg : Sg, tiled ? -ntile : ldt, mmg, gen);
     a.l2_pin = l2_pin;
     CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, nb, st), "stft_kernel", 1);
     SvdWs w{};
@@ -1100,7 +1128,7 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     w.jacobi = jac[li];
     // Sg holds the raw log image until the rank-1 projection normalises it in place (see svd_run)
     if ((rc = svd_run(ctx, w, Sg, mmg, nb, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, fallback, Dg, 0, ldt, nullptr,
-                      info ? info + b0 * 4 : nullptr, st, l2_pin)))
+                      info ? info + b0 * 4 : nullptr, st, l2_pin, Lg, tiled ? -ntile : 0)))
       return rc;
     if (tiles && ntiles > 0)
       CHECK_LAUNCH(ctx, launch_patch(Dg, nb, rows, ldt, tile_w, ntiles, tiles + (size_t)b0 * ntiles * rows * tile_w, 0, st), "patch", 1);

@@ -132,10 +132,12 @@ __host__ __device__ constexpr int stft_min_blocks(int log2n, int mode) {
   return log2n == 10 ? 2 : 1;
 }
 
+#ifndef SPECGPU_GRID_CONSTANT
 #if defined(SPECGPU_EMULATE)
 #define SPECGPU_GRID_CONSTANT
 #else
 #define SPECGPU_GRID_CONSTANT __grid_constant__
+#endif
 #endif
 
 template <int LOG2N, int MODE>
@@ -334,14 +336,15 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       const bool two = GENERIC || km != k;
       if (MODE == STFT_MODE_SPECTRA) {
         if (live) {
-          int ck = k, cm = km;
+          const int ck = k, cm = km;
           if (a.fblock_w > 0) {     // blocked columns; (k + 0.5) / w in float is exact for these small integers
             const int hk = (int)(((float)k + 0.5f) * fblock_inv), hm = (int)(((float)km + 0.5f) * fblock_inv);
-            ck = hk * a.fblock_ld + (k - hk * a.fblock_w);
-            cm = hm * a.fblock_ld + (km - hm * a.fblock_w);
+            o2[hk * a.fblock_stride + (k - hk * a.fblock_w)] = make_float2(0.5f * xk.x, 0.5f * xk.y);
+            if (two) o2[hm * a.fblock_stride + (km - hm * a.fblock_w)] = make_float2(0.5f * xm.x, 0.5f * xm.y);
+          } else {
+            o2[ck] = make_float2(0.5f * xk.x, 0.5f * xk.y);
+            if (two) o2[cm] = make_float2(0.5f * xm.x, 0.5f * xm.y);
           }
-          o2[ck] = make_float2(0.5f * xk.x, 0.5f * xk.y);
-          if (two) o2[cm] = make_float2(0.5f * xm.x, 0.5f * xm.y);
         }
       } else if (MODE == STFT_MODE_COMPLEX) {
         *reinterpret_cast<float2*>(s_tile + offk) = make_float2(xk.x * cscale, xk.y * cscale);
@@ -420,6 +423,20 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       vmin = fminf(vmin, rmin);
       vmax = fmaxf(vmax, rmax);
     }
+    if (LOGM && a.ld_out < 0 && !live) {
+      // tiled scratch image: the columns of dead segments (past the end of the record, last tile only) are part of the
+      // tile the Gram kernel loads -- they must be exact zeros.  Overwrite what this thread stored for them.
+      const int ob = tl * E;
+      auto zero_row = [&](int row) {
+        const int o = row * ROWB + ob;
+        *reinterpret_cast<float*>(s_tile + (o ^ ((o >> 3) & SWMASK))) = 0.f;
+      };
+      for (int j = 0; j < R0 / 2; ++j) {
+        zero_row(tg + j * G);
+        zero_row(M - tg - j * G);
+      }
+      if (tg == 0) zero_row(M / 2);
+    }
   }
 
   if (MODE == STFT_MODE_SPECTRA) continue;
@@ -440,14 +457,20 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   __syncthreads();   // the tile is complete
 
   // ---- write the tile: rows = frequency, runs of up to TT consecutive segments ----
-  const int64_t ncol = (a.nseg - seg0 < TT) ? (a.nseg - seg0) : TT;
+  // (the tiled scratch image takes all TT columns: dead segments were zeroed above and the Gram kernel reads whole tiles)
+  const int64_t ncol = (a.ld_out >= 0 && a.nseg - seg0 < TT) ? (a.nseg - seg0) : TT;
   const int rows_out = LOGM ? (F - 1) : F;  // Nyquist row dropped after min/max
   int row_first = 0;                        // rows below this leave through the tensor store
 #if !defined(SPECGPU_EMULATE)
   if (tma_out) {
     if (tid == 0) {
-      for (int rb = 0; rb < a.tma_nbox; ++rb)
-        tma_store_3d(&tmap, smem_u32(s_tile + (size_t)rb * a.tma_rows * ROWB), (int)(seg0 * (E / 4)), rb * a.tma_rows, (int)b, pol_out);
+      for (int rb = 0; rb < a.tma_nbox; ++rb) {
+        if (a.ld_out < 0)   // tiled scratch image: tile seg0 / 32, columns seg0 % 32 ... of its [rows x 32] block
+          tma_store_3d(&tmap, smem_u32(s_tile + (size_t)rb * a.tma_rows * ROWB), (int)(seg0 & 31), (int)(seg0 >> 5) * rows_out + rb * a.tma_rows,
+                       (int)b, pol_out);
+        else
+          tma_store_3d(&tmap, smem_u32(s_tile + (size_t)rb * a.tma_rows * ROWB), (int)(seg0 * (E / 4)), rb * a.tma_rows, (int)b, pol_out);
+      }
       bulk_commit();
     }
     row_first = a.tma_nbox * a.tma_rows;
@@ -456,7 +479,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   const int lt = lane % LANES_T, lr = lane / LANES_T;
   for (int k = row_first + warp * ROWS_W + lr; k < rows_out; k += (kStftThreads / 32) * ROWS_W) {
     for (int t = lt; t < ncol; t += LANES_T) {
-      const int64_t o = (b * rows_out + k) * a.ld_out + seg0 + t;
+      const int64_t o = img_off(b, k, seg0 + t, rows_out, a.ld_out);
       const int so = k * ROWB + t * E;
       const unsigned char* sp = s_tile + (so ^ ((so >> 3) & SWMASK));
       if (MODE == STFT_MODE_COMPLEX) reinterpret_cast<float2*>(a.out)[o] = *reinterpret_cast<const float2*>(sp);
@@ -526,12 +549,17 @@ static int launch_stft_t(const StftArgs& a, int64_t B, cudaStream_t stream) {
   constexpr int TT = C::tile_w(E);
   constexpr int ROWB = TT * E;
   auto kern = stft_kernel<LOG2N, MODE>;
-  const int64_t tiles = ceil_div(a.nseg, TT);
+  int64_t tiles = ceil_div(a.nseg, TT);
   if (tiles == 0 || B == 0) return 0;
+  // tiled scratch image: cover every 32-column tile completely (an all-dead CTA tile writes the zeros the Gram kernel
+  // expects in the columns past the end of the record)
+  if (a.ld_out < 0 && TT < kTileCols) tiles = ceil_div(tiles, kTileCols / TT) * (kTileCols / TT);
   StftArgs args = a;
   args.tiles_per_signal = tiles;
   args.ntiles = tiles * B;
   if (args.ntiles >= ((int64_t)1 << 31)) return (int)cudaErrorInvalidValue;
+  if (a.ld_out < 0 && (!stft_mode_is_log(MODE) || kTileCols % TT != 0 || -a.ld_out < ceil_div(a.nseg, kTileCols)))
+    return (int)cudaErrorInvalidValue;     // the tiled layout is for the log image only, tiles of 32 = whole CTA tiles
   // ---- input staging: the span of a tile ((TT-1) hops + one segment) goes through shared memory when it fits ----
   const int64_t span = (int64_t)(TT - 1) * a.hop + C::N;
   args.span = (int)span;
@@ -548,8 +576,16 @@ static int launch_stft_t(const StftArgs& a, int64_t B, cudaStream_t stream) {
     const int rows_out = stft_mode_is_log(MODE) ? C::F - 1 : C::F;
     const int box_rows = rows_out < 256 ? rows_out : 256;
     const uint64_t w = E / 4;    // floats per element
-    if (make_tensor_map_f32_3d(&tmap, a.out, (uint64_t)a.nseg * w, (uint64_t)rows_out, (uint64_t)B, (uint64_t)a.ld_out * w,
-                               (uint64_t)rows_out * a.ld_out * w, (uint32_t)(TT * w), (uint32_t)box_rows, ROWB >= 32 ? ROWB : 0)) {
+    bool ok;
+    if (a.ld_out < 0) {   // tiled scratch image [B][ntile][rows_out][32]: rows of 128 bytes, a tile's rows contiguous
+      const uint64_t nt = (uint64_t)(-a.ld_out);
+      ok = make_tensor_map_f32_3d(&tmap, a.out, kTileCols, nt * rows_out, (uint64_t)B, kTileCols, nt * rows_out * kTileCols,
+                                  (uint32_t)TT, (uint32_t)box_rows, ROWB >= 32 ? ROWB : 0);
+    } else {
+      ok = make_tensor_map_f32_3d(&tmap, a.out, (uint64_t)a.nseg * w, (uint64_t)rows_out, (uint64_t)B, (uint64_t)a.ld_out * w,
+                                  (uint64_t)rows_out * a.ld_out * w, (uint32_t)(TT * w), (uint32_t)box_rows, ROWB >= 32 ? ROWB : 0);
+    }
+    if (ok) {
       args.tma_out = 1;
       args.tma_rows = box_rows;
       args.tma_nbox = rows_out / box_rows;

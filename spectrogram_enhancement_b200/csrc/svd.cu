@@ -58,7 +58,6 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
   const int64_t kchunk = ((cols + ksplit - 1) / ksplit + kGramKB - 1) / kGramKB * kGramKB;
   const int64_t k0 = (int64_t)blockIdx.y * kchunk;
   const int64_t k1 = (k0 + kchunk < cols) ? k0 + kchunk : cols;
-  const float* Sb = S + b * rows * ld;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4 x 4 outputs each
   T acc[4][4] = {};
@@ -66,8 +65,8 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
     for (int i = tid; i < kGramTile * kGramKB; i += kGramThreads) {
       const int r = i / kGramKB, c = i % kGramKB;
       const int ra = ti * kGramTile + r, rb = tj * kGramTile + r;
-      float xa = (ra < rows && k + c < k1) ? Sb[(int64_t)ra * ld + k + c] : 0.f;
-      float xb = (rb < rows && k + c < k1) ? Sb[(int64_t)rb * ld + k + c] : 0.f;
+      float xa = (ra < rows && k + c < k1) ? S[img_off(b, ra, k + c, rows, ld)] : 0.f;
+      float xb = (rb < rows && k + c < k1) ? S[img_off(b, rb, k + c, rows, ld)] : 0.f;
       if (minmax != nullptr) {
         xa = (ra < rows && k + c < k1) ? div_by(xa - mn, den, inv) : 0.f;
         xb = (rb < rows && k + c < k1) ? div_by(xb - mn, den, inv) : 0.f;
@@ -285,6 +284,9 @@ constexpr int kGeThreads = 512, kGeRows = 32;
 struct GramEigArgs {
   const float* partial;
   int64_t nchunk, per;     // geometry of the gram_tc launch that wrote the partials
+  const MinMaxWord* raw_minmax;   // != nullptr: partials of the raw image + row sums, see launch_gram_eig
+  int64_t cols;
+  int per_matrix;          // partials are [b * k + part] (launch_gram_tma), else [cta][2] over global chunk ranges
   int max_iter;
   float* U;                // [B][n][n]: column 0 receives u0
   float* lam;              // [B][n]
@@ -292,22 +294,34 @@ struct GramEigArgs {
 };
 
 template <int N>
-__global__ void __launch_bounds__(kGeThreads) gram_eig_kernel(GramEigArgs a) {
+__global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) {
   constexpr int CL = N / kGeRows;                 // CTAs per cluster
-  constexpr int PW = (N == 256) ? 384 : N;
+  constexpr int PL = (N == 256) ? 384 : N;        // accumulator columns of a partial row
+  constexpr int PW = PL + 4;                      // its pitch (columns PL, PL + 1: row sums of rows r, 128 + r)
   constexpr int NJ = N / 64;                      // float4 per thread: columns q*4 + 64 j + {0..3}
   SPECGPU_DYN_SMEM(smem);
   float* sx = reinterpret_cast<float*>(smem);     // [N] current iterate (every CTA holds all of it)
   float* sy = sx + N;                             // [2][N] G x, double buffered across iterations
   float* sdiag = sy + 2 * N;                      // [CL][2] (largest diagonal, its row) per CTA
   float* sT = sdiag + 2 * CL + 8;                 // [32][132] transposed G10 rows (N == 256, ranks >= CL/2)
+  float* sr = sT + kGeRows * 132;                 // [N] row sums of the raw image (raw_minmax route)
+  float* scand = sr + N;                          // [CL][N] every CTA's candidate start row
   const int rank = SPECGPU_CLUSTER_RANK();
   const int64_t b = blockIdx.x / CL;
   const int tid = threadIdx.x, lane = tid & 31;
   const int rl = tid >> 4, q = tid & 15;
   const int row0 = rank * kGeRows;
-  const int i0 = (int)((b * a.nchunk) / a.per), i1 = (int)(((b + 1) * a.nchunk - 1) / a.per);
+  const int kparts = (int)((a.nchunk + a.per - 1) / a.per);
+  const int i0 = a.per_matrix ? (int)(b * kparts) : (int)((b * a.nchunk) / a.per);
+  const int i1 = a.per_matrix ? i0 + kparts - 1 : (int)(((b + 1) * a.nchunk - 1) / a.per);
   const int64_t bstart = b * a.nchunk;
+  // partial of CTA `cta` that belongs to this matrix
+  auto part_of = [&](int cta) -> const float* {
+    if (a.per_matrix) return a.partial + (size_t)cta * 128 * PW;
+    // a CTA whose range starts before this matrix began in matrix b-1: matrix b is its second segment
+    const int sg = ((int64_t)cta * a.per < bstart) ? 1 : 0;
+    return a.partial + (size_t)(cta * 2 + sg) * 128 * PW;
+  };
   const bool lower = (N == 256) && row0 >= 128;   // rows of [G10 | G11]
   float4 g[NJ];
 #pragma unroll
@@ -316,38 +330,103 @@ __global__ void __launch_bounds__(kGeThreads) gram_eig_kernel(GramEigArgs a) {
     for (int i = tid; i < kGeRows * 132; i += kGeThreads) sT[i] = 0.f;
     __syncthreads();
   }
-  for (int cta = i0; cta <= i1; ++cta) {
-    // a CTA whose range starts before this matrix began in matrix b-1: matrix b is its second segment
-    const int sg = ((int64_t)cta * a.per < bstart) ? 1 : 0;
-    const float* base = a.partial + (size_t)(cta * 2 + sg) * 128 * PW;
+  // The partials are summed in CTA order (deterministic) but loaded kGeBatch at a time: all loads of a batch are in flight
+  // before the first add (one memory round trip per batch instead of one per partial).
+  constexpr int kGeBatch = 3;
+  for (int c0 = i0; c0 <= i1; c0 += kGeBatch) {
+    const float* base[kGeBatch];
+#pragma unroll
+    for (int u = 0; u < kGeBatch; ++u) {
+      const int cta = (c0 + u <= i1) ? c0 + u : i1;
+      base[u] = part_of(cta);
+    }
     if (!lower) {
+      float4 v[kGeBatch][NJ];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)(row0 + rl) * PW + q * 4 + 64 * j));
-        g[j].x += v.x; g[j].y += v.y; g[j].z += v.z; g[j].w += v.w;
-      }
+      for (int u = 0; u < kGeBatch; ++u)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          v[u][j] = __ldg(reinterpret_cast<const float4*>(base[u] + (size_t)(row0 + rl) * PW + q * 4 + 64 * j));
+#pragma unroll
+      for (int u = 0; u < kGeBatch; ++u)
+        if (c0 + u <= i1) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            g[j].x += v[u][j].x; g[j].y += v[u][j].y; g[j].z += v[u][j].z; g[j].w += v[u][j].w;
+          }
+        }
     } else {
+      float4 v[kGeBatch][2], t[kGeBatch][2];
 #pragma unroll
-      for (int j = 2; j < NJ; ++j) {   // G11 from D2
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)(row0 - 128 + rl) * PW + 256 + q * 4 + 64 * (j - 2)));
-        g[j].x += v.x; g[j].y += v.y; g[j].z += v.z; g[j].w += v.w;
+      for (int u = 0; u < kGeBatch; ++u) {
+#pragma unroll
+        for (int j = 2; j < NJ; ++j)    // G11 from D2
+          v[u][j - 2] = __ldg(reinterpret_cast<const float4*>(base[u] + (size_t)(row0 - 128 + rl) * PW + 256 + q * 4 + 64 * (j - 2)));
+        // G10[row][c] = D1[c][row]: 128-byte runs D1[c][row0 .. row0 + 31], accumulated transposed in shared memory (every
+        // cell is owned by one thread for all partials: no atomics); 128 * 8 float4 = two per thread
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = tid + h * kGeThreads;
+          t[u][h] = __ldg(reinterpret_cast<const float4*>(base[u] + (size_t)(i >> 3) * PW + row0 + (i & 7) * 4));
+        }
       }
-      // G10[row][c] = D1[c][row]: 128-byte runs D1[c][row0 .. row0 + 31], accumulated transposed in shared memory (every
-      // cell is owned by one thread for all partials: no atomics)
-      for (int i = tid; i < 128 * 8; i += kGeThreads) {
-        const int c = i >> 3, e4 = i & 7;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)c * PW + row0 + e4 * 4));
-        sT[(e4 * 4 + 0) * 132 + c] += v.x;
-        sT[(e4 * 4 + 1) * 132 + c] += v.y;
-        sT[(e4 * 4 + 2) * 132 + c] += v.z;
-        sT[(e4 * 4 + 3) * 132 + c] += v.w;
-      }
+#pragma unroll
+      for (int u = 0; u < kGeBatch; ++u)
+        if (c0 + u <= i1) {
+#pragma unroll
+          for (int j = 2; j < NJ; ++j) {
+            g[j].x += v[u][j - 2].x; g[j].y += v[u][j - 2].y; g[j].z += v[u][j - 2].z; g[j].w += v[u][j - 2].w;
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = tid + h * kGeThreads;
+            const int c = i >> 3, e4 = i & 7;
+            sT[(e4 * 4 + 0) * 132 + c] += t[u][h].x;
+            sT[(e4 * 4 + 1) * 132 + c] += t[u][h].y;
+            sT[(e4 * 4 + 2) * 132 + c] += t[u][h].z;
+            sT[(e4 * 4 + 3) * 132 + c] += t[u][h].w;
+          }
+        }
     }
   }
   if (lower) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 2; ++j) g[j] = *reinterpret_cast<const float4*>(sT + rl * 132 + q * 4 + 64 * j);
+  }
+  float lam_scale = 1.0f;
+  if (a.raw_minmax != nullptr) {
+    // partials of the RAW image L: (L - m)(L - m)^T = L L^T - m (r 1^T + 1 r^T) + m^2 T 1 1^T  (the common factor
+    // 1 / (max - min)^2 of the normalised image does not change eigenvectors and is only applied to lambda)
+    if (tid < N) {
+      float rs = 0.f;
+      for (int c0 = i0; c0 <= i1; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int cta = (c0 + u <= i1) ? c0 + u : i1;
+          v[u] = __ldg(part_of(cta) + (size_t)(tid & 127) * PW + PL + (tid >> 7));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c0 + u <= i1) rs += v[u];
+      }
+      sr[tid] = rs;
+    }
+    __syncthreads();
+    const float m = minmax_get_min(a.raw_minmax, b);
+    const float den = minmax_get_max(a.raw_minmax, b) - m;
+    lam_scale = 1.0f / (den * den);
+    const float ri = sr[row0 + rl];
+    const float m2t = m * m * (float)a.cols;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float4 rc = *reinterpret_cast<const float4*>(sr + q * 4 + 64 * j);
+      g[j].x = g[j].x - m * (ri + rc.x) + m2t;
+      g[j].y = g[j].y - m * (ri + rc.y) + m2t;
+      g[j].z = g[j].z - m * (ri + rc.z) + m2t;
+      g[j].w = g[j].w - m * (ri + rc.w) + m2t;
+    }
   }
   // ---- start vector: the row of G with the largest diagonal entry, cluster-wide (see eig_power_kernel) ----
   {
@@ -384,10 +463,26 @@ __global__ void __launch_bounds__(kGeThreads) gram_eig_kernel(GramEigArgs a) {
         remote[2 * rank] = best;
         remote[2 * rank + 1] = __int_as_float(arg);
       }
+      if (tid == 0) sdiag[2 * CL] = __int_as_float(arg);     // this CTA's own candidate row
+    }
+    __syncthreads();
+    {
+      // every CTA also ships its candidate row (row == column by symmetry) to all peers in the same step, so that one
+      // cluster barrier settles both the choice and the start vector
+      const int mine = __float_as_int(sdiag[2 * CL]);
+      if (rl == mine - row0) {
+#pragma unroll
+        for (int r = 0; r < CL; ++r) {
+          float* remote = SPECGPU_MAP_SHARED(scand, r) + rank * N;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) *reinterpret_cast<float4*>(remote + q * 4 + 64 * j) = g[j];
+        }
+      }
     }
     SPECGPU_CLUSTER_SYNC();
     float best = sdiag[0];
     int arg = __float_as_int(sdiag[1]);
+    int owner = 0;
 #pragma unroll
     for (int r = 1; r < CL; ++r) {
       const float ob = sdiag[2 * r];
@@ -395,18 +490,11 @@ __global__ void __launch_bounds__(kGeThreads) gram_eig_kernel(GramEigArgs a) {
       if (ob > best || (ob == best && oa < arg)) {
         best = ob;
         arg = oa;
+        owner = r;
       }
     }
-    // the owner of that row broadcasts it (row == column by symmetry) as the unnormalised start vector
-    if (arg >= row0 && arg < row0 + kGeRows && rl == arg - row0) {
-#pragma unroll
-      for (int r = 0; r < CL; ++r) {
-        float* remote = SPECGPU_MAP_SHARED(sx, r);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) *reinterpret_cast<float4*>(remote + q * 4 + 64 * j) = g[j];
-      }
-    }
-    SPECGPU_CLUSTER_SYNC();
+    if (tid < N) sx[tid] = scand[owner * N + tid];
+    __syncthreads();
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < N / 32; ++i) ss += sx[lane + 32 * i] * sx[lane + 32 * i];
@@ -466,7 +554,7 @@ __global__ void __launch_bounds__(kGeThreads) gram_eig_kernel(GramEigArgs a) {
   SPECGPU_CLUSTER_SYNC();
   if (tid < kGeRows) a.U[b * (int64_t)N * N + (int64_t)(row0 + tid) * N] = sx[row0 + tid];
   if (rank == 0 && tid == 0) {
-    a.lam[b * N] = lambda;
+    a.lam[b * N] = lambda * lam_scale;
     a.plan[b * 4 + 0] = 1;
     a.plan[b * 4 + 1] = N;
     a.plan[b * 4 + 2] = -1;
@@ -477,7 +565,7 @@ __global__ void __launch_bounds__(kGeThreads) gram_eig_kernel(GramEigArgs a) {
 template <int N>
 static int launch_gram_eig_t(const GramEigArgs& a, int64_t B, cudaStream_t stream) {
   constexpr int CL = N / kGeRows;
-  const size_t smem = (size_t)(3 * N + 2 * CL + 8 + kGeRows * 132) * sizeof(float);
+  const size_t smem = (size_t)(3 * N + 2 * CL + 8 + kGeRows * 132 + N + CL * N) * sizeof(float);
 #ifdef SPECGPU_EMULATE
   SPECGPU_LAUNCH_CLUSTER(gram_eig_kernel<N>, (unsigned)(B * CL), kGeThreads, smem, stream, CL, a);
 #else
@@ -500,9 +588,9 @@ static int launch_gram_eig_t(const GramEigArgs& a, int64_t B, cudaStream_t strea
 }
 
 int launch_gram_eig(const float* partial, int64_t nchunk, int64_t per, int64_t B, int n, int max_iter, float* U, float* lam,
-                    int32_t* plan, cudaStream_t stream) {
+                    int32_t* plan, cudaStream_t stream, const MinMaxWord* raw_minmax, int64_t cols, int per_matrix) {
   if (B == 0) return 0;
-  GramEigArgs a{partial, nchunk, per, max_iter > 0 ? max_iter : kPowMaxIter, U, lam, plan};
+  GramEigArgs a{partial, nchunk, per, raw_minmax, cols, per_matrix, max_iter > 0 ? max_iter : kPowMaxIter, U, lam, plan};
   if (n == 256) return launch_gram_eig_t<256>(a, B, stream);
   if (n == 128) return launch_gram_eig_t<128>(a, B, stream);
   return -1;
@@ -997,10 +1085,11 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
   }
   const float inv = 1.0f / den;
   for (int r = tid; r < rows; r += kR1Threads) s_u[r] = U[b * (int64_t)rows * rows + (int64_t)r * rows];
-  const float* pl = L + (b * rows + warp) * ld + c0 + lane;
+  // row-major source, or the tiled scratch image (ld < 0): tile blockIdx.x of matrix b is one contiguous [rows x 32] block
+  const float* pl = L + img_off(b, warp, c0 + lane, rows, ld);
   float* ps = S + (b * rows + warp) * ldo + c0 + lane;
   float* pd = D + (b * rows + warp) * ldo + c0 + lane;
-  const int64_t stepl = kR1Warps * ld, stepo = kR1Warps * ldo;
+  const int64_t stepl = kR1Warps * (ld < 0 ? (int64_t)kTileCols : ld), stepo = kR1Warps * ldo;
   const bool write_s = S != nullptr && (NORM || S != L);
   float x[RPW];
   if (c0 + kRecCols <= cols && rows == kR1Warps * RPW) {

@@ -136,18 +136,15 @@ def csd_allpairs_freq_sharded(x_local, fs=1.0, window="hann", nperseg=256, nover
         raise ValueError("record shorter than nperseg")
     wf = -(-F // world)                         # bins per block
     ldb = (wf + 15) & ~15                       # 128-byte rows of a block
-    ldf = world * ldb                           # spectra rows: block h starts at column h * ldb
-    # spectra of this rank's channels, laid out [Cl, T, world, ldb] with bin k at block k // wf, column k % wf
-    X = rt.empty((Cl, T, ldf, 2))
-    rt.check(rt.lib.csd_spectra_blocked(rt._ctx, plan, xd.data_ptr(), Cl, n, api._ld(xd), X.data_ptr(), ldf, wf, ldb,
-                                        rt.stream()))
+    # spectra of this rank's channels, written block-major by the transform itself: send[h] = bins of block h
+    send = rt.empty((world, Cl, T, ldb, 2))
+    rt.check(rt.lib.csd_spectra_blocked(rt._ctx, plan, xd.data_ptr(), Cl, n, api._ld(xd), send.data_ptr(), wf, ldb, rt.stream()))
     if world > 1:
-        send = X.view(Cl, T, world, ldb, 2).permute(2, 0, 1, 3, 4).contiguous()      # [world][Cl, T, ldb]
-        recv = torch.empty_like(send)                                                 # [world (source)][Cl, T, ldb]
+        recv = torch.empty_like(send)            # [world (source rank)][Cl, T, ldb] == X_f[C, T, ldb], channels in rank order
         dist.all_to_all_single(recv, send, group=group)
-        Xf = recv                                # == X_f[C, T, ldb]: channels in rank order
+        Xf = recv
     else:
-        Xf = X
+        Xf = send
     f0, f1 = frequency_block(rank, world, F)
     P = rt.empty((C, C, max(f1 - f0, 0), 2))
     if f1 > f0:
