@@ -31,7 +31,7 @@ from . import _ffi
 
 __all__ = [
     "Runtime", "default_runtime", "DEFAULT_SPEC_PARAMS", "spectrogram", "stft", "csd", "csd_allpairs",
-    "spectrogram_batch", "specgr_array", "specgr", "load_shot", "norm", "rescale", "quantfilt", "quantfilt_mask", "gaussblr", "meansub", "morph",
+    "spectrogram_batch", "specgr_array", "specgr", "load_shot", "save_shot_hdf5", "load_hdf5_dataset", "norm", "rescale", "quantfilt", "quantfilt_mask", "gaussblr", "meansub", "morph",
     "filter_chain", "process_shot", "omega",
     "computeSignal", "denoiseSignal", "clip", "patch", "unpatch", "reshape", "pipeline", "HostPipeline", "ae_co2",
 ]
@@ -397,20 +397,34 @@ def _load_shot_pickle(fname):
     return _SHOT_CACHE["data"]
 
 
-def load_shot(fname, channels=range(1, 41), cut_shot=2, fs=500000.0):
+def _channel_signal(data, ecen, key="ece"):
+    """One channel's raw record out of a shot pickle.  key='ece': data['\\tecefNN'] (pipeline_data.py:30);
+    key='bes': data['besfuNN']['data.BES'] (the BES twin of specgr, denoising_by_svd.ipynb:50-52); or a callable
+    key(data, ecen) -> 1-D array for other diagnostics."""
+    if callable(key):
+        return key(data, ecen)
+    if key == "ece":
+        return data["\\tecef%.2i" % (ecen)]
+    if key == "bes":
+        return data["besfu{:02d}".format(ecen)]["data.BES"]
+    raise ValueError(f"unknown channel key {key!r}: use 'ece', 'bes' or a callable")
+
+
+def load_shot(fname, channels=range(1, 41), cut_shot=2, fs=500000.0, key="ece"):
     """One read of a shot pickle -> x[C, N] float32, the batched input of `pipeline` / `spectrogram_batch`
-    (channel keys and slice of pipeline_data.py:29-31)."""
+    (channel keys and slice of pipeline_data.py:29-31; key='bes' for the BES pickles of denoising_by_svd.ipynb:50-52).
+    The reference keeps the pickle's dtype; libspecgpu computes in float32, so a float64 record is rounded here."""
     data = _load_shot_pickle(fname)
     n = int(np.int_(cut_shot * fs))
-    return np.stack([np.asarray(data["\\tecef%.2i" % c][:n], dtype=np.float32) for c in channels])
+    return np.stack([np.asarray(_channel_signal(data, c, key)[:n], dtype=np.float32) for c in channels])
 
 
-def specgr(fname, ecen, spec_params, cut_shot=2, runtime=None):
+def specgr(fname, ecen, spec_params, cut_shot=2, runtime=None, key="ece"):
     """pipeline_data.py:28-36, same signature: load the shot pickle (cached between calls), take channel `ecen`, the
-    first cut_shot*fs samples, and return (Sxx[nperseg/2, T], f, t)."""
+    first cut_shot*fs samples, and return (Sxx[nperseg/2, T], f, t).  key='bes' is the notebook's BES variant
+    (denoising_by_svd.ipynb:49-63: 'besfuNN' -> ['data.BES'])."""
     ece_data = _load_shot_pickle(fname)
-    ece_num = "\\tecef%.2i" % (ecen)
-    sig_in = ece_data[ece_num][:np.int_(cut_shot * spec_params["fs"])]
+    sig_in = _channel_signal(ece_data, ecen, key)[:np.int_(cut_shot * spec_params["fs"])]
     return spectrogram_batch(np.asarray(sig_in), spec_params, runtime)
 
 
@@ -727,13 +741,14 @@ def pipeline(x, spec_params=DEFAULT_SPEC_PARAMS, clip=True, tiles=False, tile=12
     return tuple(res)
 
 
-def process_shot(x, spec_params=DEFAULT_SPEC_PARAMS, thr=0.9, filt=(31, 3), channels=range(1, 41), cut_shot=2, runtime=None):
+def process_shot(x, spec_params=DEFAULT_SPEC_PARAMS, thr=0.9, filt=(31, 3), channels=range(1, 41), cut_shot=2, runtime=None,
+                 key="ece"):
     """One shot of the reference's main loop (pipeline_data.py:92-116) in two library calls: `x` is the shot pickle's
     path (read once with `load_shot`) or the signals x[C, N].  Returns the datasets the loop writes per channel, stacked
     over channels: {'spec': Sxx[C, F, T], 'f': f, 't': t, 'pipeline_out': [C, F, T] float64}."""
     rt = _rt(runtime)
     if isinstance(x, (str, os.PathLike)):
-        x = load_shot(x, channels=channels, cut_shot=cut_shot, fs=spec_params["fs"])
+        x = load_shot(x, channels=channels, cut_shot=cut_shot, fs=spec_params["fs"], key=key)
     plan = rt.plan_from_params(spec_params)
     xd, as_torch = rt.to_device(x)
     if xd.dim() != 2:
@@ -742,6 +757,68 @@ def process_shot(x, spec_params=DEFAULT_SPEC_PARAMS, thr=0.9, filt=(31, 3), chan
     S = rt.specgr_dev(plan, xd)                                  # stays on the device between the two calls
     out = filter_chain(S, thr, filt, runtime=rt)
     return {"spec": rt.ret(S, as_torch), "f": f[:-1], "t": t, "pipeline_out": rt.ret(out, as_torch)}
+
+
+def _h5py():
+    try:
+        import h5py
+    except ImportError as e:      # the interchange file is optional: everything else works without h5py
+        raise ImportError("the HDF5 interchange (save_shot_hdf5 / load_hdf5_dataset) needs h5py") from e
+    return h5py
+
+
+def save_shot_hdf5(out_file, shotn, result, channels=None):
+    """Write one shot in the reference's interchange layout (pipeline_data.py:112-116): group
+    'ece_<shotn>/chn_<n>' with datasets 'spec', 'f', 't', 'pipeline_out' per channel.  `result` is what `process_shot`
+    returns ({'spec': [C, F, T], 'f', 't', 'pipeline_out': [C, F, T]}); `channels` are the 1-based channel numbers
+    (default 1..C); `out_file` is an open h5py.File (or Group) or a path, opened in 'a' mode like the reference.
+    Unlike the reference (whose create_group raises on a second run) an existing channel group is replaced."""
+    def cpu(a):
+        return a.cpu().numpy() if _is_torch(a) else np.asarray(a)
+    spec, out = cpu(result["spec"]), cpu(result["pipeline_out"])
+    f, t = np.asarray(result["f"]), np.asarray(result["t"])
+    if spec.ndim != 3 or out.shape != spec.shape:
+        raise ValueError("expected result['spec'] and result['pipeline_out'] as [C, F, T]")
+    chans = list(range(1, spec.shape[0] + 1)) if channels is None else list(channels)
+    if len(chans) != spec.shape[0]:
+        raise ValueError("one channel number per row of result['spec']")
+    own = isinstance(out_file, (str, os.PathLike))
+    fh = _h5py().File(out_file, "a") if own else out_file
+    try:
+        for i, chn in enumerate(chans):
+            name = "ece_" + str(shotn) + "/chn_" + str(chn)
+            if name in fh:
+                del fh[name]
+            grp = fh.create_group(name)
+            grp.create_dataset("spec", data=spec[i])
+            grp.create_dataset("f", data=f)
+            grp.create_dataset("t", data=t)
+            grp.create_dataset("pipeline_out", data=out[i])
+    finally:
+        if own:
+            fh.close()
+
+
+def load_hdf5_dataset(in_file, shots=None, n_channels=20):
+    """Read (spectrograms, final) lists the way the VAE scripts do (VAE/manual_scan.py:137-148): for every shot group
+    (all of them, or the names in `shots`) and channel 1..n_channels, file[shot/'chn_<n>']['spec'] and ['pipeline_out'].
+    Returns two lists of [F, T] arrays, ready for `patch`."""
+    own = isinstance(in_file, (str, os.PathLike))
+    fh = _h5py().File(in_file, "r") if own else in_file
+    try:
+        names = list(fh.keys()) if shots is None else list(shots)
+        spectrograms, final = [], []
+        for fname in names:
+            for chn in range(n_channels):
+                name = fname + "/chn_" + str(chn + 1)
+                if name not in fh:
+                    continue
+                spectrograms.append(np.array(fh[name]["spec"]))
+                final.append(np.array(fh[name]["pipeline_out"]))
+        return spectrograms, final
+    finally:
+        if own:
+            fh.close()
 
 
 class HostPipeline:

@@ -74,7 +74,7 @@ int launch_eig_power(const float* G, int64_t B, int n, int max_iter /* <= 0: def
 // eigenvectors do not care); raw_minmax == nullptr: the partials already are of the operands to decompose.
 int launch_gram_eig(const float* partial, int64_t nchunk, int64_t per, int64_t B, int n, int max_iter, float* U, float* lam,
                     int32_t* plan, cudaStream_t stream, const MinMaxWord* raw_minmax = nullptr, int64_t cols = 0,
-                    int per_matrix = 0 /* partials written by launch_gram_tma */);
+                    int per_matrix = 0 /* partials written by launch_gram_tma */, int32_t* flagged = nullptr);
 size_t jacobi_workspace_bytes(int64_t B, int n);
 bool eig_jacobi_f64_supported(int n);
 int launch_eig_jacobi(const void* G, int g_f64, int64_t B, int n, int skip_converged, float* U, float* lam, int32_t* plan, void* ws,
@@ -85,7 +85,8 @@ int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int
 // Leading-component removal fused with the min-max normalisation: L (log image) -> S = (L-min)/(max-min) and
 // D = S - u0 (u0^T S) [clipped]; S may alias L.  minmax == nullptr: L is already normalised (S not written if null).
 int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const MinMaxWord* minmax, const float* U,
-                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out = 0);
+                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out = 0,
+                     const int32_t* only_flagged = nullptr /* [B]: skip matrices whose entry is 0 */);
 int launch_svd_project(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U, const int32_t* plan,
                        int clip, void* out, int out_f64, int64_t ldo, cudaStream_t stream);
 

@@ -26,6 +26,8 @@ struct specgpu_ctx {
   MinMaxWord* mm64 = nullptr;
   unsigned mm_gen = 0;
   int pipe_group = 0;      // channels per group (0: automatic, see specgpu_set_pipeline_group)
+  cudaStream_t repair_stream = nullptr;      // side stream of the non-converged-channel repair (see svd_run)
+  cudaEvent_t ev_repair_fork = nullptr, ev_repair_join = nullptr;
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   // optional per-kernel timing (specgpu_profile_*): CUDA events recorded around every launch group
@@ -287,6 +289,9 @@ int specgpu_destroy(specgpu_ctx* ctx) {
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->repair_stream) cudaStreamDestroy(ctx->repair_stream);
+  if (ctx->ev_repair_fork) cudaEventDestroy(ctx->ev_repair_fork);
+  if (ctx->ev_repair_join) cudaEventDestroy(ctx->ev_repair_join);
   prof_collect(ctx);
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
 #endif
@@ -616,6 +621,7 @@ namespace {
 double omega_of(double beta) { return 0.56 * std::pow(beta, 3.0) - 0.95 * std::pow(beta, 2.0) + 1.82 * beta + 1.43; }   // as Python: beta ** 3
 
 struct SvdWs {
+  int32_t* flagged = nullptr;   // [B] status snapshot for the side-stream repair (pipeline, tiled scratch image)
   float* G;
   float* U;
   float* lam;
@@ -661,6 +667,7 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
   const bool tc = power_ok && gram_tc_supported(rows);   // TF32 Gram only feeds the leading-pair route
   // full decomposition: Gram and Jacobi in double (float would square the condition number into the noise floor)
   const int g_f64 = (!power_ok && eig_jacobi_f64_supported((int)rows)) ? 1 : 0;
+  bool side_repair = false;
   bool gram_raw = false;     // the Gram partials are of the un-normalised image (TMA-fed kernel) and carry row sums
   bool gram_tma = false;
   if (tc) {
@@ -691,7 +698,7 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
       int64_t nchunk = 0, per = 0;
       gram_tc_geometry(B, cols, ctx->num_sms, gram_tma ? 1 : 0, &nchunk, &per);
       CHECK_LAUNCH(ctx, launch_gram_eig(w.gram_partial, nchunk, per, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st,
-                                        gram_raw ? raw_mm : nullptr, cols, gram_tma ? 1 : 0),
+                                        gram_raw ? raw_mm : nullptr, cols, gram_tma ? 1 : 0, w.flagged),
                    "gram_eig", 1);
     } else {
       CHECK_LAUNCH(ctx, launch_eig_power(w.G, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st), "eig_power", 1);
@@ -700,7 +707,13 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
     // redone by the full solver in float64: Gram matrix of the flagged matrices only, straight from the image (the
     // TF32 Gram is dead after the power iteration and is overwritten), then the cluster Jacobi, which skips the
     // converged ones.  All three launches return at once when nothing is flagged.
-    if (fallback) {
+    // When the image is in the separate (tiled) scratch buffer, the repair runs on a side stream UNDER the projection
+    // and a second, flagged-only projection pass fixes up the (rare) flagged matrices afterwards: with nothing flagged
+    // the critical path only sees one launch that exits at once.  Otherwise it runs in line before the projection.
+#ifndef SPECGPU_EMULATE
+    side_repair = fallback && Limg != nullptr && w.flagged != nullptr && !out_f64 && ctx->repair_stream != nullptr;
+#endif
+    if (fallback && !side_repair) {
       CHECK_LAUNCH(ctx, launch_gram_simt(Lsrc, B, rows, cols, ldsrc, w.G, 1, st, raw_mm, w.plan), "gram_simt_flagged", 1);
       CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 1, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
     }
@@ -713,8 +726,28 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
                  "svd_plan", 1);
   if (power_ok && !out_f64) {
     // power_ok implies the range [1, rows): only the leading component is removed
+#ifndef SPECGPU_EMULATE
+    if (side_repair) {
+      cudaStream_t rs = ctx->repair_stream;
+      cudaEventRecord(ctx->ev_repair_fork, st);
+      cudaStreamWaitEvent(rs, ctx->ev_repair_fork, 0);
+      {
+        void* stream = (void*)rs;     // CHECK_LAUNCH takes the stream from this name
+        CHECK_LAUNCH(ctx, launch_gram_simt(Lsrc, B, rows, cols, ldsrc, w.G, 1, rs, raw_mm, w.plan), "gram_simt_flagged", 1);
+        CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 1, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, rs), "eig_jacobi", 2);
+      }
+      cudaEventRecord(ctx->ev_repair_join, rs);
+    }
+#endif
     CHECK_LAUNCH(ctx, launch_svd_rank1(Lsrc, B, (int)rows, cols, ldsrc, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, l2_pin > 0.f ? 1 : 0),
                  "svd_rank1", 1);
+#ifndef SPECGPU_EMULATE
+    if (side_repair) {
+      cudaStreamWaitEvent(st, ctx->ev_repair_join, 0);
+      CHECK_LAUNCH(ctx, launch_svd_rank1(Lsrc, B, (int)rows, cols, ldsrc, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, 0, w.flagged),
+                   "svd_rank1_flagged", 1);
+    }
+#endif
   } else {
     CHECK_LAUNCH(ctx, launch_svd_project(S, B, (int)rows, cols, ld, w.U, w.plan, clip, out, out_f64, ldo, st), "svd_project", 1);
   }
@@ -1059,7 +1092,7 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
   const size_t scratch_bytes = tiled ? (size_t)B * ntile * rows * kTileCols * sizeof(float) : 0;
   if ((rc = ensure_ws(ctx, carve_size({(size_t)B * rows * rows * 8, (size_t)B * rows * rows * 4,
                                        (size_t)B * rows * 4, (size_t)B * 16, part_bytes, part_bytes, jac_bytes, jac_bytes,
-                                       scratch_bytes}))))
+                                       scratch_bytes, (size_t)B * 4}))))
     return rc;
   MinMaxWord* mm = nullptr;
   unsigned gen = 0;
@@ -1074,6 +1107,21 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
   for (int i = 0; i < 2; ++i) part[i] = tc ? cv.take<float>(part_bytes / 4) : nullptr;
   for (int i = 0; i < 2; ++i) jac[i] = cv.take<char>(jac_bytes);
   float* Lt = tiled ? cv.take<float>(scratch_bytes / sizeof(float)) : nullptr;
+  int32_t* flagged_all = cv.take<int32_t>(B);
+#ifndef SPECGPU_EMULATE
+  // (Measured on B200: the side-stream variant is no faster than the in-line repair -- 288.1 vs 287.9 us per 40-channel shot,
+  // 278.6 without any repair: the projection's grid leaves the repair kernels no SMs to overlap on -- so it is opt-in.)
+  if (tiled && fallback && !ctx->repair_stream && std::getenv("SPECGPU_SIDE_REPAIR")) {
+    // highest priority: the repair kernels (which return at once unless a channel is flagged) take SMs as the projection's
+    // short CTAs retire instead of queueing behind its whole grid
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&ctx->repair_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_repair_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_repair_join, cudaEventDisableTiming) != cudaSuccess)
+      return cuda_fail(ctx, (int)cudaGetLastError(), "repair stream");
+  }
+#endif
 
   cudaStream_t user = (cudaStream_t)stream;
   cudaStream_t lane[2] = {user, user};
@@ -1126,6 +1174,7 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     w.plan = plan_all + b0 * 4;
     w.gram_partial = part[li];
     w.jacobi = jac[li];
+    w.flagged = flagged_all + b0;
     // Sg holds the raw log image until the rank-1 projection normalises it in place (see svd_run)
     if ((rc = svd_run(ctx, w, Sg, mmg, nb, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, fallback, Dg, 0, ldt, nullptr,
                       info ? info + b0 * 4 : nullptr, st, l2_pin, Lg, tiled ? -ntile : 0)))

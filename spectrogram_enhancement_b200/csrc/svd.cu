@@ -279,7 +279,9 @@ int launch_eig_power(const float* G, int64_t B, int n, int max_iter, float* U, f
 //   partial layout (gram_tc.cu): [cta][2][128][PW], PW = 384: D1 = [G00 | G01] in columns 0..255 of rows 0..127,
 //   D2 = G11 in columns 256..383; PW = 128 for 128 rows (D1 = G only).  G10 = G01^T is transposed through shared memory.
 // ======================================================================================================
-constexpr int kGeThreads = 512, kGeRows = 32;
+// 256 threads per CTA (8 per row of G, 32 columns each): 320 CTAs of 40 matrices then fit the 148 SMs in ONE wave (three
+// or more per SM); with 512-thread CTAs at two per SM the last three clusters ran as a second wave and doubled the kernel.
+constexpr int kGeThreads = 256, kGeRows = 32, kGeTpr = 8;
 
 struct GramEigArgs {
   const float* partial;
@@ -291,14 +293,16 @@ struct GramEigArgs {
   float* U;                // [B][n][n]: column 0 receives u0
   float* lam;              // [B][n]
   int32_t* plan;           // [B][4] = {1, n, -1, status}
+  int32_t* flagged;        // optional [B]: copy of status that survives the repair pass (which rewrites plan[b][3])
 };
 
 template <int N>
-__global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) {
+__global__ void __launch_bounds__(kGeThreads, 3) gram_eig_kernel(GramEigArgs a) {
   constexpr int CL = N / kGeRows;                 // CTAs per cluster
   constexpr int PL = (N == 256) ? 384 : N;        // accumulator columns of a partial row
   constexpr int PW = PL + 4;                      // its pitch (columns PL, PL + 1: row sums of rows r, 128 + r)
-  constexpr int NJ = N / 64;                      // float4 per thread: columns q*4 + 64 j + {0..3}
+  constexpr int NJ = N / (4 * kGeTpr);            // float4 per thread: columns q*4 + 32 j + {0..3}
+  constexpr int CS = 4 * kGeTpr;                  // column stride between a thread's float4
   SPECGPU_DYN_SMEM(smem);
   float* sx = reinterpret_cast<float*>(smem);     // [N] current iterate (every CTA holds all of it)
   float* sy = sx + N;                             // [2][N] G x, double buffered across iterations
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
   const int rank = SPECGPU_CLUSTER_RANK();
   const int64_t b = blockIdx.x / CL;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int rl = tid >> 4, q = tid & 15;
+  const int rl = tid / kGeTpr, q = tid % kGeTpr;
   const int row0 = rank * kGeRows;
   const int kparts = (int)((a.nchunk + a.per - 1) / a.per);
   const int i0 = a.per_matrix ? (int)(b * kparts) : (int)((b * a.nchunk) / a.per);
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
   }
   // The partials are summed in CTA order (deterministic) but loaded kGeBatch at a time: all loads of a batch are in flight
   // before the first add (one memory round trip per batch instead of one per partial).
-  constexpr int kGeBatch = 3;
+  constexpr int kGeBatch = 1;
   for (int c0 = i0; c0 <= i1; c0 += kGeBatch) {
     const float* base[kGeBatch];
 #pragma unroll
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
       for (int u = 0; u < kGeBatch; ++u)
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
-          v[u][j] = __ldg(reinterpret_cast<const float4*>(base[u] + (size_t)(row0 + rl) * PW + q * 4 + 64 * j));
+          v[u][j] = __ldg(reinterpret_cast<const float4*>(base[u] + (size_t)(row0 + rl) * PW + q * 4 + CS * j));
 #pragma unroll
       for (int u = 0; u < kGeBatch; ++u)
         if (c0 + u <= i1) {
@@ -356,16 +360,16 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
           }
         }
     } else {
-      float4 v[kGeBatch][2], t[kGeBatch][2];
+      float4 v[kGeBatch][NJ / 2], t[kGeBatch][1024 / kGeThreads];
 #pragma unroll
       for (int u = 0; u < kGeBatch; ++u) {
 #pragma unroll
-        for (int j = 2; j < NJ; ++j)    // G11 from D2
-          v[u][j - 2] = __ldg(reinterpret_cast<const float4*>(base[u] + (size_t)(row0 - 128 + rl) * PW + 256 + q * 4 + 64 * (j - 2)));
+        for (int j = NJ / 2; j < NJ; ++j)    // G11 from D2
+          v[u][j - NJ / 2] = __ldg(reinterpret_cast<const float4*>(base[u] + (size_t)(row0 - 128 + rl) * PW + 256 + q * 4 + CS * (j - NJ / 2)));
         // G10[row][c] = D1[c][row]: 128-byte runs D1[c][row0 .. row0 + 31], accumulated transposed in shared memory (every
         // cell is owned by one thread for all partials: no atomics); 128 * 8 float4 = two per thread
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 1024 / kGeThreads; ++h) {
           const int i = tid + h * kGeThreads;
           t[u][h] = __ldg(reinterpret_cast<const float4*>(base[u] + (size_t)(i >> 3) * PW + row0 + (i & 7) * 4));
         }
@@ -374,11 +378,11 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
       for (int u = 0; u < kGeBatch; ++u)
         if (c0 + u <= i1) {
 #pragma unroll
-          for (int j = 2; j < NJ; ++j) {
-            g[j].x += v[u][j - 2].x; g[j].y += v[u][j - 2].y; g[j].z += v[u][j - 2].z; g[j].w += v[u][j - 2].w;
+          for (int j = NJ / 2; j < NJ; ++j) {
+            g[j].x += v[u][j - NJ / 2].x; g[j].y += v[u][j - NJ / 2].y; g[j].z += v[u][j - NJ / 2].z; g[j].w += v[u][j - NJ / 2].w;
           }
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < 1024 / kGeThreads; ++h) {
             const int i = tid + h * kGeThreads;
             const int c = i >> 3, e4 = i & 7;
             sT[(e4 * 4 + 0) * 132 + c] += t[u][h].x;
@@ -392,7 +396,7 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
   if (lower) {
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 2; ++j) g[j] = *reinterpret_cast<const float4*>(sT + rl * 132 + q * 4 + 64 * j);
+    for (int j = 0; j < NJ / 2; ++j) g[j] = *reinterpret_cast<const float4*>(sT + rl * 132 + q * 4 + CS * j);
   }
   float lam_scale = 1.0f;
   if (a.raw_minmax != nullptr) {
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
     const float m2t = m * m * (float)a.cols;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const float4 rc = *reinterpret_cast<const float4*>(sr + q * 4 + 64 * j);
+      const float4 rc = *reinterpret_cast<const float4*>(sr + q * 4 + CS * j);
       g[j].x = g[j].x - m * (ri + rc.x) + m2t;
       g[j].y = g[j].y - m * (ri + rc.y) + m2t;
       g[j].z = g[j].z - m * (ri + rc.z) + m2t;
@@ -435,15 +439,15 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
     float dval = -INFINITY;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int c0 = q * 4 + 64 * j;
+      const int c0 = q * 4 + CS * j;
       if (dc >= c0 && dc < c0 + 4) {
         const int e = dc - c0;
         dval = e == 0 ? g[j].x : (e == 1 ? g[j].y : (e == 2 ? g[j].z : g[j].w));
       }
     }
-    // reduce over the 16 threads of the row, then over the 32 rows (2 rows per warp)
+    // reduce over the threads of the row, then over the 32 rows
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) dval = fmaxf(dval, __shfl_xor_sync(0xffffffffu, dval, o));
+    for (int o = kGeTpr / 2; o > 0; o >>= 1) dval = fmaxf(dval, __shfl_xor_sync(0xffffffffu, dval, o));
     if (q == 0) sy[rl] = dval;
     __syncthreads();
     if (tid < 32) {
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
         for (int r = 0; r < CL; ++r) {
           float* remote = SPECGPU_MAP_SHARED(scand, r) + rank * N;
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) *reinterpret_cast<float4*>(remote + q * 4 + 64 * j) = g[j];
+          for (int j = 0; j < NJ; ++j) *reinterpret_cast<float4*>(remote + q * 4 + CS * j) = g[j];
         }
       }
     }
@@ -511,11 +515,11 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
     float acc = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const float4 xv = *reinterpret_cast<const float4*>(sx + q * 4 + 64 * j);
+      const float4 xv = *reinterpret_cast<const float4*>(sx + q * 4 + CS * j);
       acc += g[j].x * xv.x + g[j].y * xv.y + g[j].z * xv.z + g[j].w * xv.w;
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = kGeTpr / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (q < CL) {   // thread q of the row sends y[row] to CTA q
       float* remote = SPECGPU_MAP_SHARED(syc, q);
       remote[row0 + rl] = acc;
@@ -559,6 +563,7 @@ __global__ void __launch_bounds__(kGeThreads, 2) gram_eig_kernel(GramEigArgs a) 
     a.plan[b * 4 + 1] = N;
     a.plan[b * 4 + 2] = -1;
     a.plan[b * 4 + 3] = status;
+    if (a.flagged != nullptr) a.flagged[b] = status;
   }
 }
 
@@ -588,9 +593,10 @@ static int launch_gram_eig_t(const GramEigArgs& a, int64_t B, cudaStream_t strea
 }
 
 int launch_gram_eig(const float* partial, int64_t nchunk, int64_t per, int64_t B, int n, int max_iter, float* U, float* lam,
-                    int32_t* plan, cudaStream_t stream, const MinMaxWord* raw_minmax, int64_t cols, int per_matrix) {
+                    int32_t* plan, cudaStream_t stream, const MinMaxWord* raw_minmax, int64_t cols, int per_matrix,
+                    int32_t* flagged) {
   if (B == 0) return 0;
-  GramEigArgs a{partial, nchunk, per, raw_minmax, cols, per_matrix, max_iter > 0 ? max_iter : kPowMaxIter, U, lam, plan};
+  GramEigArgs a{partial, nchunk, per, raw_minmax, cols, per_matrix, max_iter > 0 ? max_iter : kPowMaxIter, U, lam, plan, flagged};
   if (n == 256) return launch_gram_eig_t<256>(a, B, stream);
   if (n == 128) return launch_gram_eig_t<128>(a, B, stream);
   return -1;
@@ -1065,9 +1071,8 @@ __device__ __forceinline__ void r1_store(float* p, float v, uint64_t pol) {
 }
 
 template <int RPW, bool NORM, bool CLIP, bool STREAM>   // RPW = rows per thread = ceil(rows / 16)
-__global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L, int rows, int64_t cols, int64_t ld,
-                                                                  const MinMaxWord* minmax, const float* U, float* S,
-                                                                  float* D, int64_t ldo) {
+__device__ __forceinline__ void svd_rank1_tile(const int64_t b, const float* L, int rows, int64_t cols, int64_t ld,
+                                               const MinMaxWord* minmax, const float* U, float* S, float* D, int64_t ldo) {
   uint64_t pol = 0;
 #if !defined(SPECGPU_EMULATE)
   if (STREAM) pol = l2_policy_evict_first();
@@ -1075,7 +1080,6 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
   SPECGPU_DYN_SMEM(smem);
   float* s_u = reinterpret_cast<float*>(smem);          // [rows]
   float* s_w = s_u + rows;                              // [16][32] partial coefficients
-  const int64_t b = blockIdx.y;
   const int64_t c0 = (int64_t)blockIdx.x * kRecCols;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float mn = 0.f, den = 1.f;
@@ -1155,30 +1159,49 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
   }
 }
 
+// only_flagged == nullptr: CTA (x, y) does column tile x of matrix y.  Repair pass (only_flagged != nullptr): a SMALL grid
+// (a big one costs microseconds even when every CTA returns at once) whose CTAs walk the matrices and redo the flagged ones.
+template <int RPW, bool NORM, bool CLIP, bool STREAM>
+__global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L, int rows, int64_t cols, int64_t ld,
+                                                                  const MinMaxWord* minmax, const float* U, float* S,
+                                                                  float* D, int64_t ldo, const int32_t* only_flagged, int64_t B) {
+  if (only_flagged == nullptr) {
+    svd_rank1_tile<RPW, NORM, CLIP, STREAM>(blockIdx.y, L, rows, cols, ld, minmax, U, S, D, ldo);
+    return;
+  }
+  for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+    if (only_flagged[b] == 0) continue;      // uniform over the CTA
+    svd_rank1_tile<RPW, NORM, CLIP, STREAM>(b, L, rows, cols, ld, minmax, U, S, D, ldo);
+    __syncthreads();                         // the tile's shared scratch is reused
+  }
+}
+
 template <int RPW, bool STREAM>
 static void launch_rank1_ts(dim3 grid, size_t smem, cudaStream_t stream, const float* L, int rows, int64_t cols, int64_t ld,
-                            const MinMaxWord* minmax, const float* U, int clip, float* S, float* D, int64_t ldo) {
+                            const MinMaxWord* minmax, const float* U, int clip, float* S, float* D, int64_t ldo,
+                            const int32_t* only_flagged, int64_t B) {
   const bool nrm = minmax != nullptr;
-  if (nrm && clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, true, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
-  else if (nrm) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, false, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
-  else if (clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, true, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
-  else SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, false, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo);
+  if (nrm && clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, true, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
+  else if (nrm) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, false, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
+  else if (clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, true, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
+  else SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, false, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
 }
 template <int RPW>
 static void launch_rank1_t(dim3 grid, size_t smem, cudaStream_t stream, const float* L, int rows, int64_t cols, int64_t ld,
-                           const MinMaxWord* minmax, const float* U, int clip, float* S, float* D, int64_t ldo, int stream_out) {
-  if (stream_out) launch_rank1_ts<RPW, true>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
-  else launch_rank1_ts<RPW, false>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo);
+                           const MinMaxWord* minmax, const float* U, int clip, float* S, float* D, int64_t ldo, int stream_out,
+                           const int32_t* only_flagged, int64_t B) {
+  if (stream_out) launch_rank1_ts<RPW, true>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, only_flagged, B);
+  else launch_rank1_ts<RPW, false>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, only_flagged, B);
 }
 
 int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const MinMaxWord* minmax, const float* U,
-                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out) {
+                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out, const int32_t* only_flagged) {
   if (B == 0 || rows == 0 || cols == 0) return 0;
   const size_t smem = ((size_t)rows + kR1Warps * 32) * sizeof(float);
-  const dim3 grid((unsigned)ceil_div(cols, kRecCols), (unsigned)B);
-  if (rows <= 64) launch_rank1_t<4>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out);
-  else if (rows <= 128) launch_rank1_t<8>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out);
-  else if (rows <= 256) launch_rank1_t<16>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out);
+  const dim3 grid((unsigned)ceil_div(cols, kRecCols), (unsigned)(only_flagged ? std::min<int64_t>(B, 2) : B));
+  if (rows <= 64) launch_rank1_t<4>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out, only_flagged, B);
+  else if (rows <= 128) launch_rank1_t<8>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out, only_flagged, B);
+  else if (rows <= 256) launch_rank1_t<16>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out, only_flagged, B);
   else return -1;
   return (int)cudaGetLastError();
 }

@@ -269,3 +269,81 @@ def test_launch_counter(emu_rt):
     before = emu_rt.launch_count()
     api.spectrogram(np.zeros(1000, np.float32), nperseg=64, noverlap=32, runtime=emu_rt)
     assert emu_rt.launch_count() == before + 1
+
+
+# ---- shot files: BES keys and the HDF5 interchange layout ------------------------------------------------------------
+class _FakeH5Group(dict):
+    """The few h5py calls save_shot_hdf5 / load_hdf5_dataset make, on nested dicts (h5py is not in this image)."""
+
+    def _walk(self, name, create=False):
+        node = self
+        for part in name.split("/"):
+            if part not in dict.keys(node):
+                if not create:
+                    raise KeyError(name)
+                dict.__setitem__(node, part, _FakeH5Group())
+            node = dict.__getitem__(node, part)
+        return node
+
+    def __contains__(self, name):
+        try:
+            self._walk(name)
+            return True
+        except KeyError:
+            return False
+
+    def __getitem__(self, name):
+        return self._walk(name)
+
+    def __delitem__(self, name):
+        head, _, tail = name.rpartition("/")
+        dict.__delitem__(self._walk(head) if head else self, tail)
+
+    def create_group(self, name):
+        if name in self:
+            raise ValueError("group exists")
+        return self._walk(name, create=True)
+
+    def create_dataset(self, name, data):
+        dict.__setitem__(self, name, np.array(data))
+
+
+def test_bes_keys_and_hdf5_layout(emu_rt, tmp_path):
+    import pickle
+    sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=64, noverlap=32)
+    n = 3000
+    sig = {c: oc.synth_ece(9, c, n=n) for c in (1, 2)}
+    ece, bes = tmp_path / "ece_123456.pkl", tmp_path / "bes_123456.pkl"
+    pickle.dump({"\\tecef%.2i" % c: sig[c] for c in sig}, open(ece, "wb"))
+    pickle.dump({"besfu{:02d}".format(c): {"data.BES": sig[c]} for c in sig}, open(bes, "wb"))
+    cut = n / sp["fs"]
+    S_e, f_e, t_e = api.specgr(str(ece), 2, sp, cut, runtime=emu_rt)
+    S_b, f_b, t_b = api.specgr(str(bes), 2, sp, cut, runtime=emu_rt, key="bes")        # denoising_by_svd.ipynb:49-63
+    assert np.array_equal(S_e, S_b) and np.array_equal(t_e, t_b)
+    Sr, fr, tr = oc.specgr_array(sig[2].astype(np.float64), sp)
+    np.testing.assert_allclose(S_b, Sr, rtol=0, atol=pc.ATOL_IMAGE)
+    assert np.array_equal(api.load_shot(str(bes), channels=(1, 2), cut_shot=cut, fs=sp["fs"], key="bes"), np.stack([sig[1], sig[2]]))
+    with pytest.raises(ValueError):
+        api.specgr(str(ece), 1, sp, cut, runtime=emu_rt, key="co2")
+    # the interchange layout of pipeline_data.py:112-116, read back the way VAE/manual_scan.py:137-148 does
+    res = api.process_shot(str(ece), sp, channels=(1, 2), cut_shot=cut, runtime=emu_rt)
+    root = _FakeH5Group()
+    api.save_shot_hdf5(root, "123456", res, channels=(1, 2))
+    api.save_shot_hdf5(root, "123456", res, channels=(1, 2))          # re-runnable (the reference's create_group is not)
+    assert sorted(dict.keys(root)) == ["ece_123456"] and sorted(dict.keys(root["ece_123456"])) == ["chn_1", "chn_2"]
+    g = root["ece_123456/chn_2"]
+    assert sorted(dict.keys(g)) == ["f", "pipeline_out", "spec", "t"]
+    assert np.array_equal(g["spec"], res["spec"][1]) and g["pipeline_out"].dtype == np.float64
+    assert np.array_equal(g["f"], res["f"]) and np.array_equal(g["t"], res["t"])
+    specs, final = api.load_hdf5_dataset(root, n_channels=20)
+    assert len(specs) == 2 and np.array_equal(final[1], res["pipeline_out"][1])
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            api.save_shot_hdf5(str(tmp_path / "x.hdf5"), "1", res, channels=(1, 2))
+    else:
+        path = str(tmp_path / "x.hdf5")
+        api.save_shot_hdf5(path, "123456", res, channels=(1, 2))
+        specs2, final2 = api.load_hdf5_dataset(path)
+        assert np.array_equal(specs2[0], res["spec"][0]) and np.array_equal(final2[1], res["pipeline_out"][1])
