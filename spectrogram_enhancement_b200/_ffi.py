@@ -119,5 +119,15 @@ _lib = None
 def load() -> Library:
     global _lib
     if _lib is None:
+        if "SPECGPU_LIB" not in os.environ:
+            try:        # a library older than its sources is a silent way to measure the wrong code: say so
+                from . import build as _build
+                digest = _build._deps_digest() + "|" + " ".join(_build.NVCC_FLAGS)
+                if not _build._up_to_date(LIB_PATH, digest):
+                    import sys
+                    print("libspecgpu: WARNING: libspecgpu.so is older than csrc/ -- run "
+                          "`python -m spectrogram_enhancement_b200.build`", file=sys.stderr)
+            except Exception:
+                pass
         _lib = Library(LIB_PATH)
     return _lib

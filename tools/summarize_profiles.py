@@ -19,7 +19,7 @@ command = sys.argv[6] if len(sys.argv) > 6 else "python bench.py --steps 3 --war
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
-OURS = ("stft_kernel", "gram_tc_kernel", "gram_reduce", "gram_simt", "eig_power", "eig_jacobi", "eig_sort", "svd_", "lognorm",
+OURS = ("stft_kernel", "gram_tc_kernel", "gram_tma_kernel", "gram_eig_kernel", "gram_reduce", "gram_simt", "eig_power", "eig_jacobi", "eig_sort", "svd_", "lognorm",
         "minmax", "quantfilt", "patch_kernel", "unpatch", "csd_", "rescale", "moments", "norm_apply", "img_", "blur_", "morph_",
         "meansub_", "u8_lut")
 
@@ -51,7 +51,8 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
-           "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct"]
+           "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rr[0], rr[1], rr[2:]
