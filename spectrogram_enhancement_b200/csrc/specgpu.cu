@@ -739,7 +739,7 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
       cudaEventRecord(ctx->ev_repair_join, rs);
     }
 #endif
-    CHECK_LAUNCH(ctx, launch_svd_rank1(Lsrc, B, (int)rows, cols, ldsrc, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, l2_pin > 0.f ? 1 : 0),
+    CHECK_LAUNCH(ctx, launch_svd_rank1(Lsrc, B, (int)rows, cols, ldsrc, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, 0),
                  "svd_rank1", 1);
 #ifndef SPECGPU_EMULATE
     if (side_repair) {
