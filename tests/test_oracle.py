@@ -224,6 +224,7 @@ def test_against_reference_functions():
 # ---- cv2 chain restatement vs OpenCV itself and vs the reference's golden outputs ----------------
 def test_cv2_chain_restatement_matches_opencv():
     cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(0)     # OpenCV's own thread pool once returned a different blur for a 9x9 image late in a long suite run
     rng = np.random.default_rng(0)
     for n in (3, 5, 7, 9, 15, 31, 41):          # Q8.8 taps: read them off a constant-column probe image
         img = np.zeros((9, 4 * n + 1), np.uint8)
