@@ -47,6 +47,11 @@ int launch_stft(int log2n, int mode, const StftArgs& a, int64_t B, cudaStream_t 
 int launch_lognorm(float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, const MinMaxWord* mm, float* mm_out,
                    cudaStream_t stream);
 
+// stft_gram.cu: the nperseg-512 log-PSD STFT that also accumulates the Gram partials of the raw image (device build only)
+bool stft_gram_supported(int log2n);
+int launch_stft_gram(const StftArgs& a, int64_t B, float* partial_ws, int num_sms, int64_t* nchunk, int64_t* per,
+                     cudaStream_t stream);
+
 // elementwise.cu
 int launch_rescale(const float* src, int64_t B, int64_t rows, int64_t cols, int64_t ld, float* dst, unsigned* mm_ws,
                    cudaStream_t stream);

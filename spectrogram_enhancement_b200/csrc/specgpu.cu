@@ -660,7 +660,7 @@ SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
 int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm, int64_t B, int64_t rows, int64_t cols,
             int64_t ld, int kind, int start, int stop, int clip, bool power_ok, bool fallback, void* out, int out_f64,
             int64_t ldo, float* s_out, int32_t* info, cudaStream_t st, float l2_pin = 0.f, const float* Limg = nullptr,
-            int64_t ldL = 0) {
+            int64_t ldL = 0, const int64_t* pre_gram = nullptr /* {nchunk, per}: partials already written by stft_gram */) {
   void* stream = (void*)st;
   const float* Lsrc = Limg ? Limg : S;       // what the Gram and projection kernels read
   const int64_t ldsrc = Limg ? ldL : ld;
@@ -670,7 +670,9 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
   bool side_repair = false;
   bool gram_raw = false;     // the Gram partials are of the un-normalised image (TMA-fed kernel) and carry row sums
   bool gram_tma = false;
-  if (tc) {
+  if (tc && pre_gram != nullptr) {
+    gram_raw = true;            // the fused STFT kernel left raw-operand partials (with row sums) behind
+  } else if (tc) {
     // tensor-core Gram partials, then ONE cluster kernel per matrix that sums them and runs the power iteration
     int e__ = 1;
     if (!std::getenv("SPECGPU_NO_GRAM_TMA")) {
@@ -696,7 +698,12 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
   if (power_ok) {
     if (tc) {
       int64_t nchunk = 0, per = 0;
-      gram_tc_geometry(B, cols, ctx->num_sms, gram_tma ? 1 : 0, &nchunk, &per);
+      if (pre_gram != nullptr) {
+        nchunk = pre_gram[0];
+        per = pre_gram[1];
+      } else {
+        gram_tc_geometry(B, cols, ctx->num_sms, gram_tma ? 1 : 0, &nchunk, &per);
+      }
       CHECK_LAUNCH(ctx, launch_gram_eig(w.gram_partial, nchunk, per, B, (int)rows, ctx->power_max_iter, w.U, w.lam, w.plan, st,
                                         gram_raw ? raw_mm : nullptr, cols, gram_tma ? 1 : 0, w.flagged),
                    "gram_eig", 1);
@@ -1166,7 +1173,22 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     float* Lg = tiled ? Lt + (size_t)b0 * ntile * rows * kTileCols : nullptr;
     StftArgs a = make_args(plan, x + b0 * ldx, n, ldx, 0, nseg, (float)plan->scale, tiled ? Lg : Sg, tiled ? -ntile : ldt, mmg, gen);
     a.l2_pin = l2_pin;
-    CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, nb, st), "stft_kernel", 1);
+    int64_t pre_gram[2] = {0, 0};
+    bool fused = false;
+    if (tiled && stft_gram_supported(plan->log2n) && std::getenv("SPECGPU_FUSED_GRAM")) {
+      int e__;
+      {
+        ProfScope prof__(ctx, st, "stft_gram");
+        e__ = launch_stft_gram(a, nb, part[li], ctx->num_sms, &pre_gram[0], &pre_gram[1], st);
+      }
+      if (e__ == 0) {
+        fused = true;
+        ctx->launches += 1;
+      } else if (e__ != 1) {
+        return cuda_fail(ctx, e__, "stft_gram");
+      }
+    }
+    if (!fused) CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, nb, st), "stft_kernel", 1);
     SvdWs w{};
     w.G = reinterpret_cast<float*>(Gall + b0 * rows * rows);
     w.U = Uall + b0 * rows * rows;
@@ -1177,7 +1199,7 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     w.flagged = flagged_all + b0;
     // Sg holds the raw log image until the rank-1 projection normalises it in place (see svd_run)
     if ((rc = svd_run(ctx, w, Sg, mmg, nb, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, fallback, Dg, 0, ldt, nullptr,
-                      info ? info + b0 * 4 : nullptr, st, l2_pin, Lg, tiled ? -ntile : 0)))
+                      info ? info + b0 * 4 : nullptr, st, l2_pin, Lg, tiled ? -ntile : 0, fused ? pre_gram : nullptr)))
       return rc;
     if (tiles && ntiles > 0)
       CHECK_LAUNCH(ctx, launch_patch(Dg, nb, rows, ldt, tile_w, ntiles, tiles + (size_t)b0 * ntiles * rows * tile_w, 0, st), "patch", 1);

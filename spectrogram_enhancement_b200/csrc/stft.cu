@@ -8,137 +8,9 @@
 // memory tile so that the [freq][time] output is written in time-contiguous runs.
 #include <type_traits>
 
-#include "fft.cuh"
-#include "kernels.h"
-#include "ptx.cuh"
+#include "stft_common.cuh"
 
 namespace specgpu {
-
-constexpr int kStftThreads = 256;
-// internal variant of STFT_MODE_LOGPSD: eps >= FLT_MIN, so log2's argument is never subnormal and the
-// flush-to-zero MUFU form (no range-scaling instructions) is exact enough
-constexpr int STFT_MODE_LOGPSD_FAST = 4;
-
-template <int LOG2N>
-struct StftCfg {
-  static constexpr int N = 1 << LOG2N;
-  static constexpr int LOG2M = LOG2N - 1;
-  static constexpr int M = N / 2;
-  static constexpr int F = M + 1;
-  static constexpr int R0 = fft_radix_at(LOG2M, 0);
-  static constexpr int G = M / R0;                      // threads per segment
-  static constexpr int NG = kStftThreads / G;           // segments in flight per CTA
-  static constexpr int LINE = M + (M >> 4) + 1;          // padded float2 per FFT line
-  // tile width (segments per CTA tile): >= NG, grown towards 16 while the tile stays <= 36 KB.  (nperseg 512: 16
-  // segments = 64-byte rows of the float tile, one round of the 16 segment groups per tile.)
-  __host__ __device__ static constexpr int tile_w(int bytes_per_elem) {
-    int tt = NG;
-    while (tt < 16 && (long)F * (2 * tt) * bytes_per_elem <= 36 * 1024) tt *= 2;
-    return tt;
-  }
-};
-
-__host__ __device__ constexpr bool stft_mode_is_log(int mode) { return mode == STFT_MODE_LOGPSD || mode == STFT_MODE_LOGPSD_FAST; }
-__host__ __device__ constexpr int stft_elem_bytes(int mode) { return mode == STFT_MODE_COMPLEX ? 8 : 4; }
-
-// The output tile [F rows][TT segments] lives in shared memory as dense rows of ROWB = TT * elem bytes with the
-// 16-byte chunks of a row XOR-swizzled by the row index -- exactly the CU_TENSOR_MAP_SWIZZLE_{32,64,128}B patterns
-// (address bits 4..6 ^= bits 7..9, masked to the span), so that a TMA tensor store can read it in place while the
-// column-wise writes of the segment groups spread over the banks.  The tile base is 1024-byte aligned.
-__host__ __device__ constexpr int stft_swizzle_mask(int rowb) { return rowb >= 128 ? 0x70 : (rowb == 64 ? 0x30 : (rowb == 32 ? 0x10 : 0)); }
-
-struct StftSmem {
-  int window_off, twm_off, twn_off, line_off, red_off, bar_off, in_off, tile_off, total;
-};
-
-// span_floats: samples of the staged input span of one tile, (TT-1)*hop + N (0: segments are loaded straight from
-// global memory).
-template <int LOG2N>
-__host__ __device__ inline StftSmem stft_smem_layout(int mode, int span_floats) {
-  using C = StftCfg<LOG2N>;
-  StftSmem s;
-  int off = 0;
-  s.window_off = off; off += C::N * 4;
-  s.twm_off = off;    off += (fft_twiddle_count(C::LOG2M) > 0 ? fft_twiddle_count(C::LOG2M) : 1) * 8;
-  s.twn_off = off;    off += (C::M / 2 + 1) * 8;
-  off = (off + 15) & ~15;
-  s.line_off = off;   off += C::NG * C::LINE * 8;
-  s.red_off = off;    off += (kStftThreads / 32) * 2 * 4 + 64;
-  off = (off + 15) & ~15;
-  s.bar_off = off;    off += 16;
-  off = (off + 127) & ~127;
-  s.in_off = off;     off += (span_floats * 4 + 127) & ~127;
-  s.tile_off = off;
-  if (mode != STFT_MODE_SPECTRA) {
-    off = (off + 1023) & ~1023;
-    s.tile_off = off;
-    off += C::F * C::tile_w(stft_elem_bytes(mode)) * stft_elem_bytes(mode);
-  }
-  s.total = off;
-  return s;
-}
-
-// Sum of (a, b) over the G threads of a segment group.
-template <int G>
-__device__ __forceinline__ void group_sum2(float& a, float& b, float* red, int tid) {
-  if constexpr (G == 1) {
-    return;
-  } else if constexpr (G <= 32) {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-  } else {
-    a = warp_sum(a);
-    b = warp_sum(b);
-    const int w = tid >> 5;
-    if ((tid & 31) == 0) {
-      red[2 * w] = a;
-      red[2 * w + 1] = b;
-    }
-    __syncthreads();
-    constexpr int WPG = G / 32;
-    const int w0 = (w / WPG) * WPG;
-    float sa = 0.f, sb = 0.f;
-#pragma unroll
-    for (int i = 0; i < WPG; ++i) {
-      sa += red[2 * (w0 + i)];
-      sb += red[2 * (w0 + i) + 1];
-    }
-    a = sa;
-    b = sb;
-    __syncthreads();
-  }
-}
-
-// log2 for arguments known to be normal (>= FLT_MIN): one MUFU, no subnormal range scaling.
-__device__ __forceinline__ float log2_normal(float x) {
-#if defined(SPECGPU_EMULATE)
-  return __log2f(x);
-#else
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-#endif
-}
-
-// Resident CTAs per SM the register allocator should aim for: what the shared-memory footprint of the mode allows
-// (the spectra mode has no output tile).  Without it the 3-pass sizes compile to ~195 registers = one CTA per SM.
-__host__ __device__ constexpr int stft_min_blocks(int log2n, int mode) {
-  if (mode == STFT_MODE_COMPLEX) return log2n <= 9 ? 2 : 1;
-  if (log2n <= 9) return 3;
-  if (mode == STFT_MODE_SPECTRA) return log2n <= 12 ? 3 : 1;
-  return log2n == 10 ? 2 : 1;
-}
-
-#ifndef SPECGPU_GRID_CONSTANT
-#if defined(SPECGPU_EMULATE)
-#define SPECGPU_GRID_CONSTANT
-#else
-#define SPECGPU_GRID_CONSTANT __grid_constant__
-#endif
-#endif
 
 template <int LOG2N, int MODE>
 __global__ void __launch_bounds__(kStftThreads, stft_min_blocks(LOG2N, MODE))
