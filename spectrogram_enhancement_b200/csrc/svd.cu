@@ -647,12 +647,12 @@ __device__ __forceinline__ bool jacobi_pair(T* x, T* y, int n, int lane) {
   a = warp_sum(a);
   bq = warp_sum(bq);
   g = warp_sum(g);
-  const T ag = g < 0 ? -g : g;
-  if (!(ag > (T)JacTol<T>::value * (T)sqrt((double)(a * bq)))) return false;
+  // |g| > tol sqrt(a b)  <=>  g^2 > tol^2 a b   (no square root on the path every pair takes)
+  if (!(g * g > ((T)JacTol<T>::value * (T)JacTol<T>::value) * (a * bq))) return false;
   const T zeta = (bq - a) / ((T)2 * g);
   const T az = zeta < 0 ? -zeta : zeta;
   const T t = (zeta < 0 ? (T)-1 : (T)1) / (az + (T)sqrt((double)((T)1 + zeta * zeta)));
-  const T c = (T)1 / (T)sqrt((double)((T)1 + t * t)), s = c * t;
+  const T c = (T)rsqrt((double)((T)1 + t * t)), s = c * t;
   for (int i = lane; i < n; i += 32) {
     const T xv = x[i], yv = y[i];
     x[i] = c * xv - s * yv;

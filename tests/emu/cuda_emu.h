@@ -355,6 +355,7 @@ static inline float emu_fast_log2f(float a) { return std::log2(a); }
 #define __expf emu_fast_expf
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
+static inline double rsqrt(double a) { return 1.0 / std::sqrt(a); }
 static inline float __saturatef(float a) { return a < 0.f ? 0.f : (a > 1.f ? 1.f : a); }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
