@@ -21,7 +21,7 @@ CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(ROOT, "build")
 LIB = os.path.join(PKG, "libspecgpu.so")
 
-SOURCES = ["specgpu.cu", "stft.cu", "stft_gram.cu", "elementwise.cu", "quantile.cu", "svd.cu", "gram_tc.cu", "csd.cu", "imgchain.cu"]
+SOURCES = ["specgpu.cu", "stft.cu", "stft_gram.cu", "elementwise.cu", "quantile.cu", "svd.cu", "eig_tridiag.cu", "gram_tc.cu", "csd.cu", "imgchain.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",

@@ -95,6 +95,14 @@ int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t 
 int launch_svd_project(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U, const int32_t* plan,
                        int clip, void* out, int out_f64, int64_t ldo, cudaStream_t stream);
 
+// eig_tridiag.cu: values-first float64 eigensolver (Householder tridiagonalisation + bisection + inverse iteration) for the
+// use_optimal / computeSignal modes; matrices it cannot serve are flagged in plan[b][3] for the Jacobi solver.
+bool eig_tridiag_supported(int n);
+size_t eig_tridiag_workspace_bytes(int64_t B, int n);
+int launch_eig_tridiag_values(double* W /* work copy of G, destroyed */, int64_t B, int n, float* lam, void* ws, cudaStream_t stream);
+int launch_eig_tridiag_vectors(const double* W, const double* G, int64_t B, int n, int32_t* plan, float* U, void* ws,
+                               cudaStream_t stream);
+
 // gram_tc.cu
 bool gram_tc_supported(int64_t rows);
 size_t gram_tc_workspace_bytes(int64_t B, int64_t rows);

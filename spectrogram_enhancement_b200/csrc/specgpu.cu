@@ -621,6 +621,7 @@ namespace {
 double omega_of(double beta) { return 0.56 * std::pow(beta, 3.0) - 0.95 * std::pow(beta, 2.0) + 1.82 * beta + 1.43; }   // as Python: beta ** 3
 
 struct SvdWs {
+  void* tri = nullptr;          // scratch of the values-first eigensolver (eig_tridiag.cu)
   int32_t* flagged = nullptr;   // [B] status snapshot for the side-stream repair (pipeline, tiled scratch image)
   float* G;
   float* U;
@@ -632,7 +633,8 @@ struct SvdWs {
 
 size_t svd_ws_bytes(int64_t B, int64_t rows, bool tc, bool full) {
   return carve_size({(size_t)B * rows * rows * 8, (size_t)B * rows * rows * 4, (size_t)B * rows * 4, (size_t)B * 16,
-                     tc ? gram_tc_workspace_bytes(B, rows) : 0, full ? jacobi_workspace_bytes(B, (int)rows) : 0});
+                     tc ? gram_tc_workspace_bytes(B, rows) : 0, full ? jacobi_workspace_bytes(B, (int)rows) : 0,
+                     full && eig_tridiag_supported((int)rows) ? eig_tridiag_workspace_bytes(B, (int)rows) : 0});
 }
 
 SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
@@ -644,6 +646,7 @@ SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
   w.plan = cv.take<int32_t>(B * 4);
   w.gram_partial = tc ? cv.take<float>(gram_tc_workspace_bytes(B, rows) / 4) : nullptr;
   w.jacobi = full ? (void*)cv.take<char>(jacobi_workspace_bytes(B, (int)rows)) : nullptr;
+  w.tri = (full && eig_tridiag_supported((int)rows)) ? (void*)cv.take<char>(eig_tridiag_workspace_bytes(B, (int)rows)) : nullptr;
   return w;
 }
 
@@ -725,7 +728,34 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
       CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 1, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
     }
   } else {
-    CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, g_f64, B, (int)rows, 0, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+    // Full-spectrum modes.  use_optimal / computeSignal need every singular VALUE but only a few leading vectors: the
+    // values-first solver (tridiagonalisation + bisection, then inverse iteration for the vectors the plan asks for) serves
+    // them; explicit ranges go there too when the host can see that they only need a few leading vectors.  Whatever it
+    // cannot serve is flagged and redone by the Jacobi solver (which skips the rest).
+    bool tri = g_f64 && w.tri != nullptr && eig_tridiag_supported((int)rows) && !std::getenv("SPECGPU_NO_TRIDIAG");
+    if (tri && kind == 0) {
+      int a0 = start < 0 ? 0 : start, e0 = stop > (int)rows ? (int)rows : stop;
+      if (e0 < 0) e0 = (e0 + (int)rows > 0) ? e0 + (int)rows : 0;
+      if (a0 > (int)rows) a0 = (int)rows;
+      if (e0 < a0) e0 = a0;
+      const int nk = e0 - a0;
+      const bool complement = ((int)rows - nk) < nk;
+      const int lead = complement ? a0 : (nk > 0 ? e0 : 0), trailing = complement ? (int)rows - e0 : 0;
+      tri = trailing == 0 && lead <= 16;
+    }
+    if (tri) {
+      const double beta0 = (double)std::min(rows, cols) / (double)std::max(rows, cols);
+      double* Wcopy = static_cast<double*>(w.jacobi);       // the Jacobi scratch is free until the fallback below
+      cudaError_t ce = cudaMemcpyAsync(Wcopy, w.G, (size_t)B * rows * rows * sizeof(double), cudaMemcpyDeviceToDevice, st);
+      if (ce != cudaSuccess) return cuda_fail(ctx, (int)ce, "tridiag copy");
+      CHECK_LAUNCH(ctx, launch_eig_tridiag_values(Wcopy, B, (int)rows, w.lam, w.tri, st), "eig_tridiag", 2);
+      CHECK_LAUNCH(ctx, launch_svd_plan(w.lam, B, (int)rows, kind, start, stop, omega_of(beta0), w.plan, nullptr, st), "svd_plan", 1);
+      CHECK_LAUNCH(ctx, launch_eig_tridiag_vectors(Wcopy, reinterpret_cast<const double*>(w.G), B, (int)rows, w.plan, w.U, w.tri, st),
+                   "eig_trivec", 2);
+      CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 1, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+    } else {
+      CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, g_f64, B, (int)rows, 0, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+    }
   }
   const double beta = (double)std::min(rows, cols) / (double)std::max(rows, cols);
   if (!power_ok)   // the power kernel writes the (fixed) default plan itself

@@ -166,6 +166,11 @@ def test_pipeline_fallback_route(emu_rt):
     pc.case_pipeline_fallback(emu_rt, dict(oc.DEFAULT_SPEC_PARAMS, nperseg=64, noverlap=32), 6000, B=2)
 
 
+def test_svd_optimal_repeated_value(emu_rt):
+    # a repeated singular value inside the kept range (values-first solver: inverse iteration + Gram-Schmidt, or Jacobi)
+    pc.case_svd_optimal(emu_rt, 48, 200, [30.0, 30.0, 12.0, 5.0], noise=0.02)
+
+
 def test_svd_degenerate_leading_pair_and_null_start(emu_rt):
     pc.case_svd_degenerate(emu_rt, rows=32, cols=120)
 

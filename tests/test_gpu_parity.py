@@ -207,6 +207,10 @@ def test_svd_range_optimal_compute(cuda_rt):
     pc.case_svd_range(cuda_rt, 32, 80, [40, 20, 10, 5], 1, -28)
     pc.case_svd_optimal(cuda_rt, 256, 3905, [400.0, 200.0, 100.0], noise=0.05)
     pc.case_svd_optimal(cuda_rt, 100, 333, [40, 20, 10])
+    # a (nearly) repeated singular value inside the kept range: the values-first solver's inverse iteration has to
+    # Gram-Schmidt the pair apart (or hand the matrix to the Jacobi solver)
+    pc.case_svd_optimal(cuda_rt, 128, 600, [60.0, 60.0, 25.0, 10.0], noise=0.02)
+    pc.case_svd_optimal(cuda_rt, 256, 1200, [300.0, 299.9999, 80.0, 79.0, 20.0], noise=0.02, seed=9)
     pc.case_compute_signal(cuda_rt, 64, 300, [40, 20])
 
 
