@@ -99,7 +99,8 @@ int launch_svd_project(const float* S, int64_t B, int rows, int64_t cols, int64_
 // use_optimal / computeSignal modes; matrices it cannot serve are flagged in plan[b][3] for the Jacobi solver.
 bool eig_tridiag_supported(int n);
 size_t eig_tridiag_workspace_bytes(int64_t B, int n);
-int launch_eig_tridiag_values(double* W /* work copy of G, destroyed */, int64_t B, int n, float* lam, void* ws, cudaStream_t stream);
+int launch_eig_tridiag_values(const double* G, double* W /* [B][n][n]: receives the reflectors */, int64_t B, int n, float* lam, void* ws,
+                              cudaStream_t stream);
 int launch_eig_tridiag_vectors(const double* W, const double* G, int64_t B, int n, int32_t* plan, float* U, void* ws,
                                cudaStream_t stream);
 

@@ -745,14 +745,14 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
     }
     if (tri) {
       const double beta0 = (double)std::min(rows, cols) / (double)std::max(rows, cols);
-      double* Wcopy = static_cast<double*>(w.jacobi);       // the Jacobi scratch is free until the fallback below
-      cudaError_t ce = cudaMemcpyAsync(Wcopy, w.G, (size_t)B * rows * rows * sizeof(double), cudaMemcpyDeviceToDevice, st);
-      if (ce != cudaSuccess) return cuda_fail(ctx, (int)ce, "tridiag copy");
-      CHECK_LAUNCH(ctx, launch_eig_tridiag_values(Wcopy, B, (int)rows, w.lam, w.tri, st), "eig_tridiag", 2);
+      double* Wrefl = static_cast<double*>(w.jacobi);       // the Jacobi scratch is free until the fallback below
+      CHECK_LAUNCH(ctx, launch_eig_tridiag_values(reinterpret_cast<const double*>(w.G), Wrefl, B, (int)rows, w.lam, w.tri, st),
+                   "eig_tridiag", 2);
       CHECK_LAUNCH(ctx, launch_svd_plan(w.lam, B, (int)rows, kind, start, stop, omega_of(beta0), w.plan, nullptr, st), "svd_plan", 1);
-      CHECK_LAUNCH(ctx, launch_eig_tridiag_vectors(Wcopy, reinterpret_cast<const double*>(w.G), B, (int)rows, w.plan, w.U, w.tri, st),
+      CHECK_LAUNCH(ctx, launch_eig_tridiag_vectors(Wrefl, reinterpret_cast<const double*>(w.G), B, (int)rows, w.plan, w.U, w.tri, st),
                    "eig_trivec", 2);
-      CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 1, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
+      if (!std::getenv("SPECGPU_TRIDIAG_STRICT"))   // (tests: without the fallback a matrix this route gave up on fails parity)
+        CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, 1, B, (int)rows, 1, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
     } else {
       CHECK_LAUNCH(ctx, launch_eig_jacobi(w.G, g_f64, B, (int)rows, 0, w.U, w.lam, w.plan, w.jacobi, st), "eig_jacobi", 2);
     }

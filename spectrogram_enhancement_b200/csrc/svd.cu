@@ -10,17 +10,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
-#ifndef SPECGPU_EMULATE
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
-#define SPECGPU_CLUSTER_SYNC() cg::this_cluster().sync()
-#define SPECGPU_CLUSTER_RANK() ((int)cg::this_cluster().block_rank())
-#define SPECGPU_MAP_SHARED(p, r) cg::this_cluster().map_shared_rank((p), (r))
-#else
-#define SPECGPU_CLUSTER_SYNC() emu::cluster_sync()
-#define SPECGPU_CLUSTER_RANK() ((int)emu::cluster_ctarank())
-#define SPECGPU_MAP_SHARED(p, r) emu::map_shared_rank((p), (r))
-#endif
+#include "cluster.cuh"
 
 namespace specgpu {
 

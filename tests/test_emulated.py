@@ -171,6 +171,14 @@ def test_svd_optimal_repeated_value(emu_rt):
     pc.case_svd_optimal(emu_rt, 48, 200, [30.0, 30.0, 12.0, 5.0], noise=0.02)
 
 
+def test_svd_optimal_values_first_route_alone(emu_rt, monkeypatch):
+    # SPECGPU_TRIDIAG_STRICT drops the Jacobi fallback: the cluster tridiagonalisation (3 CTAs under emulation), the
+    # division-free bisection, inverse iteration and the back-transformation have to carry the case by themselves
+    monkeypatch.setenv("SPECGPU_TRIDIAG_STRICT", "1")
+    pc.case_svd_optimal(emu_rt, 40, 150, [30.0, 12.0, 5.0], noise=0.02)
+    pc.case_svd_optimal(emu_rt, 33, 90, [20.0, 20.0, 6.0], noise=0.02, seed=4)
+
+
 def test_svd_degenerate_leading_pair_and_null_start(emu_rt):
     pc.case_svd_degenerate(emu_rt, rows=32, cols=120)
 

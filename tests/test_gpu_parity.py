@@ -214,6 +214,19 @@ def test_svd_range_optimal_compute(cuda_rt):
     pc.case_compute_signal(cuda_rt, 64, 300, [40, 20])
 
 
+@pytest.mark.gpu
+def test_svd_optimal_values_first_route_alone(cuda_rt, monkeypatch):
+    # SPECGPU_TRIDIAG_STRICT drops the Jacobi fallback: the values-first solver (cluster tridiagonalisation, bisection,
+    # inverse iteration, back-transformation) has to carry these by itself, cluster sizes 1 (n <= 154), 2 and 3
+    monkeypatch.setenv("SPECGPU_TRIDIAG_STRICT", "1")
+    pc.case_svd_optimal(cuda_rt, 256, 3905, [400.0, 200.0, 100.0], noise=0.05)
+    pc.case_svd_optimal(cuda_rt, 200, 900, [100.0, 50.0, 20.0], noise=0.03, seed=2)
+    pc.case_svd_optimal(cuda_rt, 100, 333, [40, 20, 10])
+    pc.case_svd_optimal(cuda_rt, 128, 600, [60.0, 60.0, 25.0, 10.0], noise=0.02)
+    pc.case_svd_optimal(cuda_rt, 256, 1200, [300.0, 299.9999, 80.0, 79.0, 20.0], noise=0.02, seed=9)
+    pc.case_svd_optimal(cuda_rt, 3, 40, [5.0, 2.0], noise=0.05)
+
+
 def test_svd_batched_and_tall(cuda_rt):
     ms = np.stack([oc.synth_lowrank(128, 500, [300.0, 20.0], 0.05, 30 + i) for i in range(5)])
     d = api.denoiseSignal(ms, runtime=cuda_rt)
