@@ -45,9 +45,22 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   for (int i = tid; i < fft_twiddle_count(C::LOG2M); i += kStftThreads) s_twm[i] = a.twM[i];
   for (int i = tid; i <= M / 2; i += kStftThreads) s_twn[i] = a.twN[i];
 #if !defined(SPECGPU_EMULATE)
+  // Barrier-free tile loop (the log-PSD hot path: one round per tile, groups inside a warp, staged bulk input, the whole
+  // tile through the tensor store).  No CTA barrier: the LAST warp to hold its samples issues the next bulk copy, the LAST
+  // warp to finish its columns issues the tensor store (two shared arrival counters); the only waits are on data (span
+  // landed) and on the previous store having read the tile, both normally long satisfied.  Warps of a CTA drift apart,
+  // so their shared-memory and FP32 phases overlap instead of colliding.
+  constexpr bool FLOWC = (ROUNDS == 1) && (G <= 32) && LOGM;
+  const bool flow = FLOWC && a.flow != 0;
   const uint32_t bar = smem_u32(smem + L.bar_off);
+  const uint32_t bar_tfree = bar + 8;
+  unsigned* cnt_free = reinterpret_cast<unsigned*>(smem + L.bar_off + 16);
+  unsigned* cnt_full = cnt_free + 1;
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar_tfree, 1);
+    *cnt_free = 0;
+    *cnt_full = 0;
     mbar_fence_init();
     if (tma_out) tma_prefetch_desc(&tmap);
   }
@@ -55,6 +68,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   // image, which the Gram and projection kernels read back while it is still in L2
   const uint64_t pol_in = l2_policy_evict_first();
   const uint64_t pol_out = a.l2_pin > 0.f ? l2_policy_pin_fraction(a.l2_pin) : l2_policy_evict_normal();
+#else
+  constexpr bool flow = false;
 #endif
   __syncthreads();
 
@@ -93,7 +108,17 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
 
   float2* line = s_line + grp * C::LINE;
   unsigned bulk_parity = 0;
-  if (stage && blockIdx.x < ntiles) prefetch(blockIdx.x);
+  unsigned flow_it = 0;                                    // tiles this CTA has stored (flow mode)
+  auto tile_start = [&](unsigned tile) -> int64_t {
+    const unsigned b32 = tile / tps;
+    return a.first_start + (int64_t)(tile - b32 * tps) * TT * (int64_t)a.hop;
+  };
+  if (flow) {
+    // bulk tiles are prefetched by one thread; the others (first / last tiles of a signal) are filled at the loop top
+    if (blockIdx.x < ntiles && tile_bulk(blockIdx.x / tps, tile_start(blockIdx.x)) && tid == 0) prefetch(blockIdx.x);
+  } else if (stage && blockIdx.x < ntiles) {
+    prefetch(blockIdx.x);
+  }
   // persistent CTAs: the tables above are loaded once, then the CTA walks tiles (signal b, TT segments)
   for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
   const unsigned b32 = tile / tps;
@@ -104,15 +129,26 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   const bool bulk = stage && tile_bulk(b, a.first_start + seg0 * (int64_t)a.hop);
 
 #if !defined(SPECGPU_EMULATE)
-  // the previous tile's tensor store must have finished reading the shared tile before anybody rewrites it; with one
-  // round per tile the barrier inside the round orders this wait before the first tile write
-  if (tma_out && tid == 0) bulk_wait_read<0>();
-  if (bulk) {
-    mbar_wait(bar, bulk_parity);
-    bulk_parity ^= 1u;
+  if (flow) {
+    if (bulk) {
+      mbar_wait(bar, bulk_parity);
+      bulk_parity ^= 1u;
+    } else {
+      __syncthreads();          // every warp holds its samples of the previous tile
+      prefetch(tile);           // guarded cooperative fill
+      __syncthreads();
+    }
+  } else {
+    // the previous tile's tensor store must have finished reading the shared tile before anybody rewrites it; with one
+    // round per tile the barrier inside the round orders this wait before the first tile write
+    if (tma_out && tid == 0) bulk_wait_read<0>();
+    if (bulk) {
+      mbar_wait(bar, bulk_parity);
+      bulk_parity ^= 1u;
+    }
   }
 #endif
-  if (!bulk || (tma_out && ROUNDS > 1)) __syncthreads();   // guarded fill visible / tile free
+  if (!flow && (!bulk || (tma_out && ROUNDS > 1))) __syncthreads();   // guarded fill visible / tile free
 
   for (int round = 0; round < ROUNDS; ++round) {
     const int tl = round * NG + grp;  // column inside the tile
@@ -130,7 +166,26 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
 #pragma unroll
         for (int r = 0; r < R0; ++r) v[r] = make_float2(p[2 * r * G], p[2 * r * G + 1]);
       }
-      if (round == ROUNDS - 1) {
+      if (flow) {
+#if !defined(SPECGPU_EMULATE)
+        // the last warp to hold its samples issues the bulk copy of the CTA's next tile (non-bulk tiles are filled
+        // cooperatively at the top of their own iteration)
+        const unsigned next = tile + gridDim.x;
+        if (next < ntiles && tile_bulk(next / tps, tile_start(next))) {
+          __syncwarp();
+          if ((tid & 31) == 0) {
+            __threadfence_block();
+            if (atomicAdd(cnt_free, 1u) == kStftThreads / 32 - 1) {
+              *cnt_free = 0;
+              __threadfence_block();
+              const unsigned nb = next / tps;
+              mbar_arrive_expect_tx(bar, (uint32_t)a.span * 4u);
+              bulk_g2s(smem_u32(s_in), a.x + (int64_t)nb * a.ldx + tile_start(next), (uint32_t)a.span * 4u, bar, pol_in);
+            }
+          }
+        }
+#endif
+      } else if (round == ROUNDS - 1) {
         __syncthreads();     // every thread holds its samples: the span may be overwritten
         if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);
       }
@@ -149,35 +204,41 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
         }
       }
     }
-    // ---- detrend (scipy.signal.detrend per segment) ----
+    // ---- detrend (scipy.signal.detrend per segment) + window, in packed (x[2m], x[2m+1]) pairs ----
+    // sum x and sum c x with c_n = n - (N-1)/2: lane-wise suffix sums T_r = sum_{q >= r} v[q], Q = sum_{r >= 1} T_r =
+    // sum_r r v[r], so that sum c x = cb T + 2G Q + T.y (cb = c of this thread's first sample) -- two packed adds per pair.
     if (a.detrend != SPECGPU_DETREND_NONE) {
-      float sx = 0.f, sc = 0.f;
-      const float cb = (float)(2 * tg) - 0.5f * (float)(N - 1);    // c_n = n - (N-1)/2 of this thread's first sample
+      const float cb = (float)(2 * tg) - 0.5f * (float)(N - 1);
+      float2 T = v[R0 - 1], Q = v[R0 - 1];
 #pragma unroll
-      for (int r = 0; r < R0; ++r) {
-        const float c0 = cb + (float)(2 * r * G);
-        sx += v[r].x + v[r].y;
-        sc += c0 * v[r].x + (c0 + 1.0f) * v[r].y;
+      for (int r = R0 - 2; r >= 1; --r) {
+        T = add2(T, v[r]);
+        Q = add2(Q, T);
       }
+      T = add2(T, v[0]);
+      float sx = T.x + T.y;
+      float sc = fmaf(cb, sx, fmaf((float)(2 * G), Q.x + Q.y, T.y));
       group_sum2<G>(sx, sc, s_red, tid);
       const float mean = sx * (1.0f / (float)N);
       // sum_n c_n^2 = N (N^2 - 1) / 12
       const float slope = (a.detrend == SPECGPU_DETREND_LINEAR)
                               ? sc * (12.0f / ((float)N * ((float)N * (float)N - 1.0f)))
                               : 0.f;
+      const float t0 = fmaf(slope, cb, mean);
+      float2 t = make_float2(t0, t0 + slope);                 // the fitted line at this thread's pair r
+      const float2 step = bcast2(slope * (float)(2 * G));
 #pragma unroll
       for (int r = 0; r < R0; ++r) {
-        const float c0 = cb + (float)(2 * r * G);
-        v[r].x -= mean + slope * c0;
-        v[r].y -= mean + slope * (c0 + 1.0f);
+        const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * (tg + r * G));
+        v[r] = mul2(sub2(v[r], t), w);
+        t = add2(t, step);
       }
-    }
-    // ---- window ----
+    } else {
 #pragma unroll
-    for (int r = 0; r < R0; ++r) {
-      const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * (tg + r * G));
-      v[r].x *= w.x;
-      v[r].y *= w.y;
+      for (int r = 0; r < R0; ++r) {
+        const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * (tg + r * G));
+        v[r] = mul2(v[r], w);
+      }
     }
     // ---- M-point complex FFT of the packed segment ----
     // Groups that live inside one warp keep the outputs of the last pass in registers and fetch the mirrored bins
@@ -198,12 +259,15 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
     float rmin = INFINITY, rmax = -INFINITY;         // this segment's extremes (merged below if the segment is live)
     auto bin_pair = [&](int k, float2 zk, float2 zm, int offk, int offm, auto generic_c) {
       constexpr bool GENERIC = decltype(generic_c)::value;     // 0 < k < M/2: two distinct, doubled bins
-      const float2 e = make_float2(zk.x + zm.x, zk.y - zm.y);
-      const float2 o = make_float2(zk.y + zm.y, zm.x - zk.x);
-      const float2 wo = cmul(s_twn[k], o);
-      const float2 xk = cadd(e, wo);
-      float2 xm = csub(e, wo);
-      xm.y = -xm.y;
+      // packed: e = zk + conj(zm), d = zk - conj(zm) (O = -i d), 2 X[k] = e + W O, 2 conj(X[M-k]) = e - W O with
+      // W O = W.x (d.y, -d.x) + W.y (d.x, d.y): six two-lane instructions per bin pair (patterns on the data operand)
+      const float2 zc = make_float2(zm.x, -zm.y);
+      const float2 e = add2(zk, zc);
+      const float2 d = sub2(zk, zc);
+      const float2 w = s_twn[k];
+      const float2 xk = fma2(d, bcast2(w.y), fma2(make_float2(d.y, -d.x), bcast2(w.x), e));
+      float2 xm = fma2(make_float2(-d.x, -d.y), bcast2(w.y), fma2(make_float2(-d.y, d.x), bcast2(w.x), e));
+      if (MODE == STFT_MODE_SPECTRA || MODE == STFT_MODE_COMPLEX) xm.y = -xm.y;
       const int km = M - k;
       const bool two = GENERIC || km != k;
       if (MODE == STFT_MODE_SPECTRA) {
@@ -236,8 +300,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
             pk = __log2f(fmaf(pk, ps, a.eps));
             pm = __log2f(fmaf(pm, ps, a.eps));
           }
-          rmin = fminf(rmin, fminf(pk, pm));       // k == km (k = M/2) gives pk == pm: harmless
-          rmax = fmaxf(rmax, fmaxf(pk, pm));
+          rmin = fmin3(rmin, pk, pm);              // k == km (k = M/2) gives pk == pm: harmless
+          rmax = fmax3(rmax, pk, pm);
         } else {
           pk *= ps;
           pm *= ps;
@@ -246,6 +310,9 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
         if (two) *reinterpret_cast<float*>(s_tile + offm) = pm;
       }
     };
+#if !defined(SPECGPU_EMULATE)
+    if (flow && flow_it > 0) mbar_wait(bar_tfree, (flow_it - 1) & 1u);   // the previous store has read the tile
+#endif
     {
       auto tile_off = [&](int row) {
         const int o = row * ROWB + tl * E;
@@ -312,6 +379,46 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   }
 
   if (MODE == STFT_MODE_SPECTRA) continue;
+#if !defined(SPECGPU_EMULATE)
+  if (flow) {
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kStftThreads / 32;
+    float* red = s_red + (flow_it & 1u) * (2 * NW);      // two sets: a fast warp may be one tile ahead of the reducer
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    fence_proxy_async();       // this thread's tile writes -> visible to the TMA engine (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      red[2 * warp] = vmin;
+      red[2 * warp + 1] = vmax;
+      __threadfence_block();
+      if (atomicAdd(cnt_full, 1u) == NW - 1) {           // last warp of the tile: store it
+        *cnt_full = 0;
+        __threadfence_block();
+        const int rows_out = F - 1;
+        for (int rb = 0; rb < a.tma_nbox; ++rb) {
+          if (a.ld_out < 0)
+            tma_store_3d(&tmap, smem_u32(s_tile + (size_t)rb * a.tma_rows * ROWB), (int)(seg0 & 31), (int)(seg0 >> 5) * rows_out + rb * a.tma_rows,
+                         (int)b, pol_out);
+          else
+            tma_store_3d(&tmap, smem_u32(s_tile + (size_t)rb * a.tma_rows * ROWB), (int)(seg0 * (E / 4)), rb * a.tma_rows, (int)b, pol_out);
+        }
+        bulk_commit();
+        float mn = red[0], mx = red[1];
+        for (int w = 1; w < NW; ++w) {
+          mn = fminf(mn, red[2 * w]);
+          mx = fmaxf(mx, red[2 * w + 1]);
+        }
+        atomicMax(a.minmax + 2 * b, minmax_word_min(a.minmax_gen, mn));
+        atomicMax(a.minmax + 2 * b + 1, minmax_word_max(a.minmax_gen, mx));
+        bulk_wait_read<0>();
+        mbar_arrive(bar_tfree);
+      }
+    }
+    ++flow_it;
+    continue;
+  }
+#endif
   constexpr int LANES_T = TT < 32 ? TT : 32;   // lanes along time
   constexpr int ROWS_W = 32 / LANES_T;         // rows per warp step
   const int lane = tid & 31, warp = tid >> 5;
@@ -372,7 +479,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   if (!(stage && tma_out && ROUNDS == 1 && G <= 32)) __syncthreads();
   }  // tile loop
 #if !defined(SPECGPU_EMULATE)
-  if (tma_out && tid == 0) bulk_wait<0>();   // the last store must be complete before the CTA's shared memory goes away
+  if (tma_out && tid == 0 && !flow) bulk_wait<0>();   // the last store must be complete before the CTA's shared memory goes away
+  // (flow mode: whichever thread issued a store has already waited for its shared-memory reads)
 #endif
 }
 
@@ -442,6 +550,7 @@ static int launch_stft_t(const StftArgs& a, int64_t B, cudaStream_t stream) {
   // ---- output: TMA tensor store of the swizzled shared tile when the layout allows it ----
   TensorMap tmap{};
   args.tma_out = 0;
+  args.flow = 0;
   args.tma_rows = args.tma_nbox = 0;
 #if !defined(SPECGPU_EMULATE)
   if (MODE != STFT_MODE_SPECTRA && (ROWB == 16 || ROWB == 32 || ROWB == 64 || ROWB == 128)) {
@@ -462,6 +571,9 @@ static int launch_stft_t(const StftArgs& a, int64_t B, cudaStream_t stream) {
       args.tma_rows = box_rows;
       args.tma_nbox = rows_out / box_rows;
     }
+    static const bool flow_env = !(std::getenv("SPECGPU_STFT_FLOW") && std::getenv("SPECGPU_STFT_FLOW")[0] == '0');
+    args.flow = (flow_env && ok && args.stage_in && args.bulk_ok && stft_mode_is_log(MODE) && args.tma_nbox * args.tma_rows == rows_out &&
+                 TT == C::NG && C::G <= 32) ? 1 : 0;
   }
 #endif
   if (L.total > 48 * 1024) {

@@ -58,7 +58,7 @@ __host__ __device__ inline StftSmem stft_smem_layout(int mode, int span_floats) 
   s.line_off = off;   off += C::NG * C::LINE * 8;
   s.red_off = off;    off += (kStftThreads / 32) * 2 * 4 + 64;
   off = (off + 15) & ~15;
-  s.bar_off = off;    off += 16;
+  s.bar_off = off;    off += 32;     // two mbarriers (span full, tile free) + two arrival counters
   off = (off + 127) & ~127;
   s.in_off = off;     off += (span_floats * 4 + 127) & ~127;
   s.tile_off = off;

@@ -339,6 +339,10 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+// packed FP32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100a): lane-wise, one rounding per lane
+static inline float2 __fadd2_rn(float2 a, float2 b) { volatile float x = a.x + b.x, y = a.y + b.y; return make_float2(x, y); }
+static inline float2 __fmul2_rn(float2 a, float2 b) { volatile float x = a.x * b.x, y = a.y * b.y; return make_float2(x, y); }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline long long __double_as_longlong(double d) { long long i; std::memcpy(&i, &d, 8); return i; }
 static inline double __longlong_as_double(long long i) { double d; std::memcpy(&d, &i, 8); return d; }
