@@ -86,10 +86,11 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
 #endif
   };
   // Stage the span of `tile` (all threads call this; only after every thread is done reading the previous span).
-  auto prefetch = [&](unsigned tile) {
-    const unsigned b32 = tile / tps;
+  // (signal b32, tile t32 within the signal): kept incrementally along the CTA's tile walk, no division per tile
+  auto tile_start = [&](unsigned t32) -> int64_t { return a.first_start + (int64_t)t32 * TT * (int64_t)a.hop; };
+  auto prefetch = [&](unsigned b32, unsigned t32) {
     const int64_t b = b32;
-    const int64_t s0 = a.first_start + (int64_t)(tile - b32 * tps) * TT * (int64_t)a.hop;
+    const int64_t s0 = tile_start(t32);
     const float* xb = a.x + b * a.ldx;
     if (tile_bulk(b, s0)) {
 #if !defined(SPECGPU_EMULATE)
@@ -109,21 +110,25 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   float2* line = s_line + grp * C::LINE;
   unsigned bulk_parity = 0;
   unsigned flow_it = 0;                                    // tiles this CTA has stored (flow mode)
-  auto tile_start = [&](unsigned tile) -> int64_t {
-    const unsigned b32 = tile / tps;
-    return a.first_start + (int64_t)(tile - b32 * tps) * TT * (int64_t)a.hop;
-  };
+  unsigned cur_b = blockIdx.x / tps, cur_t = blockIdx.x - cur_b * tps;
+  const unsigned step_b = gridDim.x / tps, step_t = gridDim.x - step_b * tps;
+  unsigned nxt_b = 0, nxt_t = 0;
   if (flow) {
     // bulk tiles are prefetched by one thread; the others (first / last tiles of a signal) are filled at the loop top
-    if (blockIdx.x < ntiles && tile_bulk(blockIdx.x / tps, tile_start(blockIdx.x)) && tid == 0) prefetch(blockIdx.x);
+    if (blockIdx.x < ntiles && tile_bulk(cur_b, tile_start(cur_t)) && tid == 0) prefetch(cur_b, cur_t);
   } else if (stage && blockIdx.x < ntiles) {
-    prefetch(blockIdx.x);
+    prefetch(cur_b, cur_t);
   }
   // persistent CTAs: the tables above are loaded once, then the CTA walks tiles (signal b, TT segments)
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-  const unsigned b32 = tile / tps;
-  const int64_t b = b32;
-  const int64_t seg0 = (int64_t)(tile - b32 * tps) * TT;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur_b = nxt_b, cur_t = nxt_t) {
+  const int64_t b = cur_b;
+  const int64_t seg0 = (int64_t)cur_t * TT;
+  nxt_b = cur_b + step_b;
+  nxt_t = cur_t + step_t;
+  if (nxt_t >= tps) {
+    nxt_t -= tps;
+    ++nxt_b;
+  }
   const float* xb = a.x + b * a.ldx;
   float vmin = INFINITY, vmax = -INFINITY;
   const bool bulk = stage && tile_bulk(b, a.first_start + seg0 * (int64_t)a.hop);
@@ -135,7 +140,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       bulk_parity ^= 1u;
     } else {
       __syncthreads();          // every warp holds its samples of the previous tile
-      prefetch(tile);           // guarded cooperative fill
+      prefetch(cur_b, cur_t);   // guarded cooperative fill
       __syncthreads();
     }
   } else {
@@ -171,23 +176,22 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
         // the last warp to hold its samples issues the bulk copy of the CTA's next tile (non-bulk tiles are filled
         // cooperatively at the top of their own iteration)
         const unsigned next = tile + gridDim.x;
-        if (next < ntiles && tile_bulk(next / tps, tile_start(next))) {
+        if (next < ntiles && tile_bulk(nxt_b, tile_start(nxt_t))) {
           __syncwarp();
           if ((tid & 31) == 0) {
             __threadfence_block();
             if (atomicAdd(cnt_free, 1u) == kStftThreads / 32 - 1) {
               *cnt_free = 0;
               __threadfence_block();
-              const unsigned nb = next / tps;
               mbar_arrive_expect_tx(bar, (uint32_t)a.span * 4u);
-              bulk_g2s(smem_u32(s_in), a.x + (int64_t)nb * a.ldx + tile_start(next), (uint32_t)a.span * 4u, bar, pol_in);
+              bulk_g2s(smem_u32(s_in), a.x + (int64_t)nxt_b * a.ldx + tile_start(nxt_t), (uint32_t)a.span * 4u, bar, pol_in);
             }
           }
         }
 #endif
       } else if (round == ROUNDS - 1) {
         __syncthreads();     // every thread holds its samples: the span may be overwritten
-        if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);
+        if (tile + gridDim.x < ntiles) prefetch(nxt_b, nxt_t);
       }
     } else {
       const int64_t s0 = a.first_start + seg * (int64_t)a.hop;

@@ -39,6 +39,9 @@ __host__ __device__ constexpr int stft_elem_bytes(int mode) { return mode == STF
 // (address bits 4..6 ^= bits 7..9, masked to the span), so that a TMA tensor store can read it in place while the
 // column-wise writes of the segment groups spread over the banks.  The tile base is 1024-byte aligned.
 __host__ __device__ constexpr int stft_swizzle_mask(int rowb) { return rowb >= 128 ? 0x70 : (rowb == 64 ? 0x30 : (rowb == 32 ? 0x10 : 0)); }
+// (Tried: SWIZZLE_128B for the 64-byte-row tile, which would take the column writes of rows k and k + 8 of a 16-thread
+// group off the same bank -- the tensor store then faults: with a 64-byte box row the engine does not read the tile as
+// dense 64-byte rows.  The 2-way conflict on the 17 tile stores per thread stays.)
 
 struct StftSmem {
   int window_off, twm_off, twn_off, line_off, red_off, bar_off, in_off, tile_off, total;
