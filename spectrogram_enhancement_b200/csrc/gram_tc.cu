@@ -402,7 +402,11 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tma_kernel(const GramTmaA
   const int64_t b_first = blockIdx.x / kparts;
   const int64_t g0 = b_first * a.nchunk + (blockIdx.x % kparts) * a.per;
   const int64_t g1 = (g0 + a.per < (b_first + 1) * a.nchunk) ? g0 + a.per : (b_first + 1) * a.nchunk;
-  if (g0 >= g1) return;                          // uniform over the CTA
+  pdl_trigger();                                 // one resident wave (common.cuh: programmatic dependent launch)
+  if (g0 >= g1) {                                // uniform over the CTA
+    pdl_wait();
+    return;
+  }
   constexpr int nsegs = 1;
   float* part0 = a.partial + (size_t)blockIdx.x * 128 * PP;
 #if defined(SPECGPU_EMULATE)
@@ -467,6 +471,7 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tma_kernel(const GramTmaA
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  pdl_wait();      // barriers, tensor memory and the descriptor prefetch overlapped the tail of the STFT; its image is now complete
 
   int64_t g = g0;                                   // first chunk of the current segment
   for (int sg = 0; sg < nsegs; ++sg) {
@@ -702,11 +707,11 @@ int launch_gram_tma(const float* S, int64_t B, int64_t rows, int64_t cols, int64
   if (rows == 256) {
     cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    SPECGPU_LAUNCH(gram_tma_kernel<256>, (unsigned)g.grid, kGtcThreads, smem, stream, a, S, ld, tmap);
+    SPECGPU_LAUNCH_PDL(gram_tma_kernel<256>, (unsigned)g.grid, kGtcThreads, smem, stream, 1, a, S, ld, tmap);
   } else {
     cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    SPECGPU_LAUNCH(gram_tma_kernel<128>, (unsigned)g.grid, kGtcThreads, smem, stream, a, S, ld, tmap);
+    SPECGPU_LAUNCH_PDL(gram_tma_kernel<128>, (unsigned)g.grid, kGtcThreads, smem, stream, 1, a, S, ld, tmap);
   }
   return (int)cudaGetLastError();
 }

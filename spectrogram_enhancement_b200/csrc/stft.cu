@@ -71,6 +71,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
 #else
   constexpr bool flow = false;
 #endif
+  pdl_trigger();     // persistent grid, all CTAs resident: the next kernel may move in as CTAs retire
+  pdl_wait();        // the previous kernel of the stream (reader of the image this one overwrites) has completed
   __syncthreads();
 
   const unsigned tps = (unsigned)a.tiles_per_signal;      // ntiles < 2^31 is checked by the launcher
@@ -580,15 +582,17 @@ static int launch_stft_t(const StftArgs& a, int64_t B, cudaStream_t stream) {
                  TT == C::NG && C::G <= 32) ? 1 : 0;
   }
 #endif
-  if (L.total > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  int smem_total = L.total;
+  if (const char* pad = std::getenv("SPECGPU_STFT_SMEM_PAD")) smem_total += std::atoi(pad);   // occupancy experiments
+  if (smem_total > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
     if (e != cudaSuccess) return (int)e;
   }
   // persistent grid: as many CTAs as can be resident (the kernel is smem/register limited to 1-3 per SM)
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStftThreads, L.total) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStftThreads, smem_total) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t grid = std::min<int64_t>(args.ntiles, (int64_t)per_sm * stft_num_sms());
-  SPECGPU_LAUNCH(kern, (unsigned)grid, kStftThreads, L.total, stream, args, tmap);
+  SPECGPU_LAUNCH_PDL(kern, (unsigned)grid, kStftThreads, smem_total, stream, 1, args, tmap);
   return (int)cudaGetLastError();
 }
 

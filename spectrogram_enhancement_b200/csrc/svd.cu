@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
   __shared__ float sa[kGramTile][kGramKB + 1];
   __shared__ float sb[kGramTile][kGramKB + 1];
   const int64_t b = blockIdx.z;
+  pdl_trigger();
+  pdl_wait();
   if (only_flagged != nullptr && only_flagged[b * 4 + 3] == 0) return;   // uniform over the CTA
   float mn = 0.f, den = 1.f;
   if (minmax != nullptr) {
@@ -116,9 +118,9 @@ int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int6
   }
   const dim3 grid((unsigned)npairs, (unsigned)ksplit, (unsigned)B);
   if (g_f64)
-    SPECGPU_LAUNCH(gram_simt_kernel<double>, grid, kGramThreads, 0, stream, S, (int)rows, cols, ld, ksplit, (double*)G, minmax, only_flagged);
+    SPECGPU_LAUNCH_PDL(gram_simt_kernel<double>, grid, kGramThreads, 0, stream, 1, S, (int)rows, cols, ld, ksplit, (double*)G, minmax, only_flagged);
   else
-    SPECGPU_LAUNCH(gram_simt_kernel<float>, grid, kGramThreads, 0, stream, S, (int)rows, cols, ld, ksplit, (float*)G, minmax, only_flagged);
+    SPECGPU_LAUNCH_PDL(gram_simt_kernel<float>, grid, kGramThreads, 0, stream, 1, S, (int)rows, cols, ld, ksplit, (float*)G, minmax, only_flagged);
   return (int)cudaGetLastError();
 }
 
@@ -293,6 +295,8 @@ __global__ void __launch_bounds__(kGeThreads, 3) gram_eig_kernel(GramEigArgs a) 
   constexpr int PW = PL + 4;                      // its pitch (columns PL, PL + 1: row sums of rows r, 128 + r)
   constexpr int NJ = N / (4 * kGeTpr);            // float4 per thread: columns q*4 + 32 j + {0..3}
   constexpr int CS = 4 * kGeTpr;                  // column stride between a thread's float4
+  pdl_trigger();
+  pdl_wait();
   SPECGPU_DYN_SMEM(smem);
   float* sx = reinterpret_cast<float*>(smem);     // [N] current iterate (every CTA holds all of it)
   float* sy = sx + N;                             // [2][N] G x, double buffered across iterations
@@ -561,24 +565,7 @@ template <int N>
 static int launch_gram_eig_t(const GramEigArgs& a, int64_t B, cudaStream_t stream) {
   constexpr int CL = N / kGeRows;
   const size_t smem = (size_t)(3 * N + 2 * CL + 8 + kGeRows * 132 + N + CL * N) * sizeof(float);
-#ifdef SPECGPU_EMULATE
-  SPECGPU_LAUNCH_CLUSTER(gram_eig_kernel<N>, (unsigned)(B * CL), kGeThreads, smem, stream, CL, a);
-#else
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(B * CL));
-  cfg.blockDim = dim3(kGeThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gram_eig_kernel<N>, a);
-  if (e != cudaSuccess) return (int)e;
-#endif
+  SPECGPU_LAUNCH_PDL(gram_eig_kernel<N>, (unsigned)(B * CL), kGeThreads, smem, stream, CL, a);
   return (int)cudaGetLastError();
 }
 
@@ -653,6 +640,8 @@ __device__ __forceinline__ bool jacobi_pair(T* x, T* y, int n, int lane) {
 
 template <class T>
 __global__ void __launch_bounds__(kJacThreads) eig_jacobi_kernel(JacobiArgs<T> a) {
+  pdl_trigger();
+  pdl_wait();
   SPECGPU_DYN_SMEM(smem);
   const int n = a.n, np = a.n_pad, cb = a.cb, CL = a.cl;
   const int rank = SPECGPU_CLUSTER_RANK();
@@ -794,6 +783,8 @@ template <class T>
 __global__ void eig_sort_kernel(const T* Ucols, const T* lam_raw, const int32_t* jstatus, int n, int n_pad,
                                 int skip_converged, float* U, float* lam, int32_t* plan) {
   const int64_t b = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (skip_converged && plan[b * 4 + 3] == 0) return;
   __shared__ int s_rank[512];
   const T* lr = lam_raw + b * n_pad;
@@ -854,27 +845,13 @@ static int launch_eig_jacobi_t(const T* G, int64_t B, int n, int skip_converged,
   w += (((size_t)B * g.n_pad * sizeof(T)) + 255) & ~(size_t)255;
   int32_t* jstatus = reinterpret_cast<int32_t*>(w);
   JacobiArgs<T> a{G, n, g.n_pad, g.cb, g.cl, plan, skip_converged, Ucols, lam_raw, jstatus};
-#ifdef SPECGPU_EMULATE
-  SPECGPU_LAUNCH_CLUSTER(eig_jacobi_kernel<T>, (unsigned)(B * g.cl), kJacThreads, g.smem, stream, g.cl, a);
-#else
+#ifndef SPECGPU_EMULATE
   cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(B * g.cl));
-  cfg.blockDim = dim3(kJacThreads);
-  cfg.dynamicSmemBytes = g.smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)g.cl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, eig_jacobi_kernel<T>, a);
-  if (e != cudaSuccess) return (int)e;
 #endif
-  SPECGPU_LAUNCH(eig_sort_kernel<T>, (unsigned)B, 512, 0, stream, (const T*)Ucols, (const T*)lam_raw, (const int32_t*)jstatus, n,
+  SPECGPU_LAUNCH_PDL(eig_jacobi_kernel<T>, (unsigned)(B * g.cl), kJacThreads, g.smem, stream, g.cl, a);
+  if (cudaPeekAtLastError() != cudaSuccess) return (int)cudaGetLastError();
+  SPECGPU_LAUNCH_PDL(eig_sort_kernel<T>, (unsigned)B, 512, 0, stream, 1, (const T*)Ucols, (const T*)lam_raw, (const int32_t*)jstatus, n,
                  g.n_pad, skip_converged, U, lam, plan);
   return (int)cudaGetLastError();
 }
@@ -1155,6 +1132,7 @@ template <int RPW, bool NORM, bool CLIP, bool STREAM>
 __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L, int rows, int64_t cols, int64_t ld,
                                                                   const MinMaxWord* minmax, const float* U, float* S,
                                                                   float* D, int64_t ldo, const int32_t* only_flagged, int64_t B) {
+  pdl_wait();      // (a multi-wave grid: dependents are released when its CTAs exit)
   if (only_flagged == nullptr) {
     svd_rank1_tile<RPW, NORM, CLIP, STREAM>(blockIdx.y, L, rows, cols, ld, minmax, U, S, D, ldo);
     return;
@@ -1171,10 +1149,10 @@ static void launch_rank1_ts(dim3 grid, size_t smem, cudaStream_t stream, const f
                             const MinMaxWord* minmax, const float* U, int clip, float* S, float* D, int64_t ldo,
                             const int32_t* only_flagged, int64_t B) {
   const bool nrm = minmax != nullptr;
-  if (nrm && clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, true, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
-  else if (nrm) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, true, false, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
-  else if (clip) SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, true, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
-  else SPECGPU_LAUNCH((svd_rank1_kernel<RPW, false, false, STREAM>), grid, kR1Threads, smem, stream, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
+  if (nrm && clip) SPECGPU_LAUNCH_PDL((svd_rank1_kernel<RPW, true, true, STREAM>), grid, kR1Threads, smem, stream, 1, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
+  else if (nrm) SPECGPU_LAUNCH_PDL((svd_rank1_kernel<RPW, true, false, STREAM>), grid, kR1Threads, smem, stream, 1, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
+  else if (clip) SPECGPU_LAUNCH_PDL((svd_rank1_kernel<RPW, false, true, STREAM>), grid, kR1Threads, smem, stream, 1, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
+  else SPECGPU_LAUNCH_PDL((svd_rank1_kernel<RPW, false, false, STREAM>), grid, kR1Threads, smem, stream, 1, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
 }
 template <int RPW>
 static void launch_rank1_t(dim3 grid, size_t smem, cudaStream_t stream, const float* L, int rows, int64_t cols, int64_t ld,
