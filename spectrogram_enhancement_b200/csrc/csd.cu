@@ -105,8 +105,7 @@ __global__ void __launch_bounds__(kCsdThreads) csd_pairs_kernel(CsdArgs a) {
 #pragma unroll
         for (int j = 0; j < TJ; ++j) {
           // conj(xi) * xj
-          acc[i][j].x = fmaf(xi[i].x, xj[j].x, fmaf(xi[i].y, xj[j].y, acc[i][j].x));
-          acc[i][j].y = fmaf(xi[i].x, xj[j].y, fmaf(-xi[i].y, xj[j].x, acc[i][j].y));
+          acc[i][j] = cmac_conj(acc[i][j], xi[i], xj[j]);
         }
     }
   }
@@ -273,8 +272,7 @@ __global__ void __launch_bounds__(kCsdThreads, 1) csd_pairs_staged_kernel(CsdArg
         for (int i = 0; i < TI; ++i)
 #pragma unroll
           for (int j = 0; j < TJ; ++j) {
-            acc[i][j].x = fmaf(xi[i].x, xj[j].x, fmaf(xi[i].y, xj[j].y, acc[i][j].x));
-            acc[i][j].y = fmaf(xi[i].x, xj[j].y, fmaf(-xi[i].y, xj[j].x, acc[i][j].y));
+            acc[i][j] = cmac_conj(acc[i][j], xi[i], xj[j]);
           }
       }
     }

@@ -278,7 +278,11 @@ constexpr int kBisK = 2, kBisPasses = 37;
 #else
 constexpr int kBisK = 4, kBisPasses = 25;
 #endif
-constexpr int kBisThreads = kTriMaxN * kBisK;
+// One CTA of kTriMaxN threads serves kTriMaxN / kBisK eigenvalues; a matrix is spread over kBisK CTAs (grid.y) so that 40
+// matrices occupy every SM -- with one 1024-thread CTA per matrix the 25 x 256 dependent Sturm steps ran on 40 SMs'
+// float64 units (0.63 ms).  Every CTA repeats the cheap Gershgorin / scaling prologue.
+constexpr int kBisThreads = kTriMaxN;
+constexpr int kBisEigs = kBisThreads / kBisK;
 
 struct SturmState {
   double pa, pb;
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(kBisThreads) bisect_kernel(const double* dall,
     se2[tid] = es * es;                 // e[tid]^2 couples tid and tid + 1
   }
   __syncthreads();
-  const int eig = tid / kBisK, s = tid % kBisK;         // the kBisK threads of an eigenvalue sit in one warp
+  const int eig = blockIdx.y * kBisEigs + tid / kBisK, s = tid % kBisK;     // the kBisK threads of an eigenvalue sit in one warp
   const int lane0 = (tid & 31) - s;
   const double slack = 2.0 * 2.22e-16 * n + 2e-30;
   lo = gl * scale - slack;
@@ -741,7 +745,7 @@ int launch_eig_tridiag_values(const double* G, double* W, int64_t B, int n, floa
   TriClArgs ta{G, W, d, e, beta, n, 1};
   const int rc = launch_tridiag_cluster(ta, B, stream);
   if (rc != 0) return rc;
-  SPECGPU_LAUNCH(bisect_kernel, (unsigned)B, kBisThreads, 0, stream, (const double*)d, (const double*)e, n, lam, lamd);
+  SPECGPU_LAUNCH(bisect_kernel, dim3((unsigned)B, (unsigned)((n + kBisEigs - 1) / kBisEigs)), kBisThreads, 0, stream, (const double*)d, (const double*)e, n, lam, lamd);
   return (int)cudaGetLastError();
 }
 
