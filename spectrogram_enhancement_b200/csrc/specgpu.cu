@@ -1117,7 +1117,10 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
   const bool tc = power_ok && gram_tc_supported(rows);
   const int64_t gsz = pipeline_group_size(ctx, B, rows, ldt);
   const int64_t ngroups = ceil_div(B, gsz);
-  const int nlanes = ngroups > 1 ? 2 : 1;        // streams in use
+  // groups alternate between two side streams, or (SPECGPU_PIPELINE_LANES=1) follow each other in the caller's stream,
+  // where the programmatic dependent launches chain them without a gap
+  static const bool one_lane = std::getenv("SPECGPU_PIPELINE_LANES") && std::getenv("SPECGPU_PIPELINE_LANES")[0] == '1';
+  const int nlanes = (ngroups > 1 && !one_lane) ? 2 : 1;        // streams in use
   // ---- workspace: min/max pairs and per-channel SVD arrays for the whole batch; Gram partials and Jacobi scratch per lane ----
   const size_t part_bytes = tc ? gram_tc_workspace_bytes(gsz, rows) : 0;
   const size_t jac_bytes = jacobi_workspace_bytes(gsz, (int)rows);

@@ -18,12 +18,13 @@ namespace specgpu {
 // Gram matrix, SIMT fp32 (any shape).  64x64 output tile per CTA, split along K; partial sums are
 // accumulated with float atomics into a zeroed G, lower triangle mirrored from the upper.
 // ======================================================================================================
-constexpr int kGramTile = 64, kGramKB = 32, kGramThreads = 256;
+constexpr int kGramThreads = 256;
+// (tile, K block) are template parameters: 64 x 64 outputs with 4 x 4 per thread, K blocks of 32.
 
 // minmax != nullptr: S holds an un-normalised log image, operands are (x - min) / (max - min) exactly as the
 // rank-1 projection writes them.  only_flagged != nullptr: only matrices whose plan[b][3] != 0 (leading pair not
 // converged) are computed; that launch uses ksplit == 1 and stores its tiles directly (no atomics, no zeroed G).
-template <class T>
+template <class T, int kGramTile, int kGramKB>
 __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S, int rows, int64_t cols, int64_t ld,
                                                                  int ksplit, T* G, const MinMaxWord* minmax,
                                                                  const int32_t* only_flagged) {
@@ -53,8 +54,9 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
   const int64_t k0 = (int64_t)blockIdx.y * kchunk;
   const int64_t k1 = (k0 + kchunk < cols) ? k0 + kchunk : cols;
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4 x 4 outputs each
-  T acc[4][4] = {};
+  constexpr int R = kGramTile / 16;        // outputs per thread and direction
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, R x R outputs each
+  T acc[R][R] = {};
   for (int64_t k = k0; k < k1; k += kGramKB) {
     for (int i = tid; i < kGramTile * kGramKB; i += kGramThreads) {
       const int r = i / kGramKB, c = i % kGramKB;
@@ -69,26 +71,26 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
       sb[r][c] = (T)xb;
     }
     __syncthreads();
-#pragma unroll 8
+#pragma unroll (R == 4 ? 8 : 2)
     for (int c = 0; c < kGramKB; ++c) {
-      T av[4], bv[4];
+      T av[R], bv[R];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < R; ++i) {
         av[i] = sa[ty + 16 * i][c];
         bv[i] = sb[tx + 16 * i][c];
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+        for (int j = 0; j < R; ++j) acc[i][j] += av[i] * bv[j];
     }
     __syncthreads();
   }
   T* Gb = G + b * (int64_t)rows * rows;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < R; ++j) {
       const int r = ti * kGramTile + ty + 16 * i, c = tj * kGramTile + tx + 16 * j;
       if (r < rows && c < rows) {
         if (ti != tj || c >= r) {
@@ -109,7 +111,11 @@ __global__ void __launch_bounds__(kGramThreads) gram_simt_kernel(const float* S,
 int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int64_t ld, void* G, int g_f64, cudaStream_t stream,
                      const MinMaxWord* minmax, const int32_t* only_flagged) {
   if (B == 0 || rows == 0) return 0;
-  const int nt = (int)ceil_div(rows, kGramTile);
+  // (128 x 128 tiles with 8 x 8 outputs per thread were tried for the float64 route: 194 registers, one CTA per SM, the
+  // unpipelined staging exposed -- 1.32 ms against 0.87 ms for 40 x [256 x 3905]; the template stays, the launch does not)
+  const bool big = false;
+  const int nt = (int)ceil_div(rows, big ? 128 : 64);
+  (void)big;
   const int npairs = nt * (nt + 1) / 2;
   int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(cols, 512), 16));
   if (only_flagged != nullptr) {
@@ -120,9 +126,9 @@ int launch_gram_simt(const float* S, int64_t B, int64_t rows, int64_t cols, int6
   }
   const dim3 grid((unsigned)npairs, (unsigned)ksplit, (unsigned)B);
   if (g_f64)
-    SPECGPU_LAUNCH_PDL(gram_simt_kernel<double>, grid, kGramThreads, 0, stream, 1, S, (int)rows, cols, ld, ksplit, (double*)G, minmax, only_flagged);
+    SPECGPU_LAUNCH_PDL((gram_simt_kernel<double, 64, 32>), grid, kGramThreads, 0, stream, 1, S, (int)rows, cols, ld, ksplit, (double*)G, minmax, only_flagged);
   else
-    SPECGPU_LAUNCH_PDL(gram_simt_kernel<float>, grid, kGramThreads, 0, stream, 1, S, (int)rows, cols, ld, ksplit, (float*)G, minmax, only_flagged);
+    SPECGPU_LAUNCH_PDL((gram_simt_kernel<float, 64, 32>), grid, kGramThreads, 0, stream, 1, S, (int)rows, cols, ld, ksplit, (float*)G, minmax, only_flagged);
   return (int)cudaGetLastError();
 }
 
