@@ -151,7 +151,12 @@ __host__ __device__ constexpr int fft_out_reg(int log2m, int m) {
 // KEEP_REGS = true : the outputs of the last pass stay in registers -- thread tg holds Z[tg + G m] in
 //                    v[fft_out_reg(LOG2M, m)] -- and the line is only used between passes.
 // All threads of the CTA must call this together (groups of more than 32 threads use __syncthreads()).
-template <int LOG2M, bool KEEP_REGS = false>
+// HALF_LINE (two-pass sizes whose groups live inside one warp, KEEP_REGS only): the exchange between the two passes goes
+// through a line of M + M/16 FLOATS -- real parts first, then imaginary parts through the same words.  Same number of
+// shared-memory wavefronts as the float2 line (a 64-bit warp access takes two), twice the LSU instructions, half the
+// shared memory: that half pays for the second output tile of the STFT kernel.  With a line stride of M + M/16 floats
+// (= 16 mod 32 for M = 256) the groups of a warp fall on disjoint banks.
+template <int LOG2M, bool KEEP_REGS = false, bool HALF_LINE = false>
 __device__ __forceinline__ void fft_group(float2 (&v)[fft_radix_at(LOG2M, 0)], float2* line, const float2* tw, int tg) {
   constexpr int M = 1 << LOG2M;
   constexpr int R0 = fft_radix_at(LOG2M, 0);
@@ -161,6 +166,35 @@ __device__ __forceinline__ void fft_group(float2 (&v)[fft_radix_at(LOG2M, 0)], f
   // pass 0: a single radix-R0 butterfly straight from registers
   FftPass<M, R0, R0, 1>::butterflies(v);
   if constexpr (R1 == 1 && KEEP_REGS) return;
+  if constexpr (HALF_LINE) {
+    static_assert(KEEP_REGS && R1 > 1 && R2 == 1 && G <= 32, "half line: two passes, group inside a warp, outputs in registers");
+    float* lf = reinterpret_cast<float*>(line);
+    constexpr int NB = R0 / R1;
+    const int j0 = tg * R0;                       // pass-0 store index of element r: (i - k) R + k + r p with p = 1, k = 0
+    float2 u[R0];
+#pragma unroll
+    for (int r = 0; r < R0; ++r) lf[fft_pad(j0 + r)] = v[r].x;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+#pragma unroll
+      for (int r = 0; r < R1; ++r) u[q * R1 + r].x = lf[fft_pad(tg + q * G + r * (M / R1))];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R0; ++r) lf[fft_pad(j0 + r)] = v[r].y;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int k = (tg + q * G) & (R0 - 1);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        u[q * R1 + r].y = lf[fft_pad(tg + q * G + r * (M / R1))];
+        v[q * R1 + r] = (r > 0) ? cmul(u[q * R1 + r], tw[r * R0 + k]) : u[q * R1 + r];
+      }
+    }
+    FftPass<M, R0, R1, R0>::butterflies(v);
+    return;
+  }
   FftPass<M, R0, R0, 1>::store(v, line, tg);
   fft_group_sync<G>();
   if constexpr (R1 > 1) {

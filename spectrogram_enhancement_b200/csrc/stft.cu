@@ -25,6 +25,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   constexpr int SWMASK = stft_swizzle_mask(ROWB);
   constexpr int JSTEP = G * ROWB;                     // tile byte offset between rows k and k + G
   static_assert(JSTEP % 1024 == 0, "row stride between a thread's bins must not touch the swizzle bits");
+  constexpr bool TWO_TILES = stft_two_tiles<LOG2N>(MODE);   // second output tile + (two-pass sizes) half-width exchange line
+  constexpr bool HALF_LINE = stft_half_line<LOG2N>(MODE);
   SPECGPU_DYN_SMEM(smem);
   const StftSmem L = stft_smem_layout<LOG2N>(MODE, a.stage_in ? a.span : 0);
   float* s_win = reinterpret_cast<float*>(smem + L.window_off);
@@ -50,17 +52,19 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   // warp to finish its columns issues the tensor store (two shared arrival counters); the only waits are on data (span
   // landed) and on the previous store having read the tile, both normally long satisfied.  Warps of a CTA drift apart,
   // so their shared-memory and FP32 phases overlap instead of colliding.
-  constexpr bool FLOWC = (ROUNDS == 1) && (G <= 32) && LOGM;
+  constexpr bool FLOWC = TWO_TILES;
   const bool flow = FLOWC && a.flow != 0;
   const uint32_t bar = smem_u32(smem + L.bar_off);
-  const uint32_t bar_tfree = bar + 8;
-  unsigned* cnt_free = reinterpret_cast<unsigned*>(smem + L.bar_off + 16);
-  unsigned* cnt_full = cnt_free + 1;
+  const uint32_t bar_tfree = bar + 8;                  // [2]: tile buffer p has been read by its tensor store
+  unsigned* cnt_free = reinterpret_cast<unsigned*>(smem + L.bar_off + 24);
+  unsigned* cnt_full = cnt_free + 1;                   // [2]: warps that have finished their columns of tile buffer p
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_init(bar_tfree, 1);
+    mbar_init(bar_tfree + 8, 1);
     *cnt_free = 0;
-    *cnt_full = 0;
+    cnt_full[0] = 0;
+    cnt_full[1] = 0;
     mbar_fence_init();
     if (tma_out) tma_prefetch_desc(&tmap);
   }
@@ -109,9 +113,12 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
     }
   };
 
-  float2* line = s_line + grp * C::LINE;
+  float2* line = HALF_LINE ? s_line + grp * (C::LINEH / 2) : s_line + grp * C::LINE;
   unsigned bulk_parity = 0;
   unsigned flow_it = 0;                                    // tiles this CTA has stored (flow mode)
+  unsigned pend = 0;                                       // flow mode, lane 0: 1 + buffer of a tensor store this thread issued
+                                                           // and has not yet seen through its shared-memory reads
+  unsigned char* const s_tile0 = s_tile;
   unsigned cur_b = blockIdx.x / tps, cur_t = blockIdx.x - cur_b * tps;
   const unsigned step_b = gridDim.x / tps, step_t = gridDim.x - step_b * tps;
   unsigned nxt_b = 0, nxt_t = 0;
@@ -134,6 +141,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   const float* xb = a.x + b * a.ldx;
   float vmin = INFINITY, vmax = -INFINITY;
   const bool bulk = stage && tile_bulk(b, a.first_start + seg0 * (int64_t)a.hop);
+  const unsigned tbuf = (TWO_TILES && flow) ? (flow_it & 1u) : 0u;       // output tile buffer of this tile
+  s_tile = s_tile0 + tbuf * (unsigned)L.tile_stride;
 
 #if !defined(SPECGPU_EMULATE)
   if (flow) {
@@ -250,7 +259,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
     // Groups that live inside one warp keep the outputs of the last pass in registers and fetch the mirrored bins
     // from their partner thread with shuffles (no second trip through the line); wider groups go through the line.
     constexpr bool REGS = (G <= 32);
-    fft_group<C::LOG2M, REGS>(v, line, s_twm, tg);
+    fft_group<C::LOG2M, REGS, HALF_LINE>(v, line, s_twm, tg);
 
     // ---- untangle: 2 X[k] = E + W_N^k O, 2 X[M-k] = conj(E - W_N^k O) with E = Z[k] + conj(Z[M-k]),
     //      O = -i (Z[k] - conj(Z[M-k])); the factor 2 is folded into the output scales.  Thread tg owns the bin pairs
@@ -317,7 +326,17 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       }
     };
 #if !defined(SPECGPU_EMULATE)
-    if (flow && flow_it > 0) mbar_wait(bar_tfree, (flow_it - 1) & 1u);   // the previous store has read the tile
+    if (flow) {
+      // a store this thread issued one tile ago has long finished reading its buffer: release that buffer now (not
+      // right after issuing it, which stalled the last -- slowest -- warp of every tile for the engine's read latency)
+      if (pend) {
+        bulk_wait_read<0>();
+        mbar_arrive(bar_tfree + 8u * (pend - 1u));
+        pend = 0;
+      }
+      // buffer tbuf was last used two tiles ago: its store (completion flow_it / 2 - 1 of that barrier) has read it
+      if (flow_it >= 2) mbar_wait(bar_tfree + 8u * tbuf, ((flow_it >> 1) - 1u) & 1u);
+    }
 #endif
     {
       auto tile_off = [&](int row) {
@@ -398,8 +417,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       red[2 * warp] = vmin;
       red[2 * warp + 1] = vmax;
       __threadfence_block();
-      if (atomicAdd(cnt_full, 1u) == NW - 1) {           // last warp of the tile: store it
-        *cnt_full = 0;
+      if (atomicAdd(cnt_full + tbuf, 1u) == NW - 1) {    // last warp of the tile: store it
+        cnt_full[tbuf] = 0;
         __threadfence_block();
         const int rows_out = F - 1;
         for (int rb = 0; rb < a.tma_nbox; ++rb) {
@@ -417,8 +436,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
         }
         atomicMax(a.minmax + 2 * b, minmax_word_min(a.minmax_gen, mn));
         atomicMax(a.minmax + 2 * b + 1, minmax_word_max(a.minmax_gen, mx));
-        bulk_wait_read<0>();
-        mbar_arrive(bar_tfree);
+        pend = tbuf + 1u;
       }
     }
     ++flow_it;
@@ -486,7 +504,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   }  // tile loop
 #if !defined(SPECGPU_EMULATE)
   if (tma_out && tid == 0 && !flow) bulk_wait<0>();   // the last store must be complete before the CTA's shared memory goes away
-  // (flow mode: whichever thread issued a store has already waited for its shared-memory reads)
+  if (flow && pend) bulk_wait_read<0>();              // flow mode: whichever thread issued a store sees it through its reads
 #endif
 }
 

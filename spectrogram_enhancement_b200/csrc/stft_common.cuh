@@ -29,6 +29,7 @@ struct StftCfg {
     while (tt < 16 && (long)F * (2 * tt) * bytes_per_elem <= 36 * 1024) tt *= 2;
     return tt;
   }
+  static constexpr int LINEH = M + (M >> 4);             // floats per half-width line (see fft_group<.., HALF_LINE>)
 };
 
 __host__ __device__ constexpr bool stft_mode_is_log(int mode) { return mode == STFT_MODE_LOGPSD || mode == STFT_MODE_LOGPSD_FAST; }
@@ -43,8 +44,24 @@ __host__ __device__ constexpr int stft_swizzle_mask(int rowb) { return rowb >= 1
 // group off the same bank -- the tensor store then faults: with a 64-byte box row the engine does not read the tile as
 // dense 64-byte rows.  The 2-way conflict on the 17 tile stores per thread stays.)
 
+// Log-PSD sizes that can run the barrier-free tile loop (one round of the segment groups per tile, groups inside a
+// warp, 16..128-byte tile rows for the tensor store) keep TWO output tiles in shared memory, so that a warp can write
+// tile t + 1 while the tensor store of tile t is still reading its buffer and slower warps are still filling it (with one
+// buffer 16 % of the kernel's executed instructions were mbarrier polls on "tile free").  The second tile is paid for by
+// the half-width exchange line where the transform has two passes.
+template <int LOG2N>
+__host__ __device__ constexpr bool stft_two_tiles(int mode) {
+  using C = StftCfg<LOG2N>;
+  const int rowb = C::tile_w(4) * 4;
+  return (mode == STFT_MODE_LOGPSD || mode == STFT_MODE_LOGPSD_FAST) && C::tile_w(4) == C::NG && C::G <= 32 && rowb >= 16 && rowb <= 128;
+}
+template <int LOG2N>
+__host__ __device__ constexpr bool stft_half_line(int mode) {
+  return stft_two_tiles<LOG2N>(mode) && fft_num_passes(LOG2N - 1) == 2;
+}
+
 struct StftSmem {
-  int window_off, twm_off, twn_off, line_off, red_off, bar_off, in_off, tile_off, total;
+  int window_off, twm_off, twn_off, line_off, red_off, bar_off, in_off, tile_off, tile_stride, total;
 };
 
 // span_floats: samples of the staged input span of one tile, (TT-1)*hop + N (0: segments are loaded straight from
@@ -58,17 +75,23 @@ __host__ __device__ inline StftSmem stft_smem_layout(int mode, int span_floats) 
   s.twm_off = off;    off += (fft_twiddle_count(C::LOG2M) > 0 ? fft_twiddle_count(C::LOG2M) : 1) * 8;
   s.twn_off = off;    off += (C::M / 2 + 1) * 8;
   off = (off + 15) & ~15;
-  s.line_off = off;   off += C::NG * C::LINE * 8;
+  s.line_off = off;   off += stft_half_line<LOG2N>(mode) ? C::NG * C::LINEH * 4 : C::NG * C::LINE * 8;
   s.red_off = off;    off += (kStftThreads / 32) * 2 * 4 + 64;
   off = (off + 15) & ~15;
-  s.bar_off = off;    off += 32;     // two mbarriers (span full, tile free) + two arrival counters
+  s.bar_off = off;    off += 48;     // three mbarriers (span full, tile 0 / 1 free) + three arrival counters
   off = (off + 127) & ~127;
   s.in_off = off;     off += (span_floats * 4 + 127) & ~127;
   s.tile_off = off;
+  s.tile_stride = 0;
   if (mode != STFT_MODE_SPECTRA) {
     off = (off + 1023) & ~1023;
     s.tile_off = off;
-    off += C::F * C::tile_w(stft_elem_bytes(mode)) * stft_elem_bytes(mode);
+    const int tile_bytes = C::F * C::tile_w(stft_elem_bytes(mode)) * stft_elem_bytes(mode);
+    off += tile_bytes;
+    if (stft_two_tiles<LOG2N>(mode)) {
+      s.tile_stride = (tile_bytes + 1023) & ~1023;
+      off = s.tile_off + s.tile_stride + tile_bytes;
+    }
   }
   s.total = off;
   return s;

@@ -385,6 +385,39 @@ def test_host_pipeline_streams(cuda_rt):
         hp.run(xs[0][:3], outs[0])
 
 
+def test_shot_streams_device_resident(cuda_rt):
+    """ShotStreams (device-resident shots, several in flight on worker streams) == Runtime.pipeline_dev, bit for bit,
+    including the tiles, for more shots than streams."""
+    import torch
+    n, C = 300_000, 6
+    dev = cuda_rt.device
+    xs = [torch.from_numpy(pc.signals(C, n, shot=30 + i)).to(dev) for i in range(5)]
+    pool = api.ShotStreams(SP, n=2, device=dev)
+    plan = cuda_rt.plan_from_params(SP)
+    T = int(cuda_rt.lib.plan_num_segments(plan, n))
+    nt = T // 128
+    Sp = [pool.empty_image(C, 256, T) for _ in xs]
+    Dp = [pool.empty_image(C, 256, T) for _ in xs]
+    tp = [torch.empty((C * nt, 256, 128), device=dev) for _ in xs]
+    infos = [torch.full((C, 4), -7, dtype=torch.int32, device=dev) for _ in xs]
+    before = pool.launch_count()
+    for i, x in enumerate(xs):
+        assert pool.submit(x, Sp[i], Dp[i], clip=True, tiles=tp[i], tile_w=128, ntiles=nt, info=infos[i]) == i % 2
+    pool.join()
+    torch.cuda.current_stream().synchronize()
+    assert pool.launch_count() > before
+    for i, x in enumerate(xs):
+        S = cuda_rt.empty_image(C, 256, T)
+        D = cuda_rt.empty_image(C, 256, T)
+        tl = torch.empty_like(tp[i])
+        cuda_rt.pipeline_dev(plan, x, S, D, clip=True, tiles=tl, tile_w=128, ntiles=nt)
+        torch.cuda.synchronize()
+        assert torch.equal(Sp[i][..., :T], S[..., :T]) and torch.equal(Dp[i][..., :T], D[..., :T]) and torch.equal(tp[i], tl)
+        assert infos[i][:, 3].max().item() == 0 and infos[i][:, 0].min().item() == 1
+    Sr, _, _ = oc.specgr_array(xs[4][0].cpu().numpy().astype(np.float64), SP)
+    np.testing.assert_allclose(Sp[4][0][:, :T].cpu().numpy(), Sr, rtol=0, atol=pc.ATOL_IMAGE)
+
+
 def test_torch_cuda_zero_copy(cuda_rt):
     import torch
     x = torch.from_numpy(pc.signals(2, 100_000)).cuda()
