@@ -320,7 +320,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = pool.launch_count() - l0
-    assert all(int(t[:, 3].max().item()) == 0 for t in infos)
+    assert os.environ.get("SPECGPU_BENCH_NOASSERT") or all(int(t[:, 3].max().item()) == 0 for t in infos)
     # the same K steps one shot at a time on one stream
     ms_one = max_over_ranks(timed(step, args.steps, 3))
     # per-kernel durations: the same K steps once more with the library's per-launch CUDA events switched on

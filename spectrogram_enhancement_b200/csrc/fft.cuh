@@ -156,7 +156,7 @@ __host__ __device__ constexpr int fft_out_reg(int log2m, int m) {
 // shared-memory wavefronts as the float2 line (a 64-bit warp access takes two), twice the LSU instructions, half the
 // shared memory: that half pays for the second output tile of the STFT kernel.  With a line stride of M + M/16 floats
 // (= 16 mod 32 for M = 256) the groups of a warp fall on disjoint banks.
-template <int LOG2M, bool KEEP_REGS = false, bool HALF_LINE = false>
+template <int LOG2M, bool KEEP_REGS = false, bool HALF_LINE = false, bool ABL_TW = false /* timing ablation, see stft.cu */>
 __device__ __forceinline__ void fft_group(float2 (&v)[fft_radix_at(LOG2M, 0)], float2* line, const float2* tw, int tg) {
   constexpr int M = 1 << LOG2M;
   constexpr int R0 = fft_radix_at(LOG2M, 0);
@@ -189,7 +189,8 @@ __device__ __forceinline__ void fft_group(float2 (&v)[fft_radix_at(LOG2M, 0)], f
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
         u[q * R1 + r].y = lf[fft_pad(tg + q * G + r * (M / R1))];
-        v[q * R1 + r] = (r > 0) ? cmul(u[q * R1 + r], tw[r * R0 + k]) : u[q * R1 + r];
+        const float2 w = ABL_TW ? make_float2(1.f - (float)(tg + r) * 1e-3f, (float)(tg + r) * 1e-3f) : tw[(r > 0 ? r : 1) * R0 + k];
+        v[q * R1 + r] = (r > 0) ? cmul(u[q * R1 + r], w) : u[q * R1 + r];
       }
     }
     FftPass<M, R0, R1, R0>::butterflies(v);

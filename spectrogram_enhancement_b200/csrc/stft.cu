@@ -12,6 +12,17 @@
 
 namespace specgpu {
 
+// Timing ablations (tools/build_variant.sh; results are WRONG on purpose, never defined in the product build): a bit set in
+// SPECGPU_STFT_ABL replaces one class of shared-memory accesses by a thread-dependent register value, so that the
+// arithmetic stays and only the LDS / STS traffic goes.  1: window, 2: inter-pass twiddles, 4: tile stores, 8: staged
+// input, 16: untangle twiddles.
+#ifndef SPECGPU_STFT_ABL
+#define SPECGPU_STFT_ABL 0
+#endif
+// 32: no tensor store of the tile, 64: 16-byte bulk copies instead of the tile's span (barrier protocol unchanged),
+// 128: no transform, 256: no block-level fences around the arrival counters
+__device__ __forceinline__ uint32_t kAblSpan(int span) { return (SPECGPU_STFT_ABL & 64) ? 16u : (uint32_t)span * 4u; }
+
 template <int LOG2N, int MODE>
 __global__ void __launch_bounds__(kStftThreads, stft_min_blocks(LOG2N, MODE))
 stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
@@ -101,8 +112,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
     if (tile_bulk(b, s0)) {
 #if !defined(SPECGPU_EMULATE)
       if (tid == 0) {
-        mbar_arrive_expect_tx(bar, (uint32_t)a.span * 4u);
-        bulk_g2s(smem_u32(s_in), xb + s0, (uint32_t)a.span * 4u, bar, pol_in);
+        mbar_arrive_expect_tx(bar, kAblSpan(a.span));
+        bulk_g2s(smem_u32(s_in), xb + s0, kAblSpan(a.span), bar, pol_in);
       }
 #endif
     } else {
@@ -175,7 +186,10 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
     float2 v[R0];
     if (stage) {
       const float* p = s_in + (int64_t)tl * a.hop + 2 * tg;
-      if ((a.hop & 1) == 0) {
+      if (SPECGPU_STFT_ABL & 8) {
+#pragma unroll
+        for (int r = 0; r < R0; ++r) v[r] = make_float2((float)(tid + r) * 1e-3f, (float)(tid - r) * 1e-3f);
+      } else if ((a.hop & 1) == 0) {
 #pragma unroll
         for (int r = 0; r < R0; ++r) v[r] = *reinterpret_cast<const float2*>(p + 2 * r * G);
       } else {
@@ -190,12 +204,12 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
         if (next < ntiles && tile_bulk(nxt_b, tile_start(nxt_t))) {
           __syncwarp();
           if ((tid & 31) == 0) {
-            __threadfence_block();
+            if (!(SPECGPU_STFT_ABL & 256)) __threadfence_block();
             if (atomicAdd(cnt_free, 1u) == kStftThreads / 32 - 1) {
               *cnt_free = 0;
-              __threadfence_block();
-              mbar_arrive_expect_tx(bar, (uint32_t)a.span * 4u);
-              bulk_g2s(smem_u32(s_in), a.x + (int64_t)nxt_b * a.ldx + tile_start(nxt_t), (uint32_t)a.span * 4u, bar, pol_in);
+              if (!(SPECGPU_STFT_ABL & 256)) __threadfence_block();
+              mbar_arrive_expect_tx(bar, kAblSpan(a.span));
+              bulk_g2s(smem_u32(s_in), a.x + (int64_t)nxt_b * a.ldx + tile_start(nxt_t), kAblSpan(a.span), bar, pol_in);
             }
           }
         }
@@ -244,7 +258,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       const float2 step = bcast2(slope * (float)(2 * G));
 #pragma unroll
       for (int r = 0; r < R0; ++r) {
-        const float2 w = *reinterpret_cast<const float2*>(s_win + 2 * (tg + r * G));
+        const float2 w = (SPECGPU_STFT_ABL & 1) ? make_float2(1.f + (float)tg * 1e-3f, 1.f - (float)tg * 1e-3f)
+                                                : *reinterpret_cast<const float2*>(s_win + 2 * (tg + r * G));
         v[r] = mul2(sub2(v[r], t), w);
         t = add2(t, step);
       }
@@ -259,7 +274,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
     // Groups that live inside one warp keep the outputs of the last pass in registers and fetch the mirrored bins
     // from their partner thread with shuffles (no second trip through the line); wider groups go through the line.
     constexpr bool REGS = (G <= 32);
-    fft_group<C::LOG2M, REGS, HALF_LINE>(v, line, s_twm, tg);
+    if (!(SPECGPU_STFT_ABL & 128)) fft_group<C::LOG2M, REGS, HALF_LINE, (SPECGPU_STFT_ABL & 2) != 0>(v, line, s_twm, tg);   // 128: no transform
 
     // ---- untangle: 2 X[k] = E + W_N^k O, 2 X[M-k] = conj(E - W_N^k O) with E = Z[k] + conj(Z[M-k]),
     //      O = -i (Z[k] - conj(Z[M-k])); the factor 2 is folded into the output scales.  Thread tg owns the bin pairs
@@ -279,7 +294,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       const float2 zc = make_float2(zm.x, -zm.y);
       const float2 e = add2(zk, zc);
       const float2 d = sub2(zk, zc);
-      const float2 w = s_twn[k];
+      const float2 w = (SPECGPU_STFT_ABL & 16) ? make_float2(1.f - (float)tg * 1e-3f, (float)tg * 1e-3f) : s_twn[k];
       const float2 xk = fma2(d, bcast2(w.y), fma2(make_float2(d.y, -d.x), bcast2(w.x), e));
       float2 xm = fma2(make_float2(-d.x, -d.y), bcast2(w.y), fma2(make_float2(-d.y, d.x), bcast2(w.x), e));
       if (MODE == STFT_MODE_SPECTRA || MODE == STFT_MODE_COMPLEX) xm.y = -xm.y;
@@ -321,8 +336,10 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
           pk *= ps;
           pm *= ps;
         }
-        *reinterpret_cast<float*>(s_tile + offk) = pk;
-        if (two) *reinterpret_cast<float*>(s_tile + offm) = pm;
+        if (!(SPECGPU_STFT_ABL & 4) || pk == 123.456f) {
+          *reinterpret_cast<float*>(s_tile + offk) = pk;
+          if (two) *reinterpret_cast<float*>(s_tile + offm) = pm;
+        }
       }
     };
 #if !defined(SPECGPU_EMULATE)
@@ -416,12 +433,12 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
     if (lane == 0) {
       red[2 * warp] = vmin;
       red[2 * warp + 1] = vmax;
-      __threadfence_block();
+      if (!(SPECGPU_STFT_ABL & 256)) __threadfence_block();
       if (atomicAdd(cnt_full + tbuf, 1u) == NW - 1) {    // last warp of the tile: store it
         cnt_full[tbuf] = 0;
-        __threadfence_block();
+        if (!(SPECGPU_STFT_ABL & 256)) __threadfence_block();
         const int rows_out = F - 1;
-        for (int rb = 0; rb < a.tma_nbox; ++rb) {
+        for (int rb = 0; rb < ((SPECGPU_STFT_ABL & 32) ? 0 : a.tma_nbox); ++rb) {
           if (a.ld_out < 0)
             tma_store_3d(&tmap, smem_u32(s_tile + (size_t)rb * a.tma_rows * ROWB), (int)(seg0 & 31), (int)(seg0 >> 5) * rows_out + rb * a.tma_rows,
                          (int)b, pol_out);
