@@ -15,8 +15,18 @@
 // are summed by a second, deterministic kernel that also applies the scale (and accumulates across blocks of
 // segments for the chunked multi-GPU exchange).
 #include "kernels.h"
+#include "ptx.cuh"
+#include "tensor_map.h"
 
 namespace specgpu {
+
+#ifndef SPECGPU_GRID_CONSTANT
+#if defined(SPECGPU_EMULATE)
+#define SPECGPU_GRID_CONSTANT
+#else
+#define SPECGPU_GRID_CONSTANT __grid_constant__
+#endif
+#endif
 
 constexpr int kCsdWarps = 16, kCsdThreads = kCsdWarps * 32, kCsdTileJ = 4;   // tiles are TI x 4 pairs, TI in {4, 8}
 
@@ -288,6 +298,107 @@ __global__ void __launch_bounds__(kCsdThreads, 1) csd_pairs_staged_kernel(CsdArg
   }
 }
 
+// ---- TMA-fed variant of the staged kernel ---------------------------------------------------------------------------
+// The cp.async ring above spends a third of its instructions on the copies (per copy a 64-bit address, a predicate, a
+// size) -- integer multiply-adds that share the FMA pipe with the products (ncu: FFMA2 48 % of the executed instructions,
+// integer / control 30 %, `math_pipe_throttle` the first stall reason).  Here ONE lane of a producer warp issues one
+// cp.async.bulk.tensor.3d per stage: the box [C channels][SEGS segments][32 bins] of X[C][nseg][ldf] lands in shared
+// memory as [channel][segment][32] float2 behind an mbarrier (bins past nfreq and segments past the record arrive as
+// zeros), the 15 consumer warps read their 8 + 4 operands per segment at compile-time offsets from two bases, and hand
+// the slot back through a second mbarrier (one arrival per consumer warp): no CTA barrier, no per-thread addressing.
+// Segments of the stage that belong to the next chunk are skipped by a warp-uniform test.
+#if !defined(SPECGPU_EMULATE)
+constexpr int kCsdTmaWarps = 15;                       // consumer warps (= tiles per CTA); warp 15 is the producer
+template <int NST, int SEGS>
+__global__ void __launch_bounds__(kCsdThreads, 1) csd_pairs_tma_kernel(CsdArgs a, int tiles_per_group, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
+  constexpr int TI = 8, TJ = kCsdTileJ;
+  SPECGPU_DYN_SMEM(smem);
+  const int C = a.C;
+  const int stage_elems = C * SEGS * 32;                                   // float2 per stage
+  float2* ring = reinterpret_cast<float2*>(smem);                          // [NST][C][SEGS][32] + slack (ragged tiles)
+  // barriers behind the ring and its slack (7 channels past the last slab)
+  const uint32_t bars = smem_u32(smem) + (uint32_t)(((size_t)NST * stage_elems + 7 * SEGS * 32) * sizeof(float2));
+  auto full = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty = [&](int s) { return bars + 8u * (uint32_t)(NST + s); };
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f = blockIdx.x * 32 + lane;
+  const bool f_ok = f < a.nfreq;
+  const int chunk = blockIdx.y;
+  const int tile0 = blockIdx.z * tiles_per_group;
+  const int tiles_here = (a.ntiles - tile0 < tiles_per_group) ? (a.ntiles - tile0) : tiles_per_group;
+  const int t0 = (int)((int64_t)chunk * a.seg_per_chunk);
+  const int t1 = (int)((t0 + a.seg_per_chunk < a.nseg) ? t0 + a.seg_per_chunk : a.nseg);
+  const int nstage = (t1 - t0 + SEGS - 1) / SEGS;
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(empty(s), (uint32_t)tiles_here);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap);
+  }
+  __syncthreads();
+  if (warp == kCsdTmaWarps) {
+    // ---- producer ----
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();      // every slab is read once per tile group
+      const uint32_t bytes = (uint32_t)(stage_elems * sizeof(float2));
+      for (int st = 0; st < nstage; ++st) {
+        const int s = st % NST;
+        if (st >= NST) mbar_wait(empty(s), ((st / NST) - 1) & 1);          // the consumers are done with the slot's last use
+        mbar_arrive_expect_tx(full(s), bytes);
+        tma_load_3d(smem_u32(ring + (size_t)s * stage_elems), &tmap, blockIdx.x * 64, t0 + st * SEGS, 0, full(s), pol);
+      }
+    }
+    return;
+  }
+  if (warp >= tiles_here) return;
+  int bi = 0, bj = 0;
+  csd_tile_coords(a, tile0 + warp, &bi, &bj);
+  // operands of the tile at compile-time offsets from two bases (rows are consecutive channels)
+  const int base_i = (a.i0 + bi * TI) * SEGS * 32 + lane;
+  const int base_j = bj * TJ * SEGS * 32 + lane;
+  float2 acc[TI][TJ];
+#pragma unroll
+  for (int i = 0; i < TI; ++i)
+#pragma unroll
+    for (int j = 0; j < TJ; ++j) acc[i][j] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int st = 0; st < nstage; ++st) {
+    const int s = st % NST;
+    mbar_wait(full(s), (st / NST) & 1);
+    const float2* slab = ring + (size_t)s * stage_elems;
+    const int left = t1 - (t0 + st * SEGS);            // segments of this stage that belong to the chunk
+#pragma unroll
+    for (int sg = 0; sg < SEGS; ++sg) {
+      if (sg < left) {
+        const float2* si = slab + sg * 32 + base_i;
+        const float2* sj = slab + sg * 32 + base_j;
+        float2 xi[TI], xj[TJ];
+#pragma unroll
+        for (int k = 0; k < TI; ++k) xi[k] = si[k * SEGS * 32];
+#pragma unroll
+        for (int k = 0; k < TJ; ++k) xj[k] = sj[k * SEGS * 32];
+#pragma unroll
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+          for (int j = 0; j < TJ; ++j) acc[i][j] = cmac_conj(acc[i][j], xi[i], xj[j]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty(s));
+  }
+  if (f_ok) {
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+      for (int j = 0; j < TJ; ++j)
+        if (bi * TI + i < a.ni && bj * TJ + j < C)
+          a.partial[(((int64_t)chunk * a.ni + (bi * TI + i)) * C + (bj * TJ + j)) * a.nfreq + f] = acc[i][j];
+  }
+}
+#endif
+
 // f0 / nfreq_total: the nfreq columns are bins f0 .. f0 + nfreq - 1 of a one-sided spectrum of nfreq_total bins (a
 // frequency block of a sharded run); only global bins 0 and nfreq_total - 1 are not doubled.
 __global__ void csd_reduce_kernel(const float2* partial, int nchunk, int ni, int C, int nfreq, int sym, int ti, float scale,
@@ -435,6 +546,29 @@ int launch_csd_pairs(const float* X, int64_t C, int64_t nseg, int64_t nseg_total
   a.nbj = g.nbj;
   a.seg_per_chunk = g.seg_per_chunk;
   a.partial = reinterpret_cast<float2*>(partial_ws);
+#if !defined(SPECGPU_EMULATE)
+  static const bool tma_env = !(std::getenv("SPECGPU_CSD_TMA") && std::getenv("SPECGPU_CSD_TMA")[0] == '0');
+  if (g.staged && tma_env && g.tiles_per_group <= kCsdTmaWarps) {
+    // TMA-fed kernel: box [C][SEGS][32 bins] per stage, as many stages as fit ~200 KB (at least 3)
+    constexpr int SEGS = 4;
+    const size_t stage_bytes = (size_t)C * SEGS * 32 * sizeof(float2);
+    const size_t tail = (size_t)7 * SEGS * 32 * sizeof(float2) + 64;
+    const int nst = (4 * stage_bytes + tail <= 208 * 1024) ? 4 : ((3 * stage_bytes + tail <= 208 * 1024) ? 3 : 0);
+    TensorMap tmap{};
+    if (nst && make_tensor_map_f32_3d(&tmap, X, (uint64_t)nfreq * 2, (uint64_t)nseg, (uint64_t)C, (uint64_t)ldf * 2,
+                                      (uint64_t)ldf * 2 * (uint64_t)nseg, 64, SEGS, 0, (uint32_t)C)) {
+      const dim3 sgrid((unsigned)ceil_div(nfreq, 32), (unsigned)g.nchunk, (unsigned)g.ngroups);
+      const size_t sm = (size_t)nst * stage_bytes + tail;
+      auto kern = nst == 4 ? csd_pairs_tma_kernel<4, SEGS> : csd_pairs_tma_kernel<3, SEGS>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e != cudaSuccess) return (int)e;
+      SPECGPU_LAUNCH(kern, sgrid, kCsdThreads, sm, stream, a, g.tiles_per_group, tmap);
+      int err = (int)cudaGetLastError();
+      if (err) return err;
+      return launch_csd_reduce(a, g, ni, C, nfreq, scale / (float)nseg_total, accumulate, f0, nfreq_total, P, stream);
+    }
+  }
+#endif
   if (g.staged) {
     const size_t pair_bytes = (size_t)2 * C * 32 * sizeof(float2);      // two segments of the [C x 32] slab
     const dim3 sgrid((unsigned)ceil_div(nfreq, 32), (unsigned)g.nchunk, (unsigned)g.ngroups);

@@ -381,14 +381,6 @@ struct GramTmaArgs {
   float* partial;
 };
 
-#if !defined(SPECGPU_EMULATE)
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-      : "memory");
-}
-#endif
 
 template <int ROWS>
 __global__ void __launch_bounds__(kGtcThreads, 1) gram_tma_kernel(const GramTmaArgs a, const float* S, int64_t ld,

@@ -79,6 +79,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
+// Tensor-map (TMA) load of one box global -> shared (SASS UTMALDG); elements outside the tensor arrive as zeros;
+// completes the box's bytes of transaction on the mbarrier.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 // Tensor-map (TMA) store of one box shared -> global (SASS UTMASTG); elements outside the tensor are clipped.
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, uint64_t policy) {
   asm volatile(
