@@ -5,7 +5,7 @@
 // complex values in registers, performs R0/R radix-R butterflies on them, and exchanges through a
 // padded shared-memory line.  Radices per size (first pass = R0):
 //   M:   4    8    16    32     64    128     256      512      1024      2048       4096
-//        4    8    16   8,4    8,8   16,8   16,16    8,8,8    16,8,8   16,16,8   16,16,16
+//        4    8    16   8,4    8,8   16,8   16,16   16,8,4    16,8,8   16,16,8   16,16,16
 #pragma once
 #include "common.cuh"
 
@@ -13,7 +13,7 @@ namespace specgpu {
 
 __host__ __device__ constexpr int fft_radix_at(int log2m, int idx) {
   constexpr int T[13][3] = {{1, 1, 1},  {1, 1, 1},   {4, 1, 1},   {8, 1, 1},   {16, 1, 1},
-                            {8, 4, 1},  {8, 8, 1},   {16, 8, 1},  {16, 16, 1}, {8, 8, 8},
+                            {8, 4, 1},  {8, 8, 1},   {16, 8, 1},  {16, 16, 1}, {16, 8, 4},
                             {16, 8, 8}, {16, 16, 8}, {16, 16, 16}};
   return T[log2m][idx];
 }

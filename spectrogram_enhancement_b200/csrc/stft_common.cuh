@@ -145,7 +145,7 @@ __device__ __forceinline__ float log2_normal(float x) {
 // Resident CTAs per SM the register allocator should aim for: what the shared-memory footprint of the mode allows
 // (the spectra mode has no output tile).  Without it the 3-pass sizes compile to ~195 registers = one CTA per SM.
 __host__ __device__ constexpr int stft_min_blocks(int log2n, int mode) {
-  if (mode == STFT_MODE_COMPLEX) return log2n <= 9 ? 2 : 1;
+  if (mode == STFT_MODE_COMPLEX) return log2n <= 10 ? 2 : 1;
   if (log2n <= 9) return 3;
   if (mode == STFT_MODE_SPECTRA) return log2n <= 12 ? 3 : 1;
   return log2n == 10 ? 2 : 1;
