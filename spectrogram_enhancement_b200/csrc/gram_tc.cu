@@ -566,22 +566,38 @@ __global__ void __launch_bounds__(kGtcThreads, 1) gram_tma_kernel(const GramTmaA
       float* part = part0 + (size_t)sg * 128 * PP;
       const int q = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
       constexpr int NCG = PW / 32;            // 32-column groups, dealt round-robin to the warps of a quarter
-      // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns = 128 contiguous bytes of its partial
-      // row): eight 16-byte stores per lane, no trip through shared memory
+      // tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns).  The partial [128][PP] is assembled in
+      // the (now idle) ring in its global layout -- lane = row, 16-byte stores at a pitch of PP floats = 4 banks mod 32:
+      // a quarter-warp covers all 32 banks, conflict-free -- and leaves as ONE contiguous bulk copy.  (Storing straight
+      // from the registers, eight 16-byte pieces per lane 1552 bytes apart, cost 8.3 us of the kernel's 41.)
+      float* stage_out = reinterpret_cast<float*>(slabs);
+      // every worker warp is here: the MMAs have retired (s_accum) AND the row-sum warps have read the last stages and
+      // published s_rowsum -- only now may the ring be overwritten
+      named_bar_sync(kSegBarrier + 1, kGtcWarps * 32);
       for (int cg = warp >> 2; cg < NCG && !(a.debug & 2); cg += kGtcWarps / 4) {
         const int c = cg * 32;
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        float4* dst = reinterpret_cast<float4*>(part + (size_t)(q * 32 + lane) * PP + c);
+        float4* dst = reinterpret_cast<float4*>(stage_out + (size_t)(q * 32 + lane) * PP + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                __uint_as_float(v[4 * j + 3]));
       }
-      named_bar_sync(kSegBarrier + 1, kGtcWarps * 32);      // the row-sum warps have published s_rowsum
       if (warp < 4) {
-        part[(size_t)(warp * 32 + lane) * PP + PW] = s_rowsum[warp * 32 + lane];
-        part[(size_t)(warp * 32 + lane) * PP + PW + 1] = (ROWS == 256) ? s_rowsum[128 + warp * 32 + lane] : 0.f;
+        float4 tail;
+        tail.x = s_rowsum[warp * 32 + lane];
+        tail.y = (ROWS == 256) ? s_rowsum[128 + warp * 32 + lane] : 0.f;
+        tail.z = 0.f;
+        tail.w = 0.f;
+        *reinterpret_cast<float4*>(stage_out + (size_t)(warp * 32 + lane) * PP + PW) = tail;
+      }
+      fence_proxy_async();                                   // this thread's staging writes -> visible to the bulk copy
+      named_bar_sync(kSegBarrier + 2, kGtcWarps * 32);
+      if (tid == 0 && !(a.debug & 2)) {
+        bulk_s2g(part, smem_u32(stage_out), (uint32_t)(128 * PP * sizeof(float)));
+        bulk_commit();
+        bulk_wait_read<0>();                                 // the ring may be refilled / the CTA may exit
       }
       tc_fence_before();
       // every worker warp has read its part of TMEM and is done with its transpose tile before the next segment's
@@ -695,7 +711,8 @@ int launch_gram_tma(const float* S, int64_t B, int64_t rows, int64_t cols, int64
   a.l2_pin = l2_pin;
   a.partial = partial_ws;
   if (const char* env = std::getenv("SPECGPU_GRAM_DEBUG")) a.debug = std::atoi(env);
-  const size_t smem = (size_t)kGtmStages * 2 * rows * 128 + 1024;
+  // the ring; the epilogue assembles the [128][PW + 4] partial in it (a little larger than the ring for 256 rows)
+  const size_t smem = std::max((size_t)kGtmStages * 2 * rows * 128, (size_t)128 * ((rows == 256 ? 384 : rows) + 4) * sizeof(float)) + 1024;
   if (rows == 256) {
     cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

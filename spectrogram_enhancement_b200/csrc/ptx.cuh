@@ -79,6 +79,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
+// 1-D bulk copy shared -> global (bulk async-group completion): 16-byte aligned addresses, size a multiple of 16.
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
 // Tensor-map (TMA) load of one box global -> shared (SASS UTMALDG); elements outside the tensor arrive as zeros;
 // completes the box's bytes of transaction on the mbarrier.
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar, uint64_t policy) {

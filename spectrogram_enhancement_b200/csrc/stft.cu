@@ -539,6 +539,21 @@ __global__ void lognorm_kernel(float* S, int64_t rows, int64_t cols, int64_t ld,
   }
   float* row = S + (b * rows + r) * ld;
   const unsigned n = (unsigned)cols;
+  if (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0)) {
+    // 16-byte aligned rows (the pitched images of Runtime.empty_image): whole float4, then the ragged tail
+    float4* row4 = reinterpret_cast<float4*>(row);
+    const unsigned n4 = n >> 2;
+    for (unsigned c = threadIdx.x; c < n4; c += blockDim.x) {
+      float4 v = row4[c];
+      v.x = div_by(v.x - mn, den, inv);
+      v.y = div_by(v.y - mn, den, inv);
+      v.z = div_by(v.z - mn, den, inv);
+      v.w = div_by(v.w - mn, den, inv);
+      row4[c] = v;
+    }
+    for (unsigned c = 4 * n4 + threadIdx.x; c < n; c += blockDim.x) row[c] = div_by(row[c] - mn, den, inv);
+    return;
+  }
   for (unsigned c = threadIdx.x; c < n; c += blockDim.x) row[c] = div_by(row[c] - mn, den, inv);
 }
 

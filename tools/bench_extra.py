@@ -78,7 +78,10 @@ report("filter_chain fused (quantfilt -> gaussblr -> meansub -> morph -> meansub
 xs = [torch.randn((40, 1_000_000), device=dev, generator=g) for _ in range(NB)]
 plan = rt.plan_from_params(api.DEFAULT_SPEC_PARAMS)
 S = rt.empty((40, 256, 3905))
-report("specgr 40ch x 1M (STFT+log+min-max)", timeit(lambda i: rt.specgr_dev(plan, xs[i % NB], S)), 40 * (4e6 + 4 * 256 * 3905))
+report("specgr 40ch x 1M (STFT+log+min-max), dense 3905-float rows", timeit(lambda i: rt.specgr_dev(plan, xs[i % NB], S)), 40 * (4e6 + 4 * 256 * 3905))
+Sp = rt.empty_image(40, 256, 3905)
+report("specgr 40ch x 1M (STFT+log+min-max), pitched rows (Runtime.empty_image, the API default)",
+       timeit(lambda i: rt.specgr_dev(plan, xs[i % NB], Sp)), 40 * (4e6 + 4 * 256 * 3905))
 # ---- config 1: STFT 1024/512 hann, complex output, 40 channels batched ----
 p1 = rt.plan(1024, 512, 500000, "hann", "spectrum", False)
 T1 = rt.lib.stft_num_segments(p1, 1_000_000, 1, 1)
