@@ -90,9 +90,16 @@ int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int
                     float* s_out, cudaStream_t stream);
 // Leading-component removal fused with the min-max normalisation: L (log image) -> S = (L-min)/(max-min) and
 // D = S - u0 (u0^T S) [clipped]; S may alias L.  minmax == nullptr: L is already normalised (S not written if null).
+// Optional second destination of the rank-1 projection: the VAE tiles of the denoised image (VAE/manual_scan.py:28-36,
+// float32 [B * ntiles][rows][tile_w]; column c of matrix b goes to tile c / tile_w when that is < ntiles) written in the
+// same pass, instead of a separate tile cut that reads D back.
+struct R1Tiles {
+  float* ptr = nullptr;
+  int tile_w = 0, ntiles = 0;
+};
 int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const MinMaxWord* minmax, const float* U,
                      int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out = 0,
-                     const int32_t* only_flagged = nullptr /* [B]: skip matrices whose entry is 0 */);
+                     const int32_t* only_flagged = nullptr /* [B]: skip matrices whose entry is 0 */, R1Tiles tiles = R1Tiles{});
 int launch_svd_project(const float* S, int64_t B, int rows, int64_t cols, int64_t ld, const float* U, const int32_t* plan,
                        int clip, void* out, int out_f64, int64_t ldo, cudaStream_t stream);
 

@@ -663,7 +663,8 @@ SvdWs svd_carve(void* ws, int64_t B, int64_t rows, bool tc, bool full) {
 int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm, int64_t B, int64_t rows, int64_t cols,
             int64_t ld, int kind, int start, int stop, int clip, bool power_ok, bool fallback, void* out, int out_f64,
             int64_t ldo, float* s_out, int32_t* info, cudaStream_t st, float l2_pin = 0.f, const float* Limg = nullptr,
-            int64_t ldL = 0, const int64_t* pre_gram = nullptr /* {nchunk, per}: partials already written by stft_gram */) {
+            int64_t ldL = 0, const int64_t* pre_gram = nullptr /* {nchunk, per}: partials already written by stft_gram */,
+            R1Tiles r1_tiles = R1Tiles{} /* float32 tiles of the projection written in the same pass (rank-1 route only) */) {
   void* stream = (void*)st;
   const float* Lsrc = Limg ? Limg : S;       // what the Gram and projection kernels read
   const int64_t ldsrc = Limg ? ldL : ld;
@@ -776,12 +777,12 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
       cudaEventRecord(ctx->ev_repair_join, rs);
     }
 #endif
-    CHECK_LAUNCH(ctx, launch_svd_rank1(Lsrc, B, (int)rows, cols, ldsrc, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, 0),
+    CHECK_LAUNCH(ctx, launch_svd_rank1(Lsrc, B, (int)rows, cols, ldsrc, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, 0, nullptr, r1_tiles),
                  "svd_rank1", 1);
 #ifndef SPECGPU_EMULATE
     if (side_repair) {
       cudaStreamWaitEvent(st, ctx->ev_repair_join, 0);
-      CHECK_LAUNCH(ctx, launch_svd_rank1(Lsrc, B, (int)rows, cols, ldsrc, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, 0, w.flagged),
+      CHECK_LAUNCH(ctx, launch_svd_rank1(Lsrc, B, (int)rows, cols, ldsrc, raw_mm, w.U, clip, raw_mm ? S : nullptr, (float*)out, ldo, st, 0, w.flagged, r1_tiles),
                    "svd_rank1_flagged", 1);
     }
 #endif
@@ -1231,10 +1232,18 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     w.jacobi = jac[li];
     w.flagged = flagged_all + b0;
     // Sg holds the raw log image until the rank-1 projection normalises it in place (see svd_run)
+    // the rank-1 projection (rows <= 256) writes the tiles itself; the general projection leaves them to the tile cut
+    const bool r1_writes_tiles = tiles && ntiles > 0 && power_ok && !std::getenv("SPECGPU_NO_FUSED_TILES");
+    R1Tiles r1t;
+    if (r1_writes_tiles) {
+      r1t.ptr = tiles + (size_t)b0 * ntiles * rows * tile_w;
+      r1t.tile_w = tile_w;
+      r1t.ntiles = ntiles;
+    }
     if ((rc = svd_run(ctx, w, Sg, mmg, nb, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, fallback, Dg, 0, ldt, nullptr,
-                      info ? info + b0 * 4 : nullptr, st, l2_pin, Lg, tiled ? -ntile : 0, fused ? pre_gram : nullptr)))
+                      info ? info + b0 * 4 : nullptr, st, l2_pin, Lg, tiled ? -ntile : 0, fused ? pre_gram : nullptr, r1t)))
       return rc;
-    if (tiles && ntiles > 0)
+    if (tiles && ntiles > 0 && !r1_writes_tiles)
       CHECK_LAUNCH(ctx, launch_patch(Dg, nb, rows, ldt, tile_w, ntiles, tiles + (size_t)b0 * ntiles * rows * tile_w, 0, st), "patch", 1);
   }
 #ifndef SPECGPU_EMULATE

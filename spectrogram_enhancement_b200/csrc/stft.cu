@@ -36,8 +36,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   constexpr int SWMASK = stft_swizzle_mask(ROWB);
   constexpr int JSTEP = G * ROWB;                     // tile byte offset between rows k and k + G
   static_assert(JSTEP % 1024 == 0, "row stride between a thread's bins must not touch the swizzle bits");
-  constexpr bool TWO_TILES = stft_two_tiles<LOG2N>(MODE);   // second output tile + (two-pass sizes) half-width exchange line
-  constexpr bool HALF_LINE = stft_half_line<LOG2N>(MODE);
+  constexpr int NTB = stft_num_tiles<LOG2N>(MODE);          // output tiles in shared memory (two on the barrier-free path)
+  constexpr bool HALF_LINE = stft_half_line<LOG2N>(MODE);   // half-width exchange line (pays for the second tile)
   SPECGPU_DYN_SMEM(smem);
   const StftSmem L = stft_smem_layout<LOG2N>(MODE, a.stage_in ? a.span : 0);
   float* s_win = reinterpret_cast<float*>(smem + L.window_off);
@@ -63,7 +63,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   // warp to finish its columns issues the tensor store (two shared arrival counters); the only waits are on data (span
   // landed) and on the previous store having read the tile, both normally long satisfied.  Warps of a CTA drift apart,
   // so their shared-memory and FP32 phases overlap instead of colliding.
-  constexpr bool FLOWC = TWO_TILES;
+  constexpr bool FLOWC = stft_flow_capable<LOG2N>(MODE);
   const bool flow = FLOWC && a.flow != 0;
   const uint32_t bar = smem_u32(smem + L.bar_off);
   const uint32_t bar_tfree = bar + 8;                  // [2]: tile buffer p has been read by its tensor store
@@ -152,7 +152,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   const float* xb = a.x + b * a.ldx;
   float vmin = INFINITY, vmax = -INFINITY;
   const bool bulk = stage && tile_bulk(b, a.first_start + seg0 * (int64_t)a.hop);
-  const unsigned tbuf = (TWO_TILES && flow) ? (flow_it & 1u) : 0u;       // output tile buffer of this tile
+  const unsigned tbuf = (NTB > 1 && flow) ? (flow_it % NTB) : 0u;        // output tile buffer of this tile
   s_tile = s_tile0 + tbuf * (unsigned)L.tile_stride;
 
 #if !defined(SPECGPU_EMULATE)
@@ -351,8 +351,8 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
         mbar_arrive(bar_tfree + 8u * (pend - 1u));
         pend = 0;
       }
-      // buffer tbuf was last used two tiles ago: its store (completion flow_it / 2 - 1 of that barrier) has read it
-      if (flow_it >= 2) mbar_wait(bar_tfree + 8u * tbuf, ((flow_it >> 1) - 1u) & 1u);
+      // buffer tbuf was last used NTB tiles ago: its store (completion flow_it / NTB - 1 of that barrier) has read it
+      if (flow_it >= NTB) mbar_wait(bar_tfree + 8u * tbuf, ((flow_it / NTB) - 1u) & 1u);
     }
 #endif
     {

@@ -50,14 +50,23 @@ __host__ __device__ constexpr int stft_swizzle_mask(int rowb) { return rowb >= 1
 // buffer 16 % of the kernel's executed instructions were mbarrier polls on "tile free").  The second tile is paid for by
 // the half-width exchange line where the transform has two passes.
 template <int LOG2N>
-__host__ __device__ constexpr bool stft_two_tiles(int mode) {
+__host__ __device__ constexpr bool stft_flow_capable(int mode) {
   using C = StftCfg<LOG2N>;
   const int rowb = C::tile_w(4) * 4;
   return (mode == STFT_MODE_LOGPSD || mode == STFT_MODE_LOGPSD_FAST) && C::tile_w(4) == C::NG && C::G <= 32 && rowb >= 16 && rowb <= 128;
 }
+// output tiles in shared memory (experiment knob SPECGPU_STFT_TILES: 1 = single tile)
+template <int LOG2N>
+__host__ __device__ constexpr int stft_num_tiles(int mode) {
+#ifdef SPECGPU_STFT_TILES
+  return stft_flow_capable<LOG2N>(mode) ? SPECGPU_STFT_TILES : 1;
+#else
+  return stft_flow_capable<LOG2N>(mode) ? 2 : 1;
+#endif
+}
 template <int LOG2N>
 __host__ __device__ constexpr bool stft_half_line(int mode) {
-  return stft_two_tiles<LOG2N>(mode) && fft_num_passes(LOG2N - 1) == 2;
+  return stft_flow_capable<LOG2N>(mode) && fft_num_passes(LOG2N - 1) == 2;
 }
 
 struct StftSmem {
@@ -84,12 +93,16 @@ __host__ __device__ inline StftSmem stft_smem_layout(int mode, int span_floats) 
   s.tile_off = off;
   s.tile_stride = 0;
   if (mode != STFT_MODE_SPECTRA) {
-    off = (off + 1023) & ~1023;
+    // the swizzle pattern XORs address bits 4..6 with bits 7..9: a 64-byte-row tile (bits 4, 5 <- 7, 8) needs a 512-byte
+    // aligned base, wider rows 1024
+    const int rowb = C::tile_w(stft_elem_bytes(mode)) * stft_elem_bytes(mode);
+    const int al = rowb <= 64 ? 512 : 1024;
+    off = (off + al - 1) & ~(al - 1);
     s.tile_off = off;
-    const int tile_bytes = C::F * C::tile_w(stft_elem_bytes(mode)) * stft_elem_bytes(mode);
+    const int tile_bytes = C::F * rowb;
     off += tile_bytes;
-    if (stft_two_tiles<LOG2N>(mode)) {
-      s.tile_stride = (tile_bytes + 1023) & ~1023;
+    if (stft_num_tiles<LOG2N>(mode) > 1) {
+      s.tile_stride = (tile_bytes + al - 1) & ~(al - 1);
       off = s.tile_off + s.tile_stride + tile_bytes;
     }
   }
@@ -146,6 +159,9 @@ __device__ __forceinline__ float log2_normal(float x) {
 // (the spectra mode has no output tile).  Without it the 3-pass sizes compile to ~195 registers = one CTA per SM.
 __host__ __device__ constexpr int stft_min_blocks(int log2n, int mode) {
   if (mode == STFT_MODE_COMPLEX) return log2n <= 10 ? 2 : 1;
+#ifdef SPECGPU_STFT_MINBLOCKS9     // experiment knob (tools/build_variant.sh): resident CTAs the nperseg <= 512 kernels are compiled for
+  if (log2n <= 9) return SPECGPU_STFT_MINBLOCKS9;
+#endif
   if (log2n <= 9) return 3;
   if (mode == STFT_MODE_SPECTRA) return log2n <= 12 ? 3 : 1;
   return log2n == 10 ? 2 : 1;

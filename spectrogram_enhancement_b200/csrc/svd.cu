@@ -1045,9 +1045,10 @@ __device__ __forceinline__ void r1_store(float* p, float v, uint64_t pol) {
   *p = v;
 }
 
-template <int RPW, bool NORM, bool CLIP, bool STREAM>   // RPW = rows per thread = ceil(rows / 16)
+template <int RPW, bool NORM, bool CLIP, bool STREAM, bool TILES = false>   // RPW = rows per thread = ceil(rows / 16)
 __device__ __forceinline__ void svd_rank1_tile(const int64_t b, const float* L, int rows, int64_t cols, int64_t ld,
-                                               const MinMaxWord* minmax, const float* U, float* S, float* D, int64_t ldo) {
+                                               const MinMaxWord* minmax, const float* U, float* S, float* D, int64_t ldo,
+                                               const R1Tiles tl) {
   uint64_t pol = 0;
 #if !defined(SPECGPU_EMULATE)
   if (STREAM) pol = l2_policy_evict_first();
@@ -1070,6 +1071,14 @@ __device__ __forceinline__ void svd_rank1_tile(const int64_t b, const float* L, 
   float* pd = D + (b * rows + warp) * ldo + c0 + lane;
   const int64_t stepl = kR1Warps * (ld < 0 ? (int64_t)kTileCols : ld), stepo = kR1Warps * ldo;
   const bool write_s = S != nullptr && (NORM || S != L);
+  // tile copy of D: this lane's column inside its tile (columns past the last tile are not exported)
+  float* pt = nullptr;
+  int64_t stept = 0;
+  if (TILES && c0 + lane < (int64_t)tl.ntiles * tl.tile_w) {
+    const int64_t t = (c0 + lane) / tl.tile_w;
+    pt = tl.ptr + ((b * tl.ntiles + t) * rows + warp) * tl.tile_w + ((c0 + lane) - t * tl.tile_w);
+    stept = (int64_t)kR1Warps * tl.tile_w;
+  }
   float x[RPW];
   if (c0 + kRecCols <= cols && rows == kR1Warps * RPW) {
     // ---- full tile: no per-element predicates ----
@@ -1098,6 +1107,7 @@ __device__ __forceinline__ void svd_rank1_tile(const int64_t b, const float* L, 
       float v = fmaf(-u[i], w, x[i]);
       if (CLIP) v = (v < 0.f) ? 0.f : v;   // NaN stays NaN, like hacked[hacked < 0] = 0
       r1_store<STREAM>(pd + i * stepo, v, pol);
+      if (TILES && pt != nullptr) r1_store<STREAM>(pt + i * stept, v, pol);
     }
     return;
   }
@@ -1130,24 +1140,26 @@ __device__ __forceinline__ void svd_rank1_tile(const int64_t b, const float* L, 
       float v = fmaf(-s_u[warp + kR1Warps * i], w, x[i]);
       if (CLIP) v = (v < 0.f) ? 0.f : v;
       pd[i * stepo] = v;
+      if (TILES && pt != nullptr) pt[i * stept] = v;
     }
   }
 }
 
 // only_flagged == nullptr: CTA (x, y) does column tile x of matrix y.  Repair pass (only_flagged != nullptr): a SMALL grid
 // (a big one costs microseconds even when every CTA returns at once) whose CTAs walk the matrices and redo the flagged ones.
-template <int RPW, bool NORM, bool CLIP, bool STREAM>
+template <int RPW, bool NORM, bool CLIP, bool STREAM, bool TILES = false>
 __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L, int rows, int64_t cols, int64_t ld,
                                                                   const MinMaxWord* minmax, const float* U, float* S,
-                                                                  float* D, int64_t ldo, const int32_t* only_flagged, int64_t B) {
+                                                                  float* D, int64_t ldo, const int32_t* only_flagged, int64_t B,
+                                                                  const R1Tiles tl) {
   pdl_wait();      // (a multi-wave grid: dependents are released when its CTAs exit)
   if (only_flagged == nullptr) {
-    svd_rank1_tile<RPW, NORM, CLIP, STREAM>(blockIdx.y, L, rows, cols, ld, minmax, U, S, D, ldo);
+    svd_rank1_tile<RPW, NORM, CLIP, STREAM, TILES>(blockIdx.y, L, rows, cols, ld, minmax, U, S, D, ldo, tl);
     return;
   }
   for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
     if (only_flagged[b] == 0) continue;      // uniform over the CTA
-    svd_rank1_tile<RPW, NORM, CLIP, STREAM>(b, L, rows, cols, ld, minmax, U, S, D, ldo);
+    svd_rank1_tile<RPW, NORM, CLIP, STREAM, TILES>(b, L, rows, cols, ld, minmax, U, S, D, ldo, tl);
     __syncthreads();                         // the tile's shared scratch is reused
   }
 }
@@ -1155,29 +1167,40 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
 template <int RPW, bool STREAM>
 static void launch_rank1_ts(dim3 grid, size_t smem, cudaStream_t stream, const float* L, int rows, int64_t cols, int64_t ld,
                             const MinMaxWord* minmax, const float* U, int clip, float* S, float* D, int64_t ldo,
-                            const int32_t* only_flagged, int64_t B) {
+                            const int32_t* only_flagged, int64_t B, R1Tiles tl) {
   const bool nrm = minmax != nullptr;
-  if (nrm && clip) SPECGPU_LAUNCH_PDL((svd_rank1_kernel<RPW, true, true, STREAM>), grid, kR1Threads, smem, stream, 1, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
-  else if (nrm) SPECGPU_LAUNCH_PDL((svd_rank1_kernel<RPW, true, false, STREAM>), grid, kR1Threads, smem, stream, 1, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
-  else if (clip) SPECGPU_LAUNCH_PDL((svd_rank1_kernel<RPW, false, true, STREAM>), grid, kR1Threads, smem, stream, 1, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
-  else SPECGPU_LAUNCH_PDL((svd_rank1_kernel<RPW, false, false, STREAM>), grid, kR1Threads, smem, stream, 1, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B);
+#define SPECGPU_R1(NRM, CL, TL) \
+  SPECGPU_LAUNCH_PDL((svd_rank1_kernel<RPW, NRM, CL, STREAM, TL>), grid, kR1Threads, smem, stream, 1, L, rows, cols, ld, minmax, U, S, D, ldo, only_flagged, B, tl)
+  if (tl.ptr != nullptr) {    // the instantiations without tiles stay what they were (the extra pointer costs the plain path 2.6 us)
+    if (nrm && clip) SPECGPU_R1(true, true, true);
+    else if (nrm) SPECGPU_R1(true, false, true);
+    else if (clip) SPECGPU_R1(false, true, true);
+    else SPECGPU_R1(false, false, true);
+  } else {
+    if (nrm && clip) SPECGPU_R1(true, true, false);
+    else if (nrm) SPECGPU_R1(true, false, false);
+    else if (clip) SPECGPU_R1(false, true, false);
+    else SPECGPU_R1(false, false, false);
+  }
+#undef SPECGPU_R1
 }
 template <int RPW>
 static void launch_rank1_t(dim3 grid, size_t smem, cudaStream_t stream, const float* L, int rows, int64_t cols, int64_t ld,
                            const MinMaxWord* minmax, const float* U, int clip, float* S, float* D, int64_t ldo, int stream_out,
-                           const int32_t* only_flagged, int64_t B) {
-  if (stream_out) launch_rank1_ts<RPW, true>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, only_flagged, B);
-  else launch_rank1_ts<RPW, false>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, only_flagged, B);
+                           const int32_t* only_flagged, int64_t B, R1Tiles tl) {
+  if (stream_out) launch_rank1_ts<RPW, true>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, only_flagged, B, tl);
+  else launch_rank1_ts<RPW, false>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, only_flagged, B, tl);
 }
 
 int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const MinMaxWord* minmax, const float* U,
-                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out, const int32_t* only_flagged) {
+                     int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out, const int32_t* only_flagged,
+                     R1Tiles tl) {
   if (B == 0 || rows == 0 || cols == 0) return 0;
   const size_t smem = ((size_t)rows + kR1Warps * 32) * sizeof(float);
   const dim3 grid((unsigned)ceil_div(cols, kRecCols), (unsigned)(only_flagged ? std::min<int64_t>(B, 2) : B));
-  if (rows <= 64) launch_rank1_t<4>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out, only_flagged, B);
-  else if (rows <= 128) launch_rank1_t<8>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out, only_flagged, B);
-  else if (rows <= 256) launch_rank1_t<16>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out, only_flagged, B);
+  if (rows <= 64) launch_rank1_t<4>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out, only_flagged, B, tl);
+  else if (rows <= 128) launch_rank1_t<8>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out, only_flagged, B, tl);
+  else if (rows <= 256) launch_rank1_t<16>(grid, smem, stream, L, rows, cols, ld, minmax, U, clip, S, D, ldo, stream_out, only_flagged, B, tl);
   else return -1;
   return (int)cudaGetLastError();
 }
