@@ -525,7 +525,7 @@ def run_ours(args):
         "ms_per_step_one_shot_at_a_time": ms_one / args.steps,
         "value_dense_layout": value_dense, "ms_per_step_dense_layout": ms_dense / args.steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_CH * N_SAMP * 4,
-                "d2h_bytes_per_step": N_CH * ROWS * NSEG * 4, "steps": e2e_steps, "api": "HostPipeline(groups=8, streams=3).submit, two shots in flight",
+                "d2h_bytes_per_step": N_CH * ROWS * NSEG * 4, "steps": e2e_steps, "api": "HostPipeline(groups=8, streams=3).submit (one upload stream, one download stream, 3 staging sets with their own compute stream), shots submitted back to back",
                 "gpu_launches": int(e2e_launches), "matches_device_path": e2e_ok,
                 "copy_only_ceiling": e2e_ceiling,
                 "frac_of_copy_ceiling": (e2e_value / e2e_ceiling) if e2e_value and e2e_ceiling else None},

@@ -33,7 +33,7 @@ __all__ = [
     "Runtime", "default_runtime", "DEFAULT_SPEC_PARAMS", "spectrogram", "stft", "csd", "csd_allpairs",
     "spectrogram_batch", "specgr_array", "specgr", "load_shot", "save_shot_hdf5", "load_hdf5_dataset", "norm", "rescale", "quantfilt", "quantfilt_mask", "gaussblr", "meansub", "morph",
     "filter_chain", "process_shot", "omega",
-    "computeSignal", "denoiseSignal", "clip", "patch", "unpatch", "reshape", "pipeline", "HostPipeline", "ae_co2",
+    "computeSignal", "denoiseSignal", "clip", "patch", "unpatch", "reshape", "pipeline", "HostPipeline", "ShotStreams", "ae_co2",
 ]
 
 # spec_denoising/pipeline_data.py:77-84
@@ -824,10 +824,13 @@ def load_hdf5_dataset(in_file, shots=None, n_channels=20):
 class HostPipeline:
     """The whole path for shots that live in HOST memory: x[C, N] (pinned) -> D[C, rows, T] (pinned), optionally S.
 
-    The channels of a shot are cut into `groups`; group g runs on CUDA stream g % streams as
-    H2D(x_g) -> specgpu_pipeline -> D2H(D_g), so the uploads of one group overlap the kernels and the downloads of
-    the others (PCIe is full duplex).  Every stream owns a libspecgpu context (its own workspace) and its own
-    device staging buffers; nothing is allocated after construction."""
+    The channels of a shot are cut into `groups`; group g goes through staging set g % streams as
+    H2D(x_g) on ONE upload stream -> specgpu_pipeline on the set's compute stream -> D2H(D_g) on ONE download stream,
+    chained by events.  The two copy engines therefore run back to back (PCIe is full duplex) and never wait for each
+    other's stream: with upload, kernels and download of a group on the same stream (the first version of this class) the
+    next upload of a set queued behind its previous download although the upload engine was idle (3.6 ms per 40-channel
+    shot; the duplex copies alone take 3.24).  Every staging set owns a libspecgpu context (its own workspace) and its
+    own device buffers; nothing is allocated after construction."""
 
     def __init__(self, spec_params=DEFAULT_SPEC_PARAMS, channels=40, samples=1_000_000, groups=8, streams=3, clip=True,
                  want_S=False, device=None, lib=None):
@@ -844,7 +847,13 @@ class HostPipeline:
         gmax = max(b - a for a, b in self.ranges)
         self.rts = [Runtime(lib=lib, device=self.device) for _ in range(streams)]
         self.plans = [rt.plan_from_params(spec_params) for rt in self.rts]
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(streams)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(streams)]      # compute, one per staging set
+        self.up = torch.cuda.Stream(device=self.device)
+        self.down = torch.cuda.Stream(device=self.device)
+        self.ev_up = [torch.cuda.Event() for _ in range(streams)]        # the set's input has arrived
+        self.ev_comp = [torch.cuda.Event() for _ in range(streams)]      # its kernels are done (input buffer free, outputs ready)
+        self.ev_down = [torch.cuda.Event() for _ in range(streams)]      # its outputs have left (output buffers free)
+        self._k = 0
         rt0 = self.rts[0]
         self.T = int(rt0.lib.plan_num_segments(self.plans[0], samples))
         self.rows = int(rt0.lib.plan_num_freqs(self.plans[0])) - 1
@@ -861,7 +870,7 @@ class HostPipeline:
         return sum(rt.launch_count() for rt in self.rts)
 
     class _Done:
-        """Completion handle of one submitted shot: one CUDA event per worker stream."""
+        """Completion handle of one submitted shot: a CUDA event behind its last download."""
 
         def __init__(self, events):
             self.events = events
@@ -871,37 +880,45 @@ class HostPipeline:
                 e.synchronize()
 
     def _download(self, i, dst_host, src_dev):
-        """Pitched device image [n, rows, T] -> dense host array, one strided DMA copy on stream i."""
+        """Pitched device image [n, rows, T] -> dense host array, one strided DMA copy on the download stream."""
         rt = self.rts[i]
         n = src_dev.shape[0]
         if not dst_host.is_contiguous():
             raise ValueError("host result buffers must be contiguous")
         rt.check(rt.lib.copy_rows(rt._ctx, dst_host.data_ptr(), self.T * 4, src_dev.data_ptr(), int(src_dev.stride(1)) * 4,
-                                  self.T * 4, n * self.rows, C.c_void_p(self.streams[i].cuda_stream)))
+                                  self.T * 4, n * self.rows, C.c_void_p(self.down.cuda_stream)))
 
     def submit(self, x_host, D_host, S_host=None, copy_only=False):
-        """Enqueue one shot (uploads, kernels, downloads) on the worker streams and return a handle whose
-        synchronize() returns when its last download has completed.  The shot is ordered only after earlier work on
-        the same worker streams, so shots submitted back to back overlap (the downloads of one run under the uploads
-        of the next); x_host must already be final (host memory), and D_host must not be read before synchronize()."""
+        """Enqueue one shot (uploads, kernels, downloads) and return a handle whose synchronize() returns when its last
+        download has completed.  The shot is ordered only after earlier shots of this object, so shots submitted back to
+        back overlap (the downloads of one run under the uploads of the next); x_host must already be final (host
+        memory), and D_host must not be read before synchronize()."""
         if tuple(x_host.shape) != (self.channels, self.samples):
             raise ValueError(f"expected x[{self.channels}, {self.samples}], got {tuple(x_host.shape)}")
-        for g, (a, b) in enumerate(self.ranges):
-            i = g % len(self.streams)
+        for a, b in self.ranges:
+            i = self._k % len(self.streams)
+            self._k += 1
             n = b - a
-            with torch.cuda.stream(self.streams[i]):
+            comp = self.streams[i]
+            with torch.cuda.stream(self.up):
+                self.up.wait_event(self.ev_comp[i])          # the set's previous kernels have read its input buffer
                 self.xd[i][:n].copy_(x_host[a:b], non_blocking=True)
+                self.ev_up[i].record(self.up)
+            with torch.cuda.stream(comp):
+                comp.wait_event(self.ev_up[i])
+                comp.wait_event(self.ev_down[i])             # the set's previous outputs have been downloaded
                 if not copy_only:       # copy_only: the same transfers without the kernels (bench.py's copy ceiling)
                     self.rts[i].pipeline_dev(self.plans[i], self.xd[i][:n], self.Sd[i][:n], self.Dd[i][:n], clip=self.clip)
+                self.ev_comp[i].record(comp)
+            with torch.cuda.stream(self.down):
+                self.down.wait_event(self.ev_comp[i])
                 self._download(i, D_host[a:b], self.Dd[i][:n])
                 if S_host is not None:
                     self._download(i, S_host[a:b], self.Sd[i][:n])
-        events = []
-        for st in self.streams:
-            e = torch.cuda.Event()
-            e.record(st)
-            events.append(e)
-        return HostPipeline._Done(events)
+                self.ev_down[i].record(self.down)
+        e = torch.cuda.Event()
+        e.record(self.down)
+        return HostPipeline._Done([e])
 
     def run(self, x_host, D_host, S_host=None):
         """x_host [C, N] float32 (pinned for real overlap), D_host [C, rows, T] float32 pinned; returns after the
