@@ -234,6 +234,14 @@ int specgpu_copy_rows(specgpu_ctx* ctx, void* dst, int64_t dst_pitch, const void
  * larger than the L2 cache and for experiments.  Results do not depend on it. */
 int specgpu_set_pipeline_group(specgpu_ctx* ctx, int32_t channels);
 
+/* Interlock between two contexts that run specgpu_pipeline on two streams (shots in flight, see api.ShotStreams).
+ * `wait_event` (a cudaEvent_t, may be NULL): the call makes its stream wait for it before its first kernel (the STFT).
+ * `record_event` (may be NULL): the call records it on its stream right before the projection (its last, HBM-bound
+ * kernel).  With context A recording what context B waits for and vice versa, the instruction-bound STFT of one shot
+ * starts exactly when the memory-bound projection of the other does, instead of whenever the streams happen to drift.
+ * The events stay owned by the caller and must outlive the calls; (NULL, NULL) turns the interlock off. */
+int specgpu_set_pipeline_interlock(specgpu_ctx* ctx, void* wait_event, void* record_event);
+
 /* Cap of the power iteration that finds the leading singular pair on the default denoise route (0 restores the
  * default, 200).  A channel that does not converge within the cap is flagged (info[b][3] = 1) and, where the fallback is
  * on, redone by the full float64 eigensolver; a cap of 1 therefore sends every channel down the fallback route, which

@@ -74,6 +74,7 @@ PROTOTYPES = {
     "specgpu_pipeline": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp]),
     "specgpu_copy_rows": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "specgpu_set_pipeline_group": (C.c_int, [_vp, _i32]),
+    "specgpu_set_pipeline_interlock": (C.c_int, [_vp, _vp, _vp]),
     "specgpu_set_power_iterations": (C.c_int, [_vp, _i32]),
     "specgpu_launch_count": (_i64, [_vp]),
     "specgpu_profile_enable": (C.c_int, [_vp, C.c_int]),

@@ -938,7 +938,7 @@ class ShotStreams:
     are visible) and after the previous shot on the same worker stream; join() makes the caller's stream wait for every
     shot submitted so far."""
 
-    def __init__(self, spec_params=DEFAULT_SPEC_PARAMS, n=2, device=None, lib=None):
+    def __init__(self, spec_params=DEFAULT_SPEC_PARAMS, n=2, device=None, lib=None, interlock=False):
         if device is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("libspecgpu needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -950,6 +950,15 @@ class ShotStreams:
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n)]
         self._next = 0
         self._dirty = [False] * n
+        # interlock (specgpu_set_pipeline_interlock): the STFT of shot i + 1 starts when shot i reaches its projection
+        self._ilk = []
+        if interlock and n > 1:
+            self._ilk = [torch.cuda.Event() for _ in range(n)]
+            for e in self._ilk:
+                e.record(torch.cuda.current_stream(self.device))      # creates the CUDA event; complete at once
+            for i, rt in enumerate(self.rts):
+                rt.check(rt.lib.set_pipeline_interlock(rt._ctx, C.c_void_p(self._ilk[(i - 1) % n].cuda_event),
+                                                       C.c_void_p(self._ilk[i].cuda_event)))
 
     def launch_count(self):
         return sum(rt.launch_count() for rt in self.rts)

@@ -96,6 +96,10 @@ int launch_svd_plan(const float* lam, int64_t B, int n, int kind, int start, int
 struct R1Tiles {
   float* ptr = nullptr;
   int tile_w = 0, ntiles = 0;
+  // optional: the kernel also copies plan[b][0..3] -> info[b][0..3] (a cudaMemcpyAsync after the projection would break the
+  // programmatic launch chain into the next call's STFT: 4.6 us per shot, and most of what two shots in flight can overlap)
+  const int32_t* plan = nullptr;
+  int32_t* info = nullptr;
 };
 int launch_svd_rank1(const float* L, int64_t B, int rows, int64_t cols, int64_t ld, const MinMaxWord* minmax, const float* U,
                      int clip, float* S, float* D, int64_t ldo, cudaStream_t stream, int stream_out = 0,

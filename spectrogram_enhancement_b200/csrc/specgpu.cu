@@ -26,6 +26,8 @@ struct specgpu_ctx {
   MinMaxWord* mm64 = nullptr;
   unsigned mm_gen = 0;
   int pipe_group = 0;      // channels per group (0: automatic, see specgpu_set_pipeline_group)
+  cudaEvent_t ilk_wait = nullptr, ilk_record = nullptr;   // caller-owned events (specgpu_set_pipeline_interlock)
+  bool ilk_armed = false;                                 // true inside specgpu_pipeline only
   cudaStream_t repair_stream = nullptr;      // side stream of the non-converged-channel repair (see svd_run)
   cudaEvent_t ev_repair_fork = nullptr, ev_repair_join = nullptr;
   cudaStream_t side[2] = {nullptr, nullptr};
@@ -324,6 +326,13 @@ int specgpu_copy_rows(specgpu_ctx* ctx, void* dst, int64_t dst_pitch, const void
                                     (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(ctx, (int)e, "copy_rows");
 #endif
+  return SPECGPU_OK;
+}
+
+int specgpu_set_pipeline_interlock(specgpu_ctx* ctx, void* wait_event, void* record_event) {
+  if (!ctx) return SPECGPU_ERR_INVALID_ARG;
+  ctx->ilk_wait = (cudaEvent_t)wait_event;
+  ctx->ilk_record = (cudaEvent_t)record_event;
   return SPECGPU_OK;
 }
 
@@ -764,7 +773,12 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
                  "svd_plan", 1);
   if (power_ok && !out_f64) {
     // power_ok implies the range [1, rows): only the leading component is removed
+    if (info) {                 // the projection copies the plan rows itself (no memcpy node behind it)
+      r1_tiles.plan = w.plan;
+      r1_tiles.info = info;
+    }
 #ifndef SPECGPU_EMULATE
+    if (ctx->ilk_armed && ctx->ilk_record) cudaEventRecord(ctx->ilk_record, st);    // specgpu_set_pipeline_interlock
     if (side_repair) {
       cudaStream_t rs = ctx->repair_stream;
       cudaEventRecord(ctx->ev_repair_fork, st);
@@ -789,7 +803,7 @@ int svd_run(specgpu_ctx* ctx, const SvdWs& w, float* S, const MinMaxWord* raw_mm
   } else {
     CHECK_LAUNCH(ctx, launch_svd_project(S, B, (int)rows, cols, ld, w.U, w.plan, clip, out, out_f64, ldo, st), "svd_project", 1);
   }
-  if (info) {
+  if (info && !(power_ok && !out_f64)) {
     cudaError_t e = cudaMemcpyAsync(info, w.plan, (size_t)B * 16, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return cuda_fail(ctx, (int)e, "info copy");
   }
@@ -1222,6 +1236,9 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
         return cuda_fail(ctx, e__, "stft_gram");
       }
     }
+#ifndef SPECGPU_EMULATE
+    if (g == 0 && ctx->ilk_wait) cudaStreamWaitEvent(st, ctx->ilk_wait, 0);      // specgpu_set_pipeline_interlock
+#endif
     if (!fused) CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, nb, st), "stft_kernel", 1);
     SvdWs w{};
     w.G = reinterpret_cast<float*>(Gall + b0 * rows * rows);
@@ -1240,9 +1257,11 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
       r1t.tile_w = tile_w;
       r1t.ntiles = ntiles;
     }
-    if ((rc = svd_run(ctx, w, Sg, mmg, nb, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, fallback, Dg, 0, ldt, nullptr,
-                      info ? info + b0 * 4 : nullptr, st, l2_pin, Lg, tiled ? -ntile : 0, fused ? pre_gram : nullptr, r1t)))
-      return rc;
+    ctx->ilk_armed = (g == ngroups - 1);
+    rc = svd_run(ctx, w, Sg, mmg, nb, rows, nseg, ldt, 0, 1, (int)rows, clip, power_ok, fallback, Dg, 0, ldt, nullptr,
+                 info ? info + b0 * 4 : nullptr, st, l2_pin, Lg, tiled ? -ntile : 0, fused ? pre_gram : nullptr, r1t);
+    ctx->ilk_armed = false;
+    if (rc) return rc;
     if (tiles && ntiles > 0 && !r1_writes_tiles)
       CHECK_LAUNCH(ctx, launch_patch(Dg, nb, rows, ldt, tile_w, ntiles, tiles + (size_t)b0 * ntiles * rows * tile_w, 0, st), "patch", 1);
   }

@@ -1153,6 +1153,9 @@ __global__ void __launch_bounds__(kR1Threads, 2) svd_rank1_kernel(const float* L
                                                                   float* D, int64_t ldo, const int32_t* only_flagged, int64_t B,
                                                                   const R1Tiles tl) {
   pdl_wait();      // (a multi-wave grid: dependents are released when its CTAs exit)
+  if (tl.info != nullptr && blockIdx.x == 0 && threadIdx.x < 4) {
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) tl.info[b * 4 + threadIdx.x] = tl.plan[b * 4 + threadIdx.x];
+  }
   if (only_flagged == nullptr) {
     svd_rank1_tile<RPW, NORM, CLIP, STREAM, TILES>(blockIdx.y, L, rows, cols, ld, minmax, U, S, D, ldo, tl);
     return;

@@ -103,7 +103,7 @@ def svd(mode_opt):
 
 
 report("denoiseSignal default (power route) 40x[256x3905]", timeit(svd(0)), 40 * 256 * 3905 * 8)
-report("denoiseSignal use_optimal (float64 Gram + cluster Jacobi) 40x[256x3905]", timeit(svd(1), iters=3, warm=1), 40 * 256 * 3905 * 8)
+report("denoiseSignal use_optimal (float64 Gram + values-first eigensolver) 40x[256x3905]", timeit(svd(1), iters=3, warm=1), 40 * 256 * 3905 * 8)
 # ---- config 3: CSD 4 chords x 3.2 M, nperseg 4096 ----
 x3 = [torch.randn((4, 3_200_000), device=dev, generator=g) for _ in range(NB)]
 p3 = rt.plan(4096, 2048, 1.6e6, "hann", "density", "constant")
