@@ -385,14 +385,16 @@ def test_host_pipeline_streams(cuda_rt):
         hp.run(xs[0][:3], outs[0])
 
 
-def test_shot_streams_device_resident(cuda_rt):
-    """ShotStreams (device-resident shots, several in flight on worker streams) == Runtime.pipeline_dev, bit for bit,
-    including the tiles, for more shots than streams."""
+@pytest.mark.parametrize("interlock", [False, True])
+def test_shot_streams_device_resident(cuda_rt, interlock):
+    """ShotStreams (device-resident shots, several in flight on worker streams, with and without the STFT <-> projection
+    interlock of specgpu_set_pipeline_interlock) == Runtime.pipeline_dev, bit for bit, including the tiles and the info
+    rows (which the projection kernel copies itself), for more shots than streams."""
     import torch
     n, C = 300_000, 6
     dev = cuda_rt.device
     xs = [torch.from_numpy(pc.signals(C, n, shot=30 + i)).to(dev) for i in range(5)]
-    pool = api.ShotStreams(SP, n=2, device=dev)
+    pool = api.ShotStreams(SP, n=2, device=dev, interlock=interlock)
     plan = cuda_rt.plan_from_params(SP)
     T = int(cuda_rt.lib.plan_num_segments(plan, n))
     nt = T // 128
@@ -414,6 +416,7 @@ def test_shot_streams_device_resident(cuda_rt):
         torch.cuda.synchronize()
         assert torch.equal(Sp[i][..., :T], S[..., :T]) and torch.equal(Dp[i][..., :T], D[..., :T]) and torch.equal(tp[i], tl)
         assert infos[i][:, 3].max().item() == 0 and infos[i][:, 0].min().item() == 1
+        assert torch.equal(infos[i][:, :2].cpu(), torch.tensor([[1, 256]] * C, dtype=torch.int32))
     Sr, _, _ = oc.specgr_array(xs[4][0].cpu().numpy().astype(np.float64), SP)
     np.testing.assert_allclose(Sp[4][0][:, :T].cpu().numpy(), Sr, rtol=0, atol=pc.ATOL_IMAGE)
 
