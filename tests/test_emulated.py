@@ -159,6 +159,9 @@ def test_pipeline_fused_normalise_route(emu_rt):
     # 128 frequency rows: the tensor-core Gram + rank-1 projection route with the min-max normalisation fused
     sp = dict(oc.DEFAULT_SPEC_PARAMS, nperseg=256, noverlap=128)
     pc.case_pipeline(emu_rt, sp, 20000, B=3, tile=64)
+    # tile widths that are not a multiple of the projection's 32-column CTA tile: the lanes of one warp straddle two VAE
+    # tiles, and the columns past the last tile are not exported (the projection writes the tiles itself)
+    pc.case_pipeline(emu_rt, sp, 20000, B=2, tile=50)
 
 
 def test_pipeline_fallback_route(emu_rt):

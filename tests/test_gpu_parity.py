@@ -309,6 +309,9 @@ def test_ae_co2_time_resolved(cuda_rt):
 def test_pipeline_small(cuda_rt):
     pc.case_pipeline(cuda_rt, dict(SP, nperseg=32, noverlap=16), 9000, B=2, tile=64)
     pc.case_pipeline(cuda_rt, dict(SP, nperseg=256, noverlap=128), 60_000, B=3, tile=128)
+    # tile widths that are not a multiple of the projection's 32-column CTA tile (lanes of a warp straddle two VAE tiles)
+    pc.case_pipeline(cuda_rt, dict(SP, nperseg=256, noverlap=128), 60_000, B=2, tile=50)
+    pc.case_pipeline(cuda_rt, dict(SP, nperseg=512, noverlap=256), 80_000, B=2, tile=33)
 
 
 def test_config2_pipeline_40ch(cuda_rt):
