@@ -103,7 +103,28 @@ __global__ void __launch_bounds__(kCsdThreads) csd_pairs_kernel(CsdArgs a) {
 
   if (active && f_ok) {
     const int64_t cstride = a.nseg * a.ldf;
-    for (int64_t t = t0 + my_rep; t < t1; t += reps) {
+    // UN segments per trip: all their loads are in flight before the first product (this kernel has no staging ring;
+    // with one segment per trip a warp waited a full global round trip for every 8-12 loads)
+    constexpr int UN = (TI == 4) ? 4 : 1;
+    int64_t t = t0 + my_rep;
+    for (; t + (UN - 1) * reps < t1; t += UN * reps) {
+      float2 xi[UN][TI], xj[UN][TJ];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const float2* xt = a.X + (t + u * reps) * a.ldf + f;
+#pragma unroll
+        for (int k = 0; k < TI; ++k) xi[u][k] = __ldg(xt + ci[k] * cstride);
+#pragma unroll
+        for (int k = 0; k < TJ; ++k) xj[u][k] = __ldg(xt + cj[k] * cstride);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+          for (int j = 0; j < TJ; ++j) acc[i][j] = cmac_conj(acc[i][j], xi[u][i], xj[u][j]);     // conj(xi) * xj
+    }
+    for (; t < t1; t += reps) {
       const float2* xt = a.X + t * a.ldf + f;
       float2 xi[TI], xj[TJ];
 #pragma unroll
@@ -500,8 +521,9 @@ static CsdGeom csd_geom(int64_t C, int64_t i0, int64_t ni, int nfreq, int64_t ns
   if (g.staged) {
     g.nchunk = csd_pick_chunks(ctas, 148, maxc);                 // one 512-thread CTA per SM
   } else {
-    const int64_t want = ceil_div(148 * 2, ctas);                // ~2 CTAs per SM in flight
-    g.nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(want, maxc));
+    // one 512-thread CTA per SM here too (106-128 registers): fill whole waves (4 chords x nperseg 4096: 65 frequency
+    // blocks x 5 chunks = 325 CTAs ran as 2.2 waves)
+    g.nchunk = csd_pick_chunks(ctas, 148, maxc);
   }
   g.seg_per_chunk = ceil_div(nseg, g.nchunk);
   g.nchunk = (int)ceil_div(nseg, g.seg_per_chunk);
