@@ -10,6 +10,8 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+#include <type_traits>
+
 #include "cluster.cuh"
 
 namespace specgpu {
@@ -577,11 +579,238 @@ static int launch_gram_eig_t(const GramEigArgs& a, int64_t B, cudaStream_t strea
   return (int)cudaGetLastError();
 }
 
+// ======================================================================================================
+// The same step for 256-row matrices whose partials come one set per matrix (launch_gram_tma), as ONE CTA per matrix:
+// the symmetric three quarters of G -- the partial layout itself, [128][388] = [G00 | G01 | G11 | row sums] -- are summed
+// over the matrix's partials straight into 194 KB of shared memory (every load of a batch in flight before the first
+// add), and the power iteration runs from there: row dots for G00 | G01 and G11, column sums for G10 = G01^T.  The
+// min-max normalisation is never applied to the entries; it enters every product algebraically,
+//   G' x = G x - m (r (1.x) + 1 (r.x)) + m^2 T (1.x) 1.
+// No cluster, no distributed shared memory, no cluster barriers: the cluster kernel above spends 18.6 of its 20 us
+// outside the (two, typically) iterations -- launching 320 clustered CTAs, three dependent rounds of partial loads, four
+// cluster barriers.
+// ======================================================================================================
+#if !defined(SPECGPU_EMULATE)
+constexpr int kGe1Threads = 1024, kGe1PP = 388, kGe1PW = 384;
+
+__global__ void __launch_bounds__(kGe1Threads, 1) gram_eig1_kernel(GramEigArgs a) {
+  constexpr int N = 256, H = 128, PP = kGe1PP, PW = kGe1PW;
+  pdl_trigger();
+  SPECGPU_DYN_SMEM(smem);
+  float* P = reinterpret_cast<float*>(smem);     // [128][388]
+  float* sx = P + H * PP;                        // [256] iterate
+  float* sy = sx + N;                            // [256] G x
+  float* sr = sy + N;                            // [256] row sums of the raw image
+  float* scol = sr + N;                          // [8][128] partial column sums of G01
+  float* sred = scol + 8 * H;                    // [64] reductions
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t b = blockIdx.x;
+  const int kparts = (int)((a.nchunk + a.per - 1) / a.per);
+  const float4* part = reinterpret_cast<const float4*>(a.partial + (size_t)b * kparts * H * PP);
+  constexpr int NV = H * PP / 4;                 // float4 per partial (12416)
+  pdl_wait();
+  // ---- P = sum of the partials, in partial order (deterministic); every load of a trip (3 positions x all partials) is
+  //      in flight before the first add: five round trips for three partials instead of twelve ----
+  auto sum_partials = [&](auto kp_c) {
+    constexpr int KP = decltype(kp_c)::value;
+    for (int v0 = tid; v0 < NV; v0 += 3 * kGe1Threads) {
+      float4 w[KP][3];
+#pragma unroll
+      for (int k = 0; k < KP; ++k)
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int v = v0 + u * kGe1Threads;
+          w[k][u] = (v < NV) ? __ldg(part + (size_t)k * NV + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        float4 acc = w[0][u];
+#pragma unroll
+        for (int k = 1; k < KP; ++k) {
+          acc.x += w[k][u].x; acc.y += w[k][u].y; acc.z += w[k][u].z; acc.w += w[k][u].w;
+        }
+        const int v = v0 + u * kGe1Threads;
+        if (v < NV) reinterpret_cast<float4*>(P)[v] = acc;
+      }
+    }
+  };
+  if (kparts == 3) {
+    sum_partials(std::integral_constant<int, 3>{});
+  } else if (kparts == 2) {
+    sum_partials(std::integral_constant<int, 2>{});
+  } else if (kparts == 1) {
+    sum_partials(std::integral_constant<int, 1>{});
+  } else if (kparts == 4) {
+    sum_partials(std::integral_constant<int, 4>{});
+  } else {
+    for (int v = tid; v < NV; v += kGe1Threads) {
+      float4 acc = __ldg(part + v);
+      for (int k = 1; k < kparts; ++k) {
+        const float4 w = __ldg(part + (size_t)k * NV + v);
+        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+      }
+      reinterpret_cast<float4*>(P)[v] = acc;
+    }
+  }
+  __syncthreads();
+  float m = 0.f, m2t = 0.f, lam_scale = 1.f;
+  if (a.raw_minmax != nullptr) {
+    m = minmax_get_min(a.raw_minmax, b);
+    const float den = minmax_get_max(a.raw_minmax, b) - m;
+    lam_scale = 1.0f / (den * den);
+    m2t = m * m * (float)a.cols;
+  }
+  if (tid < N) sr[tid] = (a.raw_minmax != nullptr) ? P[(tid & (H - 1)) * PP + PW + (tid >> 7)] : 0.f;
+  __syncthreads();
+  // ---- start vector: the row of G' with the largest diagonal entry (ties: the lowest index) ----
+  if (tid < N) {
+    const float g = (tid < H) ? P[tid * PP + tid] : P[(tid - H) * PP + 2 * H + (tid - H)];
+    sy[tid] = g - 2.f * m * sr[tid] + m2t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float best = -INFINITY;
+    int arg = 0;
+    for (int i = lane; i < N; i += 32) {
+      const float v = sy[i];
+      if (v > best) {
+        best = v;
+        arg = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    if (lane == 0) sred[0] = __int_as_float(arg);
+  }
+  __syncthreads();
+  {
+    const int arow = __float_as_int(sred[0]);
+    if (tid < N) {
+      float g;     // G[arow][tid] out of the symmetric storage
+      if (arow < H) g = (tid < H) ? P[arow * PP + tid] : P[arow * PP + tid];                    // [G00 | G01] row
+      else g = (tid < H) ? P[tid * PP + H + (arow - H)] : P[(arow - H) * PP + 2 * H + (tid - H)];   // G01^T column | G11 row
+      sx[tid] = g - m * (sr[arow] + sr[tid]) + m2t;
+    }
+    __syncthreads();
+    float ss = 0.f;
+    for (int i = lane; i < N; i += 32) ss += sx[i] * sx[i];
+    ss = warp_sum(ss);
+    const float sinv = (ss > 0.f && ss < INFINITY) ? rsqrtf(ss) : 0.f;
+    __syncthreads();
+    if (tid < N) sx[tid] *= sinv;
+    __syncthreads();
+  }
+  float lambda = 0.f, prev_delta = INFINITY;
+  int status = 1;
+  for (int it = 0; it < a.max_iter; ++it) {
+    // s1 = 1.x, s2 = r.x (every warp redundantly: identical values, uniform control flow)
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < N; i += 32) {
+      s1 += sx[i];
+      s2 += sr[i] * sx[i];
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    // (a) rows 4 w .. 4 w + 3 of [G00 | G01] and of G11: lane l covers columns 4 l .. 4 l + 3 (+ 128)
+    {
+      const float4 xa = *reinterpret_cast<const float4*>(sx + 4 * lane);
+      const float4 xb = *reinterpret_cast<const float4*>(sx + H + 4 * lane);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int i = 4 * warp + rr;
+        const float4 g0 = *reinterpret_cast<const float4*>(P + i * PP + 4 * lane);
+        const float4 g1 = *reinterpret_cast<const float4*>(P + i * PP + H + 4 * lane);
+        const float4 g2 = *reinterpret_cast<const float4*>(P + i * PP + 2 * H + 4 * lane);
+        float top = g0.x * xa.x + g0.y * xa.y + g0.z * xa.z + g0.w * xa.w + g1.x * xb.x + g1.y * xb.y + g1.z * xb.z + g1.w * xb.w;
+        float bot = g2.x * xb.x + g2.y * xb.y + g2.z * xb.z + g2.w * xb.w;
+        top = warp_sum(top);
+        bot = warp_sum(bot);
+        if (lane == 0) {
+          sy[i] = top;
+          sy[H + i] = bot;
+        }
+      }
+    }
+    // (b) G10 x_top = G01^T x_top: thread (c, part) sums rows 16 part .. +15 of column c of G01
+    {
+      const int c = tid & (H - 1), pt = tid >> 7;
+      float cs = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cs = fmaf(P[(16 * pt + i) * PP + H + c], sx[16 * pt + i], cs);
+      scol[pt * H + c] = cs;
+    }
+    __syncthreads();
+    if (tid < N) {
+      float y = sy[tid];
+      if (tid >= H) {
+        const int c = tid - H;
+#pragma unroll
+        for (int pt = 0; pt < 8; ++pt) y += scol[pt * H + c];
+      }
+      sy[tid] = y - m * (sr[tid] * s1 + s2) + m2t * s1;
+    }
+    __syncthreads();
+    float yy = 0.f, xy = 0.f;
+    for (int i = lane; i < N; i += 32) {
+      const float y = sy[i], x = sx[i];
+      yy += y * y;
+      xy += x * y;
+    }
+    yy = warp_sum(yy);
+    xy = warp_sum(xy);
+    if (!(yy > 0.f) || !(yy < INFINITY)) break;   // zero / non-finite iterate: not convergence (status stays 1)
+    const float inv = rsqrtf(yy);
+    float dd = 0.f;
+    for (int i = lane; i < N; i += 32) {
+      const float d = sy[i] * inv - sx[i];
+      dd += d * d;
+    }
+    dd = warp_sum(dd);
+    lambda = xy;
+    __syncthreads();
+    if (tid < N) sx[tid] = sy[tid] * inv;
+    __syncthreads();
+    if (dd < 1e-13f || (dd < 1e-10f && dd >= prev_delta)) {
+      status = 0;
+      break;
+    }
+    prev_delta = dd;
+  }
+  __syncthreads();
+  if (tid < N) a.U[b * (int64_t)N * N + (int64_t)tid * N] = sx[tid];
+  if (tid == 0) {
+    a.lam[b * N] = lambda * lam_scale;
+    a.plan[b * 4 + 0] = 1;
+    a.plan[b * 4 + 1] = N;
+    a.plan[b * 4 + 2] = -1;
+    a.plan[b * 4 + 3] = status;
+    if (a.flagged != nullptr) a.flagged[b] = status;
+  }
+}
+#endif
+
 int launch_gram_eig(const float* partial, int64_t nchunk, int64_t per, int64_t B, int n, int max_iter, float* U, float* lam,
                     int32_t* plan, cudaStream_t stream, const MinMaxWord* raw_minmax, int64_t cols, int per_matrix,
                     int32_t* flagged) {
   if (B == 0) return 0;
   GramEigArgs a{partial, nchunk, per, raw_minmax, cols, per_matrix, max_iter > 0 ? max_iter : kPowMaxIter, U, lam, plan, flagged};
+#if !defined(SPECGPU_EMULATE)
+  static const bool one_cta = !(std::getenv("SPECGPU_GRAM_EIG1") && std::getenv("SPECGPU_GRAM_EIG1")[0] == '0');
+  if (n == 256 && per_matrix && one_cta) {
+    const size_t smem = ((size_t)128 * kGe1PP + 3 * 256 + 8 * 128 + 64) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(gram_eig1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    SPECGPU_LAUNCH_PDL(gram_eig1_kernel, (unsigned)B, kGe1Threads, smem, stream, 1, a);
+    return (int)cudaGetLastError();
+  }
+#endif
   if (n == 256) return launch_gram_eig_t<256>(a, B, stream);
   if (n == 128) return launch_gram_eig_t<128>(a, B, stream);
   return -1;
