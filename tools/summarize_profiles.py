@@ -19,7 +19,7 @@ command = sys.argv[6] if len(sys.argv) > 6 else "python bench.py --steps 3 --war
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
-OURS = ("stft_kernel", "gram_tc_kernel", "gram_tma_kernel", "gram_eig_kernel", "gram_reduce", "gram_simt", "eig_power", "eig_jacobi", "eig_sort", "svd_", "lognorm",
+OURS = ("stft_kernel", "gram_tc_kernel", "gram_tma_kernel", "gram_eig_kernel", "gram_eig1_kernel", "gram_reduce", "gram_simt", "eig_power", "eig_jacobi", "eig_sort", "svd_", "lognorm",
         "minmax", "quantfilt", "patch_kernel", "unpatch", "csd_", "rescale", "moments", "norm_apply", "img_", "blur_", "morph_",
         "meansub_", "u8_lut")
 
