@@ -296,6 +296,7 @@ struct GramEigArgs {
   float* lam;              // [B][n]
   int32_t* plan;           // [B][4] = {1, n, -1, status}
   int32_t* flagged;        // optional [B]: copy of status that survives the repair pass (which rewrites plan[b][3])
+  int debug = 0;           // timing ablations of gram_eig1_kernel (SPECGPU_EIG1_DEBUG): 1 = no partial loads, 2 = loads only
 };
 
 template <int N>
@@ -634,7 +635,8 @@ __global__ void __launch_bounds__(kGe1Threads, 1) gram_eig1_kernel(GramEigArgs a
       }
     }
   };
-  if (kparts == 3) {
+  if (a.debug & 1) {
+  } else if (kparts == 3) {
     sum_partials(std::integral_constant<int, 3>{});
   } else if (kparts == 2) {
     sum_partials(std::integral_constant<int, 2>{});
@@ -653,6 +655,7 @@ __global__ void __launch_bounds__(kGe1Threads, 1) gram_eig1_kernel(GramEigArgs a
     }
   }
   __syncthreads();
+  if (a.debug & 2) return;
   float m = 0.f, m2t = 0.f, lam_scale = 1.f;
   if (a.raw_minmax != nullptr) {
     m = minmax_get_min(a.raw_minmax, b);
@@ -804,6 +807,7 @@ int launch_gram_eig(const float* partial, int64_t nchunk, int64_t per, int64_t B
 #if !defined(SPECGPU_EMULATE)
   static const bool one_cta = !(std::getenv("SPECGPU_GRAM_EIG1") && std::getenv("SPECGPU_GRAM_EIG1")[0] == '0');
   if (n == 256 && per_matrix && one_cta) {
+    if (const char* env = std::getenv("SPECGPU_EIG1_DEBUG")) a.debug = std::atoi(env);
     const size_t smem = ((size_t)128 * kGe1PP + 3 * 256 + 8 * 128 + 64) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(gram_eig1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
