@@ -214,10 +214,15 @@ int specgpu_csd_allpairs(specgpu_ctx* ctx, const specgpu_plan* plan, const float
  *                               the full float64 eigensolver -- three launches that return at once when every channel
  *                               converged.  Always on when `info` is NULL (the caller could not see the status).
  * Optional tiles (NULL to skip): float32 [B*ntiles][nfreq-1][tile_w] cut from D.
+ *        SPECGPU_PIPE_STATIC_TILES  scheduling hint, results do not depend on it: the STFT's persistent CTAs walk their
+ *                               tiles with a fixed stride instead of taking them from a counter.  The counter balances
+ *                               the CTAs of a call that runs alone (-2 % per shot); with several shots in flight on
+ *                               several streams the staggered finish of the fixed walk overlaps better (api.ShotStreams
+ *                               sets it).
  * info[B][4] (optional, device) = {1, nfreq-1, -1, status}; status 1 (only possible without SPECGPU_PIPE_FALLBACK) =
  * the leading pair of that channel did not converge: D of that channel must be recomputed with
  * specgpu_svd_denoise(S, mode = 1). */
-enum { SPECGPU_PIPE_CLIP = 1, SPECGPU_PIPE_FALLBACK = 2 };
+enum { SPECGPU_PIPE_CLIP = 1, SPECGPU_PIPE_FALLBACK = 2, SPECGPU_PIPE_STATIC_TILES = 4 };
 int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, int64_t B, int64_t n, int64_t ldx,
                      float* S, float* D, int64_t ldt, int32_t flags, float* tiles, int32_t tile_w, int32_t ntiles,
                      int32_t* info, void* stream);

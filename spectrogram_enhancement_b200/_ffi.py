@@ -21,6 +21,7 @@ ERR_WORKSPACE = -5
 ERR_UNSUPPORTED_SHAPE = -6
 PIPE_CLIP = 1          # specgpu_pipeline flags
 PIPE_FALLBACK = 2
+PIPE_STATIC_TILES = 4
 
 DETREND = {False: 0, None: 0, "constant": 1, "linear": 2}
 SCALING = {"density": 0, "spectrum": 1}

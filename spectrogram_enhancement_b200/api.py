@@ -232,10 +232,11 @@ class Runtime:
         return Sxx
 
     def pipeline_dev(self, plan, x2d, S=None, D=None, clip=True, tiles=None, tile_w=128, ntiles=0, info=None,
-                     fallback=True):
+                     fallback=True, static_tiles=False):
         """specgpu_pipeline on device tensors.  `fallback` (default on): channels whose leading singular pair did not
         converge in the power iteration are redone in the stream by the float64 eigensolver; with fallback=False the
-        caller must look at info[:, 3] itself."""
+        caller must look at info[:, 3] itself.  `static_tiles`: scheduling hint for calls that overlap with others on
+        other streams (SPECGPU_PIPE_STATIC_TILES); results do not depend on it."""
         B, n = x2d.shape
         T = self.lib.plan_num_segments(plan, n)
         F = self.lib.plan_num_freqs(plan)
@@ -243,7 +244,8 @@ class Runtime:
             S = self.empty_image(B, F - 1, T)
         if D is None:
             D = self.empty_image(B, F - 1, T)
-        flags = (_ffi.PIPE_CLIP if clip else 0) | (_ffi.PIPE_FALLBACK if fallback else 0)
+        flags = ((_ffi.PIPE_CLIP if clip else 0) | (_ffi.PIPE_FALLBACK if fallback else 0)
+                 | (_ffi.PIPE_STATIC_TILES if static_tiles else 0))
         self.check(self.lib.pipeline(self._ctx, plan, x2d.data_ptr(), B, n, _ld(x2d), S.data_ptr(), D.data_ptr(),
                                      _ld(S), flags, tiles.data_ptr() if tiles is not None else None,
                                      tile_w, ntiles, info.data_ptr() if info is not None else None, self.stream()))
@@ -908,7 +910,8 @@ class HostPipeline:
                 comp.wait_event(self.ev_up[i])
                 comp.wait_event(self.ev_down[i])             # the set's previous outputs have been downloaded
                 if not copy_only:       # copy_only: the same transfers without the kernels (bench.py's copy ceiling)
-                    self.rts[i].pipeline_dev(self.plans[i], self.xd[i][:n], self.Sd[i][:n], self.Dd[i][:n], clip=self.clip)
+                    self.rts[i].pipeline_dev(self.plans[i], self.xd[i][:n], self.Sd[i][:n], self.Dd[i][:n], clip=self.clip,
+                                             static_tiles=len(self.streams) > 1)
                 self.ev_comp[i].record(comp)
             with torch.cuda.stream(self.down):
                 self.down.wait_event(self.ev_comp[i])
@@ -972,6 +975,7 @@ class ShotStreams:
         self._next = (i + 1) % len(self.streams)
         st = self.streams[i]
         st.wait_stream(torch.cuda.current_stream(self.device))
+        kw.setdefault("static_tiles", len(self.streams) > 1)      # overlapping shots: the fixed tile walk overlaps better
         with torch.cuda.stream(st):
             self.rts[i].pipeline_dev(self.plans[i], x2d, S, D, **kw)
         self._dirty[i] = True

@@ -33,6 +33,8 @@ struct StftArgs {
   int tma_out;           // whole boxes of the output tile leave through a TMA tensor store
   int tma_rows, tma_nbox;   // rows per box, boxes per tile (rows beyond tma_rows*tma_nbox use plain stores)
   int flow;              // barrier-free tile loop (stft.cu): staged bulk input + whole tile through the tensor store
+  unsigned* dyn;         // set by the caller (nullptr by default): {next tile counter, CTAs that have left}, both zero between
+                         // launches; the barrier-free path then takes its tiles from the counter (one launch at a time per pair)
   // set by the caller (0 by default): fraction of the output's cache lines to keep in L2 (evict_last) because a later
   // kernel of the same call reads the output back; the rest streams out (evict_first).  0: no preference.
   float l2_pin;

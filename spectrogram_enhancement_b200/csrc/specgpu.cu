@@ -201,12 +201,13 @@ constexpr int64_t kMaxBatch = 65535;
 int minmax_begin(specgpu_ctx* ctx, MinMaxWord** mm, unsigned* gen) {
   if (!ctx->mm64 || ctx->mm_gen == 0xffffffffu) {
     if (!ctx->mm64) {
-      cudaError_t e = cudaMalloc(&ctx->mm64, (size_t)kMaxBatch * 2 * sizeof(MinMaxWord));
+      // (+ 2 words behind the pairs: the STFT's dynamic tile counter and its exit count, zero between launches)
+      cudaError_t e = cudaMalloc(&ctx->mm64, (size_t)(kMaxBatch * 2 + 2) * sizeof(MinMaxWord));
       if (e != cudaSuccess) return fail(ctx, SPECGPU_ERR_WORKSPACE, "min/max buffer: %s", cudaGetErrorString(e));
     } else {
       cudaDeviceSynchronize();     // generation counter wrapped (once per 4 billion calls)
     }
-    cudaMemset(ctx->mm64, 0, (size_t)kMaxBatch * 2 * sizeof(MinMaxWord));
+    cudaMemset(ctx->mm64, 0, (size_t)(kMaxBatch * 2 + 2) * sizeof(MinMaxWord));
     ctx->mm_gen = 0;
   }
   *mm = ctx->mm64;
@@ -520,6 +521,8 @@ int specgpu_specgr(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x, i
   if ((rc = minmax_begin(ctx, &mm, &gen))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   StftArgs a = make_args(plan, x, n, ldx, 0, nseg, (float)plan->scale, S, ldt, mm, gen);
+  if (!(std::getenv("SPECGPU_STFT_DYNAMIC") && std::getenv("SPECGPU_STFT_DYNAMIC")[0] == '0'))
+    a.dyn = reinterpret_cast<unsigned*>(ctx->mm64 + kMaxBatch * 2);     // dynamic tile walk (see specgpu_pipeline)
   CHECK_LAUNCH(ctx, launch_stft(plan->log2n, STFT_MODE_LOGPSD, a, B, st), "stft_kernel", 1);
   CHECK_LAUNCH(ctx, launch_lognorm(S, B, plan->p.nperseg / 2, nseg, ldt, mm, minmax, st), "lognorm", 1);
   return SPECGPU_OK;
@@ -1221,6 +1224,9 @@ int specgpu_pipeline(specgpu_ctx* ctx, const specgpu_plan* plan, const float* x,
     float* Lg = tiled ? Lt + (size_t)b0 * ntile * rows * kTileCols : nullptr;
     StftArgs a = make_args(plan, x + b0 * ldx, n, ldx, 0, nseg, (float)plan->scale, tiled ? Lg : Sg, tiled ? -ntile : ldt, mmg, gen);
     a.l2_pin = l2_pin;
+    // dynamic tile walk of the STFT (one launch at a time per counter: not with channel groups on two lanes)
+    static const bool dyn_env = !(std::getenv("SPECGPU_STFT_DYNAMIC") && std::getenv("SPECGPU_STFT_DYNAMIC")[0] == '0');
+    a.dyn = (ngroups == 1 && dyn_env && !(flags & SPECGPU_PIPE_STATIC_TILES)) ? reinterpret_cast<unsigned*>(ctx->mm64 + kMaxBatch * 2) : nullptr;
     int64_t pre_gram[2] = {0, 0};
     bool fused = false;
     if (tiled && stft_gram_supported(plan->log2n) && std::getenv("SPECGPU_FUSED_GRAM")) {

@@ -86,12 +86,36 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
 #else
   constexpr bool flow = false;
 #endif
+  const unsigned tps = (unsigned)a.tiles_per_signal;      // ntiles < 2^31 is checked by the launcher
+  const unsigned ntiles = (unsigned)a.ntiles;
+  // Dynamic tile walk (barrier-free path, a.dyn != nullptr): the first tile of a CTA is its index, every further one comes
+  // from a global counter, fetched TWO tiles ahead by whichever lane issues the bulk copy of the next tile and published
+  // through a small ring in shared memory ({tile, signal, tile within the signal}; the copy's mbarrier orders it).  With
+  // the static walk (tile += gridDim.x) a CTA that becomes resident late -- this kernel launched while another stream's
+  // Gram / eigen kernels still hold SMs, api.ShotStreams -- finishes late by the same amount while the early ones idle.
+  unsigned* s_dyn = reinterpret_cast<unsigned*>(smem + L.bar_off + 48);     // [4][4]
+#if !defined(SPECGPU_EMULATE)
+  const bool dyn = flow && a.dyn != nullptr;
+  auto dyn_publish = [&](unsigned slot, bool fetch) {
+    unsigned nn = 0xffffffffu, nb = 0, nt = 0;
+    if (fetch) {
+      nn = gridDim.x + atomicAdd(a.dyn, 1u);
+      nb = nn / tps;
+      nt = nn - nb * tps;
+    }
+    s_dyn[4 * slot] = nn;
+    s_dyn[4 * slot + 1] = nb;
+    s_dyn[4 * slot + 2] = nt;
+  };
+  if (dyn && tid == 0) dyn_publish(1u, blockIdx.x < ntiles);
+#else
+  constexpr bool dyn = false;
+  (void)s_dyn;
+#endif
   pdl_trigger();     // persistent grid, all CTAs resident: the next kernel may move in as CTAs retire
   pdl_wait();        // the previous kernel of the stream (reader of the image this one overwrites) has completed
   __syncthreads();
 
-  const unsigned tps = (unsigned)a.tiles_per_signal;      // ntiles < 2^31 is checked by the launcher
-  const unsigned ntiles = (unsigned)a.ntiles;
   // Can the span of this tile come in as ONE aligned, in-range bulk copy?  (Otherwise -- first/last tiles of a
   // signal, odd alignments -- all threads fill the span with guarded loads, zero outside [0, n).)
   auto tile_bulk = [&](int64_t b, int64_t s0) -> bool {
@@ -133,6 +157,7 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
   unsigned cur_b = blockIdx.x / tps, cur_t = blockIdx.x - cur_b * tps;
   const unsigned step_b = gridDim.x / tps, step_t = gridDim.x - step_b * tps;
   unsigned nxt_b = 0, nxt_t = 0;
+  unsigned cur_tile = blockIdx.x, nxt_tile = 0, it = 0;
   if (flow) {
     // bulk tiles are prefetched by one thread; the others (first / last tiles of a signal) are filled at the loop top
     if (blockIdx.x < ntiles && tile_bulk(cur_b, tile_start(cur_t)) && tid == 0) prefetch(cur_b, cur_t);
@@ -140,14 +165,17 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
     prefetch(cur_b, cur_t);
   }
   // persistent CTAs: the tables above are loaded once, then the CTA walks tiles (signal b, TT segments)
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur_b = nxt_b, cur_t = nxt_t) {
+  for (; cur_tile < ntiles; cur_tile = nxt_tile, cur_b = nxt_b, cur_t = nxt_t, ++it) {
   const int64_t b = cur_b;
   const int64_t seg0 = (int64_t)cur_t * TT;
-  nxt_b = cur_b + step_b;
-  nxt_t = cur_t + step_t;
-  if (nxt_t >= tps) {
-    nxt_t -= tps;
-    ++nxt_b;
+  if (!dyn) {
+    nxt_tile = cur_tile + gridDim.x;
+    nxt_b = cur_b + step_b;
+    nxt_t = cur_t + step_t;
+    if (nxt_t >= tps) {
+      nxt_t -= tps;
+      ++nxt_b;
+    }
   }
   const float* xb = a.x + b * a.ldx;
   float vmin = INFINITY, vmax = -INFINITY;
@@ -164,6 +192,11 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
       __syncthreads();          // every warp holds its samples of the previous tile
       prefetch(cur_b, cur_t);   // guarded cooperative fill
       __syncthreads();
+    }
+    if (dyn) {                  // published before this tile's copy was issued (or before the barrier above)
+      nxt_tile = s_dyn[4 * ((it + 1u) & 3u)];
+      nxt_b = s_dyn[4 * ((it + 1u) & 3u) + 1];
+      nxt_t = s_dyn[4 * ((it + 1u) & 3u) + 2];
     }
   } else {
     // the previous tile's tensor store must have finished reading the shared tile before anybody rewrites it; with one
@@ -200,23 +233,27 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
 #if !defined(SPECGPU_EMULATE)
         // the last warp to hold its samples issues the bulk copy of the CTA's next tile (non-bulk tiles are filled
         // cooperatively at the top of their own iteration)
-        const unsigned next = tile + gridDim.x;
-        if (next < ntiles && tile_bulk(nxt_b, tile_start(nxt_t))) {
+        const bool nxt_ok = nxt_tile < ntiles;
+        const bool nxt_bulk = nxt_ok && tile_bulk(nxt_b, tile_start(nxt_t));
+        if (dyn || nxt_bulk) {
           __syncwarp();
           if ((tid & 31) == 0) {
             if (!(SPECGPU_STFT_ABL & 256)) __threadfence_block();
             if (atomicAdd(cnt_free, 1u) == kStftThreads / 32 - 1) {
               *cnt_free = 0;
+              if (dyn) dyn_publish((it + 2u) & 3u, nxt_ok);        // the tile after the next one
               if (!(SPECGPU_STFT_ABL & 256)) __threadfence_block();
-              mbar_arrive_expect_tx(bar, kAblSpan(a.span));
-              bulk_g2s(smem_u32(s_in), a.x + (int64_t)nxt_b * a.ldx + tile_start(nxt_t), kAblSpan(a.span), bar, pol_in);
+              if (nxt_bulk) {
+                mbar_arrive_expect_tx(bar, kAblSpan(a.span));
+                bulk_g2s(smem_u32(s_in), a.x + (int64_t)nxt_b * a.ldx + tile_start(nxt_t), kAblSpan(a.span), bar, pol_in);
+              }
             }
           }
         }
 #endif
       } else if (round == ROUNDS - 1) {
         __syncthreads();     // every thread holds its samples: the span may be overwritten
-        if (tile + gridDim.x < ntiles) prefetch(nxt_b, nxt_t);
+        if (nxt_tile < ntiles) prefetch(nxt_b, nxt_t);
       }
     } else {
       const int64_t s0 = a.first_start + seg * (int64_t)a.hop;
@@ -522,6 +559,16 @@ stft_kernel(const StftArgs a, const SPECGPU_GRID_CONSTANT TensorMap tmap) {
 #if !defined(SPECGPU_EMULATE)
   if (tma_out && tid == 0 && !flow) bulk_wait<0>();   // the last store must be complete before the CTA's shared memory goes away
   if (flow && pend) bulk_wait_read<0>();              // flow mode: whichever thread issued a store sees it through its reads
+  if (dyn && tid == 0) {
+    // every fetch of this CTA precedes this point (the lane that fetches for tile i + 2 does so before tile i + 1's copy,
+    // which this thread has consumed): the last CTA to leave rewinds the counter for the next launch
+    __threadfence();
+    if (atomicAdd(a.dyn + 1, 1u) == gridDim.x - 1) {
+      a.dyn[0] = 0;
+      a.dyn[1] = 0;
+      __threadfence();
+    }
+  }
 #endif
 }
 

@@ -87,7 +87,7 @@ __host__ __device__ inline StftSmem stft_smem_layout(int mode, int span_floats) 
   s.line_off = off;   off += stft_half_line<LOG2N>(mode) ? C::NG * C::LINEH * 4 : C::NG * C::LINE * 8;
   s.red_off = off;    off += (kStftThreads / 32) * 2 * 4 + 64;
   off = (off + 15) & ~15;
-  s.bar_off = off;    off += 48;     // three mbarriers (span full, tile 0 / 1 free) + three arrival counters
+  s.bar_off = off;    off += 48 + 64;   // three mbarriers (span full, tile 0 / 1 free) + three arrival counters; tile ring [4][4]
   off = (off + 127) & ~127;
   s.in_off = off;     off += (span_floats * 4 + 127) & ~127;
   s.tile_off = off;
