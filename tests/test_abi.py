@@ -43,6 +43,8 @@ def test_cuda_library_is_sm100a_with_tcgen05():
     assert "sm_100a" in elf
     sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass      # tcgen05.mma / tcgen05.ld (B200_PROFILING.md)
+    # TMA: bulk copies (STFT input span, Gram partial), tensor loads (Gram operands, CSD slabs), tensor stores (STFT tile)
+    assert "UBLKCP" in sass and "UTMALDG" in sass and "UTMASTG" in sass
 
 
 def test_missing_library_raises(tmp_path):
