@@ -19,8 +19,12 @@ for i in range(8): step(i)
 pool.join(); torch.cuda.synchronize()
 K = int(os.environ.get("K", 40))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time
 e0.record()
+t0 = time.perf_counter()
 for i in range(K): step(i)
+t_host = time.perf_counter() - t0
 pool.join()
 e1.record(); torch.cuda.synchronize()
+print("host enqueue us/shot", round(1e6 * t_host / K, 1))
 print("streams", NS, "interlock", int(ILK), "pad", os.environ.get("SPECGPU_STFT_SMEM_PAD", "0"), "ms/shot", round(e0.elapsed_time(e1) / K, 4))
