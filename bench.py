@@ -440,7 +440,7 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers ----
     # api.HostPipeline: the shot sits in pinned host memory; per step H2D of the 40 channels, the whole path, D2H of
     # the denoised spectrogram (channel groups on 3 streams so uploads, kernels and downloads overlap).
-    e2e_steps = max(2, min(args.steps, 10))
+    e2e_steps = max(2, min(args.steps, 20))
     if args.no_e2e:
         e2e_steps = 0
     e2e_ok, e2e_launches, e2e_value, e2e_ceiling = None, 0, None, None
